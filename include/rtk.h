@@ -1,0 +1,139 @@
+/* rtk.h — C ABI of librtk_b200.so: the B200-native replacement for Ratatosk's per-read
+ * correction hot path.
+ *
+ * The reference (DecodeGenetics/Ratatosk) has no FFI; its seam is a set of C++ free
+ * functions called from the worker loop of search() (src/Ratatosk.cpp:808-867).  Each entry
+ * point below names the reference interface it replaces.  Plain pointers and sizes only;
+ * every function returns 0 on success or a negative RTK_E* code (never exits, unlike the
+ * reference's exit(1)); rtk_last_error() gives the message for the calling thread.
+ *
+ * Threading: a context serialises work on its own CUDA stream; distinct contexts (one per
+ * GPU) may be used concurrently from distinct host threads.
+ */
+#ifndef RTK_H
+#define RTK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTK_OK 0
+#define RTK_EINVAL (-1)
+#define RTK_ECUDA (-2)
+#define RTK_EIO (-3)
+#define RTK_ENOMEM (-4)
+#define RTK_ENOGRAPH (-5)
+#define RTK_EUNSUPPORTED (-6)
+
+typedef struct rtk_ctx rtk_ctx;          /* one GPU: stream, device graph, scratch */
+typedef struct rtk_host_graph rtk_host_graph; /* flat graph slab in host memory */
+
+/* POD mirror of the hot-path fields of Correct_Opt (src/Common.hpp:16-158). */
+typedef struct rtk_opt {
+    uint32_t k;                    /* Correct_Opt::k for this pass (31 pass 1 / 63 pass 2) */
+    uint32_t insert_sz;            /* 500 */
+    uint32_t min_cov_vertices;     /* 2 */
+    uint32_t max_km_cov;           /* 128 (max'ed with the graph's top-0.1% coverage) */
+    uint32_t max_len_weak_region1; /* 1000 */
+    uint32_t max_len_weak_region2; /* 5000 */
+    uint32_t nb_correction_rounds; /* 1 */
+    int32_t out_qual;              /* 1 */
+    int32_t max_qual;              /* 40 */
+    int32_t trim_qual;             /* 0 */
+    double weak_region_len_factor; /* 0.25 */
+    double large_k_factor;         /* 1.5 */
+    double min_score;              /* 0.0 */
+    double min_confidence_snp_corr;/* 0.9 */
+    uint32_t force_unres_snp_corr; /* 0 */
+    uint32_t reserved;
+} rtk_opt;
+
+void rtk_opt_default(rtk_opt* opt, int pass); /* pass 1: k=31, pass 2: k=63 */
+
+/* A k-mer hit: const_UnitigMap<UnitigData> with len==1 (Bifrost/src/UnitigMap.hpp:58-66). */
+typedef struct rtk_hit {
+    uint32_t pos;     /* position in the query read */
+    uint32_t unitig;  /* unitig id (order of the index FASTA) */
+    uint32_t dist;    /* k-mer offset in the unitig, forward orientation */
+    uint32_t strand;  /* 1: read k-mer equals the unitig's forward k-mer */
+} rtk_hit;
+
+typedef struct rtk_graph_info {
+    uint32_t k;
+    uint64_t n_unitigs, n_kmers, pool_bases, n_buckets, n_gsets, slab_bytes, max_km_cov_graph;
+} rtk_graph_info;
+
+int rtk_version(void);
+const char* rtk_last_error(void);
+void rtk_free(void* p); /* releases any buffer handed out by this library */
+
+/* ---- graph (replaces CompactedDBG::read + readGraphData, src/Ratatosk.cpp:1087-1089) ---- */
+int rtk_graph_load(const char* fasta_path, const char* rtsk_path, int k, rtk_host_graph** out);
+/* unitigs only (no colours / flags): synthetic graphs for benchmarks and tests */
+int rtk_graph_from_unitigs(int k, uint64_t n, const char* const* seqs, rtk_host_graph** out);
+void rtk_graph_free(rtk_host_graph* g);
+int rtk_graph_get_info(const rtk_host_graph* g, rtk_graph_info* info);
+const void* rtk_graph_slab(const rtk_host_graph* g, uint64_t* bytes);
+int rtk_graph_save(const rtk_host_graph* g, const char* path);   /* flat cache file */
+int rtk_graph_open(const char* path, rtk_host_graph** out);
+/* per-unitig accessors over the host slab (tests / host-side callers) */
+int rtk_graph_unitig_seq(const rtk_host_graph* g, uint32_t unitig, char* buf, uint64_t cap, uint64_t* len);
+int rtk_graph_unitig_words(const rtk_host_graph* g, uint32_t unitig, uint64_t* kmcov, uint64_t* shared, uint32_t adj[8]);
+int rtk_graph_unitig_colors(const rtk_host_graph* g, uint32_t unitig, const uint32_t** gids, uint64_t* n_g,
+                            const uint32_t** lids, uint64_t* n_l);
+
+/* ---- device context ---- */
+int rtk_ctx_create(int device, rtk_ctx** out);
+void rtk_ctx_destroy(rtk_ctx* ctx);
+int rtk_graph_upload(rtk_ctx* ctx, const rtk_host_graph* g);               /* H2D copy of the slab */
+/* slab already resident on this device (e.g. after an NCCL broadcast done by the caller) */
+int rtk_graph_adopt_device(rtk_ctx* ctx, const void* dev_slab, uint64_t bytes);
+int rtk_ctx_sync(rtk_ctx* ctx);
+
+/* ---- K1: CompactedDBG::searchSequence (Bifrost/src/Search.tcc:526-768) ----
+ * Batch of n_reads upper-case reads, read i = seq_pool[seq_off[i], seq_off[i+1]).
+ * flags: bit0 exact, bit1 insertion, bit2 deletion, bit3 substitution, bit4 or_exclusive_match.
+ * Supported combinations are the two the reference uses (src/Graph.cpp:97,193): exact only,
+ * or any inexact subset without exact.  Output: for read i the hits hits[hit_off[i],hit_off[i+1])
+ * in the order the reference's v_um holds them.  *hits / *hit_off are library-allocated
+ * (rtk_free).  stats (optional, 4 x u64): probes, raw hits, kernel ns, total ns. */
+#define RTK_SEARCH_EXACT 1u
+#define RTK_SEARCH_INS 2u
+#define RTK_SEARCH_DEL 4u
+#define RTK_SEARCH_SUBST 8u
+#define RTK_SEARCH_OR_EXCL 16u
+int rtk_search_sequence(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
+                        uint32_t flags, rtk_hit** hits, uint64_t** hit_off, uint64_t* stats);
+
+/* Device-resident variant for measurement: reads already in HBM (dev_seq/dev_seq_off), raw
+ * labelled hits stay in HBM; returns the number of probes and raw hits.  Timed by bench.py. */
+int rtk_k1_sweep_device(rtk_ctx* ctx, uint32_t n_reads, const char* dev_seq, const uint64_t* dev_seq_off,
+                        const uint64_t* host_seq_off, uint32_t flags, uint64_t* n_probes, uint64_t* n_raw_hits,
+                        float* kernel_ms);
+
+/* ---- getSeeds (src/Graph.cpp:3-482): solid and weak anchors of each read ---- */
+typedef struct rtk_seeds {
+    rtk_hit* solid;        /* concatenated per read */
+    uint64_t* solid_off;   /* n_reads+1 */
+    rtk_hit* weak;
+    uint64_t* weak_off;    /* n_reads+1 */
+} rtk_seeds;
+int rtk_get_seeds(rtk_ctx* ctx, const rtk_opt* opt, int pass, uint32_t n_reads, const char* seq_pool,
+                  const uint64_t* seq_off, rtk_seeds* out, uint64_t* stats);
+void rtk_seeds_free(rtk_seeds* s);
+
+/* ---- K4: edlibAlign distance modes (src/edlib.cpp:141-296) with the IUPAC equality table
+ * (src/Common.hpp:262-276).  Pair i: query q_pool[q_off[i],q_off[i+1]), target likewise.
+ * mode[i]: 0 NW, 1 SHW, 2 HW.  kmax[i]: edlib's k (-1 = unbounded).
+ * Out: dist[i] (-1 if > kmax), and all end locations with that distance:
+ * end_loc[end_off[i], end_off[i+1]) ascending (library-allocated). */
+int rtk_edlib_batch(rtk_ctx* ctx, uint32_t n, const char* q_pool, const uint64_t* q_off, const char* t_pool,
+                    const uint64_t* t_off, const uint8_t* mode, const int32_t* kmax, int32_t* dist,
+                    int32_t** end_loc, uint64_t** end_off, uint64_t* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTK_H */

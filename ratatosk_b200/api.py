@@ -1,0 +1,285 @@
+"""ctypes binding of the C ABI in include/rtk.h (librtk_b200.so).
+
+Host-side mirror of the reference's correction entry points, with the reference's names:
+
+    Graph.load(fasta, rtsk, k)          CompactedDBG::read + readGraphData (src/Ratatosk.cpp:1087-1089)
+    Context.search_sequence(reads, ...) CompactedDBG::searchSequence       (Bifrost/src/Search.tcc:526)
+    Context.get_seeds(reads, opt, pass) getSeeds                           (src/Graph.cpp:3)
+    Context.edlib_batch(...)            edlibAlign                         (src/edlib.cpp:141)
+
+There is no CPU implementation behind these calls: the library needs a CUDA device and
+`Context()` raises if none is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "librtk_b200.so")
+
+SEARCH_EXACT, SEARCH_INS, SEARCH_DEL, SEARCH_SUBST, SEARCH_OR_EXCL = 1, 2, 4, 8, 16
+
+
+class RtkError(RuntimeError):
+    pass
+
+
+class RtkOpt(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("insert_sz", C.c_uint32), ("min_cov_vertices", C.c_uint32),
+                ("max_km_cov", C.c_uint32), ("max_len_weak_region1", C.c_uint32),
+                ("max_len_weak_region2", C.c_uint32), ("nb_correction_rounds", C.c_uint32),
+                ("out_qual", C.c_int32), ("max_qual", C.c_int32), ("trim_qual", C.c_int32),
+                ("weak_region_len_factor", C.c_double), ("large_k_factor", C.c_double), ("min_score", C.c_double),
+                ("min_confidence_snp_corr", C.c_double), ("force_unres_snp_corr", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class RtkHit(C.Structure):
+    _fields_ = [("pos", C.c_uint32), ("unitig", C.c_uint32), ("dist", C.c_uint32), ("strand", C.c_uint32)]
+
+
+class RtkGraphInfo(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("n_unitigs", C.c_uint64), ("n_kmers", C.c_uint64), ("pool_bases", C.c_uint64),
+                ("n_buckets", C.c_uint64), ("n_gsets", C.c_uint64), ("slab_bytes", C.c_uint64),
+                ("max_km_cov_graph", C.c_uint64)]
+
+
+class RtkSeeds(C.Structure):
+    _fields_ = [("solid", C.POINTER(RtkHit)), ("solid_off", C.POINTER(C.c_uint64)),
+                ("weak", C.POINTER(RtkHit)), ("weak_off", C.POINTER(C.c_uint64))]
+
+
+HIT_DTYPE = np.dtype([("pos", "<u4"), ("unitig", "<u4"), ("dist", "<u4"), ("strand", "<u4")])
+
+_libs = {}
+
+
+def load_library(path=None):
+    """dlopen the C-ABI library (cached per path). Raises if the built .so is missing."""
+    path = os.path.abspath(path or os.environ.get("RTK_LIB", DEFAULT_LIB))
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise RtkError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no fallback implementation)" % path)
+    L = C.CDLL(path)
+    L.rtk_version.restype = C.c_int
+    L.rtk_last_error.restype = C.c_char_p
+    L.rtk_free.argtypes = [C.c_void_p]
+    L.rtk_opt_default.argtypes = [C.POINTER(RtkOpt), C.c_int]
+    L.rtk_graph_load.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.rtk_graph_from_unitigs.argtypes = [C.c_int, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p)]
+    L.rtk_graph_free.argtypes = [C.c_void_p]
+    L.rtk_graph_get_info.argtypes = [C.c_void_p, C.POINTER(RtkGraphInfo)]
+    L.rtk_graph_slab.restype = C.c_void_p
+    L.rtk_graph_slab.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.rtk_graph_save.argtypes = [C.c_void_p, C.c_char_p]
+    L.rtk_graph_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.rtk_graph_unitig_seq.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.rtk_graph_unitig_words.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_uint32 * 8)]
+    L.rtk_graph_unitig_colors.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(C.c_uint32)),
+                                          C.POINTER(C.c_uint64), C.POINTER(C.POINTER(C.c_uint32)),
+                                          C.POINTER(C.c_uint64)]
+    L.rtk_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.rtk_ctx_destroy.argtypes = [C.c_void_p]
+    L.rtk_graph_upload.argtypes = [C.c_void_p, C.c_void_p]
+    L.rtk_ctx_sync.argtypes = [C.c_void_p]
+    L.rtk_search_sequence.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.c_uint32,
+                                      C.POINTER(C.POINTER(RtkHit)), C.POINTER(C.POINTER(C.c_uint64)),
+                                      C.POINTER(C.c_uint64)]
+    L.rtk_get_seeds.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_int, C.c_uint32, C.c_char_p,
+                                C.POINTER(C.c_uint64), C.POINTER(RtkSeeds), C.POINTER(C.c_uint64)]
+    L.rtk_seeds_free.argtypes = [C.POINTER(RtkSeeds)]
+    for name, args in (("rtk_graph_adopt_device", [C.c_void_p, C.c_void_p, C.c_uint64]),
+                       ("rtk_k1_sweep_device", [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                                C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint64),
+                                                C.POINTER(C.c_uint64), C.POINTER(C.c_float)]),
+                       ("rtk_edlib_batch", [C.c_void_p, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.c_char_p,
+                                            C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_int32)),
+                                            C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)])):
+        if hasattr(L, name):
+            getattr(L, name).argtypes = args
+    _libs[path] = L
+    return L
+
+
+def _check(L, rc):
+    if rc != 0:
+        raise RtkError("rtk error %d: %s" % (rc, (L.rtk_last_error() or b"").decode()))
+
+
+def default_opt(pass_no=1, lib=None):
+    L = load_library(lib)
+    o = RtkOpt()
+    L.rtk_opt_default(C.byref(o), pass_no)
+    return o
+
+
+def pack_reads(reads):
+    """list of str/bytes -> (pool bytes, uint64 offsets) in the layout the C ABI takes."""
+    bs = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+    off = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    return b"".join(bs), off
+
+
+class Graph:
+    """Flat graph slab in host memory."""
+
+    def __init__(self, handle, lib=None):
+        self.L = load_library(lib)
+        self.h = handle
+
+    @classmethod
+    def load(cls, fasta, rtsk, k, lib=None):
+        L = load_library(lib)
+        h = C.c_void_p()
+        _check(L, L.rtk_graph_load(fasta.encode(), (rtsk or "").encode() if rtsk else None, k, C.byref(h)))
+        return cls(h, lib)
+
+    @classmethod
+    def from_unitigs(cls, unitigs, k, lib=None):
+        L = load_library(lib)
+        arr = (C.c_char_p * len(unitigs))(*[u.encode() if isinstance(u, str) else u for u in unitigs])
+        h = C.c_void_p()
+        _check(L, L.rtk_graph_from_unitigs(k, len(unitigs), arr, C.byref(h)))
+        return cls(h, lib)
+
+    @classmethod
+    def open(cls, path, lib=None):
+        L = load_library(lib)
+        h = C.c_void_p()
+        _check(L, L.rtk_graph_open(path.encode(), C.byref(h)))
+        return cls(h, lib)
+
+    def save(self, path):
+        _check(self.L, self.L.rtk_graph_save(self.h, path.encode()))
+
+    def info(self):
+        i = RtkGraphInfo()
+        _check(self.L, self.L.rtk_graph_get_info(self.h, C.byref(i)))
+        return {f[0]: getattr(i, f[0]) for f in RtkGraphInfo._fields_}
+
+    def slab(self):
+        """numpy uint8 view of the slab (no copy)."""
+        n = C.c_uint64()
+        p = self.L.rtk_graph_slab(self.h, C.byref(n))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,))
+
+    def unitig_seq(self, u):
+        n = C.c_uint64()
+        _check(self.L, self.L.rtk_graph_unitig_seq(self.h, u, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _check(self.L, self.L.rtk_graph_unitig_seq(self.h, u, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value].decode()
+
+    def unitig_words(self, u):
+        a, b = C.c_uint64(), C.c_uint64()
+        adj = (C.c_uint32 * 8)()
+        _check(self.L, self.L.rtk_graph_unitig_words(self.h, u, C.byref(a), C.byref(b), C.byref(adj)))
+        return a.value, b.value, list(adj)
+
+    def unitig_colors(self, u):
+        pg, pl = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+        ng, nl = C.c_uint64(), C.c_uint64()
+        _check(self.L, self.L.rtk_graph_unitig_colors(self.h, u, C.byref(pg), C.byref(ng), C.byref(pl), C.byref(nl)))
+        return [pg[i] for i in range(ng.value)], [pl[i] for i in range(nl.value)]
+
+    def close(self):
+        if self.h:
+            self.L.rtk_graph_free(self.h)
+            self.h = None
+
+
+class Context:
+    """One GPU: stream, resident graph, scratch."""
+
+    def __init__(self, device=0, lib=None):
+        self.L = load_library(lib)
+        self.h = C.c_void_p()
+        _check(self.L, self.L.rtk_ctx_create(device, C.byref(self.h)))
+        self.graph = None
+
+    def upload(self, graph):
+        _check(self.L, self.L.rtk_graph_upload(self.h, graph.h))
+        self.graph = graph
+
+    def adopt_device_slab(self, dev_ptr, nbytes):
+        _check(self.L, self.L.rtk_graph_adopt_device(self.h, C.c_void_p(dev_ptr), nbytes))
+
+    def sync(self):
+        _check(self.L, self.L.rtk_ctx_sync(self.h))
+
+    def _split(self, ptr, off, n):
+        offs = np.ctypeslib.as_array(off, shape=(n + 1,)).copy()
+        total = int(offs[-1])
+        if total:
+            raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), shape=(total, 4)).copy()
+        else:
+            raw = np.zeros((0, 4), dtype=np.uint32)
+        return [raw[int(offs[i]):int(offs[i + 1])] for i in range(n)]
+
+    def search_sequence(self, reads, exact=True, insertion=False, deletion=False, substitution=False,
+                        or_exclusive_match=False, stats=None):
+        """per read: uint32 array [n,4] of (pos, unitig, dist, strand) in the reference's order"""
+        pool, off = pack_reads(reads)
+        flags = (SEARCH_EXACT if exact else 0) | (SEARCH_INS if insertion else 0) | (SEARCH_DEL if deletion else 0) \
+            | (SEARCH_SUBST if substitution else 0) | (SEARCH_OR_EXCL if or_exclusive_match else 0)
+        ph, po = C.POINTER(RtkHit)(), C.POINTER(C.c_uint64)()
+        st = (C.c_uint64 * 8)()
+        _check(self.L, self.L.rtk_search_sequence(self.h, len(reads), pool, off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                  flags, C.byref(ph), C.byref(po), st))
+        out = self._split(ph, po, len(reads))
+        self.L.rtk_free(C.cast(ph, C.c_void_p))
+        self.L.rtk_free(C.cast(po, C.c_void_p))
+        if stats is not None:
+            stats.extend(list(st))
+        return out
+
+    def get_seeds(self, reads, opt=None, pass_no=1, stats=None):
+        """-> (solid, weak): per read uint32 arrays [n,4] of (pos, unitig, dist, strand)"""
+        opt = opt or default_opt(pass_no)
+        pool, off = pack_reads(reads)
+        s = RtkSeeds()
+        st = (C.c_uint64 * 8)()
+        _check(self.L, self.L.rtk_get_seeds(self.h, C.byref(opt), pass_no, len(reads), pool,
+                                            off.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(s), st))
+        solid = self._split(s.solid, s.solid_off, len(reads))
+        weak = self._split(s.weak, s.weak_off, len(reads))
+        self.L.rtk_seeds_free(C.byref(s))
+        if stats is not None:
+            stats.extend(list(st))
+        return solid, weak
+
+    def edlib_batch(self, queries, targets, modes, kmax=None, stats=None):
+        """Myers edit distance for pairs; modes: 0 NW, 1 SHW, 2 HW -> (dist int32[n], list of end-location arrays)"""
+        n = len(queries)
+        qp, qo = pack_reads(queries)
+        tp, to = pack_reads(targets)
+        m = np.asarray(modes, dtype=np.uint8)
+        km = np.full(n, -1, dtype=np.int32) if kmax is None else np.asarray(kmax, dtype=np.int32)
+        dist = np.zeros(n, dtype=np.int32)
+        pe, po = C.POINTER(C.c_int32)(), C.POINTER(C.c_uint64)()
+        st = (C.c_uint64 * 8)()
+        _check(self.L, self.L.rtk_edlib_batch(self.h, n, qp, qo.ctypes.data_as(C.POINTER(C.c_uint64)), tp,
+                                              to.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                              m.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                              km.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              dist.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(pe), C.byref(po), st))
+        offs = np.ctypeslib.as_array(po, shape=(n + 1,)).copy()
+        total = int(offs[-1])
+        ends = np.ctypeslib.as_array(pe, shape=(max(total, 1),)).copy()[:total]
+        self.L.rtk_free(C.cast(pe, C.c_void_p))
+        self.L.rtk_free(C.cast(po, C.c_void_p))
+        if stats is not None:
+            stats.extend(list(st))
+        return dist, [ends[int(offs[i]):int(offs[i + 1])] for i in range(n)]
+
+    def close(self):
+        if self.h:
+            self.L.rtk_ctx_destroy(self.h)
+            self.h = None

@@ -1,0 +1,232 @@
+// rtk_api.cu — C ABI (include/rtk.h): contexts, graph residency, K1 driver.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "k1_lookup.cuh"
+#include "rtk_internal.hpp"
+#include "rtk_host_common.hpp"
+
+namespace rtk {
+
+
+static inline double now_ns() {
+    return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------- K1 driver
+uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint64_t* d_seq_off,
+                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms) {
+    if (!ctx->has_graph) throw std::invalid_argument("no graph uploaded to this context");
+    if (n_reads >= (1u << RTK_HIT_READ_BITS)) throw std::invalid_argument("more than 2^24 reads in one batch");
+    const uint32_t k = ctx->hdr.k;
+    const bool exact = flags & RTK_SEARCH_EXACT;
+    const bool inexact = flags & (RTK_SEARCH_INS | RTK_SEARCH_DEL | RTK_SEARCH_SUBST);
+    if (exact && inexact) throw std::invalid_argument("exact and inexact search in one call is not a combination the reference path uses");
+    const uint64_t total = h_seq_off[n_reads] - h_seq_off[0];
+
+    const uint32_t tile = k1_tile_size(k, exact);
+    std::vector<uint32_t> tiles;
+    build_tiles(n_reads, h_seq_off, k, tile, tiles);
+    const uint32_t n_tiles = (uint32_t)(tiles.size() / 2);
+    ctx->d_counters.reserve(64);
+    RTK_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
+    if (n_tiles == 0) {
+        if (n_probes) *n_probes = 0;
+        if (kernel_ms) *kernel_ms = 0.f;
+        return 0;
+    }
+    ctx->d_tiles.reserve(tiles.size() * 4);
+    RTK_CUDA(cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+
+    uint64_t cap = std::max<uint64_t>(1u << 20, exact ? total + 1024 : 2 * total + 1024);
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        ctx->d_hits.reserve(cap * sizeof(rtk_raw_hit));
+        cap = ctx->d_hits.cap / sizeof(rtk_raw_hit);
+        rtk_k1_params p;
+        p.table = ctx->dview.table; p.n_buckets = ctx->dview.n_buckets; p.pool = ctx->dview.pool; p.k = (int)k;
+        p.seq = d_seq; p.seq_off = d_seq_off; p.tiles = ctx->d_tiles.as<uint32_t>(); p.n_tiles = n_tiles; p.tile = tile;
+        p.do_subst = (flags & RTK_SEARCH_SUBST) ? 1 : 0;
+        p.do_ins = (flags & RTK_SEARCH_INS) ? 1 : 0;
+        p.do_del = (flags & RTK_SEARCH_DEL) ? 1 : 0;
+        p.hits = ctx->d_hits.as<rtk_raw_hit>();
+        p.n_hits = ctx->d_counters.as<unsigned long long>();
+        p.hit_cap = cap;
+        p.n_probes = n_probes ? ctx->d_counters.as<unsigned long long>() + 1 : nullptr;
+        RTK_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
+        // grid: whole waves of resident CTAs (148 SMs x 8 CTAs of 256 threads), grid-stride over tiles
+        const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * 8u);
+        RTK_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        if (exact) {
+            if (k <= 32) rtk_k1_exact_kernel<uint64_t><<<grid, RTK_K1_THREADS, 0, ctx->stream>>>(p);
+            else rtk_k1_exact_kernel<rtk_u128><<<grid, RTK_K1_THREADS, 0, ctx->stream>>>(p);
+        } else {
+            if (k <= 32) rtk_k1_inexact_kernel<uint64_t><<<grid, RTK_K1_THREADS, 0, ctx->stream>>>(p);
+            else rtk_k1_inexact_kernel<rtk_u128><<<grid, RTK_K1_THREADS, 0, ctx->stream>>>(p);
+        }
+        RTK_CUDA(cudaGetLastError());
+        RTK_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        unsigned long long cnt[2];
+        RTK_CUDA(cudaMemcpyAsync(cnt, ctx->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+        RTK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (kernel_ms) RTK_CUDA(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
+        if (n_probes) *n_probes = cnt[1];
+        if (cnt[0] <= cap) return cnt[0];
+        cap = cnt[0] + 1024;  // overflow: rerun with the exact size
+    }
+    throw std::runtime_error("K1 hit buffer overflow persisted");
+}
+
+void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
+                          std::vector<std::vector<rtk_hit>>& per_read, uint64_t* stats) {
+    const double t_start = now_ns();
+    if (!ctx->has_graph || !ctx->host_graph) throw std::invalid_argument("no graph uploaded to this context");
+    const uint64_t total = seq_off[n_reads] - seq_off[0];
+    // offsets relative to the start of this batch's pool
+    std::vector<uint64_t> rel(n_reads + 1);
+    for (uint32_t i = 0; i <= n_reads; ++i) rel[i] = seq_off[i] - seq_off[0];
+    ctx->d_seq.reserve(total + 16);
+    ctx->d_seq_off.reserve((n_reads + 1) * 8);
+    RTK_CUDA(cudaMemcpyAsync(ctx->d_seq.p, seq_pool + seq_off[0], total, cudaMemcpyHostToDevice, ctx->stream));
+    RTK_CUDA(cudaMemcpyAsync(ctx->d_seq_off.p, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t probes = 0;
+    float kms = 0.f;
+    const uint64_t n_raw = k1_launch(ctx, n_reads, ctx->d_seq.as<char>(), ctx->d_seq_off.as<uint64_t>(), rel.data(), flags, &probes, &kms);
+    std::vector<RawHit> raw(n_raw);
+    if (n_raw) {
+        RTK_CUDA(cudaMemcpyAsync(raw.data(), ctx->d_hits.p, n_raw * sizeof(RawHit), cudaMemcpyDeviceToHost, ctx->stream));
+        RTK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    resolve_batch(ctx->host_graph->view, n_reads, seq_pool, seq_off, flags, raw, per_read);
+    if (stats) {
+        stats[0] += probes;
+        stats[1] += n_raw;
+        stats[2] += (uint64_t)(kms * 1e6);
+        stats[3] += (uint64_t)(now_ns() - t_start);
+    }
+}
+
+}  // namespace rtk
+
+using namespace rtk;
+
+extern "C" {
+
+int rtk_ctx_create(int device, rtk_ctx** out) {
+    return guarded([&] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) throw CudaError(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)");
+        if (device < 0 || device >= n) throw std::invalid_argument("device index out of range");
+        RTK_CUDA(cudaSetDevice(device));
+        rtk_ctx* c = new rtk_ctx();
+        c->device = device;
+        RTK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        RTK_CUDA(cudaEventCreate(&c->ev0));
+        RTK_CUDA(cudaEventCreate(&c->ev1));
+        RTK_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+        *out = c;
+    });
+}
+
+void rtk_ctx_destroy(rtk_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->owns_slab && c->d_slab) cudaFree((void*)c->d_slab);
+    c->d_seq.release(); c->d_seq_off.release(); c->d_tiles.release(); c->d_hits.release(); c->d_counters.release();
+    for (auto& b : c->d_aux) b.release();
+    for (auto& b : c->h_pin) b.release();
+    if (c->host_copy.data) free(c->host_copy.data);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int rtk_graph_upload(rtk_ctx* c, const rtk_host_graph* g) {
+    return guarded([&] {
+        if (!c || !g) throw std::invalid_argument("null argument");
+        RTK_CUDA(cudaSetDevice(c->device));
+        if (c->owns_slab && c->d_slab) RTK_CUDA(cudaFree((void*)c->d_slab));
+        void* d = nullptr;
+        RTK_CUDA(cudaMalloc(&d, g->slab.bytes));
+        RTK_CUDA(cudaMemcpyAsync(d, g->slab.data, g->slab.bytes, cudaMemcpyHostToDevice, c->stream));
+        RTK_CUDA(cudaStreamSynchronize(c->stream));
+        c->d_slab = (const unsigned char*)d;
+        c->owns_slab = true;
+        c->hdr = g->hdr;
+        c->dview = rtk_make_view(d, c->hdr);
+        c->host_graph = g;
+        c->has_graph = true;
+    });
+}
+
+int rtk_graph_adopt_device(rtk_ctx* c, const void* dev_slab, uint64_t bytes) {
+    return guarded([&] {
+        if (!c || !dev_slab) throw std::invalid_argument("null argument");
+        RTK_CUDA(cudaSetDevice(c->device));
+        if (bytes < sizeof(rtk_slab_header)) throw std::invalid_argument("slab too small");
+        // the host-side anchor logic needs a host mirror: copy the slab back once
+        if (c->host_copy.data) { free(c->host_copy.data); c->host_copy.data = nullptr; }
+        c->host_copy.data = (unsigned char*)aligned_alloc(256, (bytes + 255) & ~(uint64_t)255);
+        c->host_copy.bytes = bytes;
+        RTK_CUDA(cudaMemcpyAsync(c->host_copy.data, dev_slab, bytes, cudaMemcpyDeviceToHost, c->stream));
+        RTK_CUDA(cudaStreamSynchronize(c->stream));
+        c->host_graph_owned.slab = c->host_copy;
+        finish_host_graph(&c->host_graph_owned);
+        if (c->owns_slab && c->d_slab) RTK_CUDA(cudaFree((void*)c->d_slab));
+        c->d_slab = (const unsigned char*)dev_slab;
+        c->owns_slab = false;
+        c->hdr = c->host_graph_owned.hdr;
+        c->dview = rtk_make_view(dev_slab, c->hdr);
+        c->host_graph = &c->host_graph_owned;
+        c->has_graph = true;
+    });
+}
+
+int rtk_ctx_sync(rtk_ctx* c) {
+    return guarded([&] { RTK_CUDA(cudaStreamSynchronize(c->stream)); });
+}
+
+int rtk_search_sequence(rtk_ctx* c, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
+                        rtk_hit** hits, uint64_t** hit_off, uint64_t* stats) {
+    return guarded([&] {
+        if (!c || !seq_pool || !seq_off || !hits || !hit_off) throw std::invalid_argument("null argument");
+        RTK_CUDA(cudaSetDevice(c->device));
+        std::vector<std::vector<rtk_hit>> per_read;
+        search_sequence_host(c, n_reads, seq_pool, seq_off, flags, per_read, stats);
+        flatten_hits(per_read, hits, hit_off);
+    });
+}
+
+int rtk_k1_sweep_device(rtk_ctx* c, uint32_t n_reads, const char* dev_seq, const uint64_t* dev_seq_off,
+                        const uint64_t* host_seq_off, uint32_t flags, uint64_t* n_probes, uint64_t* n_raw_hits,
+                        float* kernel_ms) {
+    return guarded([&] {
+        if (!c || !dev_seq || !dev_seq_off || !host_seq_off) throw std::invalid_argument("null argument");
+        RTK_CUDA(cudaSetDevice(c->device));
+        uint64_t probes = 0;
+        const uint64_t n = k1_launch(c, n_reads, dev_seq, dev_seq_off, host_seq_off, flags, &probes, kernel_ms);
+        if (n_probes) *n_probes = probes;
+        if (n_raw_hits) *n_raw_hits = n;
+    });
+}
+
+int rtk_get_seeds(rtk_ctx* c, const rtk_opt* opt, int pass, uint32_t n_reads, const char* seq_pool,
+                  const uint64_t* seq_off, rtk_seeds* out, uint64_t* stats) {
+    return guarded([&] {
+        if (!c || !opt || !seq_pool || !seq_off || !out) throw std::invalid_argument("null argument");
+        RTK_CUDA(cudaSetDevice(c->device));
+        std::vector<std::vector<rtk_hit>> solid, weak;
+        get_seeds_host(c, *opt, pass, n_reads, seq_pool, seq_off, solid, weak, stats);
+        flatten_hits(solid, &out->solid, &out->solid_off);
+        flatten_hits(weak, &out->weak, &out->weak_off);
+    });
+}
+
+}  // extern "C"

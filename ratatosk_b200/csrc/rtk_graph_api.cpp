@@ -1,0 +1,158 @@
+// rtk_graph_api.cpp — host-only part of the C ABI (include/rtk.h): errors, options, graph
+// loading / flattening / accessors.  No CUDA here; shared by librtk_b200.so and tests/hostsim.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "kmer.cuh"
+#include "rtk_host_common.hpp"
+
+namespace rtk {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+void flatten_hits(const std::vector<std::vector<rtk_hit>>& per_read, rtk_hit** hits, uint64_t** off) {
+    const size_t n = per_read.size();
+    uint64_t total = 0;
+    for (const auto& v : per_read) total += v.size();
+    *off = (uint64_t*)malloc((n + 1) * sizeof(uint64_t));
+    *hits = (rtk_hit*)malloc((total + 1) * sizeof(rtk_hit));
+    if (!*off || !*hits) throw std::bad_alloc();
+    uint64_t t = 0;
+    for (size_t i = 0; i < n; ++i) {
+        (*off)[i] = t;
+        if (!per_read[i].empty()) memcpy(*hits + t, per_read[i].data(), per_read[i].size() * sizeof(rtk_hit));
+        t += per_read[i].size();
+    }
+    (*off)[n] = t;
+}
+}  // namespace rtk
+
+using namespace rtk;
+
+extern "C" {
+
+int rtk_version(void) { return 100; }
+const char* rtk_last_error(void) { return rtk::g_err.c_str(); }
+void rtk_free(void* p) { free(p); }
+
+void rtk_opt_default(rtk_opt* o, int pass) {
+    memset(o, 0, sizeof(*o));
+    o->k = (pass == 2) ? 63 : 31;
+    o->insert_sz = 500; o->min_cov_vertices = 2; o->max_km_cov = 128;
+    o->max_len_weak_region1 = 1000; o->max_len_weak_region2 = 5000; o->nb_correction_rounds = 1;
+    o->out_qual = 1; o->max_qual = 40; o->trim_qual = 0;
+    o->weak_region_len_factor = 0.25; o->large_k_factor = 1.5; o->min_score = 0.0; o->min_confidence_snp_corr = 0.9;
+}
+
+int rtk_graph_load(const char* fasta_path, const char* rtsk_path, int k, rtk_host_graph** out) {
+    return guarded([&] {
+        if (!fasta_path || !out) throw std::invalid_argument("null argument");
+        HostGraph hg = load_index(fasta_path, rtsk_path ? rtsk_path : "", k);
+        rtk_host_graph* g = new rtk_host_graph();
+        g->slab = build_slab(hg);
+        finish_host_graph(g);
+        *out = g;
+    });
+}
+
+int rtk_graph_from_unitigs(int k, uint64_t n, const char* const* seqs, rtk_host_graph** out) {
+    return guarded([&] {
+        if (!seqs || !out) throw std::invalid_argument("null argument");
+        HostGraph hg;
+        hg.k = k;
+        hg.unitigs.reserve(n);
+        for (uint64_t i = 0; i < n; ++i) hg.unitigs.emplace_back(seqs[i]);
+        rtk_host_graph* g = new rtk_host_graph();
+        g->slab = build_slab(hg);
+        finish_host_graph(g);
+        *out = g;
+    });
+}
+
+void rtk_graph_free(rtk_host_graph* g) {
+    if (!g) return;
+    free(g->slab.data);
+    delete g;
+}
+
+int rtk_graph_get_info(const rtk_host_graph* g, rtk_graph_info* info) {
+    if (!g || !info) { set_error("null argument"); return RTK_EINVAL; }
+    info->k = g->hdr.k; info->n_unitigs = g->hdr.n_unitigs; info->n_kmers = g->hdr.n_kmers;
+    info->pool_bases = g->hdr.pool_bases; info->n_buckets = g->hdr.n_buckets; info->n_gsets = g->hdr.n_gsets;
+    info->slab_bytes = g->hdr.total_bytes; info->max_km_cov_graph = g->hdr.max_km_cov_graph;
+    return RTK_OK;
+}
+
+const void* rtk_graph_slab(const rtk_host_graph* g, uint64_t* bytes) {
+    if (!g) return nullptr;
+    if (bytes) *bytes = g->slab.bytes;
+    return g->slab.data;
+}
+
+int rtk_graph_save(const rtk_host_graph* g, const char* path) {
+    return guarded([&] {
+        FILE* f = fopen(path, "wb");
+        if (!f) throw std::runtime_error(std::string("cannot write ") + path);
+        const size_t w = fwrite(g->slab.data, 1, g->slab.bytes, f);
+        fclose(f);
+        if (w != g->slab.bytes) throw std::runtime_error("short write");
+    });
+}
+
+int rtk_graph_open(const char* path, rtk_host_graph** out) {
+    return guarded([&] {
+        FILE* f = fopen(path, "rb");
+        if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+        fseek(f, 0, SEEK_END);
+        const long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        rtk_host_graph* g = new rtk_host_graph();
+        g->slab.bytes = (uint64_t)sz;
+        g->slab.data = (unsigned char*)aligned_alloc(256, ((size_t)sz + 255) & ~(size_t)255);
+        const size_t r = fread(g->slab.data, 1, (size_t)sz, f);
+        fclose(f);
+        if (r != (size_t)sz) { free(g->slab.data); delete g; throw std::runtime_error("short read"); }
+        try { finish_host_graph(g); } catch (...) { free(g->slab.data); delete g; throw; }
+        *out = g;
+    });
+}
+
+int rtk_graph_unitig_seq(const rtk_host_graph* g, uint32_t u, char* buf, uint64_t cap, uint64_t* len) {
+    if (!g || u >= g->hdr.n_unitigs) { set_error("bad unitig id"); return RTK_EINVAL; }
+    const uint64_t b = g->view.unitig_off[u], e = g->view.unitig_off[u + 1];
+    if (len) *len = e - b;
+    if (buf) {
+        if (cap < e - b) { set_error("buffer too small"); return RTK_EINVAL; }
+        for (uint64_t p = b; p < e; ++p) buf[p - b] = "ACGT"[rtk_pool_base(g->view.pool, p)];
+    }
+    return RTK_OK;
+}
+
+int rtk_graph_unitig_words(const rtk_host_graph* g, uint32_t u, uint64_t* kmcov, uint64_t* shared, uint32_t adj[8]) {
+    if (!g || u >= g->hdr.n_unitigs) { set_error("bad unitig id"); return RTK_EINVAL; }
+    if (kmcov) *kmcov = g->view.kmcov[u];
+    if (shared) *shared = g->view.shared[u];
+    if (adj) memcpy(adj, g->view.adj + 8 * (uint64_t)u, 32);
+    return RTK_OK;
+}
+
+int rtk_graph_unitig_colors(const rtk_host_graph* g, uint32_t u, const uint32_t** gids, uint64_t* n_g,
+                            const uint32_t** lids, uint64_t* n_l) {
+    if (!g || u >= g->hdr.n_unitigs) { set_error("bad unitig id"); return RTK_EINVAL; }
+    const uint32_t gs = g->view.gset_of[u];
+    if (gs == RTK_NONE32) { *gids = nullptr; *n_g = 0; }
+    else { *gids = g->view.gset_ids + g->view.gset_off[gs]; *n_g = g->view.gset_off[gs + 1] - g->view.gset_off[gs]; }
+    *lids = g->view.loc_ids + g->view.loc_off[u];
+    *n_l = g->view.loc_off[u + 1] - g->view.loc_off[u];
+    return RTK_OK;
+}
+
+
+void rtk_seeds_free(rtk_seeds* s) {
+    if (!s) return;
+    free(s->solid); free(s->solid_off); free(s->weak); free(s->weak_off);
+    memset(s, 0, sizeof(*s));
+}
+
+}  // extern "C"

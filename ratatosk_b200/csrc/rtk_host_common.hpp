@@ -1,0 +1,72 @@
+// rtk_host_common.hpp — host helpers shared by the CUDA build and the tests/hostsim build.
+#pragma once
+#include <algorithm>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "k1_lookup_layout.h"
+#include "rtk_internal.hpp"
+
+#ifndef RTK_K1_THREADS
+#define RTK_K1_THREADS 256
+#define RTK_K1_TILE 224 /* read positions per CTA: leaves room for the 1/(k-1) stretch of insertion strings */
+#endif
+
+namespace rtk {
+
+#ifdef RTK_HOSTSIM
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#endif
+
+template <typename F> inline int guarded(F&& f) {
+    try {
+        f();
+        return RTK_OK;
+    } catch (const CudaError& e) {
+        set_error(e.what());
+        return RTK_ECUDA;
+    } catch (const std::bad_alloc&) {
+        set_error("out of host memory");
+        return RTK_ENOMEM;
+    } catch (const std::invalid_argument& e) {
+        set_error(e.what());
+        return RTK_EINVAL;
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return RTK_EIO;
+    }
+}
+
+inline void finish_host_graph(rtk_host_graph* g) {
+    memcpy(&g->hdr, g->slab.data, sizeof(rtk_slab_header));
+    if (g->hdr.magic != RTK_SLAB_MAGIC || g->hdr.version != RTK_SLAB_VERSION) throw std::runtime_error("not a flat graph slab");
+    if (g->hdr.total_bytes != g->slab.bytes) throw std::runtime_error("flat graph slab size mismatch");
+    g->view = rtk_make_view(g->slab.data, g->hdr);
+}
+
+
+// read positions per K1 tile: the insertion strings stretch a tile by k/(k-1), all of its
+// variant-string positions must fit one pass of RTK_K1_THREADS threads
+inline uint32_t k1_tile_size(uint32_t k, bool exact) {
+    if (exact) return RTK_K1_THREADS;
+    const uint32_t lim = (uint32_t)((uint64_t)RTK_K1_THREADS * (k - 1) / k) - 2;
+    return std::min<uint32_t>(RTK_K1_TILE, lim);
+}
+
+inline void build_tiles(uint32_t n_reads, const uint64_t* h_seq_off, uint32_t k, uint32_t tile, std::vector<uint32_t>& tiles) {
+    tiles.clear();
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        const uint64_t len = h_seq_off[r + 1] - h_seq_off[r];
+        if (len >= (1ULL << RTK_HIT_POS_BITS)) throw std::invalid_argument("read longer than 2^30 bases");
+        if (len < k) continue;
+        // positions l with l + k - 1 <= len (one past the last full k-mer: insertion windows use k-1 read bases)
+        const uint32_t npos = (uint32_t)(len - k + 2);
+        for (uint32_t t0 = 0; t0 < npos; t0 += tile) { tiles.push_back(r); tiles.push_back(t0); }
+    }
+}
+
+void flatten_hits(const std::vector<std::vector<rtk_hit>>& per_read, rtk_hit** hits, uint64_t** off);
+
+}  // namespace rtk

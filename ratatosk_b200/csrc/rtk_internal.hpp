@@ -1,0 +1,125 @@
+// rtk_internal.hpp — private declarations shared by the translation units of librtk_b200.so.
+#pragma once
+#ifndef RTK_HOSTSIM
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/rtk.h"
+#include "flat_graph.h"
+#include "graph_build.hpp"
+#include "seeds_resolve.hpp"
+
+struct rtk_host_graph {
+    rtk::rtk_slab slab;
+    rtk_slab_header hdr;
+    rtk_graph_view view;  // host pointers
+};
+
+namespace rtk {
+
+void set_error(const std::string& msg);
+
+}  // namespace rtk
+
+#ifndef RTK_HOSTSIM
+namespace rtk {
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define RTK_CUDA(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            throw rtk::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +    \
+                                 std::to_string(__LINE__) + ")");                                            \
+    } while (0)
+
+// grow-only device / pinned-host buffers
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) RTK_CUDA(cudaFree(p));
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        RTK_CUDA(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) RTK_CUDA(cudaFreeHost(p));
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        RTK_CUDA(cudaMallocHost(&p, want));
+        cap = want;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+}  // namespace rtk
+#endif  // !RTK_HOSTSIM
+
+#ifdef RTK_HOSTSIM
+// tests/hostsim: the kernels run on the CPU simulator, the context only carries the graph
+struct rtk_ctx {
+    bool has_graph = false;
+    rtk_slab_header hdr;
+    const rtk_host_graph* host_graph = nullptr;
+};
+#else
+struct rtk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // graph
+    const unsigned char* d_slab = nullptr;
+    bool owns_slab = false;
+    bool has_graph = false;
+    rtk_slab_header hdr;
+    rtk_graph_view dview;                 // device pointers
+    const rtk_host_graph* host_graph = nullptr;  // host mirror (needed by the host-side anchor logic)
+    rtk::rtk_slab host_copy;              // when the graph was adopted from device memory
+    rtk_host_graph host_graph_owned;
+    // scratch
+    rtk::DevBuf d_seq, d_seq_off, d_tiles, d_hits, d_counters, d_aux[8];
+    rtk::PinBuf h_pin[4];
+    int sm_count = 148;
+};
+#endif
+
+namespace rtk {
+
+// sorted raw hits of a batch -> per-read hit lists in reference order (shared by product and hostsim)
+void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
+                   std::vector<RawHit>& raw, std::vector<std::vector<rtk_hit>>& per_read);
+
+// K1 driver: runs the exact and/or inexact kernels over reads resident on the device and leaves the
+// raw labelled hits in ctx->d_hits.  Returns raw hit count; *n_probes / *kernel_ms optional.
+uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint64_t* d_seq_off,
+                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms);
+
+// full searchSequence for a host batch -> per read ordered hits
+void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
+                          std::vector<std::vector<rtk_hit>>& per_read, uint64_t* stats);
+
+// getSeeds host logic over the hit lists (seeds.cpp)
+void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool,
+                    const uint64_t* seq_off, std::vector<std::vector<rtk_hit>>& solid,
+                    std::vector<std::vector<rtk_hit>>& weak, uint64_t* stats);
+
+}  // namespace rtk

@@ -1,0 +1,150 @@
+// seeds_resolve.cpp — see seeds_resolve.hpp.
+#include "seeds_resolve.hpp"
+
+#include <algorithm>
+#include <unordered_set>
+
+#include "k1_lookup_layout.h"
+#include "lookup.cuh"
+
+namespace rtk {
+
+namespace {
+
+struct Decoded {
+    uint32_t var, pos_s, unitig, off, strand;
+    uint64_t P;
+};
+
+inline Decoded decode(const rtk_graph_view& g, const RawHit& r) {
+    Decoded d;
+    d.pos_s = (uint32_t)(r.a & ((1ULL << RTK_HIT_POS_BITS) - 1));
+    d.var = (uint32_t)((r.a >> RTK_HIT_POS_BITS) & ((1ULL << RTK_HIT_VAR_BITS) - 1));
+    d.P = r.b & RTK_POS_MASK;
+    d.strand = (uint32_t)((r.b >> 40) & 1);
+    d.unitig = rtk_unitig_of(g.blk2unitig, g.unitig_off, d.P);
+    d.off = (uint32_t)(d.P - g.unitig_off[d.unitig]);
+    return d;
+}
+
+inline bool is_dna(const char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'a' || c == 'c' || c == 'g' || c == 't'; }
+
+struct PosKm {
+    uint64_t pos;
+    uint64_t km;  // (P<<1)|strand, or ~0 for the empty k-mer
+    bool operator==(const PosKm& o) const { return pos == o.pos && km == o.km; }
+};
+struct PosKmHash {
+    size_t operator()(const PosKm& p) const { return (size_t)rtk_mix64(p.pos * 0x9E3779B97F4A7C15ULL ^ rtk_mix64(p.km)); }
+};
+
+// length of the unitig run starting at raw[i]: consecutive pos_s, same unitig, offsets +-1
+inline size_t run_length(const std::vector<Decoded>& d, size_t i, size_t end, uint32_t k, const rtk_graph_view& g) {
+    const uint64_t usize = g.unitig_off[d[i].unitig + 1] - g.unitig_off[d[i].unitig];
+    if (usize == k) return 1;  // short / abundant unitigs are never extended (CompactedDBG.tcc:4489)
+    size_t len = 1;
+    while (i + len < end) {
+        const Decoded& p = d[i + len - 1];
+        const Decoded& q = d[i + len];
+        if (q.pos_s != p.pos_s + 1 || q.unitig != p.unitig || q.strand != p.strand) break;
+        if (p.strand ? (q.off != p.off + 1) : (q.off + 1 != p.off)) break;
+        ++len;
+    }
+    return len;
+}
+
+}  // namespace
+
+void resolve_exact(const rtk_graph_view& g, const RawHit* raw, size_t n, std::vector<rtk_hit>& out) {
+    std::vector<Decoded> d(n);
+    for (size_t i = 0; i < n; ++i) d[i] = decode(g, raw[i]);
+    size_t i = 0;
+    while (i < n) {
+        const size_t len = run_length(d, i, n, g.k, g);
+        if (d[i].strand) {
+            for (size_t j = 0; j < len; ++j) out.push_back({d[i + j].pos_s, d[i].unitig, d[i + j].off, 1u});
+        } else {
+            // Search.tcc:700: j ascends over unitig offsets, read position descends
+            for (size_t j = len; j-- > 0;) out.push_back({d[i + j].pos_s, d[i].unitig, d[i + j].off, 0u});
+        }
+        i += len;
+    }
+}
+
+void resolve_inexact(const rtk_graph_view& g, const char* s, uint32_t slen, bool or_exclusive, const RawHit* raw,
+                     size_t n, std::vector<rtk_hit>& out) {
+    const uint32_t k = g.k;
+    std::vector<Decoded> d(n);
+    for (size_t i = 0; i < n; ++i) d[i] = decode(g, raw[i]);
+    std::unordered_set<PosKm, PosKmHash> us_pos_km;
+    us_pos_km.reserve(n * 2 + 16);
+    size_t gi = 0;
+    while (gi < n) {
+        size_t ge = gi;
+        while (ge < n && d[ge].var == d[gi].var) ++ge;
+        // variant -> (type, shift)
+        const uint32_t var = d[gi].var;
+        uint32_t shift;
+        bool ins = false, del = false;
+        if (var < 4 * k) shift = var / 4;
+        else if (var < 8 * k) { ins = true; shift = (var - 4 * k) / 4; }
+        else { del = true; shift = var - 8 * k; }
+        // Search.tcc:586-589 / :663-664
+        auto map_pos = [&](const uint64_t pos) -> uint64_t {
+            const uint64_t sp = (pos / k) + ((pos % k) > shift ? 1 : 0);
+            if (ins) return pos - sp;
+            if (del) return pos + sp;
+            return pos;
+        };
+        size_t i = gi;
+        while (i < ge) {
+            const Decoded& h = d[i];
+            const uint64_t l_pos_s = map_pos(h.pos_s);
+            bool cond = (l_pos_s + k - 1 < slen) && is_dna(s[l_pos_s]) && is_dna(s[l_pos_s + k - 1]);
+            if (cond && or_exclusive) {
+                // rpos is empty (no exact pass in the same call); key = the variant k-mer itself
+                cond = (us_pos_km.find(PosKm{l_pos_s, (h.P << 1) | h.strand}) == us_pos_km.end());
+            }
+            if (!cond) { ++i; continue; }
+            const size_t len = run_length(d, i, ge, k, g);
+            // um.dist = smallest unitig offset of the run, um.len = len; j ascends over offsets
+            const uint32_t um_dist = h.strand ? h.off : (uint32_t)(h.off - (len - 1));
+            for (size_t jj = 0; jj < len; ++jj) {
+                const uint32_t j = um_dist + (uint32_t)jj;
+                // strand: pos_s + j - dist ; else pos_s + dist + len - j - 1
+                const uint64_t p_inexact = h.strand ? (uint64_t)h.pos_s + jj : (uint64_t)h.pos_s + (len - 1 - jj);
+                const uint64_t l_pos_seq = map_pos(p_inexact);
+                if (l_pos_seq + k - 1 >= slen) continue;
+                // getMappedKmer(j): real k-mer only when j < um.len (and j indexes the unitig)
+                const uint64_t usz = g.unitig_off[h.unitig + 1] - g.unitig_off[h.unitig];
+                uint64_t key = ~0ULL;
+                if (j < len) {
+                    if (usz == k) { if (j == 0) key = ((g.unitig_off[h.unitig]) << 1) | h.strand; }  // isShort: pos+dist==0
+                    else if (j < usz - k + 1) key = ((g.unitig_off[h.unitig] + j) << 1) | h.strand;
+                }
+                if (us_pos_km.insert(PosKm{l_pos_seq, key}).second) out.push_back({(uint32_t)l_pos_seq, h.unitig, j, h.strand});
+            }
+            i += len;
+        }
+        gi = ge;
+    }
+}
+
+void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
+                   std::vector<RawHit>& raw, std::vector<std::vector<rtk_hit>>& per_read) {
+    per_read.assign(n_reads, {});
+    std::sort(raw.begin(), raw.end(), [](const RawHit& x, const RawHit& y) { return x.a < y.a; });
+    const bool exact = flags & RTK_SEARCH_EXACT;
+    size_t i = 0;
+    while (i < raw.size()) {
+        const uint32_t r = (uint32_t)(raw[i].a >> (RTK_HIT_VAR_BITS + RTK_HIT_POS_BITS));
+        size_t e = i;
+        while (e < raw.size() && (uint32_t)(raw[e].a >> (RTK_HIT_VAR_BITS + RTK_HIT_POS_BITS)) == r) ++e;
+        if (exact) resolve_exact(hv, raw.data() + i, e - i, per_read[r]);
+        else resolve_inexact(hv, seq_pool + seq_off[r], (uint32_t)(seq_off[r + 1] - seq_off[r]), (flags & RTK_SEARCH_OR_EXCL) != 0,
+                             raw.data() + i, e - i, per_read[r]);
+        i = e;
+    }
+}
+
+}  // namespace rtk

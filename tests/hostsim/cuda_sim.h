@@ -1,0 +1,86 @@
+// cuda_sim.h — TEST INFRASTRUCTURE: runs the repo's CUDA kernel SOURCE on the CPU.
+//
+// There is no GPU in the build container, so the `-m "not gpu"` tests compile the very same
+// .cuh kernel sources with g++ against this shim and execute them with one host thread per
+// CUDA thread (blocks run one after another; __syncthreads is a pthread barrier; warp
+// collectives go through a per-warp exchange area).  This is a debugging vehicle for index
+// arithmetic and bit manipulation, NOT a product path: nothing here is linked into
+// librtk_b200.so, and the product fails loudly without a CUDA device (rtk_ctx_create).
+#pragma once
+#define RTK_HOSTSIM 1
+#include <pthread.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <atomic>
+#include <functional>
+#include <thread>
+#include <vector>
+
+struct sim_dim3 { unsigned x = 1, y = 1, z = 1; };
+struct ulonglong2 { unsigned long long x, y; };
+
+extern thread_local sim_dim3 threadIdx, blockIdx;
+extern sim_dim3 blockDim, gridDim;
+extern pthread_barrier_t sim_block_barrier;
+struct sim_warp_area { pthread_barrier_t bar; unsigned long long slot[32]; };
+extern sim_warp_area* sim_warps;
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __shared__ static
+#define __launch_bounds__(...)
+#define __CUDACC_SIM__ 1
+
+static inline void __syncthreads() { pthread_barrier_wait(&sim_block_barrier); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&sim_warps[threadIdx.x >> 5].bar); }
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
+
+// All 32 lanes of a warp must call these (full-mask use only, as in the kernels).
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    sim_warp_area& w = sim_warps[threadIdx.x >> 5];
+    w.slot[threadIdx.x & 31] = pred ? 1 : 0;
+    pthread_barrier_wait(&w.bar);
+    unsigned m = 0;
+    const unsigned nl = ((threadIdx.x >> 5) * 32 + 32 <= blockDim.x) ? 32 : (blockDim.x & 31);
+    for (unsigned i = 0; i < nl; ++i) m |= (unsigned)(w.slot[i] & 1) << i;
+    pthread_barrier_wait(&w.bar);
+    return m;
+}
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
+    sim_warp_area& w = sim_warps[threadIdx.x >> 5];
+    unsigned long long x = 0;
+    memcpy(&x, &v, sizeof(T) <= 8 ? sizeof(T) : 8);
+    w.slot[threadIdx.x & 31] = x;
+    pthread_barrier_wait(&w.bar);
+    const unsigned long long y = w.slot[src & 31];
+    pthread_barrier_wait(&w.bar);
+    T r;
+    memcpy(&r, &y, sizeof(T) <= 8 ? sizeof(T) : 8);
+    return r;
+}
+template <typename T> static inline T __shfl_down_sync(unsigned m, T v, int d) {
+    const int lane = threadIdx.x & 31;
+    const T r = __shfl_sync(m, v, (lane + d) & 31);
+    return (lane + d < 32) ? r : v;
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned m, T v, int d) { return __shfl_sync(m, v, (threadIdx.x & 31) ^ d); }
+
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicMax(unsigned* p, unsigned v) {
+    unsigned o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (o < v && !__atomic_compare_exchange_n(p, &o, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return o;
+}
+
+// Launch `body` (a lambda calling the kernel) on grid x block host threads.
+void sim_launch(unsigned grid, unsigned block, const std::function<void()>& body);

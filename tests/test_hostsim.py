@@ -1,0 +1,100 @@
+"""CPU tests of the product's own sources: the index loader / slab builder, the host-side anchor
+logic, and the K1 kernel SOURCES executed on the CPU simulator (tests/hostsim), all compared with
+golden vectors recorded from the unmodified reference."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+import ratatosk_b200 as rb
+from common import GOLDEN, golden_paths, load_golden_reads
+
+
+@pytest.fixture(scope="module", params=["F1", "F2"])
+def loaded(request, sim_lib):
+    fa, rt = golden_paths(request.param)
+    g = rb.Graph.load(fa, rt, 31, lib=sim_lib)
+    ctx = rb.Context(0, lib=sim_lib)
+    ctx.upload(g)
+    yield request.param, g, ctx
+    ctx.close()
+    g.close()
+
+
+def test_index_loader_matches_reference_dump(loaded):
+    """FASTA + .rtsk parser (PairID kinds, TinyBitmap, Roaring) vs the reference's in-memory graph."""
+    recipe, g, _ = loaded
+    info = g.info()
+    import json
+    meta = json.load(open(os.path.join(GOLDEN, recipe, "meta.json")))
+    assert info["n_unitigs"] == meta["n_unitigs"]
+    assert max(info["max_km_cov_graph"], 128) == meta["max_km_cov"]
+    n = 0
+    with gzip.open(os.path.join(GOLDEN, recipe, "ref_unitigs.tsv.gz"), "rt") as f:
+        for line in f:
+            c = line.rstrip("\n").split("\t")
+            u = int(c[0])
+            seq = g.unitig_seq(u)
+            assert seq == c[1] or seq == c[1][::-1].translate(str.maketrans("ACGT", "TGCA"))
+            w0, w1, _ = g.unitig_words(u)
+            assert (w0, w1) == (int(c[2]), int(c[3]))
+            gi, li = g.unitig_colors(u)
+            assert gi == [int(x) for x in c[4].split(",") if x]
+            assert li == [int(x) for x in c[5].split(",") if x]
+            n += 1
+    assert n == info["n_unitigs"]
+
+
+def test_adjacency_is_consistent(loaded):
+    """successor in A,C,G,T order: the (k-1)-overlap must hold and the reverse edge must exist"""
+    _, g, _ = loaded
+    k = 31
+    rc = lambda s: s[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    n = g.info()["n_unitigs"]
+    seqs = [g.unitig_seq(u) for u in range(n)]
+    for u in range(0, n, max(1, n // 400)):
+        _, _, adj = g.unitig_words(u)
+        for c in range(4):
+            v = adj[c]
+            if v == 0xFFFFFFFF:
+                continue
+            vs = seqs[v & 0x7FFFFFFF] if (v >> 31) else rc(seqs[v & 0x7FFFFFFF])
+            assert vs[:k - 1] == seqs[u][-(k - 1):] and vs[k - 1] == "ACGT"[c]
+        for c in range(4):
+            v = adj[4 + c]
+            if v == 0xFFFFFFFF:
+                continue
+            vs = seqs[v & 0x7FFFFFFF] if (v >> 31) else rc(seqs[v & 0x7FFFFFFF])
+            assert vs[-(k - 1):] == seqs[u][:k - 1] and vs[-k] == "ACGT"[c]
+
+
+def test_k1_kernel_source_matches_reference(loaded):
+    recipe, _, ctx = loaded
+    gold = np.load(os.path.join(GOLDEN, recipe, "golden_hits.npz"))
+    reads = [s for _, s, _ in load_golden_reads(recipe)][:6]
+    ex = ctx.search_sequence(reads)
+    ix = ctx.search_sequence(reads, exact=False, insertion=True, deletion=True, substitution=True, or_exclusive_match=True)
+    for i in range(len(reads)):
+        assert np.array_equal(ex[i], gold["exact_%d" % i]), (recipe, i)
+        assert np.array_equal(ix[i], gold["inexact_%d" % i]), (recipe, i)
+
+
+def test_get_seeds_matches_reference(loaded):
+    recipe, _, ctx = loaded
+    gold = np.load(os.path.join(GOLDEN, recipe, "golden_hits.npz"))
+    reads = [s for _, s, _ in load_golden_reads(recipe)][:6]
+    solid, weak = ctx.get_seeds(reads)
+    for i in range(len(reads)):
+        assert np.array_equal(solid[i], gold["solid_%d" % i]), (recipe, i)
+        assert np.array_equal(weak[i], gold["weak_%d" % i]), (recipe, i)
+
+
+def test_slab_roundtrip(loaded, tmp_path, sim_lib):
+    _, g, _ = loaded
+    p = str(tmp_path / "g.rtkflat")
+    g.save(p)
+    g2 = rb.Graph.open(p, lib=sim_lib)
+    assert g2.info() == g.info()
+    assert np.array_equal(g2.slab(), g.slab())
+    g2.close()
