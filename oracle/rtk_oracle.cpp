@@ -245,8 +245,7 @@ int orc_edit_distance(const char* q, int ql, const char* t, int tl, int mode, in
                       int** ends, int* n_ends) {
     *ends = nullptr; *n_ends = 0; *dist = -1;
     if (ql == 0) {  // src/edlib.cpp:156-170
-        *dist = (mode == 0) ? tl : 0;
-        if (kmax >= 0 && *dist > kmax) { *dist = -1; return 0; }
+        *dist = (mode == 0) ? tl : 0;  // no k check on this path (src/edlib.cpp:161-176)
         *ends = (int*)malloc(sizeof(int));
         (*ends)[0] = (mode == 0) ? tl - 1 : -1;
         *n_ends = 1;
@@ -254,7 +253,6 @@ int orc_edit_distance(const char* q, int ql, const char* t, int tl, int mode, in
     }
     if (tl == 0) {
         *dist = ql;
-        if (kmax >= 0 && *dist > kmax) { *dist = -1; return 0; }
         *ends = (int*)malloc(sizeof(int));
         (*ends)[0] = -1;
         *n_ends = 1;

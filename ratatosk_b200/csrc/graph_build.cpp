@@ -178,14 +178,15 @@ static void build_table_and_adj(const HostGraph& hg, rtk_slab_header& h, unsigne
                 const uint64_t P = uoff[u] + (i + 1 - k);
                 const KT canon = fw < rc ? fw : rc;
                 const uint64_t hh = rtk_hash_kmer<KT>(canon);
-                uint64_t b = rtk_mulhi64(hh, h.n_buckets);
-                const uint64_t entry = (rtk_tag_of(hh) << RTK_POS_BITS) | P;
+                uint64_t b = rtk_bucket_of(hh, h.n_buckets);
+                const uint64_t entry = ((uint64_t)rtk_tag_of(hh) << RTK_TAG_SHIFT) | P;
                 for (;;) {
                     bool done = false;
                     for (int e = 0; e < RTK_BUCKET_ENTRIES; ++e) {
                         if (table[4 * b + e] == 0) { table[4 * b + e] = entry; done = true; break; }
                     }
                     if (done) break;
+                    table[4 * b] |= RTK_BUMP_BIT;  // a key was bumped past this (full) bucket
                     b = (b + 1 == h.n_buckets) ? 0 : b + 1;
                 }
             }
@@ -240,6 +241,7 @@ rtk_slab build_slab(const HostGraph& hg) {
     h.pool_bases = bases; h.n_kmers = kmers;
     h.pool_words = (bases + 31) / 32 + 4;  // +4: k-mer extraction may touch two words past the end
     if (bases >= RTK_POS_MASK) throw std::runtime_error("pool exceeds 40-bit positions");
+    if (kmers / 2 >= 0xFFFFFFFFull) throw std::runtime_error("k-mer table exceeds 2^32 buckets");
     h.n_buckets = std::max<uint64_t>(16, (uint64_t)std::ceil((double)kmers / (RTK_BUCKET_ENTRIES * hg.load_factor)));
     // de-duplicate global colour sets by content (src/Graph.cpp:756-769)
     std::vector<uint32_t> gset_of(n, RTK_NONE32);

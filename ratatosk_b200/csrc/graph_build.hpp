@@ -12,7 +12,7 @@ namespace rtk {
 // Unflattened graph: what the index files (or a synthetic generator) provide per unitig.
 struct HostGraph {
     int k = 31;
-    double load_factor = 0.60;       // k-mer table fill (entries / capacity)
+    double load_factor = 0.40;       // k-mer table fill (entries / capacity)
     double top_km_cov_ratio = 0.001; // Correct_Opt::top_km_cov_ratio (src/Common.hpp:124)
     std::vector<std::string> unitigs;                // forward spelling, upper-case ACGT
     std::vector<uint64_t> kmcov;                     // UnitigData::kmCov_cardBranches

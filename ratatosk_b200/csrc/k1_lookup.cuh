@@ -116,148 +116,129 @@ __global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_exact_kernel(const rtk_
 }
 
 // ---------------------------------------------------------------- inexact sweep
+// Thread t of a CTA owns read position l = t0 + t of the tile and keeps that position's forward /
+// reverse-complement k-mer in registers.  Every variant-string window whose first read base is l
+// is generated from those two registers; the mapping (l, shift) -> variant-string position is
+// closed-form with ONE division per thread per tile (the per-shift terms are incremental), which
+// keeps the kernel off the XU pipe that runtime integer division lives on.
+template <typename KT>
+__device__ __forceinline__ void rtk_probe4_ins(const rtk_k1_params& p, const int k, const KT kmask, const KT W, const KT R,
+                                               const uint32_t o, const uint32_t read, const uint32_t var0,
+                                               const uint32_t x, unsigned long long& probes) {
+    // window = read[l, l+o) + letter + read[l+o, l+k-1)
+    // fw: top o bases of W, letter at offset o, then W's bases o..k-2 moved one to the right
+    const KT lowmask = (o == 0) ? kmask : (((KT)1 << (2 * (k - o))) - 1);  // bases o..k-1
+    const KT fw_base = (W & ~lowmask & kmask) | ((W & lowmask) >> 2 & (lowmask >> 2));
+    // rc: drop R's first base, complement letter at offset k-1-o, keep R's last o bases
+    const KT tailmask = (o == 0) ? (KT)0 : (((KT)1 << (2 * o)) - 1);
+    const KT rc_base = (((R << 2) & kmask) & ~(((KT)1 << (2 * (o + 1))) - 1)) | (R & tailmask);
+#pragma unroll
+    for (uint32_t a = 0; a < 4; ++a) {
+        const KT fw = fw_base | ((KT)a << (2 * (k - 1 - o)));
+        const KT rc = rc_base | ((KT)(3 - a) << (2 * o));
+        rtk_kmer_hit h;
+        ++probes;
+        if (rtk_lookup<KT>(p.table, p.n_buckets, p.pool, k, fw, rc, h)) rtk_emit_hit(p, read, var0 + a, x, h);
+    }
+}
+
 template <typename KT>
 __global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_inexact_kernel(const rtk_k1_params p) {
-    // W(l) for l in [t0, t0+TILE] (TILE+1 positions), codes for [t0, t0+TILE+k+2)
-    __shared__ KT s_fw[RTK_K1_TILE + 2];
-    __shared__ KT s_rc[RTK_K1_TILE + 2];
-    __shared__ uint8_t s_nbad[RTK_K1_TILE + 2];          // # non-ACGT in [l, l+k), saturated at 255
-    __shared__ uint8_t s_code[RTK_K1_TILE + 64 + 8];     // 0..3 base, 4 = non-ACGT / past the end
+    __shared__ uint8_t s_code[RTK_K1_THREADS + 64 + 8];  // 0..3 base, 4 = non-ACGT / past the end
     const int k = p.k;
     const KT kmask = KmerOps<KT>::mask(k);
     unsigned long long probes = 0;
+    const uint32_t tid = threadIdx.x;
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const uint32_t read = p.tiles[2 * tile], t0 = p.tiles[2 * tile + 1];
         const uint64_t base = p.seq_off[read];
         const uint32_t slen = (uint32_t)(p.seq_off[read + 1] - base);
         __syncthreads();
-        const uint32_t TILE = p.tile;
-        for (int i = threadIdx.x; i < (int)TILE + k + 4; i += blockDim.x) {
+        for (int i = tid; i < (int)p.tile + k + 4; i += blockDim.x) {
             const uint32_t pos = t0 + i;
             s_code[i] = (pos < slen) ? (uint8_t)rtk_base_code(p.seq[base + pos]) : (uint8_t)4;
         }
         __syncthreads();
-        if (threadIdx.x < TILE + 2) {
-            KT fw = 0, rc = 0;
-            uint32_t nb = 0;
-            for (int i = 0; i < k; ++i) {
-                const uint32_t c = s_code[threadIdx.x + i];
-                nb += (c >> 2);
-                fw = (fw << 2) | (KT)(c & 3);
-                rc = (rc >> 2) | ((KT)(3 - (c & 3)) << (2 * (k - 1)));
-            }
-            s_fw[threadIdx.x] = fw;
-            s_rc[threadIdx.x] = rc;
-            s_nbad[threadIdx.x] = (uint8_t)(nb > 255 ? 255 : nb);
+        const uint32_t l = t0 + tid;
+        if (tid >= p.tile || l + k - 1 > slen) continue;  // no window starts here (pads count as non-ACGT below)
+        // this position's k-mer, its reverse complement, and the number of non-ACGT bases in [l, l+k)
+        KT W = 0, R = 0;
+        uint32_t nbad = 0;
+        for (int i = 0; i < k; ++i) {
+            const uint32_t c = s_code[tid + i];
+            nbad += (c >> 2);
+            W = (W << 2) | (KT)(c & 3);
+            R = (R >> 2) | ((KT)(3 - (c & 3)) << (2 * (k - 1)));
         }
-        __syncthreads();
-        const uint32_t t1 = t0 + TILE;  // tile = read positions [t0, t1)
+        const uint32_t bad_last = s_code[tid + k - 1] >> 2;  // read[l+k-1]
+        const uint32_t ck = s_code[tid + k];                  // read[l+k]
 
-        // ---------------- substitution: pos_s == l, slot offset o = (shift - l) mod k
-        if (p.do_subst && threadIdx.x < TILE) {
-            const uint32_t l = t0 + threadIdx.x;
-            if (l + k <= slen && s_nbad[threadIdx.x] == 0) {
-                const KT fw0 = s_fw[threadIdx.x], rc0 = s_rc[threadIdx.x];
-                uint32_t shift = l % k;  // o = 0 first
-                for (int o = 0; o < k; ++o) {
-                    const uint32_t c = s_code[threadIdx.x + o];
-                    const int sh_fw = 2 * (k - 1 - o), sh_rc = 2 * o;
+        // ---------------- substitution: pos_s == l, slot offset o, shift = (l + o) mod k
+        if (p.do_subst && nbad == 0) {
+            uint32_t shift = l % k;
+            KT dfw = (KT)1 << (2 * (k - 1));  // unit of the base at offset o in W ...
+            KT drc = (KT)1;                   // ... and of its complement in R
+            for (int o = 0; o < k; ++o) {
+                const uint32_t c = s_code[tid + o];
 #pragma unroll
-                    for (uint32_t a = 0; a < 4; ++a) {
-                        if (a == c) continue;  // Search.tcc:620 writes 'N' where the read already has the letter
-                        const KT fw = fw0 ^ ((KT)(a ^ c) << sh_fw);
-                        const KT rc = rc0 ^ ((KT)((3 - a) ^ (3 - c)) << sh_rc);
-                        rtk_kmer_hit h;
-                        ++probes;
-                        if (rtk_lookup<KT>(p.table, p.n_buckets, p.pool, k, fw, rc, h)) rtk_emit_hit(p, read, shift * 4 + a, l, h);
-                    }
-                    shift = (shift + 1 == (uint32_t)k) ? 0 : shift + 1;
-                }
-            }
-        }
-
-        // ---------------- insertion: variant string i has a slot at inexact index i+m*k
-        if (p.do_ins) {
-            for (uint32_t i = 0; i < (uint32_t)k; ++i) {
-                if (i >= slen) break;  // string would have no slot: identical to s, Search.tcc:735 loop still runs; see below
-                // inexact length and the pos_s range whose first read base falls inside the tile
-                const uint32_t n_after = slen - i;
-                const uint32_t len_i = slen + (n_after + (k - 2)) / (k - 1);
-                if (len_i < (uint32_t)k) continue;
-                const uint32_t last_pos = len_i - k;
-                // g(x) = x - (#slots with index < x) = read index of first read base at/after x
-                auto g = [&](const uint32_t x) -> uint32_t {
-                    const uint32_t a = x / k, b = x % k;
-                    return x - (a + (b > i ? 1u : 0u));
-                };
-                uint32_t lo = t0 + t0 / (k - 1);
-                lo = lo > 2 ? lo - 2 : 0;
-                while (lo <= last_pos && g(lo) < t0) ++lo;
-                const uint32_t x = lo + threadIdx.x;
-                if (x > last_pos) continue;
-                const uint32_t l = g(x);
-                if (l >= t1) continue;
-                const uint32_t b = x % k;
-                const uint32_t o = (i + k - b) % k;  // slot offset inside the window
-                const uint32_t li = l - t0;
-                // window = read[l, l+o) + letter + read[l+o, l+k-1): needs k-1 read bases
-                const uint32_t nb = (uint32_t)s_nbad[li] - (uint32_t)(s_code[li + k - 1] >> 2);
-                if (s_nbad[li] == 255 || nb != 0) continue;
-                const KT W = s_fw[li], R = s_rc[li];
-                // fw: top o bases of W, letter at offset o, then W's bases o..k-2 moved one to the right
-                const KT lowmask = (o == 0) ? kmask : (((KT)1 << (2 * (k - o))) - 1);  // bases o..k-1
-                const KT fw_base = (W & ~lowmask & kmask) | ((W & lowmask) >> 2 & (lowmask >> 2));
-                // rc: drop R's first base, complement letter at offset k-1-o, keep R's last o bases
-                const KT tailmask = (o == 0) ? (KT)0 : (((KT)1 << (2 * o)) - 1);
-                const KT rc_base = (((R << 2) & kmask) & ~(((KT)1 << (2 * (o + 1))) - 1)) | (R & tailmask);
-#pragma unroll
-                for (uint32_t a = 0; a < 4; ++a) {
-                    const KT fw = fw_base | ((KT)a << (2 * (k - 1 - o)));
-                    const KT rc = rc_base | ((KT)(3 - a) << (2 * o));
+                for (uint32_t d = 1; d < 4; ++d) {  // the three other letters a = c ^ d (no lane skips: a != c always)
+                    const uint32_t a = c ^ d;       // Search.tcc:620 writes 'N' where the read already has the letter
+                    const KT fw = W ^ ((KT)d * dfw);
+                    const KT rc = R ^ ((KT)d * drc);  // (3-a)^(3-c) == a^c == d
                     rtk_kmer_hit h;
                     ++probes;
-                    if (rtk_lookup<KT>(p.table, p.n_buckets, p.pool, k, fw, rc, h)) rtk_emit_hit(p, read, 4 * k + i * 4 + a, x, h);
+                    if (rtk_lookup<KT>(p.table, p.n_buckets, p.pool, k, fw, rc, h)) rtk_emit_hit(p, read, shift * 4 + a, l, h);
                 }
+                dfw >>= 2; drc <<= 2;
+                shift = (shift + 1 == (uint32_t)k) ? 0 : shift + 1;
             }
         }
 
-        // ---------------- deletion: variant string i drops read positions i + m*(k+1)
+        // ---------------- insertion: string i = read with a slot before read positions i + m(k-1);
+        // in string coordinates the slots sit at i + m*k.  With l = a(k-1) + c the windows whose first
+        // read base is l start at  a*k + c (slot offset i-c, needs c <= i)  or  a*k + c + 1 (slot offset
+        // k-1-(c-i), needs c >= i), plus a*k - 1 when c == 0, i == k-1 (slot first, previous period).
+        if (p.do_ins && nbad - bad_last == 0) {  // needs read[l, l+k-1) only
+            const uint32_t a_ = l / (uint32_t)(k - 1), c_ = l - a_ * (uint32_t)(k - 1);
+            const uint32_t xk = a_ * (uint32_t)k + c_;
+            const bool room_last = (l + k <= slen);  // a slot at offset k-1 exists only before an existing read base
+            for (uint32_t i = 0; i < (uint32_t)k; ++i) {
+                const uint32_t var0 = 4 * k + i * 4;
+                const bool first = (c_ <= i);
+                const uint32_t o = first ? (i - c_) : ((uint32_t)k - 1 - (c_ - i));
+                if (o != (uint32_t)k - 1 || room_last) rtk_probe4_ins<KT>(p, k, kmask, W, R, o, read, var0, xk + (first ? 0u : 1u), probes);
+                if (c_ == i && room_last) rtk_probe4_ins<KT>(p, k, kmask, W, R, (uint32_t)k - 1, read, var0, xk + 1, probes);
+                if (c_ == 0 && i == (uint32_t)k - 1 && a_ >= 1) rtk_probe4_ins<KT>(p, k, kmask, W, R, 0, read, var0, xk - 1, probes);
+            }
+        }
+
+        // ---------------- deletion: string i drops read positions i + m(k+1).  A window whose first read
+        // base is R0 = l exists iff l is not itself dropped; with z = l - i - 1 = q(k+1) + r (r < k) it starts
+        // at string position i + q*k + r and the junction sits r == 0 ? nowhere : k - r bases into it.
         if (p.do_del && slen >= (uint32_t)k + 1) {
+            // z for i = 0, then decremented as i grows (no division inside the loop)
+            int32_t q = (int32_t)(l == 0 ? 0 : (l - 1) / (uint32_t)(k + 1));
+            int32_t r = (int32_t)(l == 0 ? 0 : (l - 1) - (uint32_t)q * (uint32_t)(k + 1));
             for (uint32_t i = 0; i <= (uint32_t)k; ++i) {
-                const uint32_t n_after = (i < slen) ? slen - i : 0;
-                const uint32_t n_del = (n_after + k) / (k + 1);
-                const uint32_t len_i = slen - n_del;
-                if (len_i < (uint32_t)k) continue;
-                const uint32_t last_pos = len_i - k;
-                // r0(x) = read index of inexact index x
-                auto r0 = [&](const uint32_t x) -> uint32_t {
-                    if (x < i) return x;
-                    const uint32_t y = x - i;
-                    return i + (y / k) * (k + 1) + (y % k) + 1;
-                };
-                uint32_t lo = t0 - t0 / (k + 1);
-                lo = lo > 2 ? lo - 2 : 0;
-                while (lo <= last_pos && r0(lo) < t0) ++lo;
-                const uint32_t x = lo + threadIdx.x;
-                if (x > last_pos) continue;
-                const uint32_t R0 = r0(x);
-                if (R0 >= t1) continue;
-                // offset of the junction inside the window (k = none: exact k-mer of the read)
-                uint32_t o;
-                if (x < i) o = (i - x < (uint32_t)k) ? (i - x) : (uint32_t)k;
-                else { const uint32_t ym = (x - i) % k; o = (ym == 0) ? (uint32_t)k : (uint32_t)k - ym; }
-                const uint32_t li = R0 - t0;
+                uint32_t x, o;
+                bool exists = true;
+                if (l < i) { x = l; o = (i - l < (uint32_t)k) ? (i - l) : (uint32_t)k; }
+                else if (l == i) exists = false;
+                else {
+                    if (r == k) exists = false;  // l is one of the dropped positions
+                    x = i + (uint32_t)q * (uint32_t)k + (uint32_t)r;
+                    o = (r == 0) ? (uint32_t)k : (uint32_t)(k - r);
+                }
+                if (l > i) { if (--r < 0) { r = k; --q; } }  // z -> z - 1 for the next shift
+                if (!exists) continue;
                 KT fw, rc;
                 if (o == (uint32_t)k) {
-                    if (s_nbad[li] != 0) continue;
-                    fw = s_fw[li]; rc = s_rc[li];
+                    if (nbad != 0) continue;
+                    fw = W; rc = R;
                 } else {
-                    // bases c_0..c_k of the read from R0, c_o deleted
-                    const uint32_t ck = s_code[li + k];
-                    const uint32_t nb = (uint32_t)s_nbad[li] + (ck >> 2) - (uint32_t)(s_code[li + o] >> 2);
-                    if (s_nbad[li] == 255 || nb != 0) continue;
-                    const KT W = s_fw[li], R = s_rc[li];
+                    // bases c_0..c_k of the read from l, c_o dropped
+                    if (nbad + (ck >> 2) - (uint32_t)(s_code[tid + o] >> 2) != 0) continue;
                     const KT lowmask = ((KT)1 << (2 * (k - o))) - 1;  // bases o..k-1
                     fw = (W & ~lowmask & kmask) | ((((W << 2) | (KT)(ck & 3))) & lowmask);
                     const KT tailmask = ((KT)1 << (2 * o)) - 1;       // last o bases
@@ -271,7 +252,7 @@ __global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_inexact_kernel(const rt
         }
     }
     if (p.n_probes) {
-        // block-level reduction of the probe counter (one atomic per warp)
+        // warp-level reduction of the probe counter (one atomic per warp)
         for (int off = 16; off > 0; off >>= 1) probes += __shfl_down_sync(0xffffffffu, probes, off);
         if ((threadIdx.x & 31) == 0 && probes) atomicAdd(p.n_probes, probes);
     }

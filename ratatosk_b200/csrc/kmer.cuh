@@ -56,16 +56,32 @@ template <> struct KmerOps<rtk_u128> {
     RTK_HD static uint64_t hi64(const rtk_u128 v) { return (uint64_t)(v >> 64); }
 };
 
-RTK_HD uint64_t rtk_mix64(uint64_t x) {  // murmur3 finaliser
+RTK_HD uint64_t rtk_mix64(uint64_t x) {  // murmur3 finaliser (host-side content hashing only)
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
     x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
     x ^= x >> 33;
     return x;
 }
 
+// Index hash: ONE 64-bit multiply (3 IMADs on the device).  The bucket comes from the high word by
+// a 32-bit multiply-high range reduction, the 24-bit tag from a second, independent 32-bit mix, so a
+// probe costs ~10 integer instructions before its single 32-byte load.
 template <typename KT> RTK_HD uint64_t rtk_hash_kmer(const KT canon) {
     const uint64_t lo = KmerOps<KT>::lo64(canon), hi = KmerOps<KT>::hi64(canon);
-    return rtk_mix64(lo ^ (rtk_mix64(hi + 0x9E3779B97F4A7C15ULL) * (hi != 0 ? 1ULL : 0ULL)));
+    const uint64_t x = lo ^ ((hi << 29) | (hi >> 35)) ^ (hi * 0xD6E8FEB86659FD93ULL);
+    return x * 0x9E3779B97F4A7C15ULL;
+}
+
+RTK_HD uint32_t rtk_mulhi32(const uint32_t a, const uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+RTK_HD uint64_t rtk_bucket_of(const uint64_t h, const uint64_t n_buckets) {  // n_buckets < 2^32
+    return (uint64_t)rtk_mulhi32((uint32_t)(h >> 32), (uint32_t)n_buckets);
 }
 
 RTK_HD uint64_t rtk_mulhi64(const uint64_t a, const uint64_t b) {
@@ -104,15 +120,20 @@ RTK_HD uint32_t rtk_pool_base(const uint64_t* __restrict__ pool, const uint64_t 
     return (uint32_t)((pool[P >> 5] >> (62 - 2 * (int)(P & 31))) & 3ULL);
 }
 
-// ---- k-mer index: 32-byte buckets of four 8-byte entries {tag:24 | pool position:40} ----
-// One bucket = one DRAM/L2 sector, so a miss costs exactly one sector read unless the
-// bucket is full (then linear probing continues with the next bucket).
+// ---- k-mer index: 32-byte buckets of four 8-byte entries {tag:24 | bumped:1 | pool position:39} ----
+// One bucket = one DRAM/L2 sector = one 256-bit load.  Entries are placed by linear probing at
+// bucket granularity; whenever an insertion finds a bucket full and moves on, it sets that bucket's
+// `bumped` bit (bit 39 of entry 0).  A lookup that sees no matching tag in a bucket whose bit is clear
+// is a definite miss - no "empty slot" test, and full-but-never-bumped buckets terminate at once - so
+// at the default fill ~97% of the misses cost exactly one sector and take the branch-free fast path.
 #define RTK_TAG_BITS 24
-#define RTK_POS_BITS 40
+#define RTK_POS_BITS 39
 #define RTK_POS_MASK ((1ULL << RTK_POS_BITS) - 1ULL)
+#define RTK_BUMP_BIT (1ULL << 39)
+#define RTK_TAG_SHIFT 40
 #define RTK_BUCKET_ENTRIES 4
 
-RTK_HD uint64_t rtk_tag_of(const uint64_t h) {
-    const uint64_t t = h & ((1ULL << RTK_TAG_BITS) - 1ULL);
-    return t ? t : 1ULL;
+RTK_HD uint32_t rtk_tag_of(const uint64_t h) {
+    const uint32_t t = (((uint32_t)(h >> 32) * 0x85EBCA6Bu) ^ (uint32_t)h) >> 8;
+    return t ? t : 1u;
 }

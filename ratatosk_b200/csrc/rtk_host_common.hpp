@@ -47,13 +47,8 @@ inline void finish_host_graph(rtk_host_graph* g) {
 }
 
 
-// read positions per K1 tile: the insertion strings stretch a tile by k/(k-1), all of its
-// variant-string positions must fit one pass of RTK_K1_THREADS threads
-inline uint32_t k1_tile_size(uint32_t k, bool exact) {
-    if (exact) return RTK_K1_THREADS;
-    const uint32_t lim = (uint32_t)((uint64_t)RTK_K1_THREADS * (k - 1) / k) - 2;
-    return std::min<uint32_t>(RTK_K1_TILE, lim);
-}
+// read positions per K1 tile: one per thread
+inline uint32_t k1_tile_size(uint32_t, bool) { return RTK_K1_THREADS; }
 
 inline void build_tiles(uint32_t n_reads, const uint64_t* h_seq_off, uint32_t k, uint32_t tile, std::vector<uint32_t>& tiles) {
     tiles.clear();
