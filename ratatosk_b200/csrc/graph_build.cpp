@@ -163,6 +163,7 @@ template <typename KT>
 static void build_table_and_adj(const HostGraph& hg, rtk_slab_header& h, unsigned char* slab) {
     const int k = (int)h.k;
     uint64_t* table = (uint64_t*)(slab + h.off_table);
+    uint32_t* t32 = (uint32_t*)table;
     const uint64_t* pool = (const uint64_t*)(slab + h.off_pool);
     const uint64_t* uoff = (const uint64_t*)(slab + h.off_unitig_off);
     const KT mask = KmerOps<KT>::mask(k);
@@ -179,14 +180,19 @@ static void build_table_and_adj(const HostGraph& hg, rtk_slab_header& h, unsigne
                 const KT canon = fw < rc ? fw : rc;
                 const uint64_t hh = rtk_hash_kmer<KT>(canon);
                 uint64_t b = rtk_bucket_of(hh, h.n_buckets);
-                const uint64_t entry = ((uint64_t)rtk_tag_of(hh) << RTK_TAG_SHIFT) | P;
+                const uint32_t hi = (rtk_tag_of(hh) << 8) | (uint32_t)(P >> 32);  // aux nibble (bits 4..7) stays 0
                 for (;;) {
                     bool done = false;
                     for (int e = 0; e < RTK_BUCKET_ENTRIES; ++e) {
-                        if (table[4 * b + e] == 0) { table[4 * b + e] = entry; done = true; break; }
+                        if ((t32[8 * b + e] >> 8) == 0) {  // tag 0 = empty (aux bits of entry 0 are only set on full buckets)
+                            t32[8 * b + e] = hi;
+                            t32[8 * b + 4 + e] = (uint32_t)P;
+                            done = true;
+                            break;
+                        }
                     }
                     if (done) break;
-                    table[4 * b] |= RTK_BUMP_BIT;  // a key was bumped past this (full) bucket
+                    t32[8 * b] |= 1u << (4 + rtk_class_of(hh));  // a key of this class was bumped past this (full) bucket
                     b = (b + 1 == h.n_buckets) ? 0 : b + 1;
                 }
             }
@@ -240,7 +246,7 @@ rtk_slab build_slab(const HostGraph& hg) {
     }
     h.pool_bases = bases; h.n_kmers = kmers;
     h.pool_words = (bases + 31) / 32 + 4;  // +4: k-mer extraction may touch two words past the end
-    if (bases >= RTK_POS_MASK) throw std::runtime_error("pool exceeds 40-bit positions");
+    if (bases >= RTK_POS_MASK) throw std::runtime_error("pool exceeds 36-bit positions");
     if (kmers / 2 >= 0xFFFFFFFFull) throw std::runtime_error("k-mer table exceeds 2^32 buckets");
     h.n_buckets = std::max<uint64_t>(16, (uint64_t)std::ceil((double)kmers / (RTK_BUCKET_ENTRIES * hg.load_factor)));
     // de-duplicate global colour sets by content (src/Graph.cpp:756-769)

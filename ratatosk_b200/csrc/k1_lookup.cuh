@@ -120,11 +120,21 @@ __global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_exact_kernel(const rtk_
 // reverse-complement k-mer in registers.  Every variant-string window whose first read base is l
 // is generated from those two registers; the mapping (l, shift) -> variant-string position is
 // closed-form with ONE division per thread per tile (the per-shift terms are incremental), which
-// keeps the kernel off the XU pipe that runtime integer division lives on.
+// keeps the kernel off the XU pipe that runtime integer division lives on.  The 3-4 letter probes of
+// one slot are issued together (independent 256-bit loads in flight) and checked afterwards.
+template <typename KT>
+__device__ __forceinline__ void rtk_finish_probe(const rtk_k1_params& p, const int k, const rtk_probe& q, const KT fw, const KT rc,
+                                                 const uint32_t read, const uint32_t var, const uint32_t x) {
+    if (rtk_probe_maybe(q)) {
+        rtk_kmer_hit h;
+        if (rtk_lookup_slow<KT>(p.table, p.n_buckets, p.pool, k, fw, rc, h)) rtk_emit_hit(p, read, var, x, h);
+    }
+}
+
 template <typename KT>
 __device__ __forceinline__ void rtk_probe4_ins(const rtk_k1_params& p, const int k, const KT kmask, const KT W, const KT R,
                                                const uint32_t o, const uint32_t read, const uint32_t var0,
-                                               const uint32_t x, unsigned long long& probes) {
+                                               const uint32_t x, uint32_t& probes) {
     // window = read[l, l+o) + letter + read[l+o, l+k-1)
     // fw: top o bases of W, letter at offset o, then W's bases o..k-2 moved one to the right
     const KT lowmask = (o == 0) ? kmask : (((KT)1 << (2 * (k - o))) - 1);  // bases o..k-1
@@ -132,22 +142,21 @@ __device__ __forceinline__ void rtk_probe4_ins(const rtk_k1_params& p, const int
     // rc: drop R's first base, complement letter at offset k-1-o, keep R's last o bases
     const KT tailmask = (o == 0) ? (KT)0 : (((KT)1 << (2 * o)) - 1);
     const KT rc_base = (((R << 2) & kmask) & ~(((KT)1 << (2 * (o + 1))) - 1)) | (R & tailmask);
+    const KT ufw = (KT)1 << (2 * (k - 1 - o)), urc = (KT)1 << (2 * o);
+    rtk_probe q[4];
 #pragma unroll
-    for (uint32_t a = 0; a < 4; ++a) {
-        const KT fw = fw_base | ((KT)a << (2 * (k - 1 - o)));
-        const KT rc = rc_base | ((KT)(3 - a) << (2 * o));
-        rtk_kmer_hit h;
-        ++probes;
-        if (rtk_lookup<KT>(p.table, p.n_buckets, p.pool, k, fw, rc, h)) rtk_emit_hit(p, read, var0 + a, x, h);
-    }
+    for (uint32_t a = 0; a < 4; ++a) rtk_probe_issue<KT>(p.table, p.n_buckets, fw_base | ((KT)a * ufw), rc_base | ((KT)(3 - a) * urc), q[a]);
+#pragma unroll
+    for (uint32_t a = 0; a < 4; ++a) rtk_finish_probe<KT>(p, k, q[a], fw_base | ((KT)a * ufw), rc_base | ((KT)(3 - a) * urc), read, var0 + a, x);
+    probes += 4;
 }
 
 template <typename KT>
-__global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_inexact_kernel(const rtk_k1_params p) {
+__global__ void __launch_bounds__(RTK_K1_THREADS, 3) rtk_k1_inexact_kernel(const rtk_k1_params p) {
     __shared__ uint8_t s_code[RTK_K1_THREADS + 64 + 8];  // 0..3 base, 4 = non-ACGT / past the end
     const int k = p.k;
     const KT kmask = KmerOps<KT>::mask(k);
-    unsigned long long probes = 0;
+    uint32_t probes = 0;  // per thread; summed into the 64-bit global counter at the end
     const uint32_t tid = threadIdx.x;
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -181,15 +190,14 @@ __global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_inexact_kernel(const rt
             KT drc = (KT)1;                   // ... and of its complement in R
             for (int o = 0; o < k; ++o) {
                 const uint32_t c = s_code[tid + o];
+                // the three other letters a = c ^ d (no lane skips a probe: Search.tcc:620 writes 'N' where the
+                // read already has the letter, i.e. exactly the d == 0 case); (3-a)^(3-c) == a^c == d
+                rtk_probe q[3];
 #pragma unroll
-                for (uint32_t d = 1; d < 4; ++d) {  // the three other letters a = c ^ d (no lane skips: a != c always)
-                    const uint32_t a = c ^ d;       // Search.tcc:620 writes 'N' where the read already has the letter
-                    const KT fw = W ^ ((KT)d * dfw);
-                    const KT rc = R ^ ((KT)d * drc);  // (3-a)^(3-c) == a^c == d
-                    rtk_kmer_hit h;
-                    ++probes;
-                    if (rtk_lookup<KT>(p.table, p.n_buckets, p.pool, k, fw, rc, h)) rtk_emit_hit(p, read, shift * 4 + a, l, h);
-                }
+                for (uint32_t d = 1; d < 4; ++d) rtk_probe_issue<KT>(p.table, p.n_buckets, W ^ ((KT)d * dfw), R ^ ((KT)d * drc), q[d - 1]);
+#pragma unroll
+                for (uint32_t d = 1; d < 4; ++d) rtk_finish_probe<KT>(p, k, q[d - 1], W ^ ((KT)d * dfw), R ^ ((KT)d * drc), read, shift * 4 + (c ^ d), l);
+                probes += 3;
                 dfw >>= 2; drc <<= 2;
                 shift = (shift + 1 == (uint32_t)k) ? 0 : shift + 1;
             }
@@ -206,10 +214,16 @@ __global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_inexact_kernel(const rt
             for (uint32_t i = 0; i < (uint32_t)k; ++i) {
                 const uint32_t var0 = 4 * k + i * 4;
                 const bool first = (c_ <= i);
-                const uint32_t o = first ? (i - c_) : ((uint32_t)k - 1 - (c_ - i));
-                if (o != (uint32_t)k - 1 || room_last) rtk_probe4_ins<KT>(p, k, kmask, W, R, o, read, var0, xk + (first ? 0u : 1u), probes);
-                if (c_ == i && room_last) rtk_probe4_ins<KT>(p, k, kmask, W, R, (uint32_t)k - 1, read, var0, xk + 1, probes);
-                if (c_ == 0 && i == (uint32_t)k - 1 && a_ >= 1) rtk_probe4_ins<KT>(p, k, kmask, W, R, 0, read, var0, xk - 1, probes);
+                // w = 0: the regular window; w = 1, 2: the rare second windows (one shared, inlined probe site)
+                const uint32_t nw = (c_ == i || (c_ == 0 && i == (uint32_t)k - 1)) ? 3u : 1u;
+                for (uint32_t w = 0; w < nw; ++w) {
+                    uint32_t o, x;
+                    bool ok;
+                    if (w == 0) { o = first ? (i - c_) : ((uint32_t)k - 1 - (c_ - i)); x = xk + (first ? 0u : 1u); ok = (o != (uint32_t)k - 1 || room_last); }
+                    else if (w == 1) { o = (uint32_t)k - 1; x = xk + 1; ok = (c_ == i && room_last); }
+                    else { o = 0; x = xk - 1; ok = (c_ == 0 && i == (uint32_t)k - 1 && a_ >= 1); }
+                    if (ok) rtk_probe4_ins<KT>(p, k, kmask, W, R, o, read, var0, x, probes);
+                }
             }
         }
 
@@ -220,9 +234,11 @@ __global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_inexact_kernel(const rt
             // z for i = 0, then decremented as i grows (no division inside the loop)
             int32_t q = (int32_t)(l == 0 ? 0 : (l - 1) / (uint32_t)(k + 1));
             int32_t r = (int32_t)(l == 0 ? 0 : (l - 1) - (uint32_t)q * (uint32_t)(k + 1));
-            for (uint32_t i = 0; i <= (uint32_t)k; ++i) {
-                uint32_t x, o;
-                bool exists = true;
+            // derive the window of shift i (advances q,r); returns false if there is none / it is not all-ACGT
+            auto derive = [&](const uint32_t i, KT& fw, KT& rc, uint32_t& x) -> bool {
+                uint32_t o = 0;
+                bool exists = (i <= (uint32_t)k);
+                x = 0;
                 if (l < i) { x = l; o = (i - l < (uint32_t)k) ? (i - l) : (uint32_t)k; }
                 else if (l == i) exists = false;
                 else {
@@ -231,29 +247,37 @@ __global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_inexact_kernel(const rt
                     o = (r == 0) ? (uint32_t)k : (uint32_t)(k - r);
                 }
                 if (l > i) { if (--r < 0) { r = k; --q; } }  // z -> z - 1 for the next shift
-                if (!exists) continue;
-                KT fw, rc;
+                if (!exists) return false;
                 if (o == (uint32_t)k) {
-                    if (nbad != 0) continue;
                     fw = W; rc = R;
-                } else {
-                    // bases c_0..c_k of the read from l, c_o dropped
-                    if (nbad + (ck >> 2) - (uint32_t)(s_code[tid + o] >> 2) != 0) continue;
-                    const KT lowmask = ((KT)1 << (2 * (k - o))) - 1;  // bases o..k-1
-                    fw = (W & ~lowmask & kmask) | ((((W << 2) | (KT)(ck & 3))) & lowmask);
-                    const KT tailmask = ((KT)1 << (2 * o)) - 1;       // last o bases
-                    const KT midmask = ((((KT)1 << (2 * (k - 1))) - 1)) & ~tailmask;
-                    rc = ((KT)(3 - (ck & 3)) << (2 * (k - 1))) | ((R >> 2) & midmask) | (R & tailmask);
+                    return nbad == 0;
                 }
-                rtk_kmer_hit h;
-                ++probes;
-                if (rtk_lookup<KT>(p.table, p.n_buckets, p.pool, k, fw, rc, h)) rtk_emit_hit(p, read, 8 * k + i, x, h);
+                // bases c_0..c_k of the read from l, c_o dropped
+                const KT lowmask = ((KT)1 << (2 * (k - o))) - 1;  // bases o..k-1
+                fw = (W & ~lowmask & kmask) | ((((W << 2) | (KT)(ck & 3))) & lowmask);
+                const KT tailmask = ((KT)1 << (2 * o)) - 1;       // last o bases
+                const KT midmask = ((((KT)1 << (2 * (k - 1))) - 1)) & ~tailmask;
+                rc = ((KT)(3 - (ck & 3)) << (2 * (k - 1))) | ((R >> 2) & midmask) | (R & tailmask);
+                return nbad + (ck >> 2) - (uint32_t)(s_code[tid + o] >> 2) == 0;
+            };
+            for (uint32_t i = 0; i <= (uint32_t)k; i += 2) {  // two shifts per round: two loads in flight
+                KT fw0 = 0, rc0 = 0, fw1 = 0, rc1 = 0;
+                uint32_t x0, x1;
+                const bool v0 = derive(i, fw0, rc0, x0);
+                const bool v1 = derive(i + 1, fw1, rc1, x1);
+                rtk_probe q0, q1;
+                if (v0) rtk_probe_issue<KT>(p.table, p.n_buckets, fw0, rc0, q0);
+                if (v1) rtk_probe_issue<KT>(p.table, p.n_buckets, fw1, rc1, q1);
+                if (v0) rtk_finish_probe<KT>(p, k, q0, fw0, rc0, read, 8 * k + i, x0);
+                if (v1) rtk_finish_probe<KT>(p, k, q1, fw1, rc1, read, 8 * k + i + 1, x1);
+                probes += (v0 ? 1u : 0u) + (v1 ? 1u : 0u);
             }
         }
     }
     if (p.n_probes) {
         // warp-level reduction of the probe counter (one atomic per warp)
-        for (int off = 16; off > 0; off >>= 1) probes += __shfl_down_sync(0xffffffffu, probes, off);
-        if ((threadIdx.x & 31) == 0 && probes) atomicAdd(p.n_probes, probes);
+        unsigned long long pr = probes;
+        for (int off = 16; off > 0; off >>= 1) pr += __shfl_down_sync(0xffffffffu, pr, off);
+        if ((threadIdx.x & 31) == 0 && pr) atomicAdd(p.n_probes, pr);
     }
 }

@@ -120,18 +120,23 @@ RTK_HD uint32_t rtk_pool_base(const uint64_t* __restrict__ pool, const uint64_t 
     return (uint32_t)((pool[P >> 5] >> (62 - 2 * (int)(P & 31))) & 3ULL);
 }
 
-// ---- k-mer index: 32-byte buckets of four 8-byte entries {tag:24 | bumped:1 | pool position:39} ----
-// One bucket = one DRAM/L2 sector = one 256-bit load.  Entries are placed by linear probing at
-// bucket granularity; whenever an insertion finds a bucket full and moves on, it sets that bucket's
-// `bumped` bit (bit 39 of entry 0).  A lookup that sees no matching tag in a bucket whose bit is clear
-// is a definite miss - no "empty slot" test, and full-but-never-bumped buckets terminate at once - so
-// at the default fill ~97% of the misses cost exactly one sector and take the branch-free fast path.
+// ---- k-mer index: 32-byte buckets of four 8-byte entries {tag:24 | aux:4 | pool position:36} ----
+// stored split: the four high words (tag | aux | pos[35:32]) first, then the four low words, so the miss
+// path needs one 128-bit load of the high words only (4 registers per probe in flight).
+// One bucket = one DRAM/L2 sector.  Entries are placed by linear probing at
+// bucket granularity.  Whenever an insertion finds a bucket full and moves on, it records that in the
+// bucket's 4-bit "bumped" filter (aux nibble of entry 0), one bit per hash class of the bumped key.
+// A lookup that sees no matching tag, in a bucket whose bit for ITS class is clear, is a definite
+// miss: no "empty slot" test, full-but-never-bumped buckets terminate at once, so at the default fill
+// ~99% of the misses cost exactly one sector and take the branch-free fast path.
 #define RTK_TAG_BITS 24
-#define RTK_POS_BITS 39
+#define RTK_POS_BITS 36
 #define RTK_POS_MASK ((1ULL << RTK_POS_BITS) - 1ULL)
-#define RTK_BUMP_BIT (1ULL << 39)
+#define RTK_AUX_SHIFT 36
 #define RTK_TAG_SHIFT 40
 #define RTK_BUCKET_ENTRIES 4
+
+RTK_HD uint32_t rtk_class_of(const uint64_t h) { return ((uint32_t)h) >> 30; }  // 2 bits, independent of tag and bucket
 
 RTK_HD uint32_t rtk_tag_of(const uint64_t h) {
     const uint32_t t = (((uint32_t)(h >> 32) * 0x85EBCA6Bu) ^ (uint32_t)h) >> 8;
