@@ -267,6 +267,10 @@ int orc_edit_distance(const char* q, int ql, const char* t, int tl, int mode, in
     for (int i = 0; i <= ql; ++i) prev[i] = i;
     int best = -1;
     std::vector<int> locs;
+    // The reference pads the query to a multiple of 64 with W wildcards and reads column c as position
+    // c - W (src/edlib.cpp:658-692): whenever W > 0 the "position -1" (query against the empty target
+    // prefix, score = query length) takes part in the minimum for SHW/HW and is reported first.
+    if (mode != 0 && (ql % 64) != 0) { best = ql; locs.push_back(-1); }
     for (int j = 1; j <= tl; ++j) {
         col[0] = (mode == 2) ? 0 : j;  // HW: free start anywhere in the target
         for (int i = 1; i <= ql; ++i) {

@@ -1,0 +1,162 @@
+// myers.cuh — K4: batched bit-parallel edit distance (Myers 1999 / Hyyro 2001 block recurrence) on
+// sm_100a, replacing edlibAlign's distance modes (src/edlib.cpp:141-296, 547-931) as the reference
+// configures them everywhere on the hot path: IUPAC equalities (src/Common.hpp:262-276), modes NW /
+// SHW / HW, result = edit distance + every end column carrying it (ascending), -1 when above k.
+//
+// The reference walks a query's 64-row blocks sequentially per target column, with Ukkonen banding
+// and k-doubling; banding only prunes cells that cannot matter, so the result is a function of the
+// plain DP and is reproduced here without it.  Mapping to the GPU: G = 1..32 lanes cooperate on one
+// alignment, lane j owns query block j (Pv/Mv and the four base profiles live in registers) and the
+// lanes sweep the DP matrix as an anti-diagonal WAVEFRONT - at step s lane j processes column s-j,
+// taking its horizontal input from lane j-1's previous step through one warp shuffle.  All lanes of
+// a group work every step (except the G-1 fill/drain steps); a warp packs 32/G short alignments.
+// Queries longer than 64*G rows are swept in ROUNDS of G blocks, the bottom lane spilling its
+// horizontal deltas (one int8 per column) to a scratch row that feeds the next round's top lane.
+#pragma once
+#ifndef RTK_HOSTSIM
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+#include "kmer.cuh"
+
+#define RTK_MYERS_THREADS 128
+
+struct rtk_myers_params {
+    const char* q_pool;
+    const uint64_t* q_off;
+    const char* t_pool;
+    const uint64_t* t_off;
+    const uint8_t* mode;     // 0 NW, 1 SHW, 2 HW
+    const int32_t* kmax;     // -1 = unbounded
+    const uint32_t* order;   // alignment ids handled by this launch (sorted by target length)
+    uint32_t n;
+    int32_t* dist;           // [alignment]
+    int32_t* n_ends;         // [alignment]
+    int32_t* ends;           // capacity: ends_off[a+1]-ends_off[a] = tlen + 1 entries
+    const uint64_t* ends_off;
+    int8_t* hbound;          // scratch: hb_off[a] .. + tlen, horizontal deltas between rounds
+    const uint64_t* hb_off;
+};
+
+// IUPAC membership mask of a character: A1 C2 G4 T8, ambiguity codes = union (the index of the letter
+// in ambiguity_c[], src/Common.hpp:260); 0 for anything else.
+RTK_HD uint32_t rtk_iupac_mask(const char c) {
+    switch (c) {
+        case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': return 8;
+        case 'M': return 3; case 'R': return 5; case 'S': return 6; case 'V': return 7;
+        case 'W': return 9; case 'Y': return 10; case 'H': return 11; case 'K': return 12;
+        case 'D': return 13; case 'B': return 14; case 'N': return 15;
+        default: return 0;
+    }
+}
+
+// edlib equality: identical characters, or {ambiguity code, one of its bases} in either order
+// (EqualityDefinition, src/edlib.cpp:50-90, with the 28 pairs of edlib_iupac_alpha)
+RTK_HD bool rtk_iupac_eq(const char a, const char b) {
+    if (a == b) return true;
+    const uint32_t ma = rtk_iupac_mask(a), mb = rtk_iupac_mask(b);
+    const bool base_a = ma && !(ma & (ma - 1)), base_b = mb && !(mb & (mb - 1));
+    return (base_a != base_b) && (ma & mb);  // exactly one side is a plain base and the code contains it
+}
+
+template <int G>
+__global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_kernel(const rtk_myers_params p) {
+    const uint32_t lane = threadIdx.x & (G - 1);
+    const uint32_t grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (grp >= p.n) return;  // whole groups drop out together; shuffles below are group-scoped
+    const uint32_t wl = threadIdx.x & 31;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(uint32_t)(G - 1)));
+
+    const uint32_t a = p.order[grp];
+    const char* q = p.q_pool + p.q_off[a];
+    const char* t = p.t_pool + p.t_off[a];
+    const int qlen = (int)(p.q_off[a + 1] - p.q_off[a]);
+    const int tlen = (int)(p.t_off[a + 1] - p.t_off[a]);
+    const int mode = p.mode[a];
+    const int nb = (qlen + 63) >> 6;
+    const int rounds = (nb + G - 1) / G;
+    int8_t* hb = p.hbound + p.hb_off[a];
+    int32_t* ends = p.ends + p.ends_off[a];
+
+    // bottom-row score of the column before the first: D[m][-1] = m ; tracked by the lane owning the last block
+    int score = qlen, best = 0x7fffffff, n_best = 0;
+    const int last_row = (qlen - 1) & 63;
+    // The reference pads the query to a multiple of 64 with W wildcards and reads column c as position
+    // c - W (src/edlib.cpp:658-692): when W > 0, "position -1" (the empty target prefix, score qlen) takes
+    // part in the SHW/HW minimum and is reported first.  Only the reporting lane's copy is ever read.
+    if (mode != 0 && (qlen & 63) != 0) { best = qlen; n_best = 1; if ((int)lane == (nb - 1) % G) ends[0] = -1; }
+
+    for (int r = 0; r < rounds; ++r) {
+        const int b = r * G + (int)lane;
+        const bool has = b < nb;
+        // base profiles of this lane's 64 query rows: bit i of PB[x] = query row accepts base x
+        uint64_t PB0 = 0, PB1 = 0, PB2 = 0, PB3 = 0;
+        if (has) {
+            const int lo = b << 6;
+            const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+            for (int i = 0; i < n; ++i) {
+                const uint64_t m = rtk_iupac_mask(q[lo + i]);
+                PB0 |= (m & 1) << i; PB1 |= ((m >> 1) & 1) << i; PB2 |= ((m >> 2) & 1) << i; PB3 |= ((m >> 3) & 1) << i;
+            }
+        }
+        uint64_t Pv = ~0ULL, Mv = 0;  // first column: D[i][-1] = i  => all vertical deltas +1
+        int hout = 0;
+        const bool is_last = has && (b == nb - 1);
+        const bool spill = (lane == G - 1) && (r + 1 < rounds);
+        const int steps = tlen + G - 1;
+        for (int s = 0; s < steps; ++s) {
+            const int from_left = __shfl_up_sync(gmask, hout, 1, G);
+            const int col = s - (int)lane;
+            hout = 0;
+            if (has && col >= 0 && col < tlen) {
+                int hin;
+                if (lane == 0) hin = (r == 0) ? ((mode == 2) ? 0 : 1) : (int)hb[col];  // D[0][j] = 0 (HW) or j
+                else hin = from_left;
+                const char tc = t[col];
+                uint64_t Eq;
+                switch (tc) {
+                    case 'A': Eq = PB0; break;
+                    case 'C': Eq = PB1; break;
+                    case 'G': Eq = PB2; break;
+                    case 'T': Eq = PB3; break;
+                    default: {  // ambiguity code (or foreign character) in the target: build the profile on the fly
+                        Eq = 0;
+                        const int lo = b << 6;
+                        const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+                        for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(q[lo + i], tc) << i;
+                    }
+                }
+                // one block of one column (Hyyro's formulation of Myers' recurrence)
+                const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
+                const uint64_t Xv = Eq | Mv;
+                Eq |= neg;
+                const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                uint64_t Ph = Mv | ~(Xh | Pv);
+                uint64_t Mh = Pv & Xh;
+                hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+                if (is_last) {
+                    score += (int)((Ph >> last_row) & 1) - (int)((Mh >> last_row) & 1);
+                    if (mode != 0) {  // SHW / HW: remember every column that carries the minimum
+                        if (score < best) { best = score; n_best = 0; }
+                        if (score == best) ends[n_best++] = col;
+                    }
+                }
+                Ph = (Ph << 1) | ((hin > 0) ? 1ULL : 0ULL);
+                Mh = (Mh << 1) | neg;
+                Pv = Mh | ~(Xv | Ph);
+                Mv = Ph & Xv;
+                if (spill) hb[col] = (int8_t)hout;
+            }
+        }
+        __syncwarp(gmask);  // the next round's top lane reads what this round's bottom lane spilled
+    }
+    // the lane that owned the last block reports
+    if ((int)lane == (nb - 1) % G) {
+        if (mode == 0) { best = score; ends[0] = tlen - 1; n_best = 1; }
+        const int kmax = p.kmax[a];
+        if (kmax >= 0 && best > kmax) { best = -1; n_best = 0; }
+        p.dist[a] = best;
+        p.n_ends[a] = n_best;
+    }
+}

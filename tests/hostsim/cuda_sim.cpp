@@ -14,6 +14,8 @@ void sim_launch(unsigned grid, unsigned block, const std::function<void()>& body
     for (unsigned w = 0; w < nw; ++w) {
         const unsigned nl = (w * 32 + 32 <= block) ? 32 : (block & 31);
         pthread_barrier_init(&sim_warps[w].bar, nullptr, nl);
+        for (int lg = 1; lg < 5; ++lg)
+            for (unsigned f = 0; f < 32; f += (1u << lg)) pthread_barrier_init(&sim_warps[w].gbar[lg][f], nullptr, 1u << lg);
     }
     pthread_barrier_init(&sim_block_barrier, nullptr, block);
     // persistent worker threads: one per CUDA thread, looping over the blocks

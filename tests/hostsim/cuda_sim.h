@@ -23,7 +23,11 @@ struct ulonglong2 { unsigned long long x, y; };
 extern thread_local sim_dim3 threadIdx, blockIdx;
 extern sim_dim3 blockDim, gridDim;
 extern pthread_barrier_t sim_block_barrier;
-struct sim_warp_area { pthread_barrier_t bar; unsigned long long slot[32]; };
+struct sim_warp_area {
+    pthread_barrier_t bar;            // all lanes of the warp
+    pthread_barrier_t gbar[5][32];    // aligned sub-groups of width 1<<w (w = 0..4), indexed by first lane
+    unsigned long long slot[32];
+};
 extern sim_warp_area* sim_warps;
 
 #define __global__
@@ -36,7 +40,16 @@ extern sim_warp_area* sim_warps;
 #define __CUDACC_SIM__ 1
 
 static inline void __syncthreads() { pthread_barrier_wait(&sim_block_barrier); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&sim_warps[threadIdx.x >> 5].bar); }
+// barrier over the lanes named by `mask` (full warp or one aligned power-of-two sub-group)
+static inline void sim_mask_barrier(unsigned mask) {
+    sim_warp_area& w = sim_warps[threadIdx.x >> 5];
+    if (mask == 0xffffffffu) { pthread_barrier_wait(&w.bar); return; }
+    const int n = __builtin_popcount(mask);
+    const int first = __builtin_ctz(mask);
+    if (n == 1) return;
+    pthread_barrier_wait(&w.gbar[__builtin_ctz((unsigned)n)][first]);
+}
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { sim_mask_barrier(mask); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
@@ -62,6 +75,22 @@ template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
     pthread_barrier_wait(&w.bar);
     const unsigned long long y = w.slot[src & 31];
     pthread_barrier_wait(&w.bar);
+    T r;
+    memcpy(&r, &y, sizeof(T) <= 8 ? sizeof(T) : 8);
+    return r;
+}
+// group-scoped shuffle-up (mask = the aligned sub-group of `width` lanes the caller belongs to)
+template <typename T> static inline T __shfl_up_sync(unsigned mask, T v, int d, int width = 32) {
+    sim_warp_area& w = sim_warps[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    unsigned long long x = 0;
+    memcpy(&x, &v, sizeof(T) <= 8 ? sizeof(T) : 8);
+    w.slot[lane] = x;
+    sim_mask_barrier(mask);
+    const int src = lane - d;
+    const bool ok = (lane & (width - 1)) >= d;
+    const unsigned long long y = ok ? w.slot[src] : x;
+    sim_mask_barrier(mask);
     T r;
     memcpy(&r, &y, sizeof(T) <= 8 ? sizeof(T) : 8);
     return r;
