@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_exact_kernel(const rtk_
         }
         __syncthreads();
         const uint32_t l = t0 + threadIdx.x;
-        bool hit = false;
+        bool hit = false, probed = false;
         rtk_kmer_hit h;
         if (l + k <= slen) {
             KT fw = 0, rc = 0;
@@ -94,7 +94,12 @@ __global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_exact_kernel(const rtk_
                 fw = (fw << 2) | (KT)(c & 3);
                 rc = (rc >> 2) | ((KT)(3 - (c & 3)) << (2 * (k - 1)));
             }
-            if (!bad) hit = rtk_lookup<KT>(p.table, p.n_buckets, p.pool, k, fw, rc, h);
+            probed = !bad;
+            if (probed) hit = rtk_lookup<KT>(p.table, p.n_buckets, p.pool, k, fw, rc, h);
+        }
+        if (p.n_probes) {
+            const unsigned pm = __ballot_sync(0xffffffffu, probed);
+            if ((threadIdx.x & 31) == 0 && pm) atomicAdd(p.n_probes, (unsigned long long)__popc(pm));
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (m) {

@@ -3,6 +3,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <mutex>
+#include <thread>
 
 #include "kmer.cuh"
 #include "rtk_host_common.hpp"
@@ -10,6 +13,43 @@
 namespace rtk {
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
+
+unsigned host_threads() {
+    static unsigned n = [] {
+        const char* e = getenv("RTK_HOST_THREADS");
+        unsigned v = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency();
+        if (v == 0) v = 1;
+        return std::min(v, 64u);
+    }();
+    return n;
+}
+
+void parallel_for(size_t n, const std::function<void(size_t, size_t)>& body) {
+    const unsigned nt = (unsigned)std::min<size_t>(host_threads(), n);
+    if (nt <= 1) { if (n) body(0, n); return; }
+    // dynamic chunks: reads differ in length by orders of magnitude
+    const size_t chunk = std::max<size_t>(1, n / (nt * 8));
+    std::atomic<size_t> next(0);
+    std::exception_ptr err;
+    std::mutex err_mu;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) {
+        th.emplace_back([&] {
+            try {
+                for (;;) {
+                    const size_t b = next.fetch_add(chunk);
+                    if (b >= n) break;
+                    body(b, std::min(n, b + chunk));
+                }
+            } catch (...) {
+                std::lock_guard<std::mutex> g(err_mu);
+                if (!err) err = std::current_exception();
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    if (err) std::rethrow_exception(err);
+}
 
 void flatten_hits(const std::vector<std::vector<rtk_hit>>& per_read, rtk_hit** hits, uint64_t** off) {
     const size_t n = per_read.size();

@@ -1,6 +1,8 @@
 // rtk_host_common.hpp — host helpers shared by the CUDA build and the tests/hostsim build.
 #pragma once
 #include <algorithm>
+#include <cstring>
+#include <functional>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -61,6 +63,11 @@ inline void build_tiles(uint32_t n_reads, const uint64_t* h_seq_off, uint32_t k,
         for (uint32_t t0 = 0; t0 < npos; t0 += tile) { tiles.push_back(r); tiles.push_back(t0); }
     }
 }
+
+// Host worker threads for the per-read anchor logic (reads are independent, like the reference's worker
+// loop, src/Ratatosk.cpp:727-906).  RTK_HOST_THREADS overrides the default of hardware_concurrency (<= 64).
+unsigned host_threads();
+void parallel_for(size_t n, const std::function<void(size_t, size_t)>& body);  // body(begin, end) on chunks
 
 void flatten_hits(const std::vector<std::vector<rtk_hit>>& per_read, rtk_hit** hits, uint64_t** off);
 

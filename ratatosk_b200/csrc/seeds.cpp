@@ -17,6 +17,7 @@
 #include "kmer.cuh"
 #include "k1_lookup_layout.h"
 #include "rtk_internal.hpp"
+#include "rtk_host_common.hpp"
 
 namespace rtk {
 
@@ -180,10 +181,9 @@ void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads
     search_sequence_host(ctx, n_reads, seq_pool, seq_off, RTK_SEARCH_EXACT, exact, stats);
 
     std::vector<std::vector<Anchor>> v_um(n_reads);
-    std::string masked;             // concatenated l_s of the reads that need the inexact sweep
-    std::vector<uint64_t> moff(1, 0);
-    std::vector<uint32_t> mread;    // which read each masked string belongs to
-    for (uint32_t r = 0; r < n_reads; ++r) {
+    std::vector<std::string> l_s_of(n_reads);  // pass 1: masked copy of each read that needs the inexact sweep
+    parallel_for(n_reads, [&](size_t rb, size_t re) {
+    for (size_t r = rb; r < re; ++r) {
         const char* s = seq_pool + seq_off[r];
         const size_t slen = seq_off[r + 1] - seq_off[r];
         if (slen <= k) continue;  // Graph.cpp:49
@@ -192,7 +192,8 @@ void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads
         for (const rtk_hit& h : exact[r]) v.push_back({h, mapped_kmer(g, h), false});
         if (pass2) continue;
         // 2. pass 1: mask the well-anchored stretches, search the rest inexactly (Graph.cpp:100-196)
-        std::string l_s(slen, 'N');
+        std::string& l_s = l_s_of[r];
+        l_s.assign(slen, 'N');
         std::sort(v.begin(), v.end(), anchor_less);
         auto unmask = [&](size_t pos, size_t len) {  // string::replace(pos, len, s, pos, len) semantics
             if (pos > slen) throw std::runtime_error("getSeeds: replace out of range");
@@ -233,9 +234,22 @@ void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads
             if (v.front().h.pos >= opt.insert_sz / 2) unmask(0, v.front().h.pos + k - 1);
             if (slen - v.back().h.pos >= opt.insert_sz / 2) unmask(v.back().h.pos + 1, slen - v.back().h.pos - 1);
         }
-        mread.push_back(r);
-        masked += l_s;
-        moff.push_back(masked.size());
+    }
+    });
+    std::string masked;             // concatenated l_s of the reads that need the inexact sweep
+    std::vector<uint64_t> moff(1, 0);
+    std::vector<uint32_t> mread;    // which read each masked string belongs to
+    if (!pass2) {
+        size_t tot = 0;
+        for (uint32_t r = 0; r < n_reads; ++r) tot += l_s_of[r].size();
+        masked.reserve(tot);
+        for (uint32_t r = 0; r < n_reads; ++r) {
+            if (l_s_of[r].empty()) continue;
+            mread.push_back(r);
+            masked += l_s_of[r];
+            moff.push_back(masked.size());
+            std::string().swap(l_s_of[r]);
+        }
     }
 
     // 3. inexact sweep over the masked strings (Graph.cpp:193)
@@ -251,7 +265,8 @@ void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads
 
     const double t0 = (double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
     // 4. per read: sort, split, prune (Graph.cpp:201-372)
-    for (uint32_t r = 0; r < n_reads; ++r) {
+    parallel_for(n_reads, [&](size_t rb, size_t re) {
+    for (size_t r = rb; r < re; ++r) {
         const char* s = seq_pool + seq_off[r];
         const size_t slen = seq_off[r + 1] - seq_off[r];
         if (slen <= k) continue;
@@ -310,6 +325,7 @@ void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads
         weak_out[r].reserve(weak.size());
         for (const Anchor& a : weak) weak_out[r].push_back(a.h);
     }
+    });
     if (stats) stats[4] += (uint64_t)((double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0);
 }
 

@@ -4,7 +4,10 @@
 #include <algorithm>
 #include <unordered_set>
 
+#include <stdexcept>
+
 #include "k1_lookup_layout.h"
+#include "rtk_host_common.hpp"
 #include "lookup.cuh"
 
 namespace rtk {
@@ -133,18 +136,32 @@ void resolve_inexact(const rtk_graph_view& g, const char* s, uint32_t slen, bool
 void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                    std::vector<RawHit>& raw, std::vector<std::vector<rtk_hit>>& per_read) {
     per_read.assign(n_reads, {});
-    std::sort(raw.begin(), raw.end(), [](const RawHit& x, const RawHit& y) { return x.a < y.a; });
-    const bool exact = flags & RTK_SEARCH_EXACT;
-    size_t i = 0;
-    while (i < raw.size()) {
-        const uint32_t r = (uint32_t)(raw[i].a >> (RTK_HIT_VAR_BITS + RTK_HIT_POS_BITS));
-        size_t e = i;
-        while (e < raw.size() && (uint32_t)(raw[e].a >> (RTK_HIT_VAR_BITS + RTK_HIT_POS_BITS)) == r) ++e;
-        if (exact) resolve_exact(hv, raw.data() + i, e - i, per_read[r]);
-        else resolve_inexact(hv, seq_pool + seq_off[r], (uint32_t)(seq_off[r + 1] - seq_off[r]), (flags & RTK_SEARCH_OR_EXCL) != 0,
-                             raw.data() + i, e - i, per_read[r]);
-        i = e;
+    // bucket the raw hits by read (counting sort on the read id), then sort + replay each read independently
+    const int sh = RTK_HIT_VAR_BITS + RTK_HIT_POS_BITS;
+    std::vector<uint64_t> start(n_reads + 1, 0);
+    for (const RawHit& h : raw) {
+        const uint32_t r = (uint32_t)(h.a >> sh);
+        if (r >= n_reads) throw std::runtime_error("corrupt hit record");
+        ++start[r + 1];
     }
+    for (uint32_t r = 0; r < n_reads; ++r) start[r + 1] += start[r];
+    std::vector<RawHit> by_read(raw.size());
+    {
+        std::vector<uint64_t> fill(start.begin(), start.end() - 1);
+        for (const RawHit& h : raw) by_read[fill[(uint32_t)(h.a >> sh)]++] = h;
+    }
+    const bool exact = flags & RTK_SEARCH_EXACT;
+    parallel_for(n_reads, [&](size_t b, size_t e) {
+        for (size_t r = b; r < e; ++r) {
+            const size_t n = start[r + 1] - start[r];
+            if (!n) continue;
+            RawHit* p = by_read.data() + start[r];
+            std::sort(p, p + n, [](const RawHit& x, const RawHit& y) { return x.a < y.a; });
+            if (exact) resolve_exact(hv, p, n, per_read[r]);
+            else resolve_inexact(hv, seq_pool + seq_off[r], (uint32_t)(seq_off[r + 1] - seq_off[r]), (flags & RTK_SEARCH_OR_EXCL) != 0,
+                                 p, n, per_read[r]);
+        }
+    });
 }
 
 }  // namespace rtk
