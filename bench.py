@@ -196,8 +196,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bases-per-step", type=int, default=32 << 20)
-    ap.add_argument("--ref-sample-bases", type=int, default=1_500_000)
-    ap.add_argument("--cpu-baseline-bases", type=int, default=1_000_000)
+    ap.add_argument("--ref-sample-bases", type=int, default=4_000_000)
+    ap.add_argument("--cpu-baseline-bases", type=int, default=16_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
