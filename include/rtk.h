@@ -133,6 +133,42 @@ int rtk_edlib_batch(rtk_ctx* ctx, uint32_t n, const char* q_pool, const uint64_t
                     const uint64_t* t_off, const uint8_t* mode, const int32_t* kmax, int32_t* dist,
                     int32_t** end_loc, uint64_t** end_off, uint64_t* stats);
 
+/* ---- K2/K3 + K4: exploreSubGraph (src/GraphTraversal.cpp:456-587) ----
+ * Bounded DFS from a start unitig towards an optional target unitig with colour-set threshold intersection
+ * (getNumberSharedPairID >= min_cov against `pids` = WeightsPairID::all_pids), edge-flag test, and scoring of
+ * every candidate by edit distance against the read window (getScorePath :867-909); returns, per call, the
+ * equal-best terminal and non-terminal paths in discovery order and the best / second-best scores. */
+typedef struct rtk_subgraph_call_t {
+    uint32_t start_unitig, start_strand;
+    uint32_t end_unitig, end_strand, end_dist; /* end_unitig = 0xFFFFFFFF: no target */
+    uint32_t level;                            /* DFS depth below the start; the reference passes level-1 = 3 */
+    uint32_t max_len_path;
+    uint32_t ref_len;
+    uint64_t ref_off;                          /* read window = ref_pool[ref_off, ref_off+ref_len) */
+    uint64_t pid_off;                          /* pids = pid_pool[pid_off, pid_off+pid_len), sorted */
+    uint32_t pid_len;                          /* 0 = no colour filter (all_pids.isEmpty()) */
+    uint32_t min_cov;                          /* Correct_Opt::min_cov_vertices */
+} rtk_subgraph_call_t;
+
+typedef struct rtk_path_node {
+    uint32_t unitig, strand, dist, len;        /* const_UnitigMap of one path vertex (Path::toVector) */
+} rtk_path_node;
+
+typedef struct rtk_subgraph_out {
+    double* scores;        /* 4 per call: best terminal, 2nd terminal, best non-terminal, 2nd non-terminal */
+    uint64_t* path_off;    /* n_calls+1: paths of call i = [path_off[i], path_off[i+1]) */
+    uint32_t* n_terminal;  /* per call: the first n_terminal of its paths are terminal */
+    uint64_t* node_off;    /* n_paths+1 */
+    rtk_path_node* nodes;
+    uint32_t* path_len;    /* per path: spelled length */
+    int32_t* path_ed;      /* per path: edit distance behind its score */
+} rtk_subgraph_out;
+
+int rtk_explore_subgraph_batch(rtk_ctx* ctx, uint32_t n_calls, const rtk_subgraph_call_t* calls, const char* ref_pool,
+                               uint64_t ref_bytes, const uint32_t* pid_pool, uint64_t n_pids, double weak_region_len_factor,
+                               rtk_subgraph_out* out, uint64_t* stats);
+void rtk_subgraph_out_free(rtk_subgraph_out* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,7 @@
 using namespace std;
 
 struct RefGraph {
+    std::unordered_map<uint64_t, const_UnitigMap<UnitigData>> by_key;  // filled lazily (ref_explore_subgraph)
     CompactedDBG<UnitigData>* dbg;
     Correct_Opt opt;
     size_t max_km_cov;
@@ -271,6 +272,64 @@ int ref_edlib(const char* q, int ql, const char* t, int tl, int mode, int task, 
     const int status = r.status;
     edlibFreeAlignResult(r);
     return status;
+}
+
+// exploreSubGraph (src/GraphTraversal.cpp:456-587) on explicit arguments.
+// start / end unitigs are given by key (see um_key) + strand (+ end dist); end_key = ~0 -> no target.
+// pids = w_pid.all_pids.  Output (malloc'd u32 stream): for terminal then non-terminal paths:
+//   n_paths, then per path: n_um, (key_lo, key_hi, strand, dist, len) * n_um, qual_len, qual bytes padded to 4
+static void serialize_paths(const vector<Path<UnitigData>>& v, vector<uint32_t>& out) {
+    out.push_back((uint32_t)v.size());
+    for (const auto& p : v) {
+        const Path<UnitigData>::PathOut po = p.toStringVector();
+        const vector<const_UnitigMap<UnitigData>>& vu = po.toVector();
+        out.push_back((uint32_t)vu.size());
+        for (const auto& um : vu) {
+            const uint64_t key = um_key(um);
+            out.push_back((uint32_t)key); out.push_back((uint32_t)(key >> 32));
+            out.push_back(um.strand ? 1u : 0u); out.push_back((uint32_t)um.dist); out.push_back((uint32_t)um.len);
+        }
+        const string& q = po.toQualityString();
+        out.push_back((uint32_t)q.size());
+        for (size_t i = 0; i < q.size(); i += 4) {
+            uint32_t w = 0;
+            for (size_t j = 0; j < 4 && i + j < q.size(); ++j) w |= ((uint32_t)(unsigned char)q[i + j]) << (8 * j);
+            out.push_back(w);
+        }
+    }
+}
+
+int ref_explore_subgraph(void* h, uint64_t start_key, int start_strand, uint64_t end_key, int end_strand, uint32_t end_dist,
+                         const char* ref, uint32_t level, uint32_t max_len_path, const uint32_t* pids, uint32_t n_pids,
+                         double* scores, uint32_t** out, uint64_t* out_words) {
+    RefGraph* g = (RefGraph*)h;
+    if (g->by_key.empty()) for (const auto& um : *g->dbg) g->by_key[um_key(um)] = um;
+    const size_t k = g->dbg->getK();
+    auto it = g->by_key.find(start_key);
+    if (it == g->by_key.end()) return -1;
+    const_UnitigMap<UnitigData> um = it->second;
+    um.dist = 0; um.len = um.size - k + 1; um.strand = (start_strand != 0);
+    const_UnitigMap<UnitigData> um_e;
+    if (end_key != 0xffffffffffffffffULL) {
+        auto ie = g->by_key.find(end_key);
+        if (ie == g->by_key.end()) return -1;
+        um_e = ie->second;
+        um_e.dist = end_dist; um_e.len = 1; um_e.strand = (end_strand != 0);
+    }
+    WeightsPairID w_pid;
+    for (uint32_t i = 0; i < n_pids; ++i) w_pid.all_pids.add(pids[i]);
+    vector<Path<UnitigData>> term, nonterm;
+    unordered_map<const SharedPairID*, pair<double, bool>, HashSharedPairIDptr> m_pid;
+    const pair<double, double> sc = exploreSubGraph(g->opt, w_pid, ref, strlen(ref), max_len_path, um, um_e, level, term, nonterm,
+                                                    0xffffffffffffffffULL, m_pid);
+    scores[0] = sc.first; scores[1] = sc.second;
+    vector<uint32_t> ser;
+    serialize_paths(term, ser);
+    serialize_paths(nonterm, ser);
+    *out = (uint32_t*)malloc(sizeof(uint32_t) * (ser.size() + 1));
+    memcpy(*out, ser.data(), sizeof(uint32_t) * ser.size());
+    *out_words = ser.size();
+    return 0;
 }
 
 void ref_free(void* p) { free(p); }

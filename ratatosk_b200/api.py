@@ -50,6 +50,24 @@ class RtkSeeds(C.Structure):
                 ("weak", C.POINTER(RtkHit)), ("weak_off", C.POINTER(C.c_uint64))]
 
 
+class RtkSubgraphCall(C.Structure):
+    _fields_ = [("start_unitig", C.c_uint32), ("start_strand", C.c_uint32), ("end_unitig", C.c_uint32),
+                ("end_strand", C.c_uint32), ("end_dist", C.c_uint32), ("level", C.c_uint32),
+                ("max_len_path", C.c_uint32), ("ref_len", C.c_uint32), ("ref_off", C.c_uint64),
+                ("pid_off", C.c_uint64), ("pid_len", C.c_uint32), ("min_cov", C.c_uint32)]
+
+
+class RtkPathNode(C.Structure):
+    _fields_ = [("unitig", C.c_uint32), ("strand", C.c_uint32), ("dist", C.c_uint32), ("len", C.c_uint32)]
+
+
+class RtkSubgraphOut(C.Structure):
+    _fields_ = [("scores", C.POINTER(C.c_double)), ("path_off", C.POINTER(C.c_uint64)),
+                ("n_terminal", C.POINTER(C.c_uint32)), ("node_off", C.POINTER(C.c_uint64)),
+                ("nodes", C.POINTER(RtkPathNode)), ("path_len", C.POINTER(C.c_uint32)),
+                ("path_ed", C.POINTER(C.c_int32))]
+
+
 HIT_DTYPE = np.dtype([("pos", "<u4"), ("unitig", "<u4"), ("dist", "<u4"), ("strand", "<u4")])
 
 _libs = {}
@@ -92,6 +110,10 @@ def load_library(path=None):
     L.rtk_get_seeds.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_int, C.c_uint32, C.c_char_p,
                                 C.POINTER(C.c_uint64), C.POINTER(RtkSeeds), C.POINTER(C.c_uint64)]
     L.rtk_seeds_free.argtypes = [C.POINTER(RtkSeeds)]
+    L.rtk_explore_subgraph_batch.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(RtkSubgraphCall), C.c_char_p, C.c_uint64,
+                                             C.POINTER(C.c_uint32), C.c_uint64, C.c_double,
+                                             C.POINTER(RtkSubgraphOut), C.POINTER(C.c_uint64)]
+    L.rtk_subgraph_out_free.argtypes = [C.POINTER(RtkSubgraphOut)]
     for name, args in (("rtk_graph_adopt_device", [C.c_void_p, C.c_void_p, C.c_uint64]),
                        ("rtk_k1_sweep_device", [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                                 C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint64),
@@ -278,6 +300,49 @@ class Context:
         if stats is not None:
             stats.extend(list(st))
         return dist, [ends[int(offs[i]):int(offs[i + 1])] for i in range(n)]
+
+    def explore_subgraph(self, calls, weak_region_len_factor=0.25, stats=None):
+        """exploreSubGraph for a batch.  calls: dicts with start=(unitig, strand), end=(unitig, strand, dist) or None,
+        ref (str), level, max_len_path, pids (sorted ints), min_cov (default 2).
+        -> per call dict(scores=(t1, t2, nt1, nt2), terminal=[path], nonterminal=[path]); path = dict(nodes=[(unitig,
+        strand, dist, len)], length, ed)"""
+        n = len(calls)
+        arr = (RtkSubgraphCall * max(n, 1))()
+        refs, pids = [], []
+        ro = po = 0
+        for i, c in enumerate(calls):
+            r = c["ref"].encode()
+            a = arr[i]
+            a.start_unitig, a.start_strand = c["start"]
+            if c.get("end") is None:
+                a.end_unitig, a.end_strand, a.end_dist = 0xFFFFFFFF, 0, 0
+            else:
+                a.end_unitig, a.end_strand, a.end_dist = c["end"]
+            a.level, a.max_len_path = c["level"], c["max_len_path"]
+            a.ref_off, a.ref_len = ro, len(r)
+            a.pid_off, a.pid_len = po, len(c["pids"])
+            a.min_cov = c.get("min_cov", 2)
+            refs.append(r); ro += len(r)
+            pids.extend(c["pids"]); po += len(c["pids"])
+        ref_pool = b"".join(refs)
+        pid_arr = (C.c_uint32 * max(len(pids), 1))(*pids)
+        out = RtkSubgraphOut()
+        st = (C.c_uint64 * 8)()
+        _check(self.L, self.L.rtk_explore_subgraph_batch(self.h, n, arr, ref_pool, len(ref_pool), pid_arr, len(pids),
+                                                         weak_region_len_factor, C.byref(out), st))
+        res = []
+        for i in range(n):
+            paths = []
+            for pi in range(out.path_off[i], out.path_off[i + 1]):
+                nodes = [(out.nodes[j].unitig, out.nodes[j].strand, out.nodes[j].dist, out.nodes[j].len)
+                         for j in range(out.node_off[pi], out.node_off[pi + 1])]
+                paths.append({"nodes": nodes, "length": out.path_len[pi], "ed": out.path_ed[pi]})
+            nt = out.n_terminal[i]
+            res.append({"scores": tuple(out.scores[4 * i + j] for j in range(4)), "terminal": paths[:nt], "nonterminal": paths[nt:]})
+        self.L.rtk_subgraph_out_free(C.byref(out))
+        if stats is not None:
+            stats.extend(list(st))
+        return res
 
     def close(self):
         if self.h:

@@ -24,9 +24,11 @@
 
 struct rtk_myers_params {
     const char* q_pool;
-    const uint64_t* q_off;
+    const uint64_t* q_beg;   // [alignment] start of the query in q_pool
+    const uint32_t* q_len;
     const char* t_pool;
-    const uint64_t* t_off;
+    const uint64_t* t_beg;
+    const uint32_t* t_len;
     const uint8_t* mode;     // 0 NW, 1 SHW, 2 HW
     const int32_t* kmax;     // -1 = unbounded
     const uint32_t* order;   // alignment ids handled by this launch (sorted by target length)
@@ -69,10 +71,10 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_kernel(const rtk_
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(uint32_t)(G - 1)));
 
     const uint32_t a = p.order[grp];
-    const char* q = p.q_pool + p.q_off[a];
-    const char* t = p.t_pool + p.t_off[a];
-    const int qlen = (int)(p.q_off[a + 1] - p.q_off[a]);
-    const int tlen = (int)(p.t_off[a + 1] - p.t_off[a]);
+    const char* q = p.q_pool + p.q_beg[a];
+    const char* t = p.t_pool + p.t_beg[a];
+    const int qlen = (int)p.q_len[a];
+    const int tlen = (int)p.t_len[a];
     const int mode = p.mode[a];
     const int nb = (qlen + 63) >> 6;
     const int rounds = (nb + G - 1) / G;

@@ -15,12 +15,12 @@ struct MyersPlan {
 };
 
 // class c uses G = 1<<c lanes per alignment: the smallest power of two covering the query's 64-row blocks
-inline MyersPlan plan_myers(uint32_t n, const uint64_t* q_off, const uint64_t* t_off) {
+inline MyersPlan plan_myers(uint32_t n, const uint32_t* q_len, const uint32_t* t_len) {
     MyersPlan pl;
     pl.ends_off.assign(n + 1, 0);
     pl.hb_off.assign(n + 1, 0);
     for (uint32_t a = 0; a < n; ++a) {
-        const uint64_t ql = q_off[a + 1] - q_off[a], tl = t_off[a + 1] - t_off[a];
+        const uint64_t ql = q_len[a], tl = t_len[a];
         pl.ends_off[a + 1] = pl.ends_off[a] + tl + 1;
         pl.hb_off[a + 1] = pl.hb_off[a] + tl;
         if (ql == 0 || tl == 0) { pl.trivial.push_back(a); continue; }
@@ -31,7 +31,7 @@ inline MyersPlan plan_myers(uint32_t n, const uint64_t* q_off, const uint64_t* t
     }
     for (int c = 0; c < 6; ++c)  // longest targets first: the groups packed into one warp finish together
         std::stable_sort(pl.order[c].begin(), pl.order[c].end(), [&](uint32_t x, uint32_t y) {
-            return (t_off[x + 1] - t_off[x]) > (t_off[y + 1] - t_off[y]);
+            return t_len[x] > t_len[y];
         });
     return pl;
 }

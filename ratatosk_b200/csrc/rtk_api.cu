@@ -140,6 +140,7 @@ void rtk_ctx_destroy(rtk_ctx* c) {
     if (c->owns_slab && c->d_slab) cudaFree((void*)c->d_slab);
     c->d_seq.release(); c->d_seq_off.release(); c->d_tiles.release(); c->d_hits.release(); c->d_counters.release();
     for (auto& b : c->d_aux) b.release();
+    for (auto& b : c->d_sub) b.release();
     for (auto& b : c->h_pin) b.release();
     if (c->host_copy.data) free(c->host_copy.data);
     if (c->ev0) cudaEventDestroy(c->ev0);

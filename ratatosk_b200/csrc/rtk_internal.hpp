@@ -96,7 +96,7 @@ struct rtk_ctx {
     rtk::rtk_slab host_copy;              // when the graph was adopted from device memory
     rtk_host_graph host_graph_owned;
     // scratch
-    rtk::DevBuf d_seq, d_seq_off, d_tiles, d_hits, d_counters, d_aux[8];
+    rtk::DevBuf d_seq, d_seq_off, d_tiles, d_hits, d_counters, d_aux[8], d_sub[8];
     rtk::PinBuf h_pin[4];
     int sm_count = 148;
 };
@@ -112,6 +112,19 @@ void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_p
 // raw labelled hits in ctx->d_hits.  Returns raw hit count; *n_probes / *kernel_ms optional.
 uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint64_t* d_seq_off,
                    const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms);
+
+#ifndef RTK_HOSTSIM
+// K4 over pools already resident on the device.  Host arrays describe the n alignments (begin/length into
+// the pools, mode, kmax).  dist gets n entries; when want_ends, *ends / *ends_off are malloc'd dense lists.
+struct MyersJobs {
+    uint32_t n;
+    const uint64_t* q_beg; const uint32_t* q_len;
+    const uint64_t* t_beg; const uint32_t* t_len;
+    const uint8_t* mode; const int32_t* kmax;   // kmax may be null (= -1 everywhere)
+};
+void myers_run(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const MyersJobs& j, int32_t* dist, bool want_ends,
+               int32_t** ends, uint64_t** ends_off, float* kernel_ms);
+#endif
 
 // full searchSequence for a host batch -> per read ordered hits
 void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,

@@ -23,11 +23,13 @@ extern "C" int rtk_edlib_batch(rtk_ctx*, uint32_t n, const char* q_pool, const u
                                const uint64_t* t_off, const uint8_t* mode, const int32_t* kmax, int32_t* dist,
                                int32_t** end_loc, uint64_t** end_off, uint64_t*) {
     return guarded([&] {
-        const MyersPlan pl = plan_myers(n, q_off, t_off);
+        std::vector<uint32_t> qlen(n + 1, 0), tlen(n + 1, 0);
+        for (uint32_t i = 0; i < n; ++i) { qlen[i] = (uint32_t)(q_off[i + 1] - q_off[i]); tlen[i] = (uint32_t)(t_off[i + 1] - t_off[i]); }
+        const MyersPlan pl = plan_myers(n, qlen.data(), tlen.data());
         std::vector<int32_t> d(n, -1), ne(n, 0), ends(pl.ends_off[n] + 1, 0);
         std::vector<int8_t> hb(pl.hb_off[n] + 1, 0);
         rtk_myers_params p;
-        p.q_pool = q_pool; p.q_off = q_off; p.t_pool = t_pool; p.t_off = t_off; p.mode = mode; p.kmax = kmax;
+        p.q_pool = q_pool; p.q_beg = q_off; p.q_len = qlen.data(); p.t_pool = t_pool; p.t_beg = t_off; p.t_len = tlen.data(); p.mode = mode; p.kmax = kmax;
         p.order = nullptr; p.n = 0; p.dist = d.data(); p.n_ends = ne.data(); p.ends = ends.data(); p.ends_off = pl.ends_off.data();
         p.hbound = hb.data(); p.hb_off = pl.hb_off.data();
         sim_class<1>(p, pl.order[0]); sim_class<2>(p, pl.order[1]); sim_class<4>(p, pl.order[2]);

@@ -48,6 +48,9 @@ def lib():
                                 C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_int)),
                                 C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.c_int)]
         L.ref_free.argtypes = [C.c_void_p]
+        L.ref_explore_subgraph.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_uint32, C.c_char_p,
+                                           C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
+                                           C.POINTER(C.c_double), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -94,6 +97,38 @@ class RefGraph:
         ns, nw = C.c_int64(), C.c_int64()
         lib().ref_get_seeds(self.h, s.encode(), q.encode(), int(pass2), C.byref(ps), C.byref(ns), C.byref(pw), C.byref(nw))
         return _hits(ps, ns.value), _hits(pw, nw.value)
+
+    def explore_subgraph(self, start_key, start_strand, end_key, end_strand, end_dist, ref, level, max_len_path, pids):
+        """-> (score_t1, score_nt1, terminal paths, non-terminal paths); path = ([(key, strand, dist, len)...], qual)"""
+        import numpy as np
+        arr = (C.c_uint32 * max(1, len(pids)))(*pids)
+        sc = (C.c_double * 2)()
+        po = C.POINTER(C.c_uint32)()
+        nw = C.c_uint64()
+        ek = 0xFFFFFFFFFFFFFFFF if end_key is None else end_key
+        rc = lib().ref_explore_subgraph(self.h, start_key, int(start_strand), ek, int(end_strand), int(end_dist), ref.encode(),
+                                        level, max_len_path, arr, len(pids), sc, C.byref(po), C.byref(nw))
+        if rc != 0:
+            raise RuntimeError("ref_explore_subgraph failed")
+        w = [po[i] for i in range(nw.value)]
+        lib().ref_free(C.cast(po, C.c_void_p))
+        pos = 0
+        groups = []
+        for _ in range(2):
+            n = w[pos]; pos += 1
+            paths = []
+            for _p in range(n):
+                m = w[pos]; pos += 1
+                ums = []
+                for _u in range(m):
+                    key = w[pos] | (w[pos + 1] << 32)
+                    ums.append((key, w[pos + 2], w[pos + 3], w[pos + 4])); pos += 5
+                ql = w[pos]; pos += 1
+                nq = (ql + 3) // 4
+                qb = b"".join(int(x).to_bytes(4, "little") for x in w[pos:pos + nq])[:ql]; pos += nq
+                paths.append((ums, qb.decode("latin1")))
+            groups.append(paths)
+        return sc[0], sc[1], groups[0], groups[1]
 
     def correct_read(self, s, q, pass2=False):
         so, qo = C.c_void_p(), C.c_void_p()
