@@ -133,6 +133,15 @@ int rtk_edlib_batch(rtk_ctx* ctx, uint32_t n, const char* q_pool, const uint64_t
                     const uint64_t* t_off, const uint8_t* mode, const int32_t* kmax, int32_t* dist,
                     int32_t** end_loc, uint64_t** end_off, uint64_t* stats);
 
+/* ---- K5: edlibAlign with EDLIB_TASK_PATH (src/edlib.cpp:262-279, obtainAlignmentTraceback :945-1134) ----
+ * mode[i]: 0 NW, 1 SHW.  Out per pair: dist, the (first) end column, and the edit operations of the path
+ * (0 match, 1 query base unaligned, 2 target base unaligned, 3 mismatch) in ops[ops_off[i], ops_off[i+1]).
+ * flags[i] = 1 when the pair is at or above edlib's 1 MiB switch to Hirschberg's recursion (or the query
+ * exceeds 2048 rows): no path is produced for it yet (dist / end are still valid for SHW). */
+int rtk_edlib_path_batch(rtk_ctx* ctx, uint32_t n, const char* q_pool, const uint64_t* q_off, const char* t_pool,
+                         const uint64_t* t_off, const uint8_t* mode, int32_t* dist, int32_t* end_loc, uint8_t** ops,
+                         uint64_t** ops_off, uint8_t* flags, uint64_t* stats);
+
 /* ---- K2/K3 + K4: exploreSubGraph (src/GraphTraversal.cpp:456-587) ----
  * Bounded DFS from a start unitig towards an optional target unitig with colour-set threshold intersection
  * (getNumberSharedPairID >= min_cov against `pids` = WeightsPairID::all_pids), edge-flag test, and scoring of

@@ -114,6 +114,10 @@ def load_library(path=None):
                                              C.POINTER(C.c_uint32), C.c_uint64, C.c_double,
                                              C.POINTER(RtkSubgraphOut), C.POINTER(C.c_uint64)]
     L.rtk_subgraph_out_free.argtypes = [C.POINTER(RtkSubgraphOut)]
+    L.rtk_edlib_path_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.c_char_p,
+                                       C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_uint8)),
+                                       C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
     for name, args in (("rtk_graph_adopt_device", [C.c_void_p, C.c_void_p, C.c_uint64]),
                        ("rtk_k1_sweep_device", [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
                                                 C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint64),
@@ -300,6 +304,32 @@ class Context:
         if stats is not None:
             stats.extend(list(st))
         return dist, [ends[int(offs[i]):int(offs[i + 1])] for i in range(n)]
+
+    def edlib_path_batch(self, queries, targets, modes, stats=None):
+        """edlibAlign with TASK_PATH; modes: 0 NW, 1 SHW -> (dist, end, [ops bytes], flags)"""
+        n = len(queries)
+        qp, qo = pack_reads(queries)
+        tp, to = pack_reads(targets)
+        m = np.asarray(modes, dtype=np.uint8)
+        dist = np.zeros(n, dtype=np.int32)
+        end = np.zeros(n, dtype=np.int32)
+        flags = np.zeros(n, dtype=np.uint8)
+        po, poff = C.POINTER(C.c_uint8)(), C.POINTER(C.c_uint64)()
+        st = (C.c_uint64 * 8)()
+        _check(self.L, self.L.rtk_edlib_path_batch(self.h, n, qp, qo.ctypes.data_as(C.POINTER(C.c_uint64)), tp,
+                                                   to.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                   m.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                                   dist.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                   end.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(po), C.byref(poff),
+                                                   flags.ctypes.data_as(C.POINTER(C.c_uint8)), st))
+        offs = np.ctypeslib.as_array(poff, shape=(n + 1,)).copy()
+        total = int(offs[-1])
+        raw = np.ctypeslib.as_array(po, shape=(max(total, 1),)).copy()[:total]
+        self.L.rtk_free(C.cast(po, C.c_void_p))
+        self.L.rtk_free(C.cast(poff, C.c_void_p))
+        if stats is not None:
+            stats.extend(list(st))
+        return dist, end, [raw[int(offs[i]):int(offs[i + 1])].tolist() for i in range(n)], flags
 
     def explore_subgraph(self, calls, weak_region_len_factor=0.25, stats=None):
         """exploreSubGraph for a batch.  calls: dicts with start=(unitig, strand), end=(unitig, strand, dist) or None,

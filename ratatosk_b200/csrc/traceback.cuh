@@ -1,0 +1,163 @@
+// traceback.cuh — K5: alignment path (edit operations) for NW alignments, replacing edlib's
+// obtainAlignmentTraceback (src/edlib.cpp:945-1134) as reached from edlibAlign with EDLIB_TASK_PATH
+// (:262-279; SHW paths are NW paths against the target prefix ending at the first best end location).
+//
+// Two kernels.  rtk_myers_fill_kernel<G> is the K4 wavefront (myers.cuh) in NW mode that additionally
+// stores, for every (query block, target column), the vertical delta words Pv/Mv after the column and the
+// score of the block's anchor row (row 63, or the query's last row in the last block) - the same state
+// edlib's AlignmentData keeps (Ps, Ms, scores), laid out [block][column] so a lane streams its own row.
+// rtk_traceback_kernel walks back from (|q|-1, |t|-1): any cell's score is the anchor score minus a
+// popcount over the delta bits between the cell and the anchor, so each step costs O(1); moves are tried
+// in edlib's priority - up (op 1, query base unaligned) > left (op 2, target base unaligned) > diagonal
+// (0 match / 3 mismatch) - which is what makes the path, not just its cost, identical.
+// edlib's Ukkonen band cannot change the walk: a move is only ever taken into a cell whose score continues
+// an optimal path, and such cells are inside the band with exact scores.
+#pragma once
+#ifndef RTK_HOSTSIM
+#include <cuda_runtime.h>
+#endif
+#include <stdint.h>
+
+#include "myers.cuh"
+
+struct rtk_fill_params {
+    const char* q_pool;
+    const uint64_t* q_beg;
+    const uint32_t* q_len;
+    const char* t_pool;
+    const uint64_t* t_beg;
+    const uint32_t* t_len;
+    const uint32_t* order;
+    uint32_t n;
+    const uint64_t* mat_off;   // [alignment] first (block 0, column 0) cell of its matrix, in cells
+    ulonglong2* mat;           // {Pv, Mv} per (block, column): index mat_off + block * t_len + column
+    int32_t* anchor;           // anchor-row score, same indexing
+    int32_t* dist;             // [alignment] NW distance
+};
+
+#if defined(__CUDACC__) || defined(__CUDACC_SIM__)
+
+template <int G>
+__global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_fill_kernel(const rtk_fill_params p) {
+    const uint32_t lane = threadIdx.x & (G - 1);
+    const uint32_t grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (grp >= p.n) return;
+    const uint32_t wl = threadIdx.x & 31;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(uint32_t)(G - 1)));
+    const uint32_t a = p.order[grp];
+    const char* q = p.q_pool + p.q_beg[a];
+    const char* t = p.t_pool + p.t_beg[a];
+    const int qlen = (int)p.q_len[a], tlen = (int)p.t_len[a];
+    const int nb = (qlen + 63) >> 6;   // nb <= G for this launch (planner guarantees it)
+    const int b = (int)lane;
+    const bool has = b < nb;
+    const int arow = (b == nb - 1) ? ((qlen - 1) & 63) : 63;  // anchor row of this block
+    uint64_t PB0 = 0, PB1 = 0, PB2 = 0, PB3 = 0;
+    if (has) {
+        const int lo = b << 6;
+        const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+        for (int i = 0; i < n; ++i) {
+            const uint64_t m = rtk_iupac_mask(q[lo + i]);
+            PB0 |= (m & 1) << i; PB1 |= ((m >> 1) & 1) << i; PB2 |= ((m >> 2) & 1) << i; PB3 |= ((m >> 3) & 1) << i;
+        }
+    }
+    uint64_t Pv = ~0ULL, Mv = 0;
+    int hout = 0;
+    int score = (b << 6) + arow + 1;   // D[anchor row][-1]
+    const uint64_t base = p.mat_off[a] + (uint64_t)b * (uint64_t)tlen;
+    const int steps = tlen + G - 1;
+    for (int s = 0; s < steps; ++s) {
+        const int from_left = __shfl_up_sync(gmask, hout, 1, G);
+        const int col = s - (int)lane;
+        hout = 0;
+        if (has && col >= 0 && col < tlen) {
+            const int hin = (lane == 0) ? 1 : from_left;   // NW: D[0][j] = j
+            const char tc = t[col];
+            uint64_t Eq;
+            switch (tc) {
+                case 'A': Eq = PB0; break;
+                case 'C': Eq = PB1; break;
+                case 'G': Eq = PB2; break;
+                case 'T': Eq = PB3; break;
+                default: {
+                    Eq = 0;
+                    const int lo = b << 6;
+                    const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+                    for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(q[lo + i], tc) << i;
+                }
+            }
+            const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
+            const uint64_t Xv = Eq | Mv;
+            Eq |= neg;
+            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            uint64_t Ph = Mv | ~(Xh | Pv);
+            uint64_t Mh = Pv & Xh;
+            hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+            score += (int)((Ph >> arow) & 1) - (int)((Mh >> arow) & 1);
+            Ph = (Ph << 1) | ((hin > 0) ? 1ULL : 0ULL);
+            Mh = (Mh << 1) | neg;
+            Pv = Mh | ~(Xv | Ph);
+            Mv = Ph & Xv;
+            ulonglong2 cell; cell.x = Pv; cell.y = Mv;
+            p.mat[base + col] = cell;
+            p.anchor[base + col] = score;
+            if (b == nb - 1 && col == tlen - 1) p.dist[a] = score;
+        }
+    }
+}
+
+struct rtk_tb_params {
+    const uint32_t* q_len;
+    const uint32_t* t_len;
+    const uint32_t* ids;       // alignment ids of this launch
+    uint32_t n;
+    const uint64_t* mat_off;
+    const ulonglong2* mat;
+    const int32_t* anchor;
+    const int32_t* dist;
+    const uint64_t* ops_off;   // [alignment] capacity q_len + t_len each
+    uint8_t* ops;              // written right-aligned inside the capacity window
+    uint32_t* ops_len;         // [alignment]
+};
+
+// score of cell (row i, column c); i == -1 / c == -1 are the NW boundaries
+__device__ __forceinline__ int rtk_tb_score(const rtk_tb_params& p, const uint64_t moff, const int tlen, const int nb,
+                                            const int last_row, const int i, const int c) {
+    if (i < 0) return c + 1;
+    if (c < 0) return i + 1;
+    const int b = i >> 6, r = i & 63;
+    const int arow = (b == nb - 1) ? last_row : 63;
+    const uint64_t idx = moff + (uint64_t)b * (uint64_t)tlen + (uint64_t)c;
+    const ulonglong2 cell = p.mat[idx];
+    // rows r+1 .. arow
+    const uint64_t hi = (arow == 63) ? ~0ULL : ((1ULL << (arow + 1)) - 1ULL);
+    const uint64_t lo = (r == 63) ? ~0ULL : ((1ULL << (r + 1)) - 1ULL);
+    const uint64_t m = hi & ~lo;
+    return p.anchor[idx] - __popcll(cell.x & m) + __popcll(cell.y & m);
+}
+
+__global__ void __launch_bounds__(128) rtk_traceback_kernel(const rtk_tb_params p) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= p.n) return;
+    const uint32_t a = p.ids[g];
+    const int qlen = (int)p.q_len[a], tlen = (int)p.t_len[a];
+    const int nb = (qlen + 63) >> 6, last_row = (qlen - 1) & 63;
+    const uint64_t moff = p.mat_off[a];
+    uint8_t* out = p.ops + p.ops_off[a];
+    uint32_t w = (uint32_t)(qlen + tlen);   // next write position (exclusive), walking backwards
+    int i = qlen - 1, c = tlen - 1, cur = p.dist[a];
+    while (i >= 0 && c >= 0) {
+        const int u = rtk_tb_score(p, moff, tlen, nb, last_row, i - 1, c);
+        if (u + 1 == cur) { out[--w] = 1; --i; cur = u; continue; }               // up: query base unaligned
+        const int l = rtk_tb_score(p, moff, tlen, nb, last_row, i, c - 1);
+        if (l + 1 == cur) { out[--w] = 2; --c; cur = l; continue; }               // left: target base unaligned
+        const int ul = rtk_tb_score(p, moff, tlen, nb, last_row, i - 1, c - 1);
+        out[--w] = (ul == cur) ? 0 : 3;                                           // diagonal: match / mismatch
+        --i; --c; cur = ul;
+    }
+    while (c >= 0) { out[--w] = 2; --c; }
+    while (i >= 0) { out[--w] = 1; --i; }
+    p.ops_len[a] = (uint32_t)(qlen + tlen) - w;
+}
+
+#endif  // __CUDACC__ || __CUDACC_SIM__
