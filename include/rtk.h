@@ -136,8 +136,8 @@ int rtk_edlib_batch(rtk_ctx* ctx, uint32_t n, const char* q_pool, const uint64_t
 /* ---- K5: edlibAlign with EDLIB_TASK_PATH (src/edlib.cpp:262-279, obtainAlignmentTraceback :945-1134) ----
  * mode[i]: 0 NW, 1 SHW.  Out per pair: dist, the (first) end column, and the edit operations of the path
  * (0 match, 1 query base unaligned, 2 target base unaligned, 3 mismatch) in ops[ops_off[i], ops_off[i+1]).
- * flags[i] = 1 when the pair is at or above edlib's 1 MiB switch to Hirschberg's recursion (or the query
- * exceeds 2048 rows): no path is produced for it yet (dist / end are still valid for SHW). */
+ * Pairs at or above edlib's 1 MiB switch go through its divide-and-conquer (split row and size switch
+ * reproduced, src/edlib.cpp:1191-1356).  flags[i] is reserved (always 0). */
 int rtk_edlib_path_batch(rtk_ctx* ctx, uint32_t n, const char* q_pool, const uint64_t* q_off, const char* t_pool,
                          const uint64_t* t_off, const uint8_t* mode, int32_t* dist, int32_t* end_loc, uint8_t** ops,
                          uint64_t** ops_off, uint8_t* flags, uint64_t* stats);
@@ -177,6 +177,16 @@ int rtk_explore_subgraph_batch(rtk_ctx* ctx, uint32_t n_calls, const rtk_subgrap
                                uint64_t ref_bytes, const uint32_t* pid_pool, uint64_t n_pids, double weak_region_len_factor,
                                rtk_subgraph_out* out, uint64_t* stats);
 void rtk_subgraph_out_free(rtk_subgraph_out* out);
+
+/* ---- explorePathsBFS2 / explorePathsBFS (src/GraphTraversal.cpp:212-454, :3-210) ----
+ * Best path between two anchors (um_e != NULL) or from one anchor into the open end of a read window
+ * (um_e == NULL), within +-weak_region_len_factor of the window length: queue of partial paths, one
+ * exploreSubGraph burst (K2/K3/K4) per pop, selectors (K4), path qualities (K5), fixRepeats.  Anchors are
+ * getSeeds hits (len 1).  Output: the path's vertices (0 = none found), its per-base quality string and
+ * spelled length; buffers are library-allocated (rtk_free). */
+int rtk_explore_paths(rtk_ctx* ctx, const rtk_opt* opt, const rtk_hit* um_s, const rtk_hit* um_e, const char* ref,
+                      uint32_t ref_len, const uint32_t* pids, uint32_t n_pids, rtk_path_node** nodes, uint32_t* n_nodes,
+                      char** qual, uint32_t* path_len);
 
 #ifdef __cplusplus
 }

@@ -332,6 +332,37 @@ int ref_explore_subgraph(void* h, uint64_t start_key, int start_strand, uint64_t
     return 0;
 }
 
+// explorePathsBFS2 (src/GraphTraversal.cpp:212) when end_key != ~0, else explorePathsBFS (:3).
+// Anchors are k-mer hits: (key, strand, dist), len = 1.  Output stream as serialize_paths().
+int ref_explore_paths(void* h, uint64_t start_key, int start_strand, uint32_t start_dist, uint64_t end_key, int end_strand,
+                      uint32_t end_dist, const char* ref, const uint32_t* pids, uint32_t n_pids, int pass2,
+                      uint32_t** out, uint64_t* out_words) {
+    RefGraph* g = (RefGraph*)h;
+    if (g->by_key.empty()) for (const auto& um : *g->dbg) g->by_key[um_key(um)] = um;
+    auto it = g->by_key.find(start_key);
+    if (it == g->by_key.end()) return -1;
+    const_UnitigMap<UnitigData> um_s = it->second;
+    um_s.dist = start_dist; um_s.len = 1; um_s.strand = (start_strand != 0);
+    WeightsPairID w_pid;
+    for (uint32_t i = 0; i < n_pids; ++i) w_pid.all_pids.add(pids[i]);
+    pair<vector<Path<UnitigData>>, bool> r;
+    if (end_key != 0xffffffffffffffffULL) {
+        auto ie = g->by_key.find(end_key);
+        if (ie == g->by_key.end()) return -1;
+        const_UnitigMap<UnitigData> um_e = ie->second;
+        um_e.dist = end_dist; um_e.len = 1; um_e.strand = (end_strand != 0);
+        r = explorePathsBFS2(g->opt, ref, strlen(ref), w_pid, um_s, um_e, pass2 != 0, 0xffffffffffffffffULL);
+    } else {
+        r = explorePathsBFS(g->opt, ref, strlen(ref), w_pid, um_s, pass2 != 0, 0xffffffffffffffffULL);
+    }
+    vector<uint32_t> ser;
+    serialize_paths(r.first, ser);
+    *out = (uint32_t*)malloc(sizeof(uint32_t) * (ser.size() + 1));
+    memcpy(*out, ser.data(), sizeof(uint32_t) * ser.size());
+    *out_words = ser.size();
+    return 0;
+}
+
 void ref_free(void* p) { free(p); }
 
 }  // extern "C"

@@ -114,6 +114,9 @@ def load_library(path=None):
                                              C.POINTER(C.c_uint32), C.c_uint64, C.c_double,
                                              C.POINTER(RtkSubgraphOut), C.POINTER(C.c_uint64)]
     L.rtk_subgraph_out_free.argtypes = [C.POINTER(RtkSubgraphOut)]
+    L.rtk_explore_paths.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.POINTER(RtkHit), C.POINTER(RtkHit), C.c_char_p, C.c_uint32,
+                                    C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.POINTER(RtkPathNode)), C.POINTER(C.c_uint32),
+                                    C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
     L.rtk_edlib_path_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.c_char_p,
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_uint8)),
@@ -304,6 +307,27 @@ class Context:
         if stats is not None:
             stats.extend(list(st))
         return dist, [ends[int(offs[i]):int(offs[i + 1])] for i in range(n)]
+
+    def explore_paths(self, start, end, ref, pids, opt=None):
+        """explorePathsBFS2 (end given) / explorePathsBFS (end None); start/end = (unitig, strand, dist) anchors.
+        -> None or dict(nodes=[(unitig, strand, dist, len)], qual=str, length=int)"""
+        opt = opt or default_opt(1)
+        hs = RtkHit(0, start[0], start[2], start[1])
+        he = RtkHit(0, end[0], end[2], end[1]) if end is not None else None
+        arr = (C.c_uint32 * max(len(pids), 1))(*pids)
+        pn = C.POINTER(RtkPathNode)()
+        nn, pl = C.c_uint32(), C.c_uint32()
+        q = C.c_char_p()
+        r = ref.encode()
+        _check(self.L, self.L.rtk_explore_paths(self.h, C.byref(opt), C.byref(hs), C.byref(he) if he is not None else None, r,
+                                                len(r), arr, len(pids), C.byref(pn), C.byref(nn), C.byref(q), C.byref(pl)))
+        if nn.value == 0:
+            return None
+        res = {"nodes": [(pn[i].unitig, pn[i].strand, pn[i].dist, pn[i].len) for i in range(nn.value)],
+               "qual": q.value.decode("latin1"), "length": pl.value}
+        self.L.rtk_free(C.cast(pn, C.c_void_p))
+        self.L.rtk_free(C.cast(q, C.c_void_p))
+        return res
 
     def edlib_path_batch(self, queries, targets, modes, stats=None):
         """edlibAlign with TASK_PATH; modes: 0 NW, 1 SHW -> (dist, end, [ops bytes], flags)"""

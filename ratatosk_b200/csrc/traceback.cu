@@ -1,6 +1,7 @@
 // traceback.cu — C ABI entry rtk_edlib_path_batch: edit distance + alignment path for NW and SHW alignments
 // (edlibAlign with EDLIB_TASK_PATH).  SHW: K4 finds the distance and its first end column, the path is the NW
-// path against that target prefix (src/edlib.cpp:262-279).
+// path against that target prefix (src/edlib.cpp:262-279).  Large problems go through edlib's divide-and-
+// conquer (traceback_host.hpp), whose per-level batches run on the device here.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -11,14 +12,130 @@
 
 namespace rtk {
 
-template <int G> static void launch_fill(rtk_ctx* c, rtk_fill_params p, const uint32_t* d_order, uint32_t n) {
+template <int G, bool LC> static void launch_fill(rtk_ctx* c, rtk_fill_params p, const uint32_t* d_order, uint32_t n) {
     if (!n) return;
     p.order = d_order;
     p.n = n;
     const uint64_t threads = (uint64_t)n * G;
-    rtk_myers_fill_kernel<G><<<(uint32_t)((threads + RTK_MYERS_THREADS - 1) / RTK_MYERS_THREADS), RTK_MYERS_THREADS, 0, c->stream>>>(p);
+    rtk_myers_fill_kernel<G, LC><<<(uint32_t)((threads + RTK_MYERS_THREADS - 1) / RTK_MYERS_THREADS), RTK_MYERS_THREADS, 0, c->stream>>>(p);
     RTK_CUDA(cudaGetLastError());
 }
+
+// device pools: d_aux[0] queries, d_aux[1] targets (effective prefixes), d_sub[7] reversed queries | reversed targets
+struct CudaTbBackend : TbBackend {
+    rtk_ctx* c;
+    const char* d_q; const char* d_t; const char* d_rq; const char* d_rt;
+    float ms = 0.f;
+
+    template <bool LC> void run_fill(const std::vector<TbItem>& items, const TbPlan& pl, rtk_fill_params& fp, uint64_t*& d_off, uint32_t*& d_len) {
+        const uint32_t n = (uint32_t)items.size();
+        cudaStream_t st = c->stream;
+        DevBuf* S = c->d_sub;  // [0] u64 arrays, [1] u32 arrays, [2] order, [3] matrix, [4] anchors, [5] ops, [6] ops_len|dist + hbound
+        std::vector<uint64_t> qb(n), tb(n);
+        std::vector<uint32_t> ql(n), tl(n);
+        // forward and reversed items may mix in one batch: rebase reversed ones onto one combined pool view
+        // (forward pools and reversed pools live in different buffers, so offsets are made absolute device addresses
+        // relative to d_q / d_t by using pointer differences)
+        for (uint32_t i = 0; i < n; ++i) {
+            const char* qp = items[i].rev ? d_rq : d_q;
+            const char* tp = items[i].rev ? d_rt : d_t;
+            qb[i] = (uint64_t)((qp + items[i].q_beg) - d_q);
+            tb[i] = (uint64_t)((tp + items[i].t_beg) - d_t);
+            ql[i] = items[i].q_len; tl[i] = items[i].t_len;
+        }
+        S[0].reserve((size_t)(n + 1) * 8 * 5);
+        S[1].reserve((size_t)(n + 1) * 4 * 2);
+        S[2].reserve((size_t)(n + 1) * 4);
+        S[3].reserve(pl.cells * 16 + 16);
+        S[4].reserve(pl.cells * 4 + 16);
+        S[5].reserve(pl.ops_off[n] + 16);
+        S[6].reserve((size_t)(n + 1) * 8 + pl.hb_off[n] + 16);
+        d_off = S[0].as<uint64_t>();
+        d_len = S[1].as<uint32_t>();
+        RTK_CUDA(cudaMemcpyAsync(d_off, qb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(cudaMemcpyAsync(d_off + (n + 1), tb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(cudaMemcpyAsync(d_off + 2 * (n + 1), pl.mat_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(cudaMemcpyAsync(d_off + 3 * (n + 1), pl.ops_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(cudaMemcpyAsync(d_off + 4 * (n + 1), pl.hb_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(cudaMemcpyAsync(d_len, ql.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(cudaMemcpyAsync(d_len + (n + 1), tl.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(cudaMemcpyAsync(S[2].p, pl.ids.data(), pl.ids.size() * 4, cudaMemcpyHostToDevice, st));
+        uint32_t* d_opslen = S[6].as<uint32_t>();
+        RTK_CUDA(cudaMemsetAsync(d_opslen, 0, (size_t)(n + 1) * 8, st));
+        fp.q_pool = d_q; fp.q_beg = d_off; fp.q_len = d_len; fp.t_pool = d_t; fp.t_beg = d_off + (n + 1); fp.t_len = d_len + (n + 1);
+        fp.order = nullptr; fp.n = 0; fp.mat_off = d_off + 2 * (n + 1); fp.mat = S[3].as<ulonglong2>(); fp.anchor = S[4].as<int32_t>();
+        fp.dist = (int32_t*)(d_opslen + (n + 1)); fp.hbound = (int8_t*)(d_opslen + 2 * (n + 1)); fp.hb_off = d_off + 4 * (n + 1);
+        RTK_CUDA(cudaEventRecord(c->ev0, st));
+        const uint32_t* d_ids = S[2].as<uint32_t>();
+        uint32_t o = 0;
+        launch_fill<1, LC>(c, fp, d_ids + o, (uint32_t)pl.order[0].size()); o += (uint32_t)pl.order[0].size();
+        launch_fill<2, LC>(c, fp, d_ids + o, (uint32_t)pl.order[1].size()); o += (uint32_t)pl.order[1].size();
+        launch_fill<4, LC>(c, fp, d_ids + o, (uint32_t)pl.order[2].size()); o += (uint32_t)pl.order[2].size();
+        launch_fill<8, LC>(c, fp, d_ids + o, (uint32_t)pl.order[3].size()); o += (uint32_t)pl.order[3].size();
+        launch_fill<16, LC>(c, fp, d_ids + o, (uint32_t)pl.order[4].size()); o += (uint32_t)pl.order[4].size();
+        launch_fill<32, LC>(c, fp, d_ids + o, (uint32_t)pl.order[5].size());
+    }
+
+    void direct(const std::vector<TbItem>& items, std::vector<std::vector<uint8_t>>& ops, std::vector<int32_t>& dist) override {
+        const uint32_t n = (uint32_t)items.size();
+        ops.assign(n, {});
+        dist.assign(n, -1);
+        if (!n) return;
+        const TbPlan pl = plan_items(items, false);
+        rtk_fill_params fp;
+        uint64_t* d_off; uint32_t* d_len;
+        run_fill<false>(items, pl, fp, d_off, d_len);
+        cudaStream_t st = c->stream;
+        DevBuf* S = c->d_sub;
+        rtk_tb_params tp;
+        tp.q_len = d_len; tp.t_len = d_len + (n + 1); tp.ids = S[2].as<uint32_t>(); tp.n = n; tp.mat_off = d_off + 2 * (n + 1);
+        tp.mat = S[3].as<ulonglong2>(); tp.anchor = S[4].as<int32_t>(); tp.dist = fp.dist; tp.ops_off = d_off + 3 * (n + 1);
+        tp.ops = S[5].as<uint8_t>(); tp.ops_len = S[6].as<uint32_t>();
+        rtk_traceback_kernel<<<(n + 127) / 128, 128, 0, st>>>(tp);
+        RTK_CUDA(cudaGetLastError());
+        RTK_CUDA(cudaEventRecord(c->ev1, st));
+        std::vector<uint32_t> h_len(n + 1);
+        std::vector<uint8_t> h_ops(pl.ops_off[n] + 1);
+        RTK_CUDA(cudaMemcpyAsync(h_len.data(), tp.ops_len, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        RTK_CUDA(cudaMemcpyAsync(dist.data(), fp.dist, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (pl.ops_off[n]) RTK_CUDA(cudaMemcpyAsync(h_ops.data(), S[5].p, pl.ops_off[n], cudaMemcpyDeviceToHost, st));
+        RTK_CUDA(cudaStreamSynchronize(st));
+        float t = 0.f;
+        RTK_CUDA(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+        ms += t;
+        for (uint32_t a = 0; a < n; ++a) {
+            const uint64_t cap = (uint64_t)items[a].q_len + items[a].t_len;
+            const uint8_t* src = h_ops.data() + pl.ops_off[a] + (cap - h_len[a]);
+            ops[a].assign(src, src + h_len[a]);
+        }
+    }
+
+    void last_column(const std::vector<TbItem>& items, std::vector<std::vector<int32_t>>& rows) override {
+        const uint32_t n = (uint32_t)items.size();
+        rows.assign(n, {});
+        if (!n) return;
+        const TbPlan pl = plan_items(items, true);
+        rtk_fill_params fp;
+        uint64_t* d_off; uint32_t* d_len;
+        run_fill<true>(items, pl, fp, d_off, d_len);
+        cudaStream_t st = c->stream;
+        RTK_CUDA(cudaEventRecord(c->ev1, st));
+        std::vector<uint64_t> cells(pl.cells * 2 + 2);
+        std::vector<int32_t> anchor(pl.cells + 1);
+        RTK_CUDA(cudaMemcpyAsync(cells.data(), c->d_sub[3].p, pl.cells * 16, cudaMemcpyDeviceToHost, st));
+        RTK_CUDA(cudaMemcpyAsync(anchor.data(), c->d_sub[4].p, pl.cells * 4, cudaMemcpyDeviceToHost, st));
+        RTK_CUDA(cudaStreamSynchronize(st));
+        float t = 0.f;
+        RTK_CUDA(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+        ms += t;
+        for (uint32_t a = 0; a < n; ++a) {
+            const uint32_t nb = (items[a].q_len + 63) / 64;
+            std::vector<uint64_t> P(nb), M(nb);
+            for (uint32_t b = 0; b < nb; ++b) { P[b] = cells[2 * (pl.mat_off[a] + b)]; M[b] = cells[2 * (pl.mat_off[a] + b) + 1]; }
+            tb_rows_from_column(items[a].q_len, P.data(), M.data(), anchor.data() + pl.mat_off[a], rows[a]);
+        }
+    }
+};
 
 }  // namespace rtk
 
@@ -64,89 +181,47 @@ extern "C" int rtk_edlib_path_batch(rtk_ctx* c, uint32_t n, const char* q_pool, 
             }
             free(e); free(eo);
         }
-        // 2. classify
+        // 2. reversed copies (each query, each effective target prefix, reversed in place of its own range)
+        std::string rq(qb + 1, 'N'), rt(tb + 1, 'N');
         for (uint32_t a = 0; a < n; ++a) {
-            if (qlen[a] == 0 || tlen[a] == 0 || teff[a] == 0) flags[a] = 2;
-            else if (tb_needs_hirschberg(qlen[a], teff[a]) || qlen[a] > 64 * 32) flags[a] = 1;
-            else flags[a] = 0;
+            const char* qs = q_pool + q_off[a];
+            for (uint32_t i = 0; i < qlen[a]; ++i) rq[qrel[a] + i] = qs[qlen[a] - 1 - i];
+            const char* ts = t_pool + t_off[a];
+            for (uint32_t i = 0; i < teff[a]; ++i) rt[trel[a] + i] = ts[teff[a] - 1 - i];
         }
-        const TbPlan pl = plan_traceback(n, qlen.data(), teff.data(), flags);
-        // 3. fill + walk (d_sub[0] offsets, [1] lens, [2] order, [3] matrix, [4] anchors, [5] ops, [6] ops_len|dist)
-        DevBuf* S = c->d_sub;
-        S[0].reserve((size_t)(n + 1) * 8 * 4);
-        S[1].reserve((size_t)(n + 1) * 4 * 2);
-        S[2].reserve((size_t)(pl.ids.size() + 1) * 4);
-        S[3].reserve(pl.cells * 16 + 16);
-        S[4].reserve(pl.cells * 4 + 16);
-        S[5].reserve(pl.ops_off[n] + 16);
-        S[6].reserve((size_t)(n + 1) * 8);
-        uint64_t* d_off = S[0].as<uint64_t>();
-        uint32_t* d_len = S[1].as<uint32_t>();
-        RTK_CUDA(cudaMemcpyAsync(d_off, qrel.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_off + (n + 1), trel.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_off + 2 * (n + 1), pl.mat_off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_off + 3 * (n + 1), pl.ops_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_len, qlen.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_len + (n + 1), teff.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        if (!pl.ids.empty()) RTK_CUDA(cudaMemcpyAsync(S[2].p, pl.ids.data(), pl.ids.size() * 4, cudaMemcpyHostToDevice, st));
-        uint32_t* d_opslen = S[6].as<uint32_t>();
-        int32_t* d_dist = (int32_t*)(d_opslen + (n + 1));
-        RTK_CUDA(cudaMemsetAsync(d_opslen, 0, (size_t)(n + 1) * 8, st));
-        rtk_fill_params fp;
-        fp.q_pool = c->d_aux[0].as<char>(); fp.q_beg = d_off; fp.q_len = d_len; fp.t_pool = c->d_aux[1].as<char>();
-        fp.t_beg = d_off + (n + 1); fp.t_len = d_len + (n + 1); fp.order = nullptr; fp.n = 0; fp.mat_off = d_off + 2 * (n + 1);
-        fp.mat = S[3].as<ulonglong2>(); fp.anchor = S[4].as<int32_t>(); fp.dist = d_dist;
-        RTK_CUDA(cudaEventRecord(c->ev0, st));
-        const uint32_t* d_ids = S[2].as<uint32_t>();
-        uint32_t o = 0;
-        launch_fill<1>(c, fp, d_ids + o, (uint32_t)pl.order[0].size()); o += (uint32_t)pl.order[0].size();
-        launch_fill<2>(c, fp, d_ids + o, (uint32_t)pl.order[1].size()); o += (uint32_t)pl.order[1].size();
-        launch_fill<4>(c, fp, d_ids + o, (uint32_t)pl.order[2].size()); o += (uint32_t)pl.order[2].size();
-        launch_fill<8>(c, fp, d_ids + o, (uint32_t)pl.order[3].size()); o += (uint32_t)pl.order[3].size();
-        launch_fill<16>(c, fp, d_ids + o, (uint32_t)pl.order[4].size()); o += (uint32_t)pl.order[4].size();
-        launch_fill<32>(c, fp, d_ids + o, (uint32_t)pl.order[5].size());
-        rtk_tb_params tp;
-        tp.q_len = d_len; tp.t_len = d_len + (n + 1); tp.ids = d_ids; tp.n = (uint32_t)pl.ids.size(); tp.mat_off = d_off + 2 * (n + 1);
-        tp.mat = S[3].as<ulonglong2>(); tp.anchor = S[4].as<int32_t>(); tp.dist = d_dist; tp.ops_off = d_off + 3 * (n + 1);
-        tp.ops = S[5].as<uint8_t>(); tp.ops_len = d_opslen;
-        if (tp.n) rtk_traceback_kernel<<<(tp.n + 127) / 128, 128, 0, st>>>(tp);
-        RTK_CUDA(cudaGetLastError());
-        RTK_CUDA(cudaEventRecord(c->ev1, st));
-        std::vector<uint32_t> h_len(n + 1);
-        std::vector<int32_t> h_dist(n + 1);
-        std::vector<uint8_t> h_ops(pl.ops_off[n] + 1);
-        RTK_CUDA(cudaMemcpyAsync(h_len.data(), d_opslen, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        RTK_CUDA(cudaMemcpyAsync(h_dist.data(), d_dist, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        if (pl.ops_off[n]) RTK_CUDA(cudaMemcpyAsync(h_ops.data(), S[5].p, pl.ops_off[n], cudaMemcpyDeviceToHost, st));
-        RTK_CUDA(cudaStreamSynchronize(st));
-        float kms = 0.f;
-        RTK_CUDA(cudaEventElapsedTime(&kms, c->ev0, c->ev1));
+        c->d_sub[7].reserve(qb + tb + 32);
+        RTK_CUDA(cudaMemcpyAsync(c->d_sub[7].p, rq.data(), qb, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(cudaMemcpyAsync(c->d_sub[7].as<char>() + qb + 8, rt.data(), tb, cudaMemcpyHostToDevice, st));
+        // 3. solve the non-trivial problems
+        std::vector<uint32_t> ids;
+        for (uint32_t a = 0; a < n; ++a) { flags[a] = 0; if (qlen[a] != 0 && tlen[a] != 0 && teff[a] != 0) ids.push_back(a); }
+        std::vector<uint64_t> sq(ids.size()), stt(ids.size());
+        std::vector<uint32_t> sql(ids.size()), stl(ids.size());
+        for (size_t i = 0; i < ids.size(); ++i) { sq[i] = qrel[ids[i]]; stt[i] = trel[ids[i]]; sql[i] = qlen[ids[i]]; stl[i] = teff[ids[i]]; }
+        CudaTbBackend be;
+        be.c = c; be.d_q = c->d_aux[0].as<char>(); be.d_t = c->d_aux[1].as<char>();
+        be.d_rq = c->d_sub[7].as<char>(); be.d_rt = c->d_sub[7].as<char>() + qb + 8;
+        std::vector<std::vector<uint8_t>> sops;
+        std::vector<int32_t> sdist;
+        solve_nw_paths(be, (uint32_t)ids.size(), sq.data(), sql.data(), stt.data(), stl.data(), sops, sdist);
         // 4. dense output
+        std::vector<std::vector<uint8_t>> all(n);
+        for (size_t i = 0; i < ids.size(); ++i) { all[ids[i]] = std::move(sops[i]); if (mode[ids[i]] == 0) dist[ids[i]] = sdist[i]; }
+        for (uint32_t a = 0; a < n; ++a) {
+            if (qlen[a] == 0 || tlen[a] == 0) {  // edlibAlign returns before any alignment is built (:160-176)
+                if (mode[a] == 0) dist[a] = (int32_t)std::max(qlen[a], tlen[a]);
+                else { dist[a] = (int32_t)qlen[a]; end_loc[a] = -1; }
+            } else if (teff[a] == 0) all[a].assign(qlen[a], 1);  // SHW ending before the target starts: every query base unaligned
+        }
         uint64_t* off = (uint64_t*)malloc((size_t)(n + 1) * 8);
         if (!off) throw std::bad_alloc();
         off[0] = 0;
-        for (uint32_t a = 0; a < n; ++a) {
-            uint64_t len = 0;
-            if (flags[a] == 0) len = h_len[a];
-            else if (flags[a] == 2 && qlen[a] != 0 && tlen[a] != 0) len = qlen[a];  // SHW that ends before the target: all query bases unaligned
-            off[a + 1] = off[a] + len;
-        }
+        for (uint32_t a = 0; a < n; ++a) off[a + 1] = off[a] + all[a].size();
         uint8_t* out = (uint8_t*)malloc(off[n] + 1);
         if (!out) { free(off); throw std::bad_alloc(); }
-        for (uint32_t a = 0; a < n; ++a) {
-            if (flags[a] == 0) {
-                const uint64_t cap = (uint64_t)qlen[a] + teff[a];
-                memcpy(out + off[a], h_ops.data() + pl.ops_off[a] + (cap - h_len[a]), h_len[a]);
-                if (mode[a] == 0) dist[a] = h_dist[a];
-            } else if (flags[a] == 2) {
-                memset(out + off[a], 1, off[a + 1] - off[a]);
-                if (mode[a] == 0) dist[a] = (int32_t)std::max(qlen[a], tlen[a]);
-                else if (qlen[a] == 0 || tlen[a] == 0) { dist[a] = (int32_t)qlen[a]; end_loc[a] = -1; }
-                flags[a] = 0;
-            } else if (mode[a] == 0) dist[a] = -1;
-        }
+        for (uint32_t a = 0; a < n; ++a) if (!all[a].empty()) memcpy(out + off[a], all[a].data(), all[a].size());
         *ops = out;
         *ops_off = off;
-        if (stats) stats[2] += (uint64_t)(kms * 1e6);
+        if (stats) stats[2] += (uint64_t)(be.ms * 1e6);
     });
 }

@@ -33,11 +33,16 @@ struct rtk_fill_params {
     ulonglong2* mat;           // {Pv, Mv} per (block, column): index mat_off + block * t_len + column
     int32_t* anchor;           // anchor-row score, same indexing
     int32_t* dist;             // [alignment] NW distance
+    int8_t* hbound;            // scratch between rounds: hb_off[a] .. + t_len
+    const uint64_t* hb_off;
 };
 
 #if defined(__CUDACC__) || defined(__CUDACC_SIM__)
 
-template <int G>
+// LASTCOL = false: store every (block, column) cell (direct traceback).  LASTCOL = true: store only the last
+// column, at mat_off + block (Hirschberg's split needs one column of the forward and of the reversed problem).
+// Queries longer than 64*G rows are swept in rounds of G blocks like K4 (hbound spill between rounds).
+template <int G, bool LASTCOL>
 __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_fill_kernel(const rtk_fill_params p) {
     const uint32_t lane = threadIdx.x & (G - 1);
     const uint32_t grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
@@ -48,61 +53,71 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_fill_kernel(const
     const char* q = p.q_pool + p.q_beg[a];
     const char* t = p.t_pool + p.t_beg[a];
     const int qlen = (int)p.q_len[a], tlen = (int)p.t_len[a];
-    const int nb = (qlen + 63) >> 6;   // nb <= G for this launch (planner guarantees it)
-    const int b = (int)lane;
-    const bool has = b < nb;
-    const int arow = (b == nb - 1) ? ((qlen - 1) & 63) : 63;  // anchor row of this block
-    uint64_t PB0 = 0, PB1 = 0, PB2 = 0, PB3 = 0;
-    if (has) {
-        const int lo = b << 6;
-        const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
-        for (int i = 0; i < n; ++i) {
-            const uint64_t m = rtk_iupac_mask(q[lo + i]);
-            PB0 |= (m & 1) << i; PB1 |= ((m >> 1) & 1) << i; PB2 |= ((m >> 2) & 1) << i; PB3 |= ((m >> 3) & 1) << i;
-        }
-    }
-    uint64_t Pv = ~0ULL, Mv = 0;
-    int hout = 0;
-    int score = (b << 6) + arow + 1;   // D[anchor row][-1]
-    const uint64_t base = p.mat_off[a] + (uint64_t)b * (uint64_t)tlen;
-    const int steps = tlen + G - 1;
-    for (int s = 0; s < steps; ++s) {
-        const int from_left = __shfl_up_sync(gmask, hout, 1, G);
-        const int col = s - (int)lane;
-        hout = 0;
-        if (has && col >= 0 && col < tlen) {
-            const int hin = (lane == 0) ? 1 : from_left;   // NW: D[0][j] = j
-            const char tc = t[col];
-            uint64_t Eq;
-            switch (tc) {
-                case 'A': Eq = PB0; break;
-                case 'C': Eq = PB1; break;
-                case 'G': Eq = PB2; break;
-                case 'T': Eq = PB3; break;
-                default: {
-                    Eq = 0;
-                    const int lo = b << 6;
-                    const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
-                    for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(q[lo + i], tc) << i;
-                }
+    const int nb = (qlen + 63) >> 6;
+    const int rounds = (nb + G - 1) / G;
+    int8_t* hb = p.hbound + p.hb_off[a];
+    for (int r = 0; r < rounds; ++r) {
+        const int b = r * G + (int)lane;
+        const bool has = b < nb;
+        const int arow = (b == nb - 1) ? ((qlen - 1) & 63) : 63;  // anchor row of this block
+        uint64_t PB0 = 0, PB1 = 0, PB2 = 0, PB3 = 0;
+        if (has) {
+            const int lo = b << 6;
+            const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+            for (int i = 0; i < n; ++i) {
+                const uint64_t m = rtk_iupac_mask(q[lo + i]);
+                PB0 |= (m & 1) << i; PB1 |= ((m >> 1) & 1) << i; PB2 |= ((m >> 2) & 1) << i; PB3 |= ((m >> 3) & 1) << i;
             }
-            const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
-            const uint64_t Xv = Eq | Mv;
-            Eq |= neg;
-            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-            uint64_t Ph = Mv | ~(Xh | Pv);
-            uint64_t Mh = Pv & Xh;
-            hout = (int)(Ph >> 63) - (int)(Mh >> 63);
-            score += (int)((Ph >> arow) & 1) - (int)((Mh >> arow) & 1);
-            Ph = (Ph << 1) | ((hin > 0) ? 1ULL : 0ULL);
-            Mh = (Mh << 1) | neg;
-            Pv = Mh | ~(Xv | Ph);
-            Mv = Ph & Xv;
-            ulonglong2 cell; cell.x = Pv; cell.y = Mv;
-            p.mat[base + col] = cell;
-            p.anchor[base + col] = score;
-            if (b == nb - 1 && col == tlen - 1) p.dist[a] = score;
         }
+        uint64_t Pv = ~0ULL, Mv = 0;
+        int hout = 0;
+        int score = (b << 6) + arow + 1;   // D[anchor row][-1]
+        const uint64_t base = LASTCOL ? (p.mat_off[a] + (uint64_t)b) : (p.mat_off[a] + (uint64_t)b * (uint64_t)tlen);
+        const bool spill = (lane == G - 1) && (r + 1 < rounds);
+        const int steps = tlen + G - 1;
+        for (int s = 0; s < steps; ++s) {
+            const int from_left = __shfl_up_sync(gmask, hout, 1, G);
+            const int col = s - (int)lane;
+            hout = 0;
+            if (has && col >= 0 && col < tlen) {
+                const int hin = (lane == 0) ? ((r == 0) ? 1 : (int)hb[col]) : from_left;   // NW: D[0][j] = j
+                const char tc = t[col];
+                uint64_t Eq;
+                switch (tc) {
+                    case 'A': Eq = PB0; break;
+                    case 'C': Eq = PB1; break;
+                    case 'G': Eq = PB2; break;
+                    case 'T': Eq = PB3; break;
+                    default: {
+                        Eq = 0;
+                        const int lo = b << 6;
+                        const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+                        for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(q[lo + i], tc) << i;
+                    }
+                }
+                const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
+                const uint64_t Xv = Eq | Mv;
+                Eq |= neg;
+                const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                uint64_t Ph = Mv | ~(Xh | Pv);
+                uint64_t Mh = Pv & Xh;
+                hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+                score += (int)((Ph >> arow) & 1) - (int)((Mh >> arow) & 1);
+                Ph = (Ph << 1) | ((hin > 0) ? 1ULL : 0ULL);
+                Mh = (Mh << 1) | neg;
+                Pv = Mh | ~(Xv | Ph);
+                Mv = Ph & Xv;
+                if (!LASTCOL || col == tlen - 1) {
+                    ulonglong2 cell; cell.x = Pv; cell.y = Mv;
+                    const uint64_t idx = LASTCOL ? base : (base + col);
+                    p.mat[idx] = cell;
+                    p.anchor[idx] = score;
+                }
+                if (b == nb - 1 && col == tlen - 1) p.dist[a] = score;
+                if (spill) hb[col] = (int8_t)hout;
+            }
+        }
+        __syncwarp(gmask);
     }
 }
 

@@ -51,6 +51,9 @@ def lib():
         L.ref_explore_subgraph.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_uint32, C.c_char_p,
                                            C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
                                            C.POINTER(C.c_double), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
+        L.ref_explore_paths.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.c_uint32, C.c_char_p,
+                                        C.POINTER(C.c_uint32), C.c_uint32, C.c_int, C.POINTER(C.POINTER(C.c_uint32)),
+                                        C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -129,6 +132,33 @@ class RefGraph:
                 paths.append((ums, qb.decode("latin1")))
             groups.append(paths)
         return sc[0], sc[1], groups[0], groups[1]
+
+    def explore_paths(self, start, end, ref, pids, pass2=False):
+        """explorePathsBFS2 (end given) / explorePathsBFS (end None); start/end = (key, strand, dist) -> [(ums, qual)]"""
+        arr = (C.c_uint32 * max(1, len(pids)))(*pids)
+        po = C.POINTER(C.c_uint32)()
+        nw = C.c_uint64()
+        ek, es, ed = (0xFFFFFFFFFFFFFFFF, 0, 0) if end is None else end
+        rc = lib().ref_explore_paths(self.h, start[0], int(start[1]), int(start[2]), ek, int(es), int(ed), ref.encode(), arr,
+                                     len(pids), int(pass2), C.byref(po), C.byref(nw))
+        if rc != 0:
+            raise RuntimeError("ref_explore_paths failed")
+        w = [po[i] for i in range(nw.value)]
+        lib().ref_free(C.cast(po, C.c_void_p))
+        pos = 0
+        n = w[pos]; pos += 1
+        paths = []
+        for _p in range(n):
+            m = w[pos]; pos += 1
+            ums = []
+            for _u in range(m):
+                key = w[pos] | (w[pos + 1] << 32)
+                ums.append((key, w[pos + 2], w[pos + 3], w[pos + 4])); pos += 5
+            ql = w[pos]; pos += 1
+            nq = (ql + 3) // 4
+            qb = b"".join(int(x).to_bytes(4, "little") for x in w[pos:pos + nq])[:ql]; pos += nq
+            paths.append((ums, qb.decode("latin1")))
+        return paths
 
     def correct_read(self, s, q, pass2=False):
         so, qo = C.c_void_p(), C.c_void_p()

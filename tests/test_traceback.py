@@ -18,12 +18,7 @@ def _check(ctx, vec):
     dist, end, ops, flags = ctx.edlib_path_batch([c["q"] for c in vec], [c["t"] for c in vec], [c["mode"] for c in vec])
     n_h = 0
     for i, c in enumerate(vec):
-        if c["hirschberg"]:
-            assert flags[i] == 1, (i, "hirschberg-sized pair must be flagged")
-            n_h += 1
-            if c["mode"] == 1:
-                assert int(dist[i]) == c["dist"]
-            continue
+        n_h += 1 if c["hirschberg"] else 0   # above edlib's 1 MiB switch: divide-and-conquer path
         assert flags[i] == 0, i
         assert int(dist[i]) == c["dist"], (i, c["mode"], len(c["q"]), len(c["t"]))
         if c["end"] is not None:
@@ -39,8 +34,8 @@ def _check(ctx, vec):
 def test_traceback_kernel_source_matches_reference(sim_lib):
     ctx = rb.Context(0, lib=sim_lib)
     vec = _vectors()
-    vec = vec[:23] + vec[23::3]
-    _check(ctx, vec)
+    vec = vec[:23] + vec[23::4] + [c for c in vec if c["hirschberg"]][:2]
+    assert _check(ctx, vec) >= 2
     ctx.close()
 
 
