@@ -188,6 +188,14 @@ int rtk_explore_paths(rtk_ctx* ctx, const rtk_opt* opt, const rtk_hit* um_s, con
                       uint32_t ref_len, const uint32_t* pids, uint32_t n_pids, rtk_path_node** nodes, uint32_t* n_nodes,
                       char** qual, uint32_t* path_len);
 
+/* ---- the per-read body of search() (src/Ratatosk.cpp:808-867): getSeeds + correctSequence for a ticket of reads ----
+ * Pass 1 (k = 31 graph coloured by short reads).  Inputs: reads and their qualities (qual_pool may be NULL).
+ * Output: corrected read i = out_seq_pool[out_off[i], out_off[i+1]) with its quality string at the same
+ * offsets of out_qual_pool - the exact bytes the reference writes to the FASTQ (library-allocated). */
+int rtk_correct_batch(rtk_ctx* ctx, const rtk_opt* opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
+                      const char* qual_pool, const uint64_t* qual_off, char** out_seq_pool, char** out_qual_pool,
+                      uint64_t** out_off, uint64_t* stats);
+
 #ifdef __cplusplus
 }
 #endif

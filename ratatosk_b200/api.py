@@ -114,6 +114,9 @@ def load_library(path=None):
                                              C.POINTER(C.c_uint32), C.c_uint64, C.c_double,
                                              C.POINTER(RtkSubgraphOut), C.POINTER(C.c_uint64)]
     L.rtk_subgraph_out_free.argtypes = [C.POINTER(RtkSubgraphOut)]
+    L.rtk_correct_batch.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_int, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64),
+                                    C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
     L.rtk_explore_paths.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.POINTER(RtkHit), C.POINTER(RtkHit), C.c_char_p, C.c_uint32,
                                     C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.POINTER(RtkPathNode)), C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
@@ -307,6 +310,33 @@ class Context:
         if stats is not None:
             stats.extend(list(st))
         return dist, [ends[int(offs[i]):int(offs[i + 1])] for i in range(n)]
+
+    def correct(self, reads, quals=None, opt=None, pass_no=1, stats=None):
+        """getSeeds + correctSequence for a batch (the per-read body of the reference's search()):
+        -> list of (corrected sequence, quality string)"""
+        opt = opt or default_opt(pass_no)
+        pool, off = pack_reads(reads)
+        if quals is not None:
+            qpool, qoff = pack_reads(quals)
+            qp, qo = qpool, qoff.ctypes.data_as(C.POINTER(C.c_uint64))
+        else:
+            qp, qo = None, None
+        os_, oq_ = C.c_void_p(), C.c_void_p()
+        oo = C.POINTER(C.c_uint64)()
+        st = (C.c_uint64 * 8)()
+        _check(self.L, self.L.rtk_correct_batch(self.h, C.byref(opt), pass_no, len(reads), pool, off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                qp, qo, C.byref(os_), C.byref(oq_), C.byref(oo), st))
+        n = len(reads)
+        offs = [oo[i] for i in range(n + 1)]
+        sbuf = C.string_at(os_, offs[-1])
+        qbuf = C.string_at(oq_, offs[-1])
+        out = [(sbuf[offs[i]:offs[i + 1]].decode("latin1"), qbuf[offs[i]:offs[i + 1]].decode("latin1")) for i in range(n)]
+        self.L.rtk_free(os_)
+        self.L.rtk_free(oq_)
+        self.L.rtk_free(C.cast(oo, C.c_void_p))
+        if stats is not None:
+            stats.extend(list(st))
+        return out
 
     def explore_paths(self, start, end, ref, pids, opt=None):
         """explorePathsBFS2 (end given) / explorePathsBFS (end None); start/end = (unitig, strand, dist) anchors.

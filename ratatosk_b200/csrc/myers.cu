@@ -135,7 +135,7 @@ extern "C" int rtk_edlib_batch(rtk_ctx* c, uint32_t n, const char* q_pool, const
         if (!c || !q_pool || !q_off || !t_pool || !t_off || !mode || !kmax || !dist || !end_loc || !end_off)
             throw std::invalid_argument("null argument");
         RTK_CUDA(cudaSetDevice(c->device));
-        for (uint32_t a = 0; a < n; ++a) if (mode[a] > 2) throw std::invalid_argument("mode must be 0 (NW), 1 (SHW) or 2 (HW)");
+        for (uint32_t a = 0; a < n; ++a) if ((mode[a] & 3) > 2 || (mode[a] & ~7u)) throw std::invalid_argument("mode must be 0 (NW), 1 (SHW) or 2 (HW), optionally | 4 (plain equality)");
         const uint64_t qb = q_off[n] - q_off[0], tb = t_off[n] - t_off[0];
         std::vector<uint64_t> qrel(n + 1), trel(n + 1);
         std::vector<uint32_t> qlen(n + 1), tlen(n + 1);

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_kernel(const rtk_
     const char* t = p.t_pool + p.t_beg[a];
     const int qlen = (int)p.q_len[a];
     const int tlen = (int)p.t_len[a];
-    const int mode = p.mode[a];
+    const bool plain = (p.mode[a] & 4) != 0;  // bit 2: no additional equalities (edlibDefaultAlignConfig)
+    const int mode = p.mode[a] & 3;
     const int nb = (qlen + 63) >> 6;
     const int rounds = (nb + G - 1) / G;
     int8_t* hb = p.hbound + p.hb_off[a];
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_kernel(const rtk_
             const int lo = b << 6;
             const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
             for (int i = 0; i < n; ++i) {
-                const uint64_t m = rtk_iupac_mask(q[lo + i]);
+                uint64_t m = rtk_iupac_mask(q[lo + i]);
+                if (plain && (m & (m - 1))) m = 0;  // ambiguity codes only match themselves
                 PB0 |= (m & 1) << i; PB1 |= ((m >> 1) & 1) << i; PB2 |= ((m >> 2) & 1) << i; PB3 |= ((m >> 3) & 1) << i;
             }
         }
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_kernel(const rtk_
                         Eq = 0;
                         const int lo = b << 6;
                         const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
-                        for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(q[lo + i], tc) << i;
+                        for (int i = 0; i < n; ++i) Eq |= (uint64_t)(plain ? (q[lo + i] == tc) : rtk_iupac_eq(q[lo + i], tc)) << i;
                     }
                 }
                 // one block of one column (Hyyro's formulation of Myers' recurrence)

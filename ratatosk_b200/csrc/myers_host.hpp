@@ -38,7 +38,7 @@ inline MyersPlan plan_myers(uint32_t n, const uint32_t* q_len, const uint32_t* t
 
 // edlibAlign's special case (src/edlib.cpp:160-176): no k check on this path
 inline void myers_trivial(uint64_t ql, uint64_t tl, int mode, int32_t& dist, int32_t& end) {
-    if (mode == 0) { dist = (int32_t)std::max(ql, tl); end = (int32_t)tl - 1; }
+    if ((mode & 3) == 0) { dist = (int32_t)std::max(ql, tl); end = (int32_t)tl - 1; }
     else { dist = (int32_t)ql; end = -1; }
 }
 

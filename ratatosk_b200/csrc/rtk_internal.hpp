@@ -130,6 +130,11 @@ void myers_run(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const Myers
 void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                           std::vector<std::vector<rtk_hit>>& per_read, uint64_t* stats);
 
+// per-read correction of a batch (correct.cpp)
+void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
+                        const char* qual_pool, const uint64_t* qual_off, std::vector<std::string>& out_seq, std::vector<std::string>& out_qual,
+                        uint64_t* stats);
+
 // getSeeds host logic over the hit lists (seeds.cpp)
 void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool,
                     const uint64_t* seq_off, std::vector<std::vector<rtk_hit>>& solid,
