@@ -19,6 +19,7 @@
 #include "lookup.cuh"
 #include "rtk_host_common.hpp"
 #include "traverse.hpp"
+#include "broker.hpp"
 
 namespace rtk {
 
@@ -728,20 +729,16 @@ ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::s
         std::vector<AlignJob> j(1);
         j[0].q = s.substr(v_s[i_s].pos, solid2_pos - v_s[i_s].pos + k);
         j[0].t = s_corrected; j[0].mode = 1;
-        // all end locations are needed: take the LAST (largest) best end
-        std::string qp = j[0].q, tp = j[0].t;
-        const uint64_t qo[2] = {0, qp.size()}, to[2] = {0, tp.size()};
-        const uint8_t md = 1; const int32_t km = -1;
-        int32_t dist = -1; int32_t* ends = nullptr; uint64_t* eoff = nullptr;
-        qp.push_back('\0'); tp.push_back('\0');
-        if (rtk_edlib_batch(C.ctx, 1, qp.data(), qo, tp.data(), to, &md, &km, &dist, &ends, &eoff, nullptr) != RTK_OK) throw std::runtime_error(rtk_last_error());
-        if (dist >= 0 && eoff[1] > eoff[0]) {
-            size_t end_location = (size_t)ends[eoff[0]];  // size_t like the reference: an end of -1 wraps and is never exceeded
-            for (uint64_t x = eoff[0] + 1; x < eoff[1]; ++x) if ((size_t)ends[x] > end_location) end_location = (size_t)ends[x];
+        // every end location is needed: keep the largest best end (:735-741)
+        std::vector<int32_t> dd;
+        std::vector<std::vector<int32_t>> ee;
+        gpu_distances_all(C.ctx, j, dd, ee);
+        if (dd[0] >= 0 && !ee[0].empty()) {
+            size_t end_location = (size_t)ee[0][0];  // size_t like the reference: an end of -1 wraps and is never exceeded
+            for (size_t x = 1; x < ee[0].size(); ++x) if ((size_t)ee[0][x] > end_location) end_location = (size_t)ee[0][x];
             s_corrected = s_corrected.substr(0, end_location + 1);
             q_corrected = q_corrected.substr(0, end_location + 1);
         }
-        rtk_free(ends); rtk_free(eoff);
     }
     res.seq = std::move(s_corrected);
     res.qual = std::move(q_corrected);
@@ -887,6 +884,13 @@ std::pair<std::string, std::string> correct_sequence(rtk_ctx* ctx, const rtk_gra
     return {corrected_s, corrected_q};
 }
 
+// reads in flight per batch (= host threads parked on the GPU broker); RTK_CORRECT_THREADS overrides
+static unsigned correct_threads() {
+    const char* e = getenv("RTK_CORRECT_THREADS");
+    const int v = e ? atoi(e) : 1024;
+    return (unsigned)std::max(1, std::min(v, 8192));
+}
+
 // ------------------------------------------------------------------ batch driver: the per-read body of search() (src/Ratatosk.cpp:808-867)
 void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
                         const char* qual_pool, const uint64_t* qual_off, std::vector<std::string>& out_seq, std::vector<std::string>& out_qual,
@@ -921,11 +925,14 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
         pool.push_back('\0');
         std::vector<std::vector<rtk_hit>> solid, weak;
         get_seeds_host(ctx, l_opt, pass, n_reads, pool.data(), off.data(), solid, weak, stats);
-        for (uint32_t r = 0; r < n_reads; ++r) {
+        // reads are corrected concurrently, one host thread each; their GPU requests are served in waves (broker.hpp)
+        GpuBroker broker(ctx);
+        broker.run(n_reads, correct_threads(), [&](size_t r) {
             std::pair<std::string, std::string> c = correct_sequence(ctx, g, l_opt, pass2, max_km_cov, out_seq[r], out_qual[r], solid[r], weak[r]);
             out_seq[r] = std::move(c.first);
             out_qual[r] = std::move(c.second);
-        }
+        });
+        if (stats) { stats[5] += broker.waves; stats[6] += broker.jobs; }
     }
 }
 

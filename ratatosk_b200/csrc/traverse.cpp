@@ -8,6 +8,7 @@
 #include <stdexcept>
 #include <unordered_map>
 
+#include "broker.hpp"
 #include "kmer.cuh"
 
 namespace rtk {
@@ -161,58 +162,30 @@ GPath GPath::from_compact(const rtk_graph_view& g, const PNode& um_start, const 
 }
 
 // ---------------------------------------------------------------------------------------------- GPU services
-static void pack(const std::vector<AlignJob>& jobs, std::string& qp, std::vector<uint64_t>& qo, std::string& tp,
-                 std::vector<uint64_t>& to, std::vector<uint8_t>& mode) {
-    qo.assign(1, 0); to.assign(1, 0);
-    for (const auto& j : jobs) {
-        qp += j.q; qo.push_back(qp.size());
-        tp += j.t; to.push_back(tp.size());
-        mode.push_back(j.mode);
-    }
+// A request is handed to the wave broker when this thread runs under one (broker.hpp), else executed at once.
+void gpu_distances_all(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<std::vector<int32_t>>& ends) {
+    dist.assign(jobs.size(), -1);
+    ends.assign(jobs.size(), {});
+    if (jobs.empty()) return;
+    DistReq r{&jobs, &dist, &ends};
+    if (GpuBroker* b = current_broker()) b->submit(&r);
+    else run_dist_batch(ctx, std::vector<DistReq*>(1, &r));
 }
 
 void gpu_distances(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<int32_t>& first_end) {
-    const uint32_t n = (uint32_t)jobs.size();
-    dist.assign(n, -1);
-    first_end.assign(n, -1);
-    if (!n) return;
-    std::string qp, tp;
-    std::vector<uint64_t> qo, to;
-    std::vector<uint8_t> mode;
-    pack(jobs, qp, qo, tp, to, mode);
-    std::vector<int32_t> kmax(n, -1);
-    int32_t* ends = nullptr;
-    uint64_t* eoff = nullptr;
-    qp.push_back('\0'); tp.push_back('\0');
-    if (rtk_edlib_batch(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), kmax.data(), dist.data(), &ends, &eoff, nullptr) != RTK_OK)
-        throw std::runtime_error(std::string("rtk_edlib_batch: ") + rtk_last_error());
-    for (uint32_t i = 0; i < n; ++i) first_end[i] = (eoff[i + 1] > eoff[i]) ? ends[eoff[i]] : -1;
-    rtk_free(ends);
-    rtk_free(eoff);
+    std::vector<std::vector<int32_t>> ends;
+    gpu_distances_all(ctx, jobs, dist, ends);
+    first_end.assign(jobs.size(), -1);
+    for (size_t i = 0; i < jobs.size(); ++i) if (!ends[i].empty()) first_end[i] = ends[i][0];
 }
 
 void gpu_paths(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<std::vector<uint8_t>>& ops) {
-    const uint32_t n = (uint32_t)jobs.size();
-    dist.assign(n, -1);
-    ops.assign(n, {});
-    if (!n) return;
-    std::string qp, tp;
-    std::vector<uint64_t> qo, to;
-    std::vector<uint8_t> mode;
-    pack(jobs, qp, qo, tp, to, mode);
-    std::vector<int32_t> end(n);
-    std::vector<uint8_t> flags(n);
-    uint8_t* o = nullptr;
-    uint64_t* ooff = nullptr;
-    qp.push_back('\0'); tp.push_back('\0');
-    if (rtk_edlib_path_batch(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), dist.data(), end.data(), &o, &ooff, flags.data(), nullptr) != RTK_OK)
-        throw std::runtime_error(std::string("rtk_edlib_path_batch: ") + rtk_last_error());
-    for (uint32_t i = 0; i < n; ++i) {
-        if (flags[i]) { rtk_free(o); rtk_free(ooff); throw std::runtime_error("alignment path beyond the direct-traceback size (Hirschberg recursion not restated yet)"); }
-        ops[i].assign(o + ooff[i], o + ooff[i + 1]);
-    }
-    rtk_free(o);
-    rtk_free(ooff);
+    dist.assign(jobs.size(), -1);
+    ops.assign(jobs.size(), {});
+    if (jobs.empty()) return;
+    PathReq r{&jobs, &dist, &ops};
+    if (GpuBroker* b = current_broker()) b->submit(&r);
+    else run_path_batch(ctx, std::vector<PathReq*>(1, &r));
 }
 
 // ---------------------------------------------------------------------------------------------- selectors
@@ -254,18 +227,21 @@ struct Burst {
     double t1 = 0.0, nt1 = 0.0;
 };
 
-// getScorePath(opt, path, ref, ref_len, score_best, score_second_best) (src/GraphTraversal.cpp:722-772) for a set of paths
-void set_qualities(rtk_ctx* ctx, const rtk_graph_view& g, const TraverseOpt& opt, std::vector<GPath>& paths, const std::string& ref,
-                   double best, double second) {
-    if (paths.empty()) return;
-    std::vector<AlignJob> jobs(paths.size());
-    for (size_t i = 0; i < paths.size(); ++i) { jobs[i].q = paths[i].to_string(g); jobs[i].t = ref; jobs[i].mode = 1; }
+// getScorePath(opt, path, ref, ref_len, score_best, score_second_best) (src/GraphTraversal.cpp:722-772) for the kept
+// terminal and non-terminal paths of one burst
+void set_qualities2(rtk_ctx* ctx, const rtk_graph_view& g, const TraverseOpt& opt, std::vector<GPath>& pa, double best_a, double second_a,
+                    std::vector<GPath>& pb, double best_b, double second_b, const std::string& ref) {
+    const size_t na = pa.size(), n = na + pb.size();
+    if (!n) return;
+    std::vector<AlignJob> jobs(n);
+    for (size_t i = 0; i < n; ++i) { jobs[i].q = (i < na ? pa[i] : pb[i - na]).to_string(g); jobs[i].t = ref; jobs[i].mode = 1; }
     std::vector<int32_t> dist;
     std::vector<std::vector<uint8_t>> ops;
     gpu_paths(ctx, jobs, dist, ops);
-    const double score_comp = best * ((best == 0.0) ? 0.0 : (1.0 - (second / best)));
-    const char c_best = rtk_get_qual(best, 0, opt.max_qual);
-    for (size_t i = 0; i < paths.size(); ++i) {
+    for (size_t i = 0; i < n; ++i) {
+        const double best = i < na ? best_a : best_b, second = i < na ? second_a : second_b;
+        const double score_comp = best * ((best == 0.0) ? 0.0 : (1.0 - (second / best)));
+        const char c_best = rtk_get_qual(best, 0, opt.max_qual);
         const std::string& ps = jobs[i].q;
         std::string q(ps.length(), rtk_get_qual(score_comp, opt.out_qual, opt.max_qual));
         size_t qp = 0, rp = 0;
@@ -274,38 +250,34 @@ void set_qualities(rtk_ctx* ctx, const rtk_graph_view& g, const TraverseOpt& opt
             else if (op == 1) ++qp;
             else ++rp;
         }
-        paths[i].set_quality(q);
+        (i < na ? pa[i] : pb[i - na]).set_quality(q);
     }
 }
 
 Burst explore_subgraph(rtk_ctx* ctx, const rtk_graph_view& g, const TraverseOpt& opt, const std::vector<uint32_t>& pids,
                        const std::string& ref, size_t max_len_path, const PNode& um, const PNode& um_e, uint32_t level) {
-    rtk_subgraph_call_t c;
-    memset(&c, 0, sizeof(c));
-    c.start_unitig = um.unitig; c.start_strand = um.strand;
-    if (um_e.empty()) { c.end_unitig = RTK_NONE32; }
-    else { c.end_unitig = um_e.unitig; c.end_strand = um_e.strand; c.end_dist = um_e.dist; }
-    c.level = level; c.max_len_path = (uint32_t)max_len_path; c.ref_off = 0; c.ref_len = (uint32_t)ref.length();
-    c.pid_off = 0; c.pid_len = (uint32_t)pids.size(); c.min_cov = opt.min_cov_vertices;
-    rtk_subgraph_out out;
-    const uint32_t dummy = 0;
-    if (rtk_explore_subgraph_batch(ctx, 1, &c, ref.data(), ref.length(), pids.empty() ? &dummy : pids.data(), pids.size(),
-                                   opt.weak_region_len_factor, &out, nullptr) != RTK_OK)
-        throw std::runtime_error(std::string("rtk_explore_subgraph_batch: ") + rtk_last_error());
+    SubgraphReq rq;
+    memset(&rq.call, 0, sizeof(rq.call));
+    rq.call.start_unitig = um.unitig; rq.call.start_strand = um.strand;
+    if (um_e.empty()) rq.call.end_unitig = RTK_NONE32;
+    else { rq.call.end_unitig = um_e.unitig; rq.call.end_strand = um_e.strand; rq.call.end_dist = um_e.dist; }
+    rq.call.level = level; rq.call.max_len_path = (uint32_t)max_len_path; rq.call.min_cov = opt.min_cov_vertices;
+    rq.ref = &ref; rq.pids = &pids; rq.wrlf = opt.weak_region_len_factor;
+    SubgraphResult res;
+    rq.out = &res;
+    if (GpuBroker* b = current_broker()) b->submit(&rq);
+    else run_subgraph_batch(ctx, std::vector<SubgraphReq*>(1, &rq));
     Burst b;
-    b.t1 = out.scores[0]; b.nt1 = out.scores[2];
-    const double t2 = out.scores[1], nt2 = out.scores[3];
-    for (uint64_t pi = out.path_off[0]; pi < out.path_off[1]; ++pi) {
-        GPath p;
-        for (uint64_t j = out.node_off[pi]; j < out.node_off[pi + 1]; ++j) {
-            PNode n; n.unitig = out.nodes[j].unitig; n.strand = out.nodes[j].strand; n.dist = out.nodes[j].dist; n.len = out.nodes[j].len;
-            p.extend(g, n);
+    b.t1 = res.scores[0]; b.nt1 = res.scores[2];
+    for (int kind = 0; kind < 2; ++kind) {
+        for (const auto& nodes : (kind == 0 ? res.terminal : res.nonterminal)) {
+            GPath p;
+            for (const PNode& n : nodes) p.extend(g, n);
+            (kind == 0 ? b.terminal : b.nonterminal).push_back(std::move(p));
         }
-        (pi - out.path_off[0] < out.n_terminal[0] ? b.terminal : b.nonterminal).push_back(std::move(p));
     }
-    rtk_subgraph_out_free(&out);
-    set_qualities(ctx, g, opt, b.terminal, ref, b.t1, t2);
-    set_qualities(ctx, g, opt, b.nonterminal, ref, b.nt1, nt2);
+    // both quality batches of the burst in one K5 request
+    set_qualities2(ctx, g, opt, b.terminal, b.t1, res.scores[1], b.nonterminal, b.nt1, res.scores[3], ref);
     return b;
 }
 

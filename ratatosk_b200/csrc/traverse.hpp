@@ -60,6 +60,7 @@ struct AlignJob {
     uint8_t mode;  // 0 NW, 1 SHW, 2 HW
 };
 void gpu_distances(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<int32_t>& first_end);
+void gpu_distances_all(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<std::vector<int32_t>>& ends);
 void gpu_paths(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<std::vector<uint8_t>>& ops);
 
 // selectors: first candidate wins ties (strict <), src/Alignment.cpp
