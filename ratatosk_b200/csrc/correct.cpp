@@ -751,34 +751,67 @@ inline bool has_min_qual(const std::string& s, const std::string& q, size_t star
     return ok;
 }
 
-}  // namespace
-
 // ------------------------------------------------------------------ correctSequence (src/Correction.cpp:159-958)
-std::pair<std::string, std::string> correct_sequence(rtk_ctx* ctx, const rtk_graph_view& g, const rtk_opt& opt, bool pass2, size_t max_km_cov,
-                                                     const std::string& s_fw, const std::string& q_fw, const std::vector<rtk_hit>& v_um_solid,
-                                                     const std::vector<rtk_hit>& v_um_weak) {
-    const size_t k = g.k;
-    const bool lrc = pass2;
-    if (s_fw.length() <= k || v_um_solid.empty() || v_um_solid.size() == s_fw.length() - k + 1) {
-        if (lrc) return {s_fw, q_fw};
-        else if (v_um_solid.size() == s_fw.length() - k + 1) return {s_fw, std::string(s_fw.length(), rtk_get_qual(1.0, 0, opt.max_qual))};
-        return {s_fw, std::string(s_fw.length(), rtk_get_qual(0.0, 0, opt.max_qual))};
-    }
-    Ctx C{ctx, g, opt, TraverseOpt(), pass2, max_km_cov};
-    C.topt.k = g.k; C.topt.min_cov_vertices = opt.min_cov_vertices; C.topt.out_qual = opt.out_qual; C.topt.max_qual = opt.max_qual;
-    C.topt.weak_region_len_factor = opt.weak_region_len_factor; C.topt.large_k_factor = opt.large_k_factor; C.topt.min_score = opt.min_score;
-    const size_t seq_len = s_fw.length();
-    const std::string s_bw = rc_string(s_fw);
-    const char q_min = rtk_get_qual(0.0, 0, opt.max_qual), q_max = rtk_get_qual(1.0, 0, opt.max_qual);
-    std::string q_bw = q_fw;
-    std::reverse(q_bw.begin(), q_bw.end());
-    size_t prev_pos = v_um_solid[0].pos, i_solid = 0, i_weak = 0;
-    std::string corrected_s, corrected_q;
-    std::vector<rtk_hit> solid_rev(v_um_solid.rbegin(), v_um_solid.rend()), weak_rev(v_um_weak.rbegin(), v_um_weak.rend());
-    for (auto& p : solid_rev) { p.pos = (uint32_t)(seq_len - p.pos - k); p.strand = 1 - p.strand; }
-    for (auto& p : weak_rev) { p.pos = (uint32_t)(seq_len - p.pos - k); p.strand = 1 - p.strand; }
+// The reference walks the solid anchors left to right and appends one piece of output per step.  Every piece
+// depends only on the read, its anchors and three loop variables (i_solid, i_weak, prev_pos) that are pure
+// functions of the anchor positions, so the pieces are planned first and computed independently (one broker
+// task each), then concatenated in order: same bytes, but a read's regions no longer wait for one another.
+struct ReadJob {
+    const std::string* s_fw; const std::string* q_fw;
+    const std::vector<rtk_hit>* solid; const std::vector<rtk_hit>* weak;
+    std::string s_bw, q_bw;
+    std::vector<rtk_hit> solid_rev, weak_rev;
+    bool trivial = false;
+    std::pair<std::string, std::string> trivial_out;
+};
+struct Piece { uint32_t read; int kind; size_t i_solid, i_weak, prev_pos; std::string s, q; };  // kind 0 leading, 1 gap, 2 trailing
 
-    if (v_um_solid[0].pos != 0) {
+void plan_read(const rtk_graph_view& g, const rtk_opt& opt, bool lrc, uint32_t r, ReadJob& J, std::vector<Piece>& pieces) {
+    const size_t k = g.k;
+    const std::string& s_fw = *J.s_fw; const std::string& q_fw = *J.q_fw;
+    const std::vector<rtk_hit>& v_um_solid = *J.solid; const std::vector<rtk_hit>& v_um_weak = *J.weak;
+    if (s_fw.length() <= k || v_um_solid.empty() || v_um_solid.size() == s_fw.length() - k + 1) {
+        J.trivial = true;
+        if (lrc) J.trivial_out = {s_fw, q_fw};
+        else if (v_um_solid.size() == s_fw.length() - k + 1) J.trivial_out = {s_fw, std::string(s_fw.length(), rtk_get_qual(1.0, 0, opt.max_qual))};
+        else J.trivial_out = {s_fw, std::string(s_fw.length(), rtk_get_qual(0.0, 0, opt.max_qual))};
+        return;
+    }
+    const size_t seq_len = s_fw.length();
+    J.s_bw = rc_string(s_fw);
+    J.q_bw = q_fw;
+    std::reverse(J.q_bw.begin(), J.q_bw.end());
+    J.solid_rev.assign(v_um_solid.rbegin(), v_um_solid.rend());
+    J.weak_rev.assign(v_um_weak.rbegin(), v_um_weak.rend());
+    for (auto& p : J.solid_rev) { p.pos = (uint32_t)(seq_len - p.pos - k); p.strand = 1 - p.strand; }
+    for (auto& p : J.weak_rev) { p.pos = (uint32_t)(seq_len - p.pos - k); p.strand = 1 - p.strand; }
+    size_t prev_pos = v_um_solid[0].pos, i_solid = 0, i_weak = 0;
+    if (v_um_solid[0].pos != 0) pieces.push_back({r, 0, 0, 0, prev_pos, {}, {}});
+    while (i_solid < v_um_solid.size() - 1) {
+        while (i_weak < v_um_weak.size() && v_um_weak[i_weak].pos < v_um_solid[i_solid].pos) ++i_weak;
+        if (v_um_solid[i_solid].pos != v_um_solid[i_solid + 1].pos - 1) {
+            pieces.push_back({r, 1, i_solid, i_weak, prev_pos, {}, {}});
+            prev_pos = v_um_solid[i_solid + 1].pos;
+        }
+        ++i_solid;
+    }
+    pieces.push_back({r, 2, i_solid, i_weak, prev_pos, {}, {}});
+}
+
+void run_piece(const Ctx& C, const ReadJob& J, Piece& P) {
+    const rtk_graph_view& g = C.g;
+    const rtk_opt& opt = C.opt;
+    const size_t k = g.k;
+    const bool lrc = C.pass2;
+    const std::string& s_fw = *J.s_fw; const std::string& q_fw = *J.q_fw;
+    const std::string& s_bw = J.s_bw; const std::string& q_bw = J.q_bw;
+    const std::vector<rtk_hit>& v_um_solid = *J.solid; const std::vector<rtk_hit>& v_um_weak = *J.weak;
+    const std::vector<rtk_hit>& solid_rev = J.solid_rev; const std::vector<rtk_hit>& weak_rev = J.weak_rev;
+    const char q_min = rtk_get_qual(0.0, 0, opt.max_qual), q_max = rtk_get_qual(1.0, 0, opt.max_qual);
+    std::string& corrected_s = P.s; std::string& corrected_q = P.q;
+    const size_t prev_pos = P.prev_pos;
+    size_t i_solid = P.i_solid, i_weak = P.i_weak;
+    if (P.kind == 0) {
         if (!lrc || q_fw.length() == 0 || !has_min_qual(s_fw, q_fw, 0, v_um_solid[0].pos + k, q_max)) {
             const size_t i_solid_rev = solid_rev.size() - 1;
             size_t i_weak_rev = weak_rev.size();
@@ -791,10 +824,10 @@ std::pair<std::string, std::string> correct_sequence(rtk_ctx* ctx, const rtk_gra
             corrected_s += s_fw.substr(0, v_um_solid[0].pos);
             corrected_q += lrc ? q_fw.substr(0, v_um_solid[0].pos) : std::string(v_um_solid[0].pos, q_min);
         }
+        return;
     }
-    while (i_solid < v_um_solid.size() - 1) {
-        while (i_weak < v_um_weak.size() && v_um_weak[i_weak].pos < v_um_solid[i_solid].pos) ++i_weak;
-        if (v_um_solid[i_solid].pos != v_um_solid[i_solid + 1].pos - 1) {
+    if (P.kind == 1) {
+        {
             bool isUncorrected = false;
             const size_t p0 = v_um_solid[i_solid].pos, p1 = v_um_solid[i_solid + 1].pos;
             if (!lrc || q_fw.length() == 0 || !has_min_qual(s_fw, q_fw, p0, p1 + k, q_max)) {
@@ -865,10 +898,10 @@ std::pair<std::string, std::string> correct_sequence(rtk_ctx* ctx, const rtk_gra
                     else corrected_q += std::string(k, q_max) + std::string(p1 - p0 - k, q_min);
                 }
             }
-            prev_pos = p1;
         }
-        ++i_solid;
+        return;
     }
+    // trailing region / tail of the read
     if ((v_um_solid.back().pos < s_fw.length() - k) &&
         (!lrc || q_fw.length() == 0 || !has_min_qual(s_fw, q_fw, v_um_solid.back().pos, s_fw.length(), q_max))) {
         while (i_weak < v_um_weak.size() && v_um_weak[i_weak].pos < v_um_solid[i_solid].pos) ++i_weak;
@@ -881,8 +914,9 @@ std::pair<std::string, std::string> correct_sequence(rtk_ctx* ctx, const rtk_gra
         corrected_q += lrc ? q_fw.substr(prev_pos)
                            : (std::string(v_um_solid[i_solid].pos - prev_pos + k, q_max) + std::string(s_fw.length() - v_um_solid[i_solid].pos - k, q_min));
     }
-    return {corrected_s, corrected_q};
 }
+
+}  // namespace
 
 // reads in flight per batch (= host threads parked on the GPU broker); RTK_CORRECT_THREADS overrides
 static unsigned correct_threads() {
@@ -925,13 +959,26 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
         pool.push_back('\0');
         std::vector<std::vector<rtk_hit>> solid, weak;
         get_seeds_host(ctx, l_opt, pass, n_reads, pool.data(), off.data(), solid, weak, stats);
-        // reads are corrected concurrently, one host thread each; their GPU requests are served in waves (broker.hpp)
+        // every region of every read is one broker task: regions run concurrently on host threads, their GPU requests
+        // are served in waves (broker.hpp); pieces are concatenated in read order afterwards
+        Ctx C{ctx, g, l_opt, TraverseOpt(), pass2, max_km_cov};
+        C.topt.k = g.k; C.topt.min_cov_vertices = l_opt.min_cov_vertices; C.topt.out_qual = l_opt.out_qual; C.topt.max_qual = l_opt.max_qual;
+        C.topt.weak_region_len_factor = l_opt.weak_region_len_factor; C.topt.large_k_factor = l_opt.large_k_factor; C.topt.min_score = l_opt.min_score;
+        std::vector<ReadJob> jobs(n_reads);
+        std::vector<Piece> pieces;
+        for (uint32_t r = 0; r < n_reads; ++r) {
+            jobs[r].s_fw = &out_seq[r]; jobs[r].q_fw = &out_qual[r]; jobs[r].solid = &solid[r]; jobs[r].weak = &weak[r];
+            plan_read(g, l_opt, pass2, r, jobs[r], pieces);
+        }
         GpuBroker broker(ctx);
-        broker.run(n_reads, correct_threads(), [&](size_t r) {
-            std::pair<std::string, std::string> c = correct_sequence(ctx, g, l_opt, pass2, max_km_cov, out_seq[r], out_qual[r], solid[r], weak[r]);
-            out_seq[r] = std::move(c.first);
-            out_qual[r] = std::move(c.second);
-        });
+        broker.run(pieces.size(), correct_threads(), [&](size_t i) { run_piece(C, jobs[pieces[i].read], pieces[i]); });
+        std::vector<std::string> ns(n_reads), nq(n_reads);
+        for (const Piece& P : pieces) { ns[P.read] += P.s; nq[P.read] += P.q; }
+        for (uint32_t r = 0; r < n_reads; ++r) {
+            if (jobs[r].trivial) { ns[r] = jobs[r].trivial_out.first; nq[r] = jobs[r].trivial_out.second; }
+            out_seq[r] = std::move(ns[r]);
+            out_qual[r] = std::move(nq[r]);
+        }
         if (stats) { stats[5] += broker.waves; stats[6] += broker.jobs; }
     }
 }
