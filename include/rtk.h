@@ -87,6 +87,11 @@ int rtk_graph_unitig_colors(const rtk_host_graph* g, uint32_t unitig, const uint
 /* ---- device context ---- */
 int rtk_ctx_create(int device, rtk_ctx** out);
 void rtk_ctx_destroy(rtk_ctx* ctx);
+/* A second context on the same device that SHARES the parent's resident graph (own stream and scratch).  One
+ * context serves one host thread at a time; forks let several host threads issue batches concurrently, the way
+ * the reference's correction threads share one CompactedDBG (src/Correction.cpp worker pool).  The parent must
+ * outlive its forks; re-fork after rtk_graph_upload / rtk_graph_adopt_device on the parent. */
+int rtk_ctx_fork(const rtk_ctx* parent, rtk_ctx** out);
 int rtk_graph_upload(rtk_ctx* ctx, const rtk_host_graph* g);               /* H2D copy of the slab */
 /* slab already resident on this device (e.g. after an NCCL broadcast done by the caller) */
 int rtk_graph_adopt_device(rtk_ctx* ctx, const void* dev_slab, uint64_t bytes);

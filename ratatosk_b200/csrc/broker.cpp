@@ -2,6 +2,9 @@
 #include "broker.hpp"
 
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <thread>
@@ -115,6 +118,12 @@ void run_subgraph_batch(rtk_ctx* ctx, const std::vector<SubgraphReq*>& reqs) {
 }
 
 // ------------------------------------------------------------------ broker
+GpuBroker::GpuBroker(rtk_ctx* c) : ctx(c) {
+    for (int i = 0; i < 2; ++i)
+        if (rtk_ctx_fork(ctx, &lane[i]) != RTK_OK) throw std::runtime_error(std::string("rtk_ctx_fork: ") + rtk_last_error());
+}
+GpuBroker::~GpuBroker() { for (int i = 0; i < 2; ++i) rtk_ctx_destroy(lane[i]); }
+
 template <typename R> void GpuBroker::park(std::vector<R*>& q, R* r) {
     std::unique_lock<std::mutex> lk(mu);
     q.push_back(r);
@@ -160,6 +169,7 @@ void GpuBroker::run(size_t n, unsigned threads, const std::function<void(size_t)
         });
     }
     // serve the GPU from this thread
+    auto t_last = std::chrono::steady_clock::now();
     for (;;) {
         std::vector<DistReq*> d;
         std::vector<PathReq*> p;
@@ -171,11 +181,32 @@ void GpuBroker::run(size_t n, unsigned threads, const std::function<void(size_t)
             d.swap(q_dist); p.swap(q_path); s.swap(q_sub);
         }
         std::string err;
-        try {
-            if (!s.empty()) run_subgraph_batch(ctx, s);
-            if (!d.empty()) run_dist_batch(ctx, d);
-            if (!p.empty()) run_path_batch(ctx, p);
-        } catch (const std::exception& e) { err = e.what(); }
+        const auto t0 = std::chrono::steady_clock::now();
+        {
+            // the three services are independent within a wave: each runs on its own context (stream + scratch)
+            std::string e_sub, e_dist, e_path;
+            auto timed = [](uint64_t& acc, std::string& e, const std::function<void()>& f) {
+                const auto a = std::chrono::steady_clock::now();
+                try { f(); } catch (const std::exception& ex) { e = ex.what(); }
+                acc += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - a).count();
+            };
+            std::thread th_sub, th_path;
+#ifdef RTK_HOSTSIM   // the CPU simulator runs one launch at a time
+            if (!s.empty()) timed(ns_sub, e_sub, [&] { run_subgraph_batch(lane[0], s); });
+            if (!p.empty()) timed(ns_path, e_path, [&] { run_path_batch(lane[1], p); });
+#else
+            if (!s.empty()) th_sub = std::thread([&] { timed(ns_sub, e_sub, [&] { run_subgraph_batch(lane[0], s); }); });
+            if (!p.empty()) th_path = std::thread([&] { timed(ns_path, e_path, [&] { run_path_batch(lane[1], p); }); });
+#endif
+            if (!d.empty()) timed(ns_dist, e_dist, [&] { run_dist_batch(ctx, d); });
+            if (th_sub.joinable()) th_sub.join();
+            if (th_path.joinable()) th_path.join();
+            n_sub += s.size(); n_dist += d.size(); n_path += p.size();
+            err = !e_sub.empty() ? e_sub : (!e_dist.empty() ? e_dist : e_path);
+        }
+        ns_wait += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t0 - t_last).count();
+        t_last = std::chrono::steady_clock::now();
+        ns_serve += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_last - t0).count();
         ++waves;
         jobs += d.size() + p.size() + s.size();
         {
@@ -187,6 +218,10 @@ void GpuBroker::run(size_t n, unsigned threads, const std::function<void(size_t)
         cv_worker.notify_all();
     }
     for (auto& th : pool) th.join();
+    if (getenv("RTK_BROKER_PROFILE"))
+        fprintf(stderr, "[broker] waves=%llu  subgraph: %llu reqs %.1f ms | dist: %llu reqs %.1f ms | path: %llu reqs %.1f ms | serving %.1f ms | waiting for workers %.1f ms\n",
+                (unsigned long long)waves, (unsigned long long)n_sub, ns_sub / 1e6, (unsigned long long)n_dist, ns_dist / 1e6,
+                (unsigned long long)n_path, ns_path / 1e6, ns_serve / 1e6, ns_wait / 1e6);
     if (!task_error.empty()) throw std::runtime_error(task_error);
 }
 

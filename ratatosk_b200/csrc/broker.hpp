@@ -49,7 +49,8 @@ void run_subgraph_batch(rtk_ctx* ctx, const std::vector<SubgraphReq*>& reqs);
 
 class GpuBroker {
 public:
-    explicit GpuBroker(rtk_ctx* c) : ctx(c) {}
+    explicit GpuBroker(rtk_ctx* c);
+    ~GpuBroker();
     // run task(i) for i in [0, n) on `threads` worker threads; the CALLING thread serves the GPU until all tasks finished
     void run(size_t n, unsigned threads, const std::function<void(size_t)>& task);
     // called from worker threads (through the thread-local current broker)
@@ -57,10 +58,12 @@ public:
     void submit(PathReq* r);
     void submit(SubgraphReq* r);
     uint64_t waves = 0, jobs = 0;
+    uint64_t ns_sub = 0, ns_dist = 0, ns_path = 0, ns_wait = 0, ns_serve = 0, n_sub = 0, n_dist = 0, n_path = 0;
 
 private:
     template <typename R> void park(std::vector<R*>& q, R* r);
     rtk_ctx* ctx;
+    rtk_ctx* lane[2] = {nullptr, nullptr};   // forks of ctx: the three services of a wave run concurrently
     std::mutex mu;
     std::condition_variable cv_broker, cv_worker;
     size_t active = 0, waiting = 0;

@@ -23,14 +23,16 @@ __global__ void rtk_compact_ends_kernel(const int32_t* __restrict__ ends, const 
     for (int32_t i = threadIdx.x; i < m; i += blockDim.x) dst[i] = src[i];
 }
 
-template <int G> static void launch_class(rtk_ctx* c, rtk_myers_params p, const uint32_t* d_order, uint32_t n) {
+// one class = one launch on its own side stream: the classes of a batch overlap on the device
+template <int G> static void launch_class(rtk_ctx* c, int k, rtk_myers_params p, const uint32_t* d_order, uint32_t n) {
     if (!n) return;
     p.order = d_order;
     p.n = n;
     const uint64_t threads = (uint64_t)n * G;
     const uint32_t grid = (uint32_t)((threads + RTK_MYERS_THREADS - 1) / RTK_MYERS_THREADS);
-    rtk_myers_kernel<G><<<grid, RTK_MYERS_THREADS, 0, c->stream>>>(p);
+    rtk_myers_kernel<G><<<grid, RTK_MYERS_THREADS, 0, side_stream(c, k)>>>(p);
     RTK_CUDA(cudaGetLastError());
+    fan_in(c, k);
 }
 
 void myers_run(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const MyersJobs& j, int32_t* dist, bool want_ends,
@@ -78,12 +80,13 @@ void myers_run(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const Myers
     p.hbound = B[7].as<int8_t>(); p.hb_off = d_off + 3 * (n + 1);
     RTK_CUDA(cudaEventRecord(c->ev0, st));
     const uint32_t* d_order = B[4].as<uint32_t>();
-    launch_class<1>(c, p, d_order + cls_off[0], cls_off[1] - cls_off[0]);
-    launch_class<2>(c, p, d_order + cls_off[1], cls_off[2] - cls_off[1]);
-    launch_class<4>(c, p, d_order + cls_off[2], cls_off[3] - cls_off[2]);
-    launch_class<8>(c, p, d_order + cls_off[3], cls_off[4] - cls_off[3]);
-    launch_class<16>(c, p, d_order + cls_off[4], cls_off[5] - cls_off[4]);
-    launch_class<32>(c, p, d_order + cls_off[5], cls_off[6] - cls_off[5]);
+    fan_out(c);
+    launch_class<32>(c, 5, p, d_order + cls_off[5], cls_off[6] - cls_off[5]);
+    launch_class<16>(c, 4, p, d_order + cls_off[4], cls_off[5] - cls_off[4]);
+    launch_class<8>(c, 3, p, d_order + cls_off[3], cls_off[4] - cls_off[3]);
+    launch_class<4>(c, 2, p, d_order + cls_off[2], cls_off[3] - cls_off[2]);
+    launch_class<2>(c, 1, p, d_order + cls_off[1], cls_off[2] - cls_off[1]);
+    launch_class<1>(c, 0, p, d_order + cls_off[0], cls_off[1] - cls_off[0]);
     RTK_CUDA(cudaEventRecord(c->ev1, st));
     std::vector<int32_t> h_dn((size_t)n * 2 + 2);
     RTK_CUDA(cudaMemcpyAsync(h_dn.data(), d_dist, (size_t)n * 8, cudaMemcpyDeviceToHost, st));

@@ -109,15 +109,17 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_kernel(const rtk_
         const bool is_last = has && (b == nb - 1);
         const bool spill = (lane == G - 1) && (r + 1 < rounds);
         const int steps = tlen + G - 1;
+        char tc_next = (lane == 0 && tlen > 0) ? t[0] : (char)0;   // the target is read one step ahead of its use
         for (int s = 0; s < steps; ++s) {
             const int from_left = __shfl_up_sync(gmask, hout, 1, G);
             const int col = s - (int)lane;
+            const char tc = tc_next;
+            tc_next = (col + 1 >= 0 && col + 1 < tlen) ? t[col + 1] : (char)0;
             hout = 0;
             if (has && col >= 0 && col < tlen) {
                 int hin;
                 if (lane == 0) hin = (r == 0) ? ((mode == 2) ? 0 : 1) : (int)hb[col];  // D[0][j] = 0 (HW) or j
                 else hin = from_left;
-                const char tc = t[col];
                 uint64_t Eq;
                 switch (tc) {
                     case 'A': Eq = PB0; break;

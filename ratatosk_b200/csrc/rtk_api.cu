@@ -114,6 +114,14 @@ void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, 
 
 using namespace rtk;
 
+static void create_side_streams(rtk_ctx* c) {
+    RTK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int k = 0; k < 6; ++k) {
+        RTK_CUDA(cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking));
+        RTK_CUDA(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+    }
+}
+
 extern "C" {
 
 int rtk_ctx_create(int device, rtk_ctx** out) {
@@ -128,7 +136,26 @@ int rtk_ctx_create(int device, rtk_ctx** out) {
         RTK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         RTK_CUDA(cudaEventCreate(&c->ev0));
         RTK_CUDA(cudaEventCreate(&c->ev1));
+        create_side_streams(c);
         RTK_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+        *out = c;
+    });
+}
+
+int rtk_ctx_fork(const rtk_ctx* parent, rtk_ctx** out) {
+    return guarded([&] {
+        if (!parent || !out) throw std::invalid_argument("null argument");
+        RTK_CUDA(cudaSetDevice(parent->device));
+        rtk_ctx* c = new rtk_ctx();
+        c->device = parent->device;
+        RTK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        RTK_CUDA(cudaEventCreate(&c->ev0));
+        RTK_CUDA(cudaEventCreate(&c->ev1));
+        create_side_streams(c);
+        c->sm_count = parent->sm_count;
+        // the graph is shared, never owned: the parent must outlive the fork
+        c->d_slab = parent->d_slab; c->owns_slab = false; c->has_graph = parent->has_graph;
+        c->hdr = parent->hdr; c->dview = parent->dview; c->host_graph = parent->host_graph;
         *out = c;
     });
 }
@@ -145,6 +172,11 @@ void rtk_ctx_destroy(rtk_ctx* c) {
     if (c->host_copy.data) free(c->host_copy.data);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int k = 0; k < 6; ++k) {
+        if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+        if (c->side[k]) cudaStreamDestroy(c->side[k]);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

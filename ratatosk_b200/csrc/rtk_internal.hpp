@@ -86,6 +86,10 @@ struct rtk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // side streams: the lane-group classes of one K4/K5 batch are independent, latency-bound launches; they run
+    // concurrently, forked from `stream` after the uploads and joined before the downloads (fan_out / fan_in)
+    cudaStream_t side[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // graph
     const unsigned char* d_slab = nullptr;
     bool owns_slab = false;
@@ -114,6 +118,15 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
                    const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms);
 
 #ifndef RTK_HOSTSIM
+// everything enqueued on the side streams after fan_out sees the work enqueued on c->stream before it;
+// fan_in(k) makes c->stream wait for side stream k
+inline void fan_out(rtk_ctx* c) { RTK_CUDA(cudaEventRecord(c->ev_fork, c->stream)); }
+inline cudaStream_t side_stream(rtk_ctx* c, int k) { RTK_CUDA(cudaStreamWaitEvent(c->side[k], c->ev_fork, 0)); return c->side[k]; }
+inline void fan_in(rtk_ctx* c, int k) {
+    RTK_CUDA(cudaEventRecord(c->ev_join[k], c->side[k]));
+    RTK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
+}
+
 // K4 over pools already resident on the device.  Host arrays describe the n alignments (begin/length into
 // the pools, mode, kmax).  dist gets n entries; when want_ends, *ends / *ends_off are malloc'd dense lists.
 struct MyersJobs {

@@ -12,13 +12,14 @@
 
 namespace rtk {
 
-template <int G, bool LC> static void launch_fill(rtk_ctx* c, rtk_fill_params p, const uint32_t* d_order, uint32_t n) {
+template <int G, bool LC> static void launch_fill(rtk_ctx* c, int k, rtk_fill_params p, const uint32_t* d_order, uint32_t n) {
     if (!n) return;
     p.order = d_order;
     p.n = n;
     const uint64_t threads = (uint64_t)n * G;
-    rtk_myers_fill_kernel<G, LC><<<(uint32_t)((threads + RTK_MYERS_THREADS - 1) / RTK_MYERS_THREADS), RTK_MYERS_THREADS, 0, c->stream>>>(p);
+    rtk_myers_fill_kernel<G, LC><<<(uint32_t)((threads + RTK_MYERS_THREADS - 1) / RTK_MYERS_THREADS), RTK_MYERS_THREADS, 0, side_stream(c, k)>>>(p);
     RTK_CUDA(cudaGetLastError());
+    fan_in(c, k);
 }
 
 // device pools: d_aux[0] queries, d_aux[1] targets (effective prefixes), d_sub[7] reversed queries | reversed targets
@@ -68,12 +69,13 @@ struct CudaTbBackend : TbBackend {
         RTK_CUDA(cudaEventRecord(c->ev0, st));
         const uint32_t* d_ids = S[2].as<uint32_t>();
         uint32_t o = 0;
-        launch_fill<1, LC>(c, fp, d_ids + o, (uint32_t)pl.order[0].size()); o += (uint32_t)pl.order[0].size();
-        launch_fill<2, LC>(c, fp, d_ids + o, (uint32_t)pl.order[1].size()); o += (uint32_t)pl.order[1].size();
-        launch_fill<4, LC>(c, fp, d_ids + o, (uint32_t)pl.order[2].size()); o += (uint32_t)pl.order[2].size();
-        launch_fill<8, LC>(c, fp, d_ids + o, (uint32_t)pl.order[3].size()); o += (uint32_t)pl.order[3].size();
-        launch_fill<16, LC>(c, fp, d_ids + o, (uint32_t)pl.order[4].size()); o += (uint32_t)pl.order[4].size();
-        launch_fill<32, LC>(c, fp, d_ids + o, (uint32_t)pl.order[5].size());
+        fan_out(c);
+        launch_fill<1, LC>(c, 0, fp, d_ids + o, (uint32_t)pl.order[0].size()); o += (uint32_t)pl.order[0].size();
+        launch_fill<2, LC>(c, 1, fp, d_ids + o, (uint32_t)pl.order[1].size()); o += (uint32_t)pl.order[1].size();
+        launch_fill<4, LC>(c, 2, fp, d_ids + o, (uint32_t)pl.order[2].size()); o += (uint32_t)pl.order[2].size();
+        launch_fill<8, LC>(c, 3, fp, d_ids + o, (uint32_t)pl.order[3].size()); o += (uint32_t)pl.order[3].size();
+        launch_fill<16, LC>(c, 4, fp, d_ids + o, (uint32_t)pl.order[4].size()); o += (uint32_t)pl.order[4].size();
+        launch_fill<32, LC>(c, 5, fp, d_ids + o, (uint32_t)pl.order[5].size());
     }
 
     void direct(const std::vector<TbItem>& items, std::vector<std::vector<uint8_t>>& ops, std::vector<int32_t>& dist) override {

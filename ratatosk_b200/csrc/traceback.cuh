@@ -75,13 +75,15 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_fill_kernel(const
         const uint64_t base = LASTCOL ? (p.mat_off[a] + (uint64_t)b) : (p.mat_off[a] + (uint64_t)b * (uint64_t)tlen);
         const bool spill = (lane == G - 1) && (r + 1 < rounds);
         const int steps = tlen + G - 1;
+        char tc_next = (lane == 0 && tlen > 0) ? t[0] : (char)0;   // the target is read one step ahead of its use
         for (int s = 0; s < steps; ++s) {
             const int from_left = __shfl_up_sync(gmask, hout, 1, G);
             const int col = s - (int)lane;
+            const char tc = tc_next;
+            tc_next = (col + 1 >= 0 && col + 1 < tlen) ? t[col + 1] : (char)0;
             hout = 0;
             if (has && col >= 0 && col < tlen) {
                 const int hin = (lane == 0) ? ((r == 0) ? 1 : (int)hb[col]) : from_left;   // NW: D[0][j] = j
-                const char tc = t[col];
                 uint64_t Eq;
                 switch (tc) {
                     case 'A': Eq = PB0; break;
@@ -135,22 +137,33 @@ struct rtk_tb_params {
     uint32_t* ops_len;         // [alignment]
 };
 
-// score of cell (row i, column c); i == -1 / c == -1 are the NW boundaries
-__device__ __forceinline__ int rtk_tb_score(const rtk_tb_params& p, const uint64_t moff, const int tlen, const int nb,
-                                            const int last_row, const int i, const int c) {
-    if (i < 0) return c + 1;
-    if (c < 0) return i + 1;
-    const int b = i >> 6, r = i & 63;
-    const int arow = (b == nb - 1) ? last_row : 63;
+// One stored column block: delta words + anchor score.  Boundary column -1 is synthesised (all deltas +1).
+struct rtk_tb_cell { uint64_t P, M; int32_t A; };
+
+__device__ __forceinline__ rtk_tb_cell rtk_tb_load(const rtk_tb_params& p, const uint64_t moff, const int tlen, const int nb,
+                                                  const int last_row, const int b, const int c) {
+    rtk_tb_cell r;
+    if (c < 0) {  // D[i][-1] = i + 1: every vertical delta is +1, anchor = its row + 1
+        const int arow = (b == nb - 1) ? last_row : 63;
+        r.P = ~0ULL; r.M = 0; r.A = (b << 6) + arow + 1;
+        return r;
+    }
     const uint64_t idx = moff + (uint64_t)b * (uint64_t)tlen + (uint64_t)c;
     const ulonglong2 cell = p.mat[idx];
-    // rows r+1 .. arow
-    const uint64_t hi = (arow == 63) ? ~0ULL : ((1ULL << (arow + 1)) - 1ULL);
-    const uint64_t lo = (r == 63) ? ~0ULL : ((1ULL << (r + 1)) - 1ULL);
-    const uint64_t m = hi & ~lo;
-    return p.anchor[idx] - __popcll(cell.x & m) + __popcll(cell.y & m);
+    r.P = cell.x; r.M = cell.y; r.A = p.anchor[idx];
+    return r;
 }
 
+// score of row r (0..63) of a block whose anchor row is arow
+__device__ __forceinline__ int rtk_tb_row(const rtk_tb_cell& c, const int arow, const int r) {
+    const uint64_t hi = (arow == 63) ? ~0ULL : ((1ULL << (arow + 1)) - 1ULL);
+    const uint64_t lo = (r == 63) ? ~0ULL : ((1ULL << (r + 1)) - 1ULL);
+    const uint64_t m = hi & ~lo;   // rows r+1 .. arow
+    return c.A - __popcll(c.P & m) + __popcll(c.M & m);
+}
+
+// The walk keeps the blocks it can touch next in registers: (b, c) `cur`, (b, c-1) `left`, and prefetches
+// (b, c-2) so that a move to the left never waits for memory; only crossing into the block above reloads.
 __global__ void __launch_bounds__(128) rtk_traceback_kernel(const rtk_tb_params p) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= p.n) return;
@@ -160,15 +173,55 @@ __global__ void __launch_bounds__(128) rtk_traceback_kernel(const rtk_tb_params 
     const uint64_t moff = p.mat_off[a];
     uint8_t* out = p.ops + p.ops_off[a];
     uint32_t w = (uint32_t)(qlen + tlen);   // next write position (exclusive), walking backwards
-    int i = qlen - 1, c = tlen - 1, cur = p.dist[a];
+    int i = qlen - 1, c = tlen - 1, cur_score = p.dist[a];
+    int b = i >> 6;
+    rtk_tb_cell cur = rtk_tb_load(p, moff, tlen, nb, last_row, b, c);
+    rtk_tb_cell left = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 1);
+    rtk_tb_cell left2 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 2);
     while (i >= 0 && c >= 0) {
-        const int u = rtk_tb_score(p, moff, tlen, nb, last_row, i - 1, c);
-        if (u + 1 == cur) { out[--w] = 1; --i; cur = u; continue; }               // up: query base unaligned
-        const int l = rtk_tb_score(p, moff, tlen, nb, last_row, i, c - 1);
-        if (l + 1 == cur) { out[--w] = 2; --c; cur = l; continue; }               // left: target base unaligned
-        const int ul = rtk_tb_score(p, moff, tlen, nb, last_row, i - 1, c - 1);
-        out[--w] = (ul == cur) ? 0 : 3;                                           // diagonal: match / mismatch
-        --i; --c; cur = ul;
+        const int r = i & 63;
+        const int arow = (b == nb - 1) ? last_row : 63;
+        // score above: same column, row i-1 (D[-1][c] = c + 1 above the first row)
+        int u, ul;
+        if (r > 0) { u = cur_score - (int)((cur.P >> r) & 1) + (int)((cur.M >> r) & 1); }
+        else if (b == 0) u = c + 1;
+        else u = -0x3fffffff;   // first row of a block above block 0: resolved below by loading the block above
+        if (r == 0 && b > 0) {
+            const rtk_tb_cell up = rtk_tb_load(p, moff, tlen, nb, last_row, b - 1, c);
+            u = up.A;            // anchor row of a non-last block is its row 63
+        }
+        if (u + 1 == cur_score) {                                   // up: query base unaligned
+            out[--w] = 1; --i; cur_score = u;
+            if (r == 0 && i >= 0) {
+                --b;
+                cur = rtk_tb_load(p, moff, tlen, nb, last_row, b, c);
+                left = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 1);
+                left2 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 2);
+            }
+            continue;
+        }
+        const int l = rtk_tb_row(left, arow, r);                   // D[i][c-1] (column -1 synthesised)
+        if (l + 1 == cur_score) {                                   // left: target base unaligned
+            out[--w] = 2; --c; cur_score = l;
+            cur = left; left = left2;
+            left2 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 2);
+            continue;
+        }
+        // diagonal: D[i-1][c-1]
+        if (r > 0) ul = l - (int)((left.P >> r) & 1) + (int)((left.M >> r) & 1);
+        else if (b == 0) ul = c;                                     // D[-1][c-1] = c
+        else { const rtk_tb_cell upl = rtk_tb_load(p, moff, tlen, nb, last_row, b - 1, c - 1); ul = (c - 1 < 0) ? ((b << 6)) : upl.A; }
+        out[--w] = (ul == cur_score) ? 0 : 3;
+        --i; --c; cur_score = ul;
+        if (r == 0 && i >= 0) {
+            --b;
+            cur = rtk_tb_load(p, moff, tlen, nb, last_row, b, c);
+            left = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 1);
+            left2 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 2);
+        } else {
+            cur = left; left = left2;
+            left2 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 2);
+        }
     }
     while (c >= 0) { out[--w] = 2; --c; }
     while (i >= 0) { out[--w] = 1; --i; }
