@@ -196,10 +196,22 @@ int rtk_explore_paths(rtk_ctx* ctx, const rtk_opt* opt, const rtk_hit* um_s, con
 /* ---- the per-read body of search() (src/Ratatosk.cpp:808-867): getSeeds + correctSequence for a ticket of reads ----
  * Pass 1 (k = 31 graph coloured by short reads).  Inputs: reads and their qualities (qual_pool may be NULL).
  * Output: corrected read i = out_seq_pool[out_off[i], out_off[i+1]) with its quality string at the same
- * offsets of out_qual_pool - the exact bytes the reference writes to the FASTQ (library-allocated). */
+ * offsets of out_qual_pool - the exact bytes the reference writes to the FASTQ (library-allocated).
+ * stats (optional, 16 x u64, accumulated): [0] K1 probes, [1] K1 raw hits, [2] K1 kernel ns, [3] K1 stage ns (copies +
+ * host replay), [5] batched GPU service calls, [6] GPU requests served, [7] K4 / [8] K5 / [9] K2+K3+K4 kernel ns (CUDA
+ * events on the launching streams; the services overlap), [10] getSeeds stage ns, [11] region stage ns, [12] bytes copied host->device, [13] device->host, [14] kernels launched
+ * (process-wide tallies: exact when one batch runs at a time). */
 int rtk_correct_batch(rtk_ctx* ctx, const rtk_opt* opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
                       const char* qual_pool, const uint64_t* qual_off, char** out_seq_pool, char** out_qual_pool,
                       uint64_t** out_off, uint64_t* stats);
+/* Same, with the reads ALSO resident in HBM already (dev_seq_pool / dev_seq_off: device copies of seq_pool / the
+ * offsets rebased to 0, upper-case): the exact k-mer sweep reads them in place instead of uploading.  Used by bench.py
+ * to separate the device-resident rate from the end-to-end rate; the host copies are still needed because the
+ * region logic runs on the host. */
+int rtk_correct_batch_resident(rtk_ctx* ctx, const rtk_opt* opt, int pass, uint32_t n_reads, const char* seq_pool,
+                               const uint64_t* seq_off, const char* dev_seq_pool, const uint64_t* dev_seq_off,
+                               const char* qual_pool, const uint64_t* qual_off, char** out_seq_pool, char** out_qual_pool,
+                               uint64_t** out_off, uint64_t* stats);
 
 #ifdef __cplusplus
 }

@@ -117,6 +117,11 @@ def load_library(path=None):
     L.rtk_correct_batch.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_int, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64),
                                     C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                     C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
+    if hasattr(L, "rtk_correct_batch_resident"):   # product library only (the CPU simulator has no device memory)
+        L.rtk_correct_batch_resident.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_int, C.c_uint32, C.c_char_p,
+                                                 C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_char_p,
+                                                 C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                 C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
     L.rtk_explore_paths.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.POINTER(RtkHit), C.POINTER(RtkHit), C.c_char_p, C.c_uint32,
                                     C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.POINTER(RtkPathNode)), C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
@@ -323,7 +328,7 @@ class Context:
             qp, qo = None, None
         os_, oq_ = C.c_void_p(), C.c_void_p()
         oo = C.POINTER(C.c_uint64)()
-        st = (C.c_uint64 * 8)()
+        st = (C.c_uint64 * 16)()
         _check(self.L, self.L.rtk_correct_batch(self.h, C.byref(opt), pass_no, len(reads), pool, off.ctypes.data_as(C.POINTER(C.c_uint64)),
                                                 qp, qo, C.byref(os_), C.byref(oq_), C.byref(oo), st))
         n = len(reads)

@@ -1,5 +1,9 @@
 // broker.cpp — see broker.hpp.
 #include "broker.hpp"
+#include "rtk_host_common.hpp"
+
+#include <sys/mman.h>
+#include <ucontext.h>
 
 #include <atomic>
 #include <chrono>
@@ -12,10 +16,22 @@
 namespace rtk {
 
 static thread_local GpuBroker* tl_broker = nullptr;
+static thread_local GpuBroker::Worker* tl_worker = nullptr;
 GpuBroker* current_broker() { return tl_broker; }
 
 // ------------------------------------------------------------------ batched execution
+// RTK_BROKER_PROFILE: host time spent assembling a batch, inside the C-ABI call, scattering the answers; GPU kernel time
+static std::atomic<uint64_t> g_prof[3][4];
+struct ProfTimer {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(int kind, int slot) {
+        const auto n = std::chrono::steady_clock::now();
+        g_prof[kind][slot] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(n - t).count();
+        t = n;
+    }
+};
 void run_dist_batch(rtk_ctx* ctx, const std::vector<DistReq*>& reqs) {
+    ProfTimer pt;
     std::string qp, tp;
     std::vector<uint64_t> qo(1, 0), to(1, 0);
     std::vector<uint8_t> mode;
@@ -25,11 +41,15 @@ void run_dist_batch(rtk_ctx* ctx, const std::vector<DistReq*>& reqs) {
     std::vector<int32_t> dist(n + 1, -1), kmax(n + 1, -1);
     int32_t* ends = nullptr;
     uint64_t* eoff = nullptr;
+    uint64_t st[8] = {0};
+    pt.lap(0, 0);
     if (n) {
         qp.push_back('\0'); tp.push_back('\0');
-        if (rtk_edlib_batch(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), kmax.data(), dist.data(), &ends, &eoff, nullptr) != RTK_OK)
+        if (rtk_edlib_batch(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), kmax.data(), dist.data(), &ends, &eoff, st) != RTK_OK)
             throw std::runtime_error(std::string("rtk_edlib_batch: ") + rtk_last_error());
     }
+    pt.lap(0, 1);
+    g_prof[0][3] += st[2];
     uint32_t a = 0;
     for (const DistReq* r : reqs) {
         const size_t m = r->jobs->size();
@@ -42,9 +62,11 @@ void run_dist_batch(rtk_ctx* ctx, const std::vector<DistReq*>& reqs) {
     }
     rtk_free(ends);
     rtk_free(eoff);
+    pt.lap(0, 2);
 }
 
 void run_path_batch(rtk_ctx* ctx, const std::vector<PathReq*>& reqs) {
+    ProfTimer pt;
     std::string qp, tp;
     std::vector<uint64_t> qo(1, 0), to(1, 0);
     std::vector<uint8_t> mode;
@@ -55,11 +77,15 @@ void run_path_batch(rtk_ctx* ctx, const std::vector<PathReq*>& reqs) {
     std::vector<uint8_t> flags(n + 1, 0);
     uint8_t* o = nullptr;
     uint64_t* ooff = nullptr;
+    uint64_t st[8] = {0};
+    pt.lap(1, 0);
     if (n) {
         qp.push_back('\0'); tp.push_back('\0');
-        if (rtk_edlib_path_batch(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), dist.data(), end.data(), &o, &ooff, flags.data(), nullptr) != RTK_OK)
+        if (rtk_edlib_path_batch(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), dist.data(), end.data(), &o, &ooff, flags.data(), st) != RTK_OK)
             throw std::runtime_error(std::string("rtk_edlib_path_batch: ") + rtk_last_error());
     }
+    pt.lap(1, 1);
+    g_prof[1][3] += st[2];
     uint32_t a = 0;
     for (const PathReq* r : reqs) {
         const size_t m = r->jobs->size();
@@ -72,10 +98,12 @@ void run_path_batch(rtk_ctx* ctx, const std::vector<PathReq*>& reqs) {
     }
     rtk_free(o);
     rtk_free(ooff);
+    pt.lap(1, 2);
 }
 
 void run_subgraph_batch(rtk_ctx* ctx, const std::vector<SubgraphReq*>& reqs) {
     if (reqs.empty()) return;
+    ProfTimer pt;
     // requests may carry different weak_region_len_factor values (multi-round correction): one call per value
     std::vector<bool> done(reqs.size(), false);
     for (size_t first = 0; first < reqs.size(); ++first) {
@@ -97,9 +125,13 @@ void run_subgraph_batch(rtk_ctx* ctx, const std::vector<SubgraphReq*>& reqs) {
         rtk_subgraph_out out;
         const uint32_t dummy = 0;
         refs.push_back('\0');
+        uint64_t st[8] = {0};
+        pt.lap(2, 0);
         if (rtk_explore_subgraph_batch(ctx, (uint32_t)calls.size(), calls.data(), refs.data(), refs.size() - 1, pids.empty() ? &dummy : pids.data(),
-                                       pids.size(), wrlf, &out, nullptr) != RTK_OK)
+                                       pids.size(), wrlf, &out, st) != RTK_OK)
             throw std::runtime_error(std::string("rtk_explore_subgraph_batch: ") + rtk_last_error());
+        pt.lap(2, 1);
+        g_prof[2][3] += st[2] + st[3];
         for (size_t ci = 0; ci < idx.size(); ++ci) {
             SubgraphResult& res = *reqs[idx[ci]]->out;
             for (int s = 0; s < 4; ++s) res.scores[s] = out.scores[4 * ci + s];
@@ -114,114 +146,289 @@ void run_subgraph_batch(rtk_ctx* ctx, const std::vector<SubgraphReq*>& reqs) {
             }
         }
         rtk_subgraph_out_free(&out);
+        pt.lap(2, 2);
     }
 }
 
 // ------------------------------------------------------------------ broker
+struct GpuBroker::Fiber {
+    ucontext_t uc;
+    char* stack = nullptr;
+    size_t task = 0;
+    bool done = false;
+    GpuBroker* broker = nullptr;
+    Worker* owner = nullptr;
+    std::string error;   // set by the service that failed this fiber's request
+};
+
+struct GpuBroker::Worker {
+    std::thread th;
+    ucontext_t sched;                 // the worker thread's own context (scheduler loop)
+    Fiber* current = nullptr;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<Fiber*> ready;        // served fibers, pushed by the service threads
+    std::vector<Fiber*> pool;         // finished fibers (stack kept) for reuse
+    char* slab = nullptr;             // one mapping holding all fiber stacks of this worker
+    size_t slab_bytes = 0, stacks_used = 0;
+    unsigned rr = 0;                  // round-robin over the service threads of a kind
+    uint64_t ns_idle = 0, n_resumes = 0;
+};
+
+struct GpuBroker::Service {
+    int kind = 0;
+    rtk_ctx* ctx = nullptr;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<std::pair<void*, Fiber*>> q;
+    bool stop = false;
+    uint64_t batches = 0, reqs = 0, ns_busy = 0;
+};
+
+static size_t fiber_stack_bytes() {
+    const char* e = getenv("RTK_FIBER_STACK_KB");
+    const long kb = e ? atol(e) : 256;
+    return (size_t)std::max(64L, std::min(kb, 8192L)) << 10;
+}
 GpuBroker::GpuBroker(rtk_ctx* c) : ctx(c) {
-    for (int i = 0; i < 2; ++i)
-        if (rtk_ctx_fork(ctx, &lane[i]) != RTK_OK) throw std::runtime_error(std::string("rtk_ctx_fork: ") + rtk_last_error());
-}
-GpuBroker::~GpuBroker() { for (int i = 0; i < 2; ++i) rtk_ctx_destroy(lane[i]); }
-
-template <typename R> void GpuBroker::park(std::vector<R*>& q, R* r) {
-    std::unique_lock<std::mutex> lk(mu);
-    q.push_back(r);
-    ++waiting;
-    const uint64_t my_epoch = epoch;
-    if (waiting == active) cv_broker.notify_one();
-    cv_worker.wait(lk, [&] { return epoch != my_epoch; });
-    if (!error.empty()) throw std::runtime_error(error);
-}
-void GpuBroker::submit(DistReq* r) { park(q_dist, r); }
-void GpuBroker::submit(PathReq* r) { park(q_path, r); }
-void GpuBroker::submit(SubgraphReq* r) { park(q_sub, r); }
-
-void GpuBroker::run(size_t n, unsigned threads, const std::function<void(size_t)>& task) {
-    if (n == 0) return;
-    threads = (unsigned)std::min<size_t>(std::max(1u, threads), n);
-    std::atomic<size_t> next(0);
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        active = threads; waiting = 0; error.clear();
-    }
-    std::vector<std::thread> pool;
-    std::string task_error;
-    std::mutex err_mu;
-    for (unsigned t = 0; t < threads; ++t) {
-        pool.emplace_back([&] {
-            tl_broker = this;
-            try {
-                for (;;) {
-                    const size_t i = next.fetch_add(1);
-                    if (i >= n) break;
-                    task(i);
-                }
-            } catch (const std::exception& e) {
-                std::lock_guard<std::mutex> g(err_mu);
-                if (task_error.empty()) task_error = e.what();
-                next.store(n);  // stop handing out work
-            }
-            tl_broker = nullptr;
-            std::lock_guard<std::mutex> lk(mu);
-            --active;
-            if (waiting == active) cv_broker.notify_one();
-        });
-    }
-    // serve the GPU from this thread
-    auto t_last = std::chrono::steady_clock::now();
-    for (;;) {
-        std::vector<DistReq*> d;
-        std::vector<PathReq*> p;
-        std::vector<SubgraphReq*> s;
-        {
-            std::unique_lock<std::mutex> lk(mu);
-            cv_broker.wait(lk, [&] { return waiting == active; });
-            if (active == 0) break;
-            d.swap(q_dist); p.swap(q_path); s.swap(q_sub);
-        }
-        std::string err;
-        const auto t0 = std::chrono::steady_clock::now();
-        {
-            // the three services are independent within a wave: each runs on its own context (stream + scratch)
-            std::string e_sub, e_dist, e_path;
-            auto timed = [](uint64_t& acc, std::string& e, const std::function<void()>& f) {
-                const auto a = std::chrono::steady_clock::now();
-                try { f(); } catch (const std::exception& ex) { e = ex.what(); }
-                acc += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - a).count();
-            };
-            std::thread th_sub, th_path;
+    // service threads per kind (each with its own forked context = stream + scratch): RTK_SERVICE_THREADS="d,p,s"
+    unsigned cnt[3] = {2, 2, 1};
+    if (const char* e = getenv("RTK_SERVICE_THREADS")) sscanf(e, "%u,%u,%u", &cnt[0], &cnt[1], &cnt[2]);
 #ifdef RTK_HOSTSIM   // the CPU simulator runs one launch at a time
-            if (!s.empty()) timed(ns_sub, e_sub, [&] { run_subgraph_batch(lane[0], s); });
-            if (!p.empty()) timed(ns_path, e_path, [&] { run_path_batch(lane[1], p); });
-#else
-            if (!s.empty()) th_sub = std::thread([&] { timed(ns_sub, e_sub, [&] { run_subgraph_batch(lane[0], s); }); });
-            if (!p.empty()) th_path = std::thread([&] { timed(ns_path, e_path, [&] { run_path_batch(lane[1], p); }); });
+    cnt[0] = cnt[1] = cnt[2] = 1;
 #endif
-            if (!d.empty()) timed(ns_dist, e_dist, [&] { run_dist_batch(ctx, d); });
-            if (th_sub.joinable()) th_sub.join();
-            if (th_path.joinable()) th_path.join();
-            n_sub += s.size(); n_dist += d.size(); n_path += p.size();
-            err = !e_sub.empty() ? e_sub : (!e_dist.empty() ? e_dist : e_path);
+    for (int k = 0; k < 3; ++k)
+        for (unsigned i = 0; i < std::max(1u, std::min(cnt[k], 8u)); ++i) {
+            Service* s = new Service();
+            s->kind = k;
+            if (rtk_ctx_fork(ctx, &s->ctx) != RTK_OK) { delete s; throw std::runtime_error(std::string("rtk_ctx_fork: ") + rtk_last_error()); }
+            services[k].push_back(s);
         }
-        ns_wait += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t0 - t_last).count();
-        t_last = std::chrono::steady_clock::now();
-        ns_serve += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_last - t0).count();
-        ++waves;
-        jobs += d.size() + p.size() + s.size();
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            if (!err.empty()) error = err;
-            waiting = 0;
-            ++epoch;
-        }
-        cv_worker.notify_all();
+}
+GpuBroker::~GpuBroker() {
+    for (int k = 0; k < 3; ++k)
+        for (Service* s : services[k]) { rtk_ctx_destroy(s->ctx); delete s; }
+}
+
+// called on a fiber: queue the request at a service thread and hand control back to the worker's scheduler.  The
+// service may answer before this fiber has switched out; that is safe because only this worker thread resumes it,
+// and it only looks at its ready list from the scheduler context.
+void GpuBroker::park(int kind, void* req) {
+    Worker* w = tl_worker;
+    if (!w || !w->current) throw std::logic_error("GpuBroker::submit called outside a broker task");
+    Fiber* f = w->current;
+    Service* s = services[kind][(w->rr++) % services[kind].size()];
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->q.emplace_back(req, f);
     }
-    for (auto& th : pool) th.join();
-    if (getenv("RTK_BROKER_PROFILE"))
-        fprintf(stderr, "[broker] waves=%llu  subgraph: %llu reqs %.1f ms | dist: %llu reqs %.1f ms | path: %llu reqs %.1f ms | serving %.1f ms | waiting for workers %.1f ms\n",
-                (unsigned long long)waves, (unsigned long long)n_sub, ns_sub / 1e6, (unsigned long long)n_dist, ns_dist / 1e6,
-                (unsigned long long)n_path, ns_path / 1e6, ns_serve / 1e6, ns_wait / 1e6);
+    s->cv.notify_one();
+    swapcontext(&f->uc, &w->sched);
+    if (!f->error.empty()) { std::string e; e.swap(f->error); throw std::runtime_error(e); }
+}
+void GpuBroker::submit(DistReq* r) { park(0, r); }
+void GpuBroker::submit(PathReq* r) { park(1, r); }
+void GpuBroker::submit(SubgraphReq* r) { park(2, r); }
+
+#ifdef RTK_HOSTSIM
+static std::mutex g_sim_launch_mu;   // the CPU simulator runs one launch at a time
+#endif
+
+void GpuBroker::service_main(Service* s) {
+    std::vector<std::pair<void*, Fiber*>> batch;
+    const char* e_mb = getenv("RTK_SERVICE_MIN_BATCH");
+    const char* e_lg = getenv("RTK_SERVICE_LINGER_US");
+    const size_t min_batch = e_mb ? (size_t)atol(e_mb) : 256;
+    const long linger_us = e_lg ? atol(e_lg) : 150;
+    for (;;) {
+        batch.clear();
+        {
+            std::unique_lock<std::mutex> lk(s->mu);
+            s->cv.wait(lk, [&] { return s->stop || !s->q.empty(); });
+            if (s->q.empty()) break;   // stop requested and nothing left
+            // a batch costs a fixed launch + copy latency: linger briefly for more requests when only a few are queued
+            if (s->q.size() < min_batch && linger_us > 0) {
+                const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(linger_us);
+                s->cv.wait_until(lk, deadline, [&] { return s->stop || s->q.size() >= min_batch; });
+            }
+            batch.swap(s->q);
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        std::string err;
+        try {
+#ifdef RTK_HOSTSIM
+            std::lock_guard<std::mutex> sim(g_sim_launch_mu);
+#endif
+            if (s->kind == 0) { std::vector<DistReq*> v; for (auto& b : batch) v.push_back((DistReq*)b.first); run_dist_batch(s->ctx, v); }
+            else if (s->kind == 1) { std::vector<PathReq*> v; for (auto& b : batch) v.push_back((PathReq*)b.first); run_path_batch(s->ctx, v); }
+            else { std::vector<SubgraphReq*> v; for (auto& b : batch) v.push_back((SubgraphReq*)b.first); run_subgraph_batch(s->ctx, v); }
+        } catch (const std::exception& e) { err = e.what(); if (err.empty()) err = "GPU service failed"; }
+        s->ns_busy += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        ++s->batches; s->reqs += batch.size();
+        if (!err.empty()) {   // no new tasks after a service error
+            std::lock_guard<std::mutex> g(mu_task);
+            next_task = n_tasks;
+        }
+        // hand the fibers back, grouped per owner so that each worker is locked / woken once
+        std::sort(batch.begin(), batch.end(), [](const std::pair<void*, Fiber*>& a, const std::pair<void*, Fiber*>& b) { return a.second->owner < b.second->owner; });
+        for (size_t i = 0; i < batch.size();) {
+            Worker* w = batch[i].second->owner;
+            size_t j = i;
+            {
+                std::lock_guard<std::mutex> lk(w->mu);
+                for (; j < batch.size() && batch[j].second->owner == w; ++j) {
+                    if (!err.empty()) batch[j].second->error = err;
+                    w->ready.push_back(batch[j].second);
+                }
+            }
+            w->cv.notify_one();
+            i = j;
+        }
+    }
+}
+
+static void fiber_entry(unsigned lo, unsigned hi) {
+    GpuBroker::Fiber* f = (GpuBroker::Fiber*)(((uintptr_t)hi << 32) | (uintptr_t)lo);
+    f->broker->fiber_body(f);
+    // returning switches to uc_link = the worker's scheduler context
+}
+
+void GpuBroker::fiber_body(Fiber* f) {
+    try {
+        (*task_fn)(f->task);
+    } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> g(mu_task);
+        if (task_error.empty()) task_error = e.what();
+        next_task = n_tasks;   // stop handing out work
+    } catch (...) {
+        std::lock_guard<std::mutex> g(mu_task);
+        if (task_error.empty()) task_error = "unknown exception in a correction task";
+        next_task = n_tasks;
+    }
+    f->done = true;
+}
+
+// scheduler loop of a worker thread: resume served fibers, start new tasks while there is room, sleep when every
+// live fiber is waiting for the GPU; exits when it has no live fiber and no task is left
+void GpuBroker::worker_main(Worker* w) {
+    tl_broker = this;
+    tl_worker = w;
+    const size_t stack_bytes = fiber_stack_bytes();
+    size_t live = 0;
+    auto enter = [&](Fiber* f) {
+        w->current = f;
+        swapcontext(&w->sched, &f->uc);
+        w->current = nullptr;
+        if (f->done) { w->pool.push_back(f); --live; }
+    };
+    std::vector<Fiber*> resume;
+    bool tasks_left = true;
+    for (;;) {
+        resume.clear();
+        {
+            std::lock_guard<std::mutex> lk(w->mu);
+            resume.swap(w->ready);
+        }
+        for (Fiber* f : resume) enter(f);
+        w->n_resumes += resume.size();
+        size_t started = 0;
+        while (tasks_left && live < cap_per_worker && started < 64) {   // in small chunks, so served fibers are resumed promptly
+            size_t i;
+            {
+                std::lock_guard<std::mutex> g(mu_task);
+                if (next_task >= n_tasks) { tasks_left = false; break; }
+                i = next_task++;
+            }
+            Fiber* f;
+            if (!w->pool.empty()) { f = w->pool.back(); w->pool.pop_back(); }
+            else {
+                f = new Fiber();
+                f->stack = w->slab + (w->stacks_used++) * stack_bytes;
+            }
+            f->task = i; f->done = false; f->broker = this; f->owner = w; f->error.clear();
+            getcontext(&f->uc);
+            f->uc.uc_stack.ss_sp = f->stack;
+            f->uc.uc_stack.ss_size = stack_bytes;
+            f->uc.uc_link = &w->sched;
+            const uintptr_t p = (uintptr_t)f;
+            makecontext(&f->uc, (void (*)())fiber_entry, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
+            ++live; ++started;
+            enter(f);
+        }
+        if (!resume.empty() || started) continue;
+        if (live == 0) {
+            if (!tasks_left) break;
+            std::lock_guard<std::mutex> g(mu_task);   // tasks_left may be stale after an error
+            if (next_task >= n_tasks) break;
+            continue;
+        }
+        const auto t_idle = std::chrono::steady_clock::now();
+        {
+            std::unique_lock<std::mutex> lk(w->mu);
+            w->cv.wait(lk, [&] { return !w->ready.empty(); });
+        }
+        w->ns_idle += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_idle).count();
+    }
+    tl_broker = nullptr;
+    tl_worker = nullptr;
+}
+
+void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t)>& task) {
+    if (n == 0) return;
+    const unsigned n_workers = (unsigned)std::min<size_t>(std::max(1u, host_threads()), n);
+    const size_t stack_bytes = fiber_stack_bytes();
+    n_tasks = n; next_task = 0; task_fn = &task; task_error.clear();
+    cap_per_worker = std::max<size_t>(1, (std::min<size_t>(std::max(1u, inflight), n) + n_workers - 1) / n_workers);
+    const auto t_begin = std::chrono::steady_clock::now();
+    uint64_t prof0[3][4];
+    for (int k = 0; k < 3; ++k) for (int j = 0; j < 4; ++j) prof0[k][j] = g_prof[k][j];
+    for (unsigned t = 0; t < n_workers; ++t) {
+        Worker* w = new Worker();
+        w->slab_bytes = cap_per_worker * stack_bytes;
+        w->slab = (char*)mmap(nullptr, w->slab_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        if (w->slab == (char*)MAP_FAILED) { delete w; for (Worker* x : workers) { munmap(x->slab, x->slab_bytes); delete x; } workers.clear(); throw std::bad_alloc(); }
+        w->rr = t;
+        workers.push_back(w);
+    }
+    for (int k = 0; k < 3; ++k)
+        for (Service* s : services[k]) { s->stop = false; s->th = std::thread([this, s] { service_main(s); }); }
+    for (Worker* w : workers) w->th = std::thread([this, w] { worker_main(w); });
+    uint64_t idle_ns = 0, resumes = 0;
+    for (Worker* w : workers) {
+        w->th.join();
+        idle_ns += w->ns_idle; resumes += w->n_resumes;
+        for (Fiber* f : w->pool) delete f;
+        munmap(w->slab, w->slab_bytes);
+        delete w;
+    }
+    workers.clear();
+    for (int k = 0; k < 3; ++k)
+        for (Service* s : services[k]) {
+            { std::lock_guard<std::mutex> lk(s->mu); s->stop = true; }
+            s->cv.notify_one();
+            s->th.join();
+            waves += s->batches; jobs += s->reqs;
+        }
+    task_fn = nullptr;
+    uint64_t prof[3][4];
+    for (int k = 0; k < 3; ++k) for (int j = 0; j < 4; ++j) prof[k][j] = g_prof[k][j] - prof0[k][j];
+    for (int k = 0; k < 3; ++k) kernel_ns[k] += prof[k][3];
+    if (getenv("RTK_BROKER_PROFILE")) {
+        const double total_ms = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count() / 1e6;
+        static const char* names[3] = {"dist", "path", "subgraph"};
+        fprintf(stderr, "[broker] tasks=%zu workers=%u inflight/worker=%zu total %.1f ms, workers idle %.1f%% |", n, n_workers, cap_per_worker, total_ms,
+                100.0 * (idle_ns / 1e6) / (total_ms * n_workers));
+        for (int k = 0; k < 3; ++k)
+            for (Service* s : services[k])
+                fprintf(stderr, " %s: %llu reqs in %llu batches, busy %.1f ms |", names[k], (unsigned long long)s->reqs, (unsigned long long)s->batches, s->ns_busy / 1e6);
+        fprintf(stderr, "\n");
+        for (int k = 0; k < 3; ++k) {
+            fprintf(stderr, "[broker]   %s service host time: assemble %.1f ms, C-ABI call %.1f ms (GPU kernels %.1f ms), scatter %.1f ms\n", names[k],
+                    prof[k][0] / 1e6, prof[k][1] / 1e6, prof[k][3] / 1e6, prof[k][2] / 1e6);
+        }
+    }
+    for (int k = 0; k < 3; ++k) for (Service* s : services[k]) { s->batches = s->reqs = s->ns_busy = 0; }
     if (!task_error.empty()) throw std::runtime_error(task_error);
 }
 

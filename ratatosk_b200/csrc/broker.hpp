@@ -1,13 +1,18 @@
-// broker.hpp — wave batching of the GPU services behind the host orchestration.
+// broker.hpp — asynchronous batching of the GPU services behind the host orchestration.
 //
-// The correction logic of a read (correct.cpp / traverse.cpp) is sequential code that needs a GPU answer
+// The correction logic of a region (correct.cpp / traverse.cpp) is sequential code that needs a GPU answer
 // every few lines (one alignment, one graph burst, one traceback).  Issued one by one these calls are
-// launch-latency bound.  The broker runs many reads concurrently, each on its own host thread; a thread
-// that needs the GPU parks its request and blocks; when EVERY live thread is parked, the broker thread
-// concatenates all parked requests of a kind into ONE batched C-ABI call (rtk_edlib_batch,
-// rtk_edlib_path_batch, rtk_explore_subgraph_batch), scatters the answers and wakes the threads.  The
-// per-read logic is untouched (and stays byte-identical to the reference); the GPU sees batches of
-// hundreds to thousands of independent jobs per launch instead of one.
+// launch-latency bound.  The broker runs tens of thousands of regions concurrently as FIBERS (stackful
+// user-level contexts, <ucontext.h>) multiplexed on a few worker threads (one per host core): a fiber that
+// needs the GPU queues its request at the service of that kind and switches back to its worker's scheduler,
+// which resumes another ready fiber or starts a new region.  Each service (K4 distances, K5 paths, K2/K3
+// graph bursts) has its own thread(s) and forked context (stream + scratch): whenever it is free it takes
+// EVERYTHING queued so far, runs it as ONE batched C-ABI call (rtk_edlib_batch, rtk_edlib_path_batch,
+// rtk_explore_subgraph_batch), scatters the answers and hands the fibers back to their workers' ready lists.
+// There is no global barrier: host logic, the three services and their H2D/D2H copies all overlap, and
+// batches size themselves to the service latency (requests accumulate while the previous batch runs).  The
+// per-region logic is untouched (and stays byte-identical to the reference).  Fibers never migrate between
+// worker threads, so thread-local state (current_broker) stays valid across a park.
 #pragma once
 #include <condition_variable>
 #include <functional>
@@ -51,27 +56,34 @@ class GpuBroker {
 public:
     explicit GpuBroker(rtk_ctx* c);
     ~GpuBroker();
-    // run task(i) for i in [0, n) on `threads` worker threads; the CALLING thread serves the GPU until all tasks finished
-    void run(size_t n, unsigned threads, const std::function<void(size_t)>& task);
-    // called from worker threads (through the thread-local current broker)
+    // run task(i) for i in [0, n) with up to `inflight` tasks alive at once (as fibers on the host worker threads);
+    // returns when all tasks have finished; throws the first service / task error
+    void run(size_t n, unsigned inflight, const std::function<void(size_t)>& task);
+    // called from inside a task (through the thread-local current broker): queue the request, resume when served
     void submit(DistReq* r);
     void submit(PathReq* r);
     void submit(SubgraphReq* r);
-    uint64_t waves = 0, jobs = 0;
-    uint64_t ns_sub = 0, ns_dist = 0, ns_path = 0, ns_wait = 0, ns_serve = 0, n_sub = 0, n_dist = 0, n_path = 0;
+    uint64_t waves = 0, jobs = 0;   // batched service calls issued / requests served
+    uint64_t kernel_ns[3] = {0, 0, 0};   // GPU kernel time (CUDA events) of the dist / path / subgraph services
+
+    struct Worker;    // one host thread: scheduler context, live fibers, ready list
+    struct Fiber;
+    struct Service;   // one GPU service thread: request queue + forked context
+    void fiber_body(Fiber* f);   // fiber entry (called by the makecontext trampoline)
 
 private:
-    template <typename R> void park(std::vector<R*>& q, R* r);
+    void park(int kind, void* req);
+    void worker_main(Worker* w);
+    void service_main(Service* s);
     rtk_ctx* ctx;
-    rtk_ctx* lane[2] = {nullptr, nullptr};   // forks of ctx: the three services of a wave run concurrently
-    std::mutex mu;
-    std::condition_variable cv_broker, cv_worker;
-    size_t active = 0, waiting = 0;
-    uint64_t epoch = 0;
-    std::vector<DistReq*> q_dist;
-    std::vector<PathReq*> q_path;
-    std::vector<SubgraphReq*> q_sub;
-    std::string error;
+    std::vector<Service*> services[3];   // 0 dist (K4), 1 path (K5), 2 subgraph (K2/K3+K4)
+    std::vector<Worker*> workers;
+    std::string task_error;    // first exception that escaped a task
+    // per run()
+    size_t n_tasks = 0, cap_per_worker = 1;
+    size_t next_task = 0;      // guarded by mu_task (tasks are handed out in index order)
+    std::mutex mu_task;
+    const std::function<void(size_t)>* task_fn = nullptr;
 };
 
 GpuBroker* current_broker();   // thread-local: set while a worker thread runs a task

@@ -19,6 +19,8 @@
 #include "lookup.cuh"
 #include "rtk_host_common.hpp"
 #include "traverse.hpp"
+#include <chrono>
+
 #include "broker.hpp"
 
 namespace rtk {
@@ -918,11 +920,11 @@ void run_piece(const Ctx& C, const ReadJob& J, Piece& P) {
 
 }  // namespace
 
-// reads in flight per batch (= host threads parked on the GPU broker); RTK_CORRECT_THREADS overrides
+// weak regions in flight per batch (= fibers parked on the GPU broker); RTK_CORRECT_INFLIGHT overrides
 static unsigned correct_threads() {
-    const char* e = getenv("RTK_CORRECT_THREADS");
-    const int v = e ? atoi(e) : 1024;
-    return (unsigned)std::max(1, std::min(v, 8192));
+    const char* e = getenv("RTK_CORRECT_INFLIGHT");
+    const int v = e ? atoi(e) : 32768;
+    return (unsigned)std::max(1, std::min(v, 1 << 20));
 }
 
 // ------------------------------------------------------------------ batch driver: the per-read body of search() (src/Ratatosk.cpp:808-867)
@@ -933,6 +935,9 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
     const rtk_graph_view& g = ctx->host_graph->view;
     if (opt.k != g.k) throw std::invalid_argument("rtk_opt.k does not match the graph's k");
     const bool pass2 = (pass == 2);
+#ifndef RTK_HOSTSIM
+    const uint64_t launches0 = g_launches, h2d0 = g_h2d_bytes, d2h0 = g_d2h_bytes;
+#endif
     const size_t max_km_cov = std::max<size_t>(ctx->host_graph->hdr.max_km_cov_graph, opt.max_km_cov);  // src/Ratatosk.cpp:625
     out_seq.assign(n_reads, std::string());
     out_qual.assign(n_reads, std::string());
@@ -958,7 +963,9 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
         for (uint32_t r = 0; r < n_reads; ++r) { pool += out_seq[r]; off.push_back(pool.size()); }
         pool.push_back('\0');
         std::vector<std::vector<rtk_hit>> solid, weak;
+        const auto t_seeds = std::chrono::steady_clock::now();
         get_seeds_host(ctx, l_opt, pass, n_reads, pool.data(), off.data(), solid, weak, stats);
+        const auto t_broker = std::chrono::steady_clock::now();
         // every region of every read is one broker task: regions run concurrently on host threads, their GPU requests
         // are served in waves (broker.hpp); pieces are concatenated in read order afterwards
         Ctx C{ctx, g, l_opt, TraverseOpt(), pass2, max_km_cov};
@@ -979,8 +986,16 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
             out_seq[r] = std::move(ns[r]);
             out_qual[r] = std::move(nq[r]);
         }
-        if (stats) { stats[5] += broker.waves; stats[6] += broker.jobs; }
+        if (stats) {
+            stats[5] += broker.waves; stats[6] += broker.jobs;
+            for (int s3 = 0; s3 < 3; ++s3) stats[7 + s3] += broker.kernel_ns[s3];
+            stats[10] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_broker - t_seeds).count();
+            stats[11] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_broker).count();
+        }
     }
+#ifndef RTK_HOSTSIM
+    if (stats) { stats[12] += g_h2d_bytes - h2d0; stats[13] += g_d2h_bytes - d2h0; stats[14] += g_launches - launches0; }
+#endif
 }
 
 }  // namespace rtk

@@ -30,6 +30,7 @@ template <int G> static void launch_class(rtk_ctx* c, int k, rtk_myers_params p,
     p.n = n;
     const uint64_t threads = (uint64_t)n * G;
     const uint32_t grid = (uint32_t)((threads + RTK_MYERS_THREADS - 1) / RTK_MYERS_THREADS);
+    ++g_launches;
     rtk_myers_kernel<G><<<grid, RTK_MYERS_THREADS, 0, side_stream(c, k)>>>(p);
     RTK_CUDA(cudaGetLastError());
     fan_in(c, k);
@@ -52,23 +53,23 @@ void myers_run(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const Myers
     B[7].reserve(pl.hb_off[n] + 16);
     cudaStream_t st = c->stream;
     uint64_t* d_off = B[2].as<uint64_t>();
-    RTK_CUDA(cudaMemcpyAsync(d_off, j.q_beg, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    RTK_CUDA(cudaMemcpyAsync(d_off + (n + 1), j.t_beg, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    RTK_CUDA(cudaMemcpyAsync(d_off + 2 * (n + 1), pl.ends_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    RTK_CUDA(cudaMemcpyAsync(d_off + 3 * (n + 1), pl.hb_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    RTK_CUDA(counted_memcpy_async(d_off, j.q_beg, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    RTK_CUDA(counted_memcpy_async(d_off + (n + 1), j.t_beg, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    RTK_CUDA(counted_memcpy_async(d_off + 2 * (n + 1), pl.ends_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    RTK_CUDA(counted_memcpy_async(d_off + 3 * (n + 1), pl.hb_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
     uint32_t* d_len = (uint32_t*)(d_off + 4 * (n + 1));  // q_len[n+1] | t_len[n+1]
-    RTK_CUDA(cudaMemcpyAsync(d_len, j.q_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    RTK_CUDA(cudaMemcpyAsync(d_len + (n + 1), j.t_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    RTK_CUDA(counted_memcpy_async(d_len, j.q_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    RTK_CUDA(counted_memcpy_async(d_len + (n + 1), j.t_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     int32_t* d_kmax = B[3].as<int32_t>();
     uint8_t* d_mode = (uint8_t*)(d_kmax + n);
-    if (j.kmax) RTK_CUDA(cudaMemcpyAsync(d_kmax, j.kmax, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (j.kmax) RTK_CUDA(counted_memcpy_async(d_kmax, j.kmax, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     else RTK_CUDA(cudaMemsetAsync(d_kmax, 0xff, (size_t)n * 4, st));
-    RTK_CUDA(cudaMemcpyAsync(d_mode, j.mode, n, cudaMemcpyHostToDevice, st));
+    RTK_CUDA(counted_memcpy_async(d_mode, j.mode, n, cudaMemcpyHostToDevice, st));
     std::vector<uint32_t> order_all;
     uint32_t cls_off[7] = {0};
     for (int k = 0; k < 6; ++k) { cls_off[k] = (uint32_t)order_all.size(); order_all.insert(order_all.end(), pl.order[k].begin(), pl.order[k].end()); }
     cls_off[6] = (uint32_t)order_all.size();
-    if (!order_all.empty()) RTK_CUDA(cudaMemcpyAsync(B[4].p, order_all.data(), order_all.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!order_all.empty()) RTK_CUDA(counted_memcpy_async(B[4].p, order_all.data(), order_all.size() * 4, cudaMemcpyHostToDevice, st));
     int32_t* d_dist = B[5].as<int32_t>();
     int32_t* d_nends = d_dist + n;
     RTK_CUDA(cudaMemsetAsync(d_dist, 0xff, (size_t)n * 8, st));
@@ -89,7 +90,7 @@ void myers_run(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const Myers
     launch_class<1>(c, 0, p, d_order + cls_off[0], cls_off[1] - cls_off[0]);
     RTK_CUDA(cudaEventRecord(c->ev1, st));
     std::vector<int32_t> h_dn((size_t)n * 2 + 2);
-    RTK_CUDA(cudaMemcpyAsync(h_dn.data(), d_dist, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    RTK_CUDA(counted_memcpy_async(h_dn.data(), d_dist, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     RTK_CUDA(cudaStreamSynchronize(st));
     if (kernel_ms) RTK_CUDA(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
     // alignments with an empty side are answered here (edlibAlign's special case)
@@ -115,11 +116,12 @@ void myers_run(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const Myers
         // trivial alignments wrote nothing on the device: their n_ends is 0 for the gather
         std::vector<int32_t> ne(h_dn.begin() + n, h_dn.begin() + 2 * (size_t)n);
         for (uint32_t a : pl.trivial) ne[a] = 0;
-        RTK_CUDA(cudaMemcpyAsync(d_nends, ne.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_out_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(d_nends, ne.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(d_out_off, off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        ++g_launches;
         rtk_compact_ends_kernel<<<n, 64, 0, st>>>(p.ends, p.ends_off, d_nends, d_out_off, d_out, n);
         RTK_CUDA(cudaGetLastError());
-        RTK_CUDA(cudaMemcpyAsync(out, d_out, off[n] * 4, cudaMemcpyDeviceToHost, st));
+        RTK_CUDA(counted_memcpy_async(out, d_out, off[n] * 4, cudaMemcpyDeviceToHost, st));
         RTK_CUDA(cudaStreamSynchronize(st));
     }
     for (size_t i = 0; i < pl.trivial.size(); ++i) out[off[pl.trivial[i]]] = triv_end[i];
@@ -146,8 +148,8 @@ extern "C" int rtk_edlib_batch(rtk_ctx* c, uint32_t n, const char* q_pool, const
         for (uint32_t i = 0; i < n; ++i) { qlen[i] = (uint32_t)(q_off[i + 1] - q_off[i]); tlen[i] = (uint32_t)(t_off[i + 1] - t_off[i]); }
         c->d_aux[0].reserve(qb + 16);
         c->d_aux[1].reserve(tb + 16);
-        RTK_CUDA(cudaMemcpyAsync(c->d_aux[0].p, q_pool + q_off[0], qb, cudaMemcpyHostToDevice, c->stream));
-        RTK_CUDA(cudaMemcpyAsync(c->d_aux[1].p, t_pool + t_off[0], tb, cudaMemcpyHostToDevice, c->stream));
+        RTK_CUDA(counted_memcpy_async(c->d_aux[0].p, q_pool + q_off[0], qb, cudaMemcpyHostToDevice, c->stream));
+        RTK_CUDA(counted_memcpy_async(c->d_aux[1].p, t_pool + t_off[0], tb, cudaMemcpyHostToDevice, c->stream));
         MyersJobs j{n, qrel.data(), qlen.data(), trel.data(), tlen.data(), mode, kmax};
         float kms = 0.f;
         myers_run(c, c->d_aux[0].as<char>(), c->d_aux[1].as<char>(), j, dist, true, end_loc, end_off, &kms);

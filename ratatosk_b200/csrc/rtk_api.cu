@@ -13,6 +13,8 @@
 
 namespace rtk {
 
+std::atomic<uint64_t> g_launches{0}, g_h2d_bytes{0}, g_d2h_bytes{0};
+
 
 static inline double now_ns() {
     return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -41,7 +43,7 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
         return 0;
     }
     ctx->d_tiles.reserve(tiles.size() * 4);
-    RTK_CUDA(cudaMemcpyAsync(ctx->d_tiles.p, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RTK_CUDA(counted_memcpy_async(ctx->d_tiles.p, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 
     uint64_t cap = std::max<uint64_t>(1u << 20, exact ? total + 1024 : 2 * total + 1024);
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -61,6 +63,7 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
         // grid: whole waves of resident CTAs (148 SMs x 8 CTAs of 256 threads), grid-stride over tiles
         const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * 8u);
         RTK_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        ++g_launches;
         if (exact) {
             if (k <= 32) rtk_k1_exact_kernel<uint64_t><<<grid, RTK_K1_THREADS, 0, ctx->stream>>>(p);
             else rtk_k1_exact_kernel<rtk_u128><<<grid, RTK_K1_THREADS, 0, ctx->stream>>>(p);
@@ -71,7 +74,7 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
         RTK_CUDA(cudaGetLastError());
         RTK_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
         unsigned long long cnt[2];
-        RTK_CUDA(cudaMemcpyAsync(cnt, ctx->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+        RTK_CUDA(counted_memcpy_async(cnt, ctx->d_counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
         RTK_CUDA(cudaStreamSynchronize(ctx->stream));
         if (kernel_ms) RTK_CUDA(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
         if (n_probes) *n_probes = cnt[1];
@@ -89,16 +92,24 @@ void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, 
     // offsets relative to the start of this batch's pool
     std::vector<uint64_t> rel(n_reads + 1);
     for (uint32_t i = 0; i <= n_reads; ++i) rel[i] = seq_off[i] - seq_off[0];
-    ctx->d_seq.reserve(total + 16);
-    ctx->d_seq_off.reserve((n_reads + 1) * 8);
-    RTK_CUDA(cudaMemcpyAsync(ctx->d_seq.p, seq_pool + seq_off[0], total, cudaMemcpyHostToDevice, ctx->stream));
-    RTK_CUDA(cudaMemcpyAsync(ctx->d_seq_off.p, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const char* d_seq;
+    const uint64_t* d_off;
+    if (flags == RTK_SEARCH_EXACT && ctx->resident_seq && ctx->resident_n == n_reads && ctx->resident_total == total) {
+        d_seq = ctx->resident_seq; d_off = ctx->resident_off;   // the caller's copy in HBM (same bytes as seq_pool)
+        ctx->resident_seq = nullptr;
+    } else {
+        ctx->d_seq.reserve(total + 16);
+        ctx->d_seq_off.reserve((n_reads + 1) * 8);
+        RTK_CUDA(counted_memcpy_async(ctx->d_seq.p, seq_pool + seq_off[0], total, cudaMemcpyHostToDevice, ctx->stream));
+        RTK_CUDA(counted_memcpy_async(ctx->d_seq_off.p, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        d_seq = ctx->d_seq.as<char>(); d_off = ctx->d_seq_off.as<uint64_t>();
+    }
     uint64_t probes = 0;
     float kms = 0.f;
-    const uint64_t n_raw = k1_launch(ctx, n_reads, ctx->d_seq.as<char>(), ctx->d_seq_off.as<uint64_t>(), rel.data(), flags, &probes, &kms);
+    const uint64_t n_raw = k1_launch(ctx, n_reads, d_seq, d_off, rel.data(), flags, &probes, &kms);
     std::vector<RawHit> raw(n_raw);
     if (n_raw) {
-        RTK_CUDA(cudaMemcpyAsync(raw.data(), ctx->d_hits.p, n_raw * sizeof(RawHit), cudaMemcpyDeviceToHost, ctx->stream));
+        RTK_CUDA(counted_memcpy_async(raw.data(), ctx->d_hits.p, n_raw * sizeof(RawHit), cudaMemcpyDeviceToHost, ctx->stream));
         RTK_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     resolve_batch(ctx->host_graph->view, n_reads, seq_pool, seq_off, flags, raw, per_read);
@@ -131,6 +142,9 @@ int rtk_ctx_create(int device, rtk_ctx** out) {
         if (e != cudaSuccess || n == 0) throw CudaError(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)");
         if (device < 0 || device >= n) throw std::invalid_argument("device index out of range");
         RTK_CUDA(cudaSetDevice(device));
+        // the GPU service threads of the correction broker wait on their streams while host worker threads need
+        // the cores: block in the driver instead of spinning (RTK_SPIN_SYNC=1 restores the default)
+        if (!getenv("RTK_SPIN_SYNC")) { if (cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync) != cudaSuccess) cudaGetLastError(); }
         rtk_ctx* c = new rtk_ctx();
         c->device = device;
         RTK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -188,7 +202,7 @@ int rtk_graph_upload(rtk_ctx* c, const rtk_host_graph* g) {
         if (c->owns_slab && c->d_slab) RTK_CUDA(cudaFree((void*)c->d_slab));
         void* d = nullptr;
         RTK_CUDA(cudaMalloc(&d, g->slab.bytes));
-        RTK_CUDA(cudaMemcpyAsync(d, g->slab.data, g->slab.bytes, cudaMemcpyHostToDevice, c->stream));
+        RTK_CUDA(counted_memcpy_async(d, g->slab.data, g->slab.bytes, cudaMemcpyHostToDevice, c->stream));
         RTK_CUDA(cudaStreamSynchronize(c->stream));
         c->d_slab = (const unsigned char*)d;
         c->owns_slab = true;
@@ -208,7 +222,7 @@ int rtk_graph_adopt_device(rtk_ctx* c, const void* dev_slab, uint64_t bytes) {
         if (c->host_copy.data) { free(c->host_copy.data); c->host_copy.data = nullptr; }
         c->host_copy.data = (unsigned char*)aligned_alloc(256, (bytes + 255) & ~(uint64_t)255);
         c->host_copy.bytes = bytes;
-        RTK_CUDA(cudaMemcpyAsync(c->host_copy.data, dev_slab, bytes, cudaMemcpyDeviceToHost, c->stream));
+        RTK_CUDA(counted_memcpy_async(c->host_copy.data, dev_slab, bytes, cudaMemcpyDeviceToHost, c->stream));
         RTK_CUDA(cudaStreamSynchronize(c->stream));
         c->host_graph_owned.slab = c->host_copy;
         finish_host_graph(&c->host_graph_owned);
@@ -260,6 +274,18 @@ int rtk_get_seeds(rtk_ctx* c, const rtk_opt* opt, int pass, uint32_t n_reads, co
         flatten_hits(solid, &out->solid, &out->solid_off);
         flatten_hits(weak, &out->weak, &out->weak_off);
     });
+}
+
+int rtk_correct_batch_resident(rtk_ctx* c, const rtk_opt* opt, int pass, uint32_t n_reads, const char* seq_pool,
+                               const uint64_t* seq_off, const char* dev_seq_pool, const uint64_t* dev_seq_off,
+                               const char* qual_pool, const uint64_t* qual_off, char** out_seq_pool, char** out_qual_pool,
+                               uint64_t** out_off, uint64_t* stats) {
+    if (!c || !seq_off || !dev_seq_pool || !dev_seq_off) { set_error("null argument"); return RTK_EINVAL; }
+    c->resident_seq = dev_seq_pool; c->resident_off = dev_seq_off; c->resident_n = n_reads;
+    c->resident_total = seq_off[n_reads] - seq_off[0];
+    const int rc = rtk_correct_batch(c, opt, pass, n_reads, seq_pool, seq_off, qual_pool, qual_off, out_seq_pool, out_qual_pool, out_off, stats);
+    c->resident_seq = nullptr;
+    return rc;
 }
 
 }  // extern "C"

@@ -5,6 +5,7 @@
 #endif
 #include <stdint.h>
 
+#include <atomic>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -39,6 +40,13 @@ struct CudaError : std::runtime_error {
             throw rtk::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +    \
                                  std::to_string(__LINE__) + ")");                                            \
     } while (0)
+
+// process-wide tallies reported through the stats of rtk_correct_batch: kernels launched, bytes copied H2D / D2H
+extern std::atomic<uint64_t> g_launches, g_h2d_bytes, g_d2h_bytes;
+inline cudaError_t counted_memcpy_async(void* dst, const void* src, size_t n, cudaMemcpyKind kind, cudaStream_t st) {
+    (kind == cudaMemcpyHostToDevice ? g_h2d_bytes : g_d2h_bytes) += n;
+    return cudaMemcpyAsync(dst, src, n, kind, st);
+}
 
 // grow-only device / pinned-host buffers
 struct DevBuf {
@@ -103,6 +111,11 @@ struct rtk_ctx {
     rtk::DevBuf d_seq, d_seq_off, d_tiles, d_hits, d_counters, d_aux[8], d_sub[8];
     rtk::PinBuf h_pin[4];
     int sm_count = 148;
+    // reads of the next exact sweep already resident in HBM (rtk_correct_batch_resident); consumed once
+    const char* resident_seq = nullptr;
+    const uint64_t* resident_off = nullptr;
+    uint32_t resident_n = 0;
+    uint64_t resident_total = 0;
 };
 #endif
 

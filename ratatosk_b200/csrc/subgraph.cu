@@ -29,8 +29,8 @@ extern "C" int rtk_explore_subgraph_batch(rtk_ctx* c, uint32_t n_calls, const rt
         S[1].reserve(n_pids * 4 + 16);
         S[2].reserve((size_t)n_calls * 12 + 16);
         S[3].reserve((size_t)(n_calls + 1) * 16 + 16);
-        RTK_CUDA(cudaMemcpyAsync(S[0].p, calls, (size_t)n_calls * sizeof(rtk_subgraph_call_t), cudaMemcpyHostToDevice, st));
-        if (n_pids) RTK_CUDA(cudaMemcpyAsync(S[1].p, pid_pool, n_pids * 4, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(S[0].p, calls, (size_t)n_calls * sizeof(rtk_subgraph_call_t), cudaMemcpyHostToDevice, st));
+        if (n_pids) RTK_CUDA(counted_memcpy_async(S[1].p, pid_pool, n_pids * 4, cudaMemcpyHostToDevice, st));
         rtk_dfs_params p;
         const rtk_graph_view& g = c->dview;
         p.unitig_off = g.unitig_off; p.pool = g.pool; p.shared = g.shared; p.adj = g.adj; p.gset_of = g.gset_of;
@@ -41,13 +41,14 @@ extern "C" int rtk_explore_subgraph_batch(rtk_ctx* c, uint32_t n_calls, const rt
         p.n_cand = d_ncand; p.n_chars = d_nchars; p.cand_off = nullptr; p.char_off = nullptr; p.cands = nullptr; p.chars = nullptr;
         const uint32_t grid = (n_calls + RTK_DFS_WARPS - 1) / RTK_DFS_WARPS;
         RTK_CUDA(cudaEventRecord(c->ev0, st));
+        if (n_calls) ++g_launches;
         if (n_calls) rtk_dfs_kernel<false><<<grid, RTK_DFS_WARPS * 32, 0, st>>>(p);
         RTK_CUDA(cudaGetLastError());
         std::vector<uint64_t> nchars(n_calls);
         std::vector<uint32_t> ncand(n_calls);
         if (n_calls) {
-            RTK_CUDA(cudaMemcpyAsync(nchars.data(), d_nchars, (size_t)n_calls * 8, cudaMemcpyDeviceToHost, st));
-            RTK_CUDA(cudaMemcpyAsync(ncand.data(), d_ncand, (size_t)n_calls * 4, cudaMemcpyDeviceToHost, st));
+            RTK_CUDA(counted_memcpy_async(nchars.data(), d_nchars, (size_t)n_calls * 8, cudaMemcpyDeviceToHost, st));
+            RTK_CUDA(counted_memcpy_async(ncand.data(), d_ncand, (size_t)n_calls * 4, cudaMemcpyDeviceToHost, st));
         }
         RTK_CUDA(cudaStreamSynchronize(st));
         std::vector<uint64_t> cand_off(n_calls + 1, 0), char_off(n_calls + 1, 0);
@@ -57,15 +58,16 @@ extern "C" int rtk_explore_subgraph_batch(rtk_ctx* c, uint32_t n_calls, const rt
         S[4].reserve(n_cands * sizeof(rtk_cand) + 16);
         S[5].reserve(ref_bytes + n_chars + 16);
         uint64_t* d_off = S[3].as<uint64_t>();
-        RTK_CUDA(cudaMemcpyAsync(d_off, cand_off.data(), (size_t)(n_calls + 1) * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_off + (n_calls + 1), char_off.data(), (size_t)(n_calls + 1) * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(S[5].p, ref_pool, ref_bytes, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(d_off, cand_off.data(), (size_t)(n_calls + 1) * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(d_off + (n_calls + 1), char_off.data(), (size_t)(n_calls + 1) * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(S[5].p, ref_pool, ref_bytes, cudaMemcpyHostToDevice, st));
         p.cand_off = d_off; p.char_off = d_off + (n_calls + 1); p.cands = S[4].as<rtk_cand>(); p.chars = S[5].as<char>() + ref_bytes;
+        if (n_calls) ++g_launches;
         if (n_calls) rtk_dfs_kernel<true><<<grid, RTK_DFS_WARPS * 32, 0, st>>>(p);
         RTK_CUDA(cudaGetLastError());
         RTK_CUDA(cudaEventRecord(c->ev1, st));
         std::vector<rtk_cand> cands(n_cands);
-        if (n_cands) RTK_CUDA(cudaMemcpyAsync(cands.data(), S[4].p, n_cands * sizeof(rtk_cand), cudaMemcpyDeviceToHost, st));
+        if (n_cands) RTK_CUDA(counted_memcpy_async(cands.data(), S[4].p, n_cands * sizeof(rtk_cand), cudaMemcpyDeviceToHost, st));
         RTK_CUDA(cudaStreamSynchronize(st));
         float dfs_ms = 0.f;
         RTK_CUDA(cudaEventElapsedTime(&dfs_ms, c->ev0, c->ev1));

@@ -17,6 +17,7 @@ template <int G, bool LC> static void launch_fill(rtk_ctx* c, int k, rtk_fill_pa
     p.order = d_order;
     p.n = n;
     const uint64_t threads = (uint64_t)n * G;
+    ++g_launches;
     rtk_myers_fill_kernel<G, LC><<<(uint32_t)((threads + RTK_MYERS_THREADS - 1) / RTK_MYERS_THREADS), RTK_MYERS_THREADS, 0, side_stream(c, k)>>>(p);
     RTK_CUDA(cudaGetLastError());
     fan_in(c, k);
@@ -53,14 +54,14 @@ struct CudaTbBackend : TbBackend {
         S[6].reserve((size_t)(n + 1) * 8 + pl.hb_off[n] + 16);
         d_off = S[0].as<uint64_t>();
         d_len = S[1].as<uint32_t>();
-        RTK_CUDA(cudaMemcpyAsync(d_off, qb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_off + (n + 1), tb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_off + 2 * (n + 1), pl.mat_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_off + 3 * (n + 1), pl.ops_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_off + 4 * (n + 1), pl.hb_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_len, ql.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(d_len + (n + 1), tl.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(S[2].p, pl.ids.data(), pl.ids.size() * 4, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(d_off, qb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(d_off + (n + 1), tb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(d_off + 2 * (n + 1), pl.mat_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(d_off + 3 * (n + 1), pl.ops_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(d_off + 4 * (n + 1), pl.hb_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(d_len, ql.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(d_len + (n + 1), tl.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(S[2].p, pl.ids.data(), pl.ids.size() * 4, cudaMemcpyHostToDevice, st));
         uint32_t* d_opslen = S[6].as<uint32_t>();
         RTK_CUDA(cudaMemsetAsync(d_opslen, 0, (size_t)(n + 1) * 8, st));
         fp.q_pool = d_q; fp.q_beg = d_off; fp.q_len = d_len; fp.t_pool = d_t; fp.t_beg = d_off + (n + 1); fp.t_len = d_len + (n + 1);
@@ -93,14 +94,15 @@ struct CudaTbBackend : TbBackend {
         tp.q_len = d_len; tp.t_len = d_len + (n + 1); tp.ids = S[2].as<uint32_t>(); tp.n = n; tp.mat_off = d_off + 2 * (n + 1);
         tp.mat = S[3].as<ulonglong2>(); tp.anchor = S[4].as<int32_t>(); tp.dist = fp.dist; tp.ops_off = d_off + 3 * (n + 1);
         tp.ops = S[5].as<uint8_t>(); tp.ops_len = S[6].as<uint32_t>();
+        ++g_launches;
         rtk_traceback_kernel<<<(n + 127) / 128, 128, 0, st>>>(tp);
         RTK_CUDA(cudaGetLastError());
         RTK_CUDA(cudaEventRecord(c->ev1, st));
         std::vector<uint32_t> h_len(n + 1);
         std::vector<uint8_t> h_ops(pl.ops_off[n] + 1);
-        RTK_CUDA(cudaMemcpyAsync(h_len.data(), tp.ops_len, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        RTK_CUDA(cudaMemcpyAsync(dist.data(), fp.dist, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        if (pl.ops_off[n]) RTK_CUDA(cudaMemcpyAsync(h_ops.data(), S[5].p, pl.ops_off[n], cudaMemcpyDeviceToHost, st));
+        RTK_CUDA(counted_memcpy_async(h_len.data(), tp.ops_len, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        RTK_CUDA(counted_memcpy_async(dist.data(), fp.dist, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (pl.ops_off[n]) RTK_CUDA(counted_memcpy_async(h_ops.data(), S[5].p, pl.ops_off[n], cudaMemcpyDeviceToHost, st));
         RTK_CUDA(cudaStreamSynchronize(st));
         float t = 0.f;
         RTK_CUDA(cudaEventElapsedTime(&t, c->ev0, c->ev1));
@@ -124,8 +126,8 @@ struct CudaTbBackend : TbBackend {
         RTK_CUDA(cudaEventRecord(c->ev1, st));
         std::vector<uint64_t> cells(pl.cells * 2 + 2);
         std::vector<int32_t> anchor(pl.cells + 1);
-        RTK_CUDA(cudaMemcpyAsync(cells.data(), c->d_sub[3].p, pl.cells * 16, cudaMemcpyDeviceToHost, st));
-        RTK_CUDA(cudaMemcpyAsync(anchor.data(), c->d_sub[4].p, pl.cells * 4, cudaMemcpyDeviceToHost, st));
+        RTK_CUDA(counted_memcpy_async(cells.data(), c->d_sub[3].p, pl.cells * 16, cudaMemcpyDeviceToHost, st));
+        RTK_CUDA(counted_memcpy_async(anchor.data(), c->d_sub[4].p, pl.cells * 4, cudaMemcpyDeviceToHost, st));
         RTK_CUDA(cudaStreamSynchronize(st));
         float t = 0.f;
         RTK_CUDA(cudaEventElapsedTime(&t, c->ev0, c->ev1));
@@ -159,8 +161,8 @@ extern "C" int rtk_edlib_path_batch(rtk_ctx* c, uint32_t n, const char* q_pool, 
         for (uint32_t i = 0; i < n; ++i) { qlen[i] = (uint32_t)(q_off[i + 1] - q_off[i]); tlen[i] = (uint32_t)(t_off[i + 1] - t_off[i]); }
         c->d_aux[0].reserve(qb + 16);
         c->d_aux[1].reserve(tb + 16);
-        RTK_CUDA(cudaMemcpyAsync(c->d_aux[0].p, q_pool + q_off[0], qb, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(c->d_aux[1].p, t_pool + t_off[0], tb, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(c->d_aux[0].p, q_pool + q_off[0], qb, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(c->d_aux[1].p, t_pool + t_off[0], tb, cudaMemcpyHostToDevice, st));
         // 1. SHW alignments: distance + first end column from K4
         std::vector<uint32_t> shw;
         for (uint32_t a = 0; a < n; ++a) if (mode[a] == 1) shw.push_back(a);
@@ -192,8 +194,8 @@ extern "C" int rtk_edlib_path_batch(rtk_ctx* c, uint32_t n, const char* q_pool, 
             for (uint32_t i = 0; i < teff[a]; ++i) rt[trel[a] + i] = ts[teff[a] - 1 - i];
         }
         c->d_sub[7].reserve(qb + tb + 32);
-        RTK_CUDA(cudaMemcpyAsync(c->d_sub[7].p, rq.data(), qb, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(cudaMemcpyAsync(c->d_sub[7].as<char>() + qb + 8, rt.data(), tb, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(c->d_sub[7].p, rq.data(), qb, cudaMemcpyHostToDevice, st));
+        RTK_CUDA(counted_memcpy_async(c->d_sub[7].as<char>() + qb + 8, rt.data(), tb, cudaMemcpyHostToDevice, st));
         // 3. solve the non-trivial problems
         std::vector<uint32_t> ids;
         for (uint32_t a = 0; a < n; ++a) { flags[a] = 0; if (qlen[a] != 0 && tlen[a] != 0 && teff[a] != 0) ids.push_back(a); }
