@@ -167,20 +167,36 @@ size_t next_kmer(const std::string& s, size_t p, size_t k) {
 }
 
 // ------------------------------------------------------------------ ResultCorrection (src/ResultCorrection.hpp)
+// pos_corrected_old_seq is a set of positions in the reference (one Roaring / std::set entry per base); here a sorted
+// vector of unique positions with the same observable behaviour (size, ordered scan, lower_bound)
 struct ResultCorrection {
-    std::set<uint32_t> pos;  // pos_corrected_old_seq
+    std::vector<uint32_t> pos;  // pos_corrected_old_seq, ascending, unique
     std::string seq, qual;
     IdSet all_pids;          // WeightsPairID::all_pids (the only part that influences results)
     size_t old_seq_len;
     bool is_corrected = false;
     explicit ResultCorrection(size_t n) : old_seq_len(n) {}
-    void add_range(uint64_t a, uint64_t b) { if (b <= a) return; for (uint64_t x = a; x < b; ++x) pos.insert((uint32_t)x); }
+    void add_range(uint64_t a, uint64_t b) {
+        if (b <= a) return;
+        if (pos.empty() || pos.back() < (uint32_t)a) {   // the usual case: regions are emitted left to right
+            pos.reserve(pos.size() + (size_t)(b - a));
+            for (uint64_t x = a; x < b; ++x) pos.push_back((uint32_t)x);
+            return;
+        }
+        std::vector<uint32_t> add, merged;
+        add.reserve((size_t)(b - a));
+        for (uint64_t x = a; x < b; ++x) add.push_back((uint32_t)x);
+        std::sort(add.begin(), add.end());   // a 32-bit wrap of the range keeps set semantics
+        add.erase(std::unique(add.begin(), add.end()), add.end());
+        merged.reserve(pos.size() + add.size());
+        std::set_union(pos.begin(), pos.end(), add.begin(), add.end(), std::back_inserter(merged));
+        pos.swap(merged);
+    }
     size_t nb_corrected() const { return pos.size(); }
     ResultCorrection& reverse_complement() {
         if (seq.length() != 0) {
-            std::set<uint32_t> t;
-            for (uint32_t p : pos) t.insert((uint32_t)(old_seq_len - p - 1));
-            pos.swap(t);
+            for (uint32_t& p : pos) p = (uint32_t)(old_seq_len - p - 1);
+            std::sort(pos.begin(), pos.end());   // a plain reversal unless a position lies beyond old_seq_len (wraps, as in the set)
             seq = rc_string(seq);
             std::reverse(qual.begin(), qual.end());
         }
@@ -188,12 +204,12 @@ struct ResultCorrection {
     }
     size_t len_corrected_region(size_t p) const {
         size_t next = p;
-        for (auto it = pos.lower_bound((uint32_t)p); it != pos.end() && *it < old_seq_len && *it == next; ++it) ++next;
+        for (auto it = std::lower_bound(pos.begin(), pos.end(), (uint32_t)p); it != pos.end() && *it < old_seq_len && *it == next; ++it) ++next;
         return next - p;
     }
     size_t len_uncorrected_region(size_t p) const {
         if (p >= old_seq_len) return 0;
-        auto it = pos.lower_bound((uint32_t)p);
+        auto it = std::lower_bound(pos.begin(), pos.end(), (uint32_t)p);
         if (it == pos.end()) return old_seq_len - p;
         return std::min<size_t>(*it, old_seq_len) - p;
     }

@@ -18,6 +18,11 @@ unsigned host_threads() {
     static unsigned n = [] {
         const char* e = getenv("RTK_HOST_THREADS");
         unsigned v = e ? (unsigned)atoi(e) : std::thread::hardware_concurrency();
+        if (!e) {   // one process per GPU (torchrun): the ranks of a node share its cores
+            const char* lws = getenv("LOCAL_WORLD_SIZE");
+            const unsigned ranks = lws ? (unsigned)atoi(lws) : 1u;
+            if (ranks > 1) v = std::max(2u, v / ranks);
+        }
         if (v == 0) v = 1;
         return std::min(v, 64u);
     }();
