@@ -353,7 +353,7 @@ def main():
         achieved = alg_bytes / (k1_ns * 1e-9) / 1e9 if k1_ns else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_inexact_traffic.json"))).get("dram_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_inexact_traffic.json")))["dram_bytes_per_probe"] * probes
         except Exception:
             pass
         fam = {"K1 lookup sweep (rtk_k1_exact/inexact_kernel)": st_res[2] / K_ / 1e6,
@@ -388,9 +388,9 @@ def main():
                              "algorithmic_bytes_per_step": alg_bytes,
                              "share_of_step_gpu_time": (st_res[2] / K_ / 1e6) / tot_fam,
                              "note": "the metric names k-mer lookups vs the HBM roofline, so K1 is the kernel reported here; by GPU "
-                                     "time the step is dominated by the bit-parallel Myers kernels (integer-issue bound, HBM "
-                                     "traffic negligible) - see `kernels`.  The 97 MB E. coli index is L2-resident, so DRAM traffic "
-                                     "is far below the algorithmic bytes"},
+                                     "time the step is dominated by the bit-parallel Myers kernels (latency-bound launches of a few CTAs, HBM "
+                                     "traffic negligible) - see `kernels` and profiles/.  traffic = measured DRAM bytes per probe (ncu, "
+                                     "profiles/k1_inexact_traffic.json) x the probes of this launch"},
                 "kernels": {"gpu_ms_per_step": fam, "share": {k: v / tot_fam for k, v in fam.items()},
                             "note": "CUDA-event time on each service's launching stream; the services run concurrently, so the "
                                     "sum can exceed the step's wall time"}}

@@ -147,7 +147,7 @@ int rtk_edlib_path_batch(rtk_ctx* ctx, uint32_t n, const char* q_pool, const uin
                          const uint64_t* t_off, const uint8_t* mode, int32_t* dist, int32_t* end_loc, uint8_t** ops,
                          uint64_t** ops_off, uint8_t* flags, uint64_t* stats);
 
-/* ---- K2/K3 + K4: exploreSubGraph (src/GraphTraversal.cpp:456-587) ----
+/* ---- K2/K3 + K4: exploreSubGraph / exploreSubGraphLong (src/GraphTraversal.cpp:456-587, :589-720) ----
  * Bounded DFS from a start unitig towards an optional target unitig with colour-set threshold intersection
  * (getNumberSharedPairID >= min_cov against `pids` = WeightsPairID::all_pids), edge-flag test, and scoring of
  * every candidate by edit distance against the read window (getScorePath :867-909); returns, per call, the
@@ -162,6 +162,10 @@ typedef struct rtk_subgraph_call_t {
     uint64_t pid_off;                          /* pids = pid_pool[pid_off, pid_off+pid_len), sorted */
     uint32_t pid_len;                          /* 0 = no colour filter (all_pids.isEmpty()) */
     uint32_t min_cov;                          /* Correct_Opt::min_cov_vertices */
+    uint32_t max_len_subpath;                  /* 0: exploreSubGraph, bursts bounded by `level` unitigs (pass 1).  > 0: exploreSubGraphLong
+                                                  (src/GraphTraversal.cpp:589-720, pass 2): a partial path is expanded while it spells fewer than
+                                                  max_len_subpath = k * large_k_factor bases; `level` is ignored */
+    uint32_t reserved;
 } rtk_subgraph_call_t;
 
 typedef struct rtk_path_node {

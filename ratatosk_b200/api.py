@@ -54,7 +54,8 @@ class RtkSubgraphCall(C.Structure):
     _fields_ = [("start_unitig", C.c_uint32), ("start_strand", C.c_uint32), ("end_unitig", C.c_uint32),
                 ("end_strand", C.c_uint32), ("end_dist", C.c_uint32), ("level", C.c_uint32),
                 ("max_len_path", C.c_uint32), ("ref_len", C.c_uint32), ("ref_off", C.c_uint64),
-                ("pid_off", C.c_uint64), ("pid_len", C.c_uint32), ("min_cov", C.c_uint32)]
+                ("pid_off", C.c_uint64), ("pid_len", C.c_uint32), ("min_cov", C.c_uint32),
+                ("max_len_subpath", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class RtkPathNode(C.Structure):

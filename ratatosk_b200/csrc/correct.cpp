@@ -987,6 +987,7 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
         Ctx C{ctx, g, l_opt, TraverseOpt(), pass2, max_km_cov};
         C.topt.k = g.k; C.topt.min_cov_vertices = l_opt.min_cov_vertices; C.topt.out_qual = l_opt.out_qual; C.topt.max_qual = l_opt.max_qual;
         C.topt.weak_region_len_factor = l_opt.weak_region_len_factor; C.topt.large_k_factor = l_opt.large_k_factor; C.topt.min_score = l_opt.min_score;
+        C.topt.long_read_correct = pass2;
         std::vector<ReadJob> jobs(n_reads);
         std::vector<Piece> pieces;
         for (uint32_t r = 0; r < n_reads; ++r) {
@@ -1023,7 +1024,7 @@ extern "C" int rtk_correct_batch(rtk_ctx* ctx, const rtk_opt* opt, int pass, uin
                                  uint64_t** out_off, uint64_t* stats) {
     return guarded([&] {
         if (!ctx || !opt || !seq_pool || !seq_off || !out_seq_pool || !out_qual_pool || !out_off) throw std::invalid_argument("null argument");
-        if (pass != 1) throw std::invalid_argument("only pass 1 (k1 graph, short-read colours) is wired end to end so far");
+        if (pass != 1 && pass != 2) throw std::invalid_argument("pass must be 1 (k1 graph, short-read colours) or 2 (k2 graph, long-read colours)");
         std::vector<std::string> os, oq;
         correct_batch_host(ctx, *opt, pass, n_reads, seq_pool, seq_off, qual_pool, qual_off, os, oq, stats);
         uint64_t total = 0;

@@ -27,7 +27,7 @@ extern "C" int rtk_explore_subgraph_batch(rtk_ctx* c, uint32_t n_calls, const rt
         DevBuf* S = c->d_sub;  // [0] calls, [1] pids, [2] n_cand|n_chars, [3] cand_off|char_off, [4] cands, [5] refs + spelled paths
         S[0].reserve((size_t)n_calls * sizeof(rtk_subgraph_call_t) + 16);
         S[1].reserve(n_pids * 4 + 16);
-        S[2].reserve((size_t)n_calls * 12 + 16);
+        S[2].reserve((size_t)n_calls * 12 + 32);
         S[3].reserve((size_t)(n_calls + 1) * 16 + 16);
         RTK_CUDA(counted_memcpy_async(S[0].p, calls, (size_t)n_calls * sizeof(rtk_subgraph_call_t), cudaMemcpyHostToDevice, st));
         if (n_pids) RTK_CUDA(counted_memcpy_async(S[1].p, pid_pool, n_pids * 4, cudaMemcpyHostToDevice, st));
@@ -39,18 +39,21 @@ extern "C" int rtk_explore_subgraph_batch(rtk_ctx* c, uint32_t n_calls, const rt
         uint64_t* d_nchars = S[2].as<uint64_t>();
         uint32_t* d_ncand = (uint32_t*)(d_nchars + n_calls);
         p.n_cand = d_ncand; p.n_chars = d_nchars; p.cand_off = nullptr; p.char_off = nullptr; p.cands = nullptr; p.chars = nullptr;
+        p.overflow = d_ncand + n_calls;   // one flag after the counts, downloaded with them
+        RTK_CUDA(cudaMemsetAsync(p.overflow, 0, 4, st));
         const uint32_t grid = (n_calls + RTK_DFS_WARPS - 1) / RTK_DFS_WARPS;
         RTK_CUDA(cudaEventRecord(c->ev0, st));
         if (n_calls) ++g_launches;
         if (n_calls) rtk_dfs_kernel<false><<<grid, RTK_DFS_WARPS * 32, 0, st>>>(p);
         RTK_CUDA(cudaGetLastError());
         std::vector<uint64_t> nchars(n_calls);
-        std::vector<uint32_t> ncand(n_calls);
+        std::vector<uint32_t> ncand(n_calls + 1, 0);
         if (n_calls) {
             RTK_CUDA(counted_memcpy_async(nchars.data(), d_nchars, (size_t)n_calls * 8, cudaMemcpyDeviceToHost, st));
-            RTK_CUDA(counted_memcpy_async(ncand.data(), d_ncand, (size_t)n_calls * 4, cudaMemcpyDeviceToHost, st));
+            RTK_CUDA(counted_memcpy_async(ncand.data(), d_ncand, (size_t)(n_calls + 1) * 4, cudaMemcpyDeviceToHost, st));
         }
         RTK_CUDA(cudaStreamSynchronize(st));
+        if (ncand[n_calls]) throw std::runtime_error("exploreSubGraph: a burst exceeded the DFS capacity (RTK_DFS_MAX_NODES / RTK_DFS_STACK)");
         std::vector<uint64_t> cand_off(n_calls + 1, 0), char_off(n_calls + 1, 0);
         for (uint32_t i = 0; i < n_calls; ++i) { cand_off[i + 1] = cand_off[i] + ncand[i]; char_off[i + 1] = char_off[i] + nchars[i]; }
         const uint64_t n_cands = cand_off[n_calls], n_chars = char_off[n_calls];

@@ -31,9 +31,9 @@
 #include "flat_graph.h"
 #include "kmer.cuh"
 
-#define RTK_DFS_WARPS 4
-#define RTK_DFS_MAX_NODES 8   /* level + 1 <= 8 */
-#define RTK_DFS_STACK 32
+#define RTK_DFS_WARPS 2
+#define RTK_DFS_MAX_NODES 40  /* pass 1: level + 1 <= 5; pass 2 (long mode): a partial path of < 1.5 k bases holds <= k/2 + 1 unitigs */
+#define RTK_DFS_STACK 100     /* LIFO depth <= 3 * (nodes per partial path) + 1 */
 
 typedef rtk_subgraph_call_t rtk_subgraph_call;  // include/rtk.h
 
@@ -70,6 +70,7 @@ struct rtk_dfs_params {
     const uint64_t* char_off;  // [call] (WRITE)
     rtk_cand* cands;           // (WRITE)
     char* chars;               // (WRITE)
+    uint32_t* overflow;        // set when a call would exceed RTK_DFS_MAX_NODES / RTK_DFS_STACK (the host then fails the batch)
 };
 
 struct rtk_dfs_frame {
@@ -192,13 +193,16 @@ __global__ void __launch_bounds__(RTK_DFS_WARPS * 32) rtk_dfs_kernel(const rtk_d
             }
             // (b) non-terminal (:530-551)
             const uint32_t nlen = (f.n == 0) ? vsize : (f.path_len + vfull);
-            if (f.l != 0) {
-                if (sp < RTK_DFS_STACK && f.n + 1 < RTK_DFS_MAX_NODES) {
+            // pass 1: expand while depth remains (:530); pass 2: while the partial path spells < max_len_subpath bases (:660)
+            const bool expand = c.max_len_subpath ? (nlen < c.max_len_subpath) : (f.l != 0);
+            if (expand) {
+                if (!(sp < RTK_DFS_STACK && f.n + 1 < RTK_DFS_MAX_NODES)) { if (lane == 0) *p.overflow = 1u; }
+                else {
                     if (lane == 0) {
                         rtk_dfs_frame& nf = st[sp];
                         for (uint32_t i = 0; i < f.n; ++i) nf.nodes[i] = f.nodes[i];
                         nf.nodes[f.n] = v | (vs << 31);
-                        nf.n = f.n + 1; nf.l = f.l - 1; nf.path_len = nlen;
+                        nf.n = f.n + 1; nf.l = f.l ? f.l - 1 : 0; nf.path_len = nlen;
                     }
                     ++sp;
                     __syncwarp();

@@ -262,6 +262,7 @@ Burst explore_subgraph(rtk_ctx* ctx, const rtk_graph_view& g, const TraverseOpt&
     if (um_e.empty()) rq.call.end_unitig = RTK_NONE32;
     else { rq.call.end_unitig = um_e.unitig; rq.call.end_strand = um_e.strand; rq.call.end_dist = um_e.dist; }
     rq.call.level = level; rq.call.max_len_path = (uint32_t)max_len_path; rq.call.min_cov = opt.min_cov_vertices;
+    rq.call.max_len_subpath = opt.long_read_correct ? (uint32_t)opt.max_len_subpath() : 0u;
     rq.ref = &ref; rq.pids = &pids; rq.wrlf = opt.weak_region_len_factor;
     SubgraphResult res;
     rq.out = &res;
@@ -383,7 +384,7 @@ std::vector<GPath> explore_paths_bfs2(rtk_ctx* ctx, const rtk_graph_view& g, con
                 Burst b = explore_step(ctx, g, opt, all_pids, ref, um, p, max_len_path, level, um_e);
                 for (const auto& path : b.terminal) v_tmp.push_back(extend_with(g, p, path));
                 for (const auto& path : b.nonterminal) {
-                    if (path.size() == level) {
+                    if ((!opt.long_read_correct && path.size() == level) || (opt.long_read_correct && path.length() >= opt.max_len_subpath())) {
                         q.push(extend_with(g, p, path));
                         if (q.size() >= max_sz_stck) resize_queue(ctx, g, q, ref);
                     }
@@ -459,7 +460,7 @@ std::vector<GPath> explore_paths_bfs(rtk_ctx* ctx, const rtk_graph_view& g, cons
                         if (p_ext.length() >= min_len_path && p_ext.length() <= max_len_path) v_tmp.push_back(p_ext);
                         j += n.len;
                     }
-                    if (path.size() == level) {
+                    if ((!opt.long_read_correct && path.size() == level) || (opt.long_read_correct && path.length() >= opt.max_len_subpath())) {
                         q.push(std::move(p_ext));
                         if (q.size() >= max_sz_stck) resize_queue(ctx, g, q, ref);
                     }

@@ -52,6 +52,8 @@ struct TraverseOpt {
     uint32_t min_cov_vertices = 2;
     int out_qual = 1, max_qual = 40;
     double weak_region_len_factor = 0.25, large_k_factor = 1.5, min_score = 0.0;
+    bool long_read_correct = false;   // pass 2: exploreSubGraphLong bursts (bounded by k * large_k_factor bases)
+    size_t max_len_subpath() const { return static_cast<size_t>(k * large_k_factor); }   // src/GraphTraversal.cpp:594
 };
 
 // the GPU services (thin wrappers over the C ABI of this library, batched)

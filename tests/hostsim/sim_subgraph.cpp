@@ -36,8 +36,11 @@ extern "C" int rtk_explore_subgraph_batch(rtk_ctx* c, uint32_t n_calls, const rt
         p.gset_off = g.gset_off; p.gset_ids = g.gset_ids; p.loc_off = g.loc_off; p.loc_ids = g.loc_ids; p.k = g.k;
         p.calls = calls; p.pid_pool = n_pids ? pid_pool : no_pids.data(); p.n_calls = n_calls;
         p.n_cand = ncand.data(); p.n_chars = nchars.data(); p.cand_off = nullptr; p.char_off = nullptr; p.cands = nullptr; p.chars = nullptr;
+        uint32_t overflow = 0;
+        p.overflow = &overflow;
         const unsigned grid = (n_calls + RTK_DFS_WARPS - 1) / RTK_DFS_WARPS;
         if (n_calls) sim_launch(grid, RTK_DFS_WARPS * 32, [&] { rtk_dfs_kernel<false>(p); });
+        if (overflow) throw std::runtime_error("exploreSubGraph: a burst exceeded the DFS capacity (RTK_DFS_MAX_NODES / RTK_DFS_STACK)");
         std::vector<uint64_t> cand_off(n_calls + 1, 0), char_off(n_calls + 1, 0);
         for (uint32_t i = 0; i < n_calls; ++i) { cand_off[i + 1] = cand_off[i] + ncand[i]; char_off[i + 1] = char_off[i] + nchars[i]; }
         const uint64_t n_cands = cand_off[n_calls], n_chars = char_off[n_calls];

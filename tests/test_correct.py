@@ -1,12 +1,16 @@
-"""End-to-end parity of the per-read correction (getSeeds + correctSequence, pass 1) with the reference's own corrected
-FASTQ records (tests/golden/*/corrected_pass1.fastq.gz, recorded from the unmodified reference and asserted equal to the
-reference CLI's output when they were made): sequence AND quality strings byte for byte."""
+"""End-to-end parity of the per-read correction (getSeeds + correctSequence) with the reference's own corrected FASTQ
+records: sequence AND quality strings byte for byte.
+  pass 1 (k = 31, short-read colours): tests/golden/*/corrected_pass1.fastq.gz, recorded from the unmodified reference and
+         asserted equal to the reference CLI's output when they were made; bench_data/F3 at E. coli scale
+  pass 2 (k = 63, long-read colours, exploreSubGraphLong bursts, qualities carried over): corrected_pass2_nophasing.fastq.gz =
+         `Ratatosk correct -2 -c 1` on the pass-1 output (tests/golden/make_golden_pass2.sh), i.e. getSeeds + correctSequence
+         without the multi-thread branch's phasing()"""
 import os
 
 import pytest
 
 import ratatosk_b200 as rb
-from common import GOLDEN, golden_paths, load_golden_reads, read_fastq
+from common import GOLDEN, ROOT, golden_paths, load_golden_reads, read_fastq
 
 
 def _run(ctx, recipe, idx):
@@ -44,5 +48,62 @@ def test_correction_cuda_matches_reference_fastq(recipe):
     assert out[1] == ("ACGT", "!!!!")
     assert out[2] == ("N" * 100, "!" * 100)
     assert out[3][0] == "ACGTTGCA" * 20 and set(out[3][1]) == {"!"}
+    ctx.close()
+    g.close()
+
+
+@pytest.mark.gpu
+def test_correction_cuda_matches_reference_cli_at_ecoli_scale():
+    """BASELINE configs[1] scale: the 4.64 Mbp index built by the unmodified reference (bench_data/F3, 52,968 unitigs,
+    6,365 shared colour sets) and the first 200 long reads of the F3 recipe; expected output = the reference CLI's
+    `correct -1 -c 8` FASTQ.  The batch is submitted twice in one call (3,200-region broker run, every service batched)
+    and in two different splits: batching must be transparent."""
+    d = os.path.join(ROOT, "bench_data", "F3")
+    g = rb.Graph.load(os.path.join(d, "index.k31.fasta.gz"), os.path.join(d, "index.k31.rtsk"), 31)
+    ctx = rb.Context(0)
+    ctx.upload(g)
+    reads = read_fastq(os.path.join(d, "reads200.fastq.gz"))
+    gold = read_fastq(os.path.join(d, "corrected200_pass1.fastq.gz"))
+    assert len(reads) == len(gold) == 200
+    seqs, quals = [r[1] for r in reads], [r[2] for r in reads]
+    out = ctx.correct(seqs + seqs, quals + quals)
+    bad = [i for i in range(400) if out[i] != (gold[i % 200][1], gold[i % 200][2])]
+    assert not bad, bad[:10]
+    part = ctx.correct(seqs[150:], quals[150:]) + ctx.correct(seqs[:3], quals[:3])
+    assert part == [(gr[1], gr[2]) for gr in gold[150:] + gold[:3]]
+    ctx.close()
+    g.close()
+
+
+def _run_pass2(ctx, recipe, idx):
+    d = os.path.join(GOLDEN, recipe)
+    p1 = read_fastq(os.path.join(d, "corrected_pass1.fastq.gz"))
+    gold = read_fastq(os.path.join(d, "corrected_pass2_nophasing.fastq.gz"))
+    out = ctx.correct([p1[i][1] for i in idx], [p1[i][2] for i in idx], pass_no=2)
+    bad = [i for i, o in zip(idx, out) if o != (gold[i][1], gold[i][2])]
+    assert not bad, (recipe, bad)
+    return sum(1 for i in idx if (p1[i][1], p1[i][2]) != (gold[i][1], gold[i][2]))
+
+
+def test_pass2_correction_kernel_sources_match_reference_fastq(sim_lib):
+    d = os.path.join(GOLDEN, "F2")
+    g = rb.Graph.load(os.path.join(d, "index.k63.fasta.gz"), os.path.join(d, "index.k63.rtsk"), 63, lib=sim_lib)
+    ctx = rb.Context(0, lib=sim_lib)
+    ctx.upload(g)
+    assert _run_pass2(ctx, "F2", [4]) == 1   # a read the second pass changes
+    ctx.close()
+    g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("recipe", ["F1", "F2"])
+def test_pass2_correction_cuda_matches_reference_fastq(recipe):
+    d = os.path.join(GOLDEN, recipe)
+    g = rb.Graph.load(os.path.join(d, "index.k63.fasta.gz"), os.path.join(d, "index.k63.rtsk"), 63)
+    ctx = rb.Context(0)
+    ctx.upload(g)
+    n = len(read_fastq(os.path.join(d, "corrected_pass1.fastq.gz")))
+    changed = _run_pass2(ctx, recipe, list(range(n)))
+    assert changed == (0 if recipe == "F1" else 18)   # what the reference's second pass changes on these fixtures
     ctx.close()
     g.close()
