@@ -217,6 +217,15 @@ int rtk_correct_batch_resident(rtk_ctx* ctx, const rtk_opt* opt, int pass, uint3
                                const char* qual_pool, const uint64_t* qual_off, char** out_seq_pool, char** out_qual_pool,
                                uint64_t** out_off, uint64_t* stats);
 
+/* ---- phasing (src/Graph.hpp:53, src/Graph.cpp:869-1097): the step the multi-thread branch of search() runs on every read
+ * of the SECOND pass before getSeeds (src/Ratatosk.cpp:832).  raw = the uncorrected read, corr / qual = its pass-1 correction.
+ * Stretches of corr whose long-read colours are compatible with no other stretch of the read are reverted to raw; output
+ * = the pair phasing() returns, to be passed to rtk_correct_batch(pass 2).  Reads upper-case.  K1 exact sweeps and one
+ * whole-read NW path alignment (K5) per read, batched over the call. */
+int rtk_phasing_batch(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const char* raw_pool, const uint64_t* raw_off,
+                      const char* corr_pool, const uint64_t* corr_off, const char* qual_pool, const uint64_t* qual_off,
+                      char** out_seq_pool, char** out_qual_pool, uint64_t** out_off);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@
 //   ref_search_sequence               CompactedDBG::searchSequence (Bifrost/src/Search.tcc:526)
 //   ref_get_seeds                     getSeeds (src/Graph.cpp:3)
 //   ref_correct_read                  the per-read body of search() (src/Ratatosk.cpp:808-867)
+//   ref_phasing                       phasing (src/Graph.cpp:869), second pass, multi-thread branch
 //   ref_edlib                         edlibAlign (src/edlib.cpp:141)
 //
 // Nothing in the product library links, includes or dlopens this file.
@@ -243,6 +244,18 @@ int ref_correct_read(void* h, const char* s_in, const char* q_in, int pass2, cha
     }
     *s_out = strdup(in_read.c_str());
     *q_out = strdup(in_qual.c_str());
+    return 0;
+}
+
+// phasing() (src/Graph.cpp:869): the step the multi-thread branch of search() runs before getSeeds in the second pass
+int ref_phasing(void* h, const char* s_raw, const char* s_corr, const char* q_corr, char** s_out, char** q_out) {
+    RefGraph* g = (RefGraph*)h;
+    string raw(s_raw), corr(s_corr), qual(q_corr);
+    std::transform(raw.begin(), raw.end(), raw.begin(), ::toupper);
+    std::transform(corr.begin(), corr.end(), corr.begin(), ::toupper);
+    pair<string, string> r = phasing(*g->dbg, g->opt, raw, corr, qual);
+    *s_out = strdup(r.first.c_str());
+    *q_out = strdup(r.second.c_str());
     return 0;
 }
 

@@ -123,6 +123,9 @@ def load_library(path=None):
                                                  C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_char_p,
                                                  C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                  C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
+    L.rtk_phasing_batch.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.c_char_p,
+                                    C.POINTER(C.c_uint64), C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64))]
     L.rtk_explore_paths.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.POINTER(RtkHit), C.POINTER(RtkHit), C.c_char_p, C.c_uint32,
                                     C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.POINTER(RtkPathNode)), C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
@@ -342,6 +345,28 @@ class Context:
         self.L.rtk_free(C.cast(oo, C.c_void_p))
         if stats is not None:
             stats.extend(list(st))
+        return out
+
+    def phasing(self, raw_reads, corr_reads, corr_quals, opt=None):
+        """phasing() of the second pass (src/Graph.cpp:869) for a batch -> list of (sequence, quality string)"""
+        opt = opt or default_opt(2)
+        rp, ro = pack_reads(raw_reads)
+        cp, co = pack_reads(corr_reads)
+        qp, qo = pack_reads(corr_quals)
+        os_, oq_ = C.c_void_p(), C.c_void_p()
+        oo = C.POINTER(C.c_uint64)()
+        u64p = C.POINTER(C.c_uint64)
+        _check(self.L, self.L.rtk_phasing_batch(self.h, C.byref(opt), len(raw_reads), rp, ro.ctypes.data_as(u64p), cp,
+                                                co.ctypes.data_as(u64p), qp, qo.ctypes.data_as(u64p), C.byref(os_),
+                                                C.byref(oq_), C.byref(oo)))
+        n = len(raw_reads)
+        offs = [oo[i] for i in range(n + 1)]
+        sbuf = C.string_at(os_, offs[-1])
+        qbuf = C.string_at(oq_, offs[-1])
+        out = [(sbuf[offs[i]:offs[i + 1]].decode("latin1"), qbuf[offs[i]:offs[i + 1]].decode("latin1")) for i in range(n)]
+        self.L.rtk_free(os_)
+        self.L.rtk_free(oq_)
+        self.L.rtk_free(C.cast(oo, C.c_void_p))
         return out
 
     def explore_paths(self, start, end, ref, pids, opt=None):

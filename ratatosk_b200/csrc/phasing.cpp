@@ -1,0 +1,269 @@
+// phasing.cpp — phasing() of the reference's second pass (src/Graph.cpp:869-1097), run by the multi-thread branch of
+// search() on every read before getSeeds (src/Ratatosk.cpp:832): stretches of the pass-1 corrected read that map to
+// unitigs whose long-read colour sets are compatible with NO other stretch of the read further than insert_sz away
+// are reverted to the raw read.
+//
+//   1. exact k-mer sweep of the corrected read (K1 exact kernel, batched over the reads of the call); consecutive hits
+//      on one unitig are one findUnitig() run (:893-915)
+//   2. a TinyBloomFilter (src/TinyBloomFilter.hpp; wyhash final version 3 of the 8-byte id, double hashing) of each
+//      kept run's colour ids, all-pairs "shares >= 85 % of the bits both ways" test in the reference's scan order
+//      (:918-983) -> positions to revert (pos2rm)
+//   3. NW alignment path raw vs corrected for the WHOLE read (K5, edlib's divide-and-conquer above 1 MiB of DP state),
+//      walked run by run like the CIGAR in :986-1052
+//   4. exact sweep of the reverted neighbourhoods; bases of the result covered by a graph k-mer get the maximum
+//      quality (:1054-1080; K1 exact kernel, batched)
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "broker.hpp"
+#include "rtk_host_common.hpp"
+#include "traverse.hpp"
+
+namespace rtk {
+namespace {
+
+// wyhash final version 3 (Wang Yi, public domain; Bifrost/src/wyhash.h) of one 8-byte little-endian key
+inline uint64_t wymix(uint64_t a, uint64_t b) {
+    const unsigned __int128 r = (unsigned __int128)a * b;
+    return (uint64_t)r ^ (uint64_t)(r >> 64);
+}
+inline uint64_t wyhash8(uint64_t key, uint64_t seed) {
+    static const uint64_t s0 = 0xa0761d6478bd642full, s1 = 0xe7037ed1a0b428dbull;
+    seed ^= s0;
+    const uint64_t lo = key & 0xffffffffull, hi = key >> 32;
+    const uint64_t a = (lo << 32) | hi, b = (hi << 32) | lo;
+    return wymix(s1 ^ 8ull, wymix(a ^ s1, b ^ seed));
+}
+
+inline uint64_t round_up_pow2(uint64_t v) { --v; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16; v |= v >> 32; return ++v; }
+
+// TinyBloomFilter<size_t>(nb_elem, bits_per_elem): geometry shared by all filters of a read
+struct BloomGeom {
+    uint64_t nb_h = 0, bits = 0;
+    BloomGeom(uint64_t nb_elem, uint64_t bits_per_elem) {
+        if (nb_elem == 0 || bits_per_elem == 0) return;
+        auto fpp = [](uint64_t b, uint64_t h) { const double bd = (double)b, hd = (double)h; return std::pow(1 - std::exp(-(hd / bd)), hd); };
+        nb_h = (uint64_t)(bits_per_elem * std::log(2));
+        nb_h += (uint64_t)(fpp(bits_per_elem, nb_h) >= fpp(bits_per_elem, nb_h + 1));
+        nb_h &= 0xffull;
+        bits = std::max<uint64_t>(round_up_pow2(bits_per_elem * nb_elem), 64);
+    }
+    size_t words() const { return (size_t)(bits / 64); }
+};
+inline void bloom_insert(uint64_t* table, const BloomGeom& gm, uint64_t id) {   // insert(): every one of the nb_h positions ends up set
+    const uint64_t mask = gm.bits - 1, h2 = wyhash8(id, 1610612741ull);
+    uint64_t h1 = wyhash8(id, 49157ull);
+    for (uint64_t i = 0; i != gm.nb_h; ++i) { table[(h1 & mask) >> 6] |= 1ull << (h1 & 0x3full); h1 += h2; }
+}
+
+struct Run { uint32_t pos, len, unitig; };
+
+inline bool is_branching(const rtk_graph_view& g, uint32_t u) { return (g.kmcov[u] >> 63) & 1ULL; }
+
+}  // namespace
+
+void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char* raw_pool, const uint64_t* raw_off, const char* corr_pool,
+                        const uint64_t* corr_off, const char* qual_pool, const uint64_t* qual_off, std::vector<std::string>& out_seq,
+                        std::vector<std::string>& out_qual) {
+    if (!ctx->has_graph || !ctx->host_graph) throw std::invalid_argument("no graph uploaded to this context");
+    const rtk_graph_view& g = ctx->host_graph->view;
+    if (opt.k != g.k) throw std::invalid_argument("rtk_opt.k does not match the graph's k");
+    const size_t k = g.k;
+    const char q_min = rtk_get_qual(0.0, 0, opt.max_qual), q_max = rtk_get_qual(1.0, 0, opt.max_qual);
+    const double t_bits_sim = 0.85;
+    const size_t max_limit_nb_pids = 1000, nb_bits_elem_tbf = 14;
+    out_seq.assign(n, std::string());
+    out_qual.assign(n, std::string());
+
+    // 1. map the corrected reads (one exact sweep for the whole batch)
+    std::vector<std::vector<rtk_hit>> hits;
+    {
+        std::vector<uint64_t> off(n + 1);
+        for (uint32_t i = 0; i <= n; ++i) off[i] = corr_off[i] - corr_off[0];
+        search_sequence_host(ctx, n, corr_pool + corr_off[0], off.data(), RTK_SEARCH_EXACT, hits, nullptr);
+    }
+
+    // 2. positions to revert, per read
+    std::vector<std::vector<uint8_t>> pos2rm(n);
+    parallel_for(n, [&](size_t rb, size_t re) {
+    for (size_t r = rb; r < re; ++r) {
+        const size_t clen = (size_t)(corr_off[r + 1] - corr_off[r]);
+        pos2rm[r].assign(clen + k + 1, 0);
+        std::vector<Run> v_um;
+        size_t max_nb_pids = 0;
+        const std::vector<rtk_hit>& h = hits[r];
+        for (size_t i = 0; i < h.size();) {   // findUnitig() runs: consecutive k-mers of the read on consecutive k-mers of one unitig
+            size_t j = i + 1;
+            while (j < h.size() && h[j].pos == h[j - 1].pos + 1 && h[j].unitig == h[i].unitig && h[j].strand == h[i].strand &&
+                   (h[i].strand ? h[j].dist == h[j - 1].dist + 1 : h[j].dist + 1 == h[j - 1].dist)) ++j;
+            const uint32_t u = h[i].unitig;
+            const uint64_t gs = (g.gset_of[u] == RTK_NONE32) ? 0 : (g.gset_off[g.gset_of[u] + 1] - g.gset_off[g.gset_of[u]]);
+            const size_t card = (size_t)(gs + (g.loc_off[u + 1] - g.loc_off[u]));
+            if (!is_branching(g, u) && card <= max_limit_nb_pids) {
+                v_um.push_back({h[i].pos, (uint32_t)(j - i), u});
+                max_nb_pids = std::max(max_nb_pids, card);
+            }
+            i = j;
+        }
+        const size_t m = v_um.size();
+        const BloomGeom gm(max_nb_pids, nb_bits_elem_tbf);
+        const size_t W = gm.words();
+        std::vector<uint64_t> tables(m * W, 0);
+        std::vector<size_t> nbits(m, 0);
+        for (size_t i = 0; i < m && W; ++i) {
+            uint64_t* t = tables.data() + i * W;
+            const uint32_t u = v_um[i].unitig;
+            if (g.gset_of[u] != RTK_NONE32) for (uint64_t x = g.gset_off[g.gset_of[u]]; x < g.gset_off[g.gset_of[u] + 1]; ++x) bloom_insert(t, gm, g.gset_ids[x]);
+            for (uint64_t x = g.loc_off[u]; x < g.loc_off[u + 1]; ++x) bloom_insert(t, gm, g.loc_ids[x]);
+            size_t c = 0;
+            for (size_t w = 0; w < W; ++w) c += (size_t)__builtin_popcountll(t[w]);
+            nbits[i] = c;
+        }
+        std::vector<uint8_t> valid(m, 0), invalid(m, 0);
+        for (size_t i = 0; i < m; ++i) {
+            if (valid[i]) continue;
+            bool found = false, compatible = false;
+            const size_t pos_i = v_um[i].pos, nb_bits_i = nbits[i];
+            const uint64_t* ti = tables.data() + i * W;
+            for (size_t j = 0; j < m; ++j) {
+                if (invalid[j]) continue;
+                const size_t pos_j = v_um[j].pos;
+                const size_t min_pos_j = (pos_j < opt.insert_sz) ? 0 : (pos_j - opt.insert_sz);
+                if (pos_i < min_pos_j || pos_i > pos_j + opt.insert_sz) {
+                    const uint64_t* tj = tables.data() + j * W;
+                    size_t shared = 0;
+                    for (size_t w = 0; w < W; ++w) shared += (size_t)__builtin_popcountll(ti[w] & tj[w]);
+                    compatible = true;
+                    if (shared >= t_bits_sim * nb_bits_i && shared >= t_bits_sim * nbits[j]) {
+                        found = true;
+                        valid[i] = 1; valid[j] = 1;
+                        break;
+                    }
+                }
+            }
+            if (!found && compatible) {
+                for (size_t j = pos_i; j < pos_i + v_um[i].len + k && j < pos2rm[r].size(); ++j) pos2rm[r][j] = 1;
+                invalid[i] = 1;
+            }
+        }
+    }
+    });
+
+    // 3. whole-read NW paths raw (query) vs corrected (target)
+    std::vector<AlignJob> jobs(n);
+    for (uint32_t r = 0; r < n; ++r) {
+        jobs[r].q.assign(raw_pool + raw_off[r], (size_t)(raw_off[r + 1] - raw_off[r]));
+        jobs[r].t.assign(corr_pool + corr_off[r], (size_t)(corr_off[r + 1] - corr_off[r]));
+        jobs[r].mode = 0;
+    }
+    std::vector<int32_t> dist;
+    std::vector<std::vector<uint8_t>> ops;
+    {
+        PathReq rq{&jobs, &dist, &ops};
+        run_path_batch(ctx, std::vector<PathReq*>(1, &rq));
+    }
+
+    // walk the alignment (:1001-1052) and collect the reverted neighbourhoods
+    std::vector<std::string> s_new(n);
+    parallel_for(n, [&](size_t rb, size_t re) {
+    for (size_t r = rb; r < re; ++r) {
+        const std::string& s_raw = jobs[r].q;
+        const std::string& s_corr = jobs[r].t;
+        const char* q_corr = qual_pool + qual_off[r];
+        const std::vector<uint8_t>& rm = pos2rm[r];
+        auto to_rm = [&](size_t p) { return p < rm.size() && rm[p]; };
+        std::string& s_out = out_seq[r];
+        std::string& q_out = out_qual[r];
+        std::vector<size_t> new_base_pos;
+        size_t target_pos = 0, query_pos = 0;
+        const std::vector<uint8_t>& o = ops[r];
+        // edlibAlign returns no alignment when one side is empty (:160-176): nothing is emitted
+        for (size_t a = 0; a < o.size();) {
+            const uint8_t kind = (o[a] == 1) ? 1 : (o[a] == 2) ? 2 : 0;   // CIGAR standard: M (match or mismatch), I, D
+            size_t b = a;
+            while (b < o.size() && (((o[b] == 1) ? 1 : (o[b] == 2) ? 2 : 0) == kind)) ++b;
+            const size_t l = b - a;
+            if (kind == 0) {
+                for (size_t i = target_pos; i < target_pos + l; ++i) {
+                    if (to_rm(i)) {
+                        if (s_corr[i] == s_raw[query_pos + i - target_pos]) q_out += q_corr[i];
+                        else { q_out += q_min; new_base_pos.push_back(s_out.length()); }
+                        s_out += s_raw[query_pos + i - target_pos];
+                    } else { s_out += s_corr[i]; q_out += q_corr[i]; }
+                }
+                query_pos += l; target_pos += l;
+            } else if (kind == 1) {
+                if (to_rm(target_pos)) {
+                    for (size_t i = 0, sl = s_out.length(); i < l; ++i) new_base_pos.push_back(sl + i);
+                    s_out += s_raw.substr(query_pos, l);
+                    q_out += std::string(l, q_min);
+                }
+                query_pos += l;
+            } else {
+                for (size_t i = target_pos; i < target_pos + l; ++i)
+                    if (!to_rm(i)) { s_out += s_corr[i]; q_out += q_corr[i]; }
+                target_pos += l;
+            }
+            a = b;
+        }
+        std::string& sn = s_new[r];
+        sn.assign(s_out.length(), 'N');
+        for (const size_t pos : new_base_pos) {
+            const size_t pos_min = (pos < (k - 1)) ? 0 : (pos - k + 1);
+            const size_t pos_max = ((pos + k) > s_out.length()) ? s_out.length() : (pos + k);
+            memcpy(&sn[pos_min], s_out.data() + pos_min, pos_max - pos_min);
+        }
+    }
+    });
+
+    // 4. reverted bases that sit in a graph k-mer after all get the maximum quality (:1081-1090)
+    {
+        std::string pool;
+        std::vector<uint64_t> off(1, 0);
+        for (uint32_t r = 0; r < n; ++r) { pool += s_new[r]; off.push_back(pool.size()); }
+        pool.push_back('\0');
+        std::vector<std::vector<rtk_hit>> h2;
+        search_sequence_host(ctx, n, pool.data(), off.data(), RTK_SEARCH_EXACT, h2, nullptr);
+        for (uint32_t r = 0; r < n; ++r)
+            for (const rtk_hit& h : h2[r])
+                for (size_t j = h.pos; j < h.pos + k && j < out_qual[r].size(); ++j)
+                    if (out_qual[r][j] == q_min) out_qual[r][j] = q_max;
+    }
+}
+
+}  // namespace rtk
+
+using namespace rtk;
+
+extern "C" int rtk_phasing_batch(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const char* raw_pool, const uint64_t* raw_off,
+                                 const char* corr_pool, const uint64_t* corr_off, const char* qual_pool, const uint64_t* qual_off,
+                                 char** out_seq_pool, char** out_qual_pool, uint64_t** out_off) {
+    return guarded([&] {
+        if (!ctx || !opt || !raw_pool || !raw_off || !corr_pool || !corr_off || !qual_pool || !qual_off || !out_seq_pool || !out_qual_pool || !out_off)
+            throw std::invalid_argument("null argument");
+        for (uint32_t r = 0; r < n_reads; ++r)
+            if (qual_off[r + 1] - qual_off[r] != corr_off[r + 1] - corr_off[r]) throw std::invalid_argument("corrected read and quality lengths differ");
+        std::vector<std::string> os, oq;
+        phasing_batch_host(ctx, *opt, n_reads, raw_pool, raw_off, corr_pool, corr_off, qual_pool, qual_off, os, oq);
+        uint64_t total = 0;
+        for (const auto& x : os) total += x.size();
+        *out_off = (uint64_t*)malloc((size_t)(n_reads + 1) * 8);
+        *out_seq_pool = (char*)malloc(total + 1);
+        *out_qual_pool = (char*)malloc(total + 1);
+        if (!*out_off || !*out_seq_pool || !*out_qual_pool) throw std::bad_alloc();
+        uint64_t t = 0;
+        for (uint32_t r = 0; r < n_reads; ++r) {
+            (*out_off)[r] = t;
+            if (os[r].size() != oq[r].size()) throw std::runtime_error("phased sequence and quality lengths differ");
+            memcpy(*out_seq_pool + t, os[r].data(), os[r].size());
+            memcpy(*out_qual_pool + t, oq[r].data(), oq[r].size());
+            t += os[r].size();
+        }
+        (*out_off)[n_reads] = t;
+    });
+}

@@ -44,6 +44,7 @@ def lib():
                                     C.POINTER(C.POINTER(RefHit)), C.POINTER(C.c_int64)]
         L.ref_correct_read.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.ref_phasing.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.ref_edlib.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_int)),
                                 C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.c_int)]
@@ -168,6 +169,18 @@ class RefGraph:
         lib().ref_free(so)
         lib().ref_free(qo)
         return rs, rq
+
+
+def _phasing(self, raw, corr, qual):
+    so, qo = C.c_void_p(), C.c_void_p()
+    lib().ref_phasing(self.h, raw.encode(), corr.encode(), qual.encode(), C.byref(so), C.byref(qo))
+    rs, rq = C.string_at(so).decode(), C.string_at(qo).decode()
+    lib().ref_free(so)
+    lib().ref_free(qo)
+    return rs, rq
+
+
+RefGraph.phasing = _phasing
 
 
 def edlib(q, t, mode, task=0, k=-1, iupac=True):

@@ -107,3 +107,48 @@ def test_pass2_correction_cuda_matches_reference_fastq(recipe):
     assert changed == (0 if recipe == "F1" else 18)   # what the reference's second pass changes on these fixtures
     ctx.close()
     g.close()
+
+
+# ---- phasing (second pass, multi-thread branch of the reference): golden = phasing() recorded through the seam probe
+# (oracle/ref_seams.cpp: ref_phasing) on the unmodified reference; phasing + correct(pass 2) = the CLI's `correct -2 -O -c 8`
+def _phasing_inputs(recipe):
+    d = os.path.join(GOLDEN, recipe)
+    raw = read_fastq(os.path.join(d, "reads.fastq.gz"))
+    p1 = read_fastq(os.path.join(d, "corrected_pass1.fastq.gz"))
+    ph = read_fastq(os.path.join(d, "phasing.fastq.gz"))
+    return raw, p1, ph
+
+
+def test_phasing_kernel_sources_match_reference(sim_lib):
+    d = os.path.join(GOLDEN, "F1")
+    g = rb.Graph.load(os.path.join(d, "index.k63.fasta.gz"), os.path.join(d, "index.k63.rtsk"), 63, lib=sim_lib)
+    ctx = rb.Context(0, lib=sim_lib)
+    ctx.upload(g)
+    raw, p1, ph = _phasing_inputs("F1")
+    idx = [7, 0]   # read 7 is the one phasing() changes on this fixture
+    out = ctx.phasing([raw[i][1].upper() for i in idx], [p1[i][1] for i in idx], [p1[i][2] for i in idx])
+    assert out == [(ph[i][1], ph[i][2]) for i in idx]
+    assert out[0] != (p1[7][1], p1[7][2])
+    ctx.close()
+    g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("recipe", ["F1", "F2"])
+def test_two_pass_cuda_matches_reference_cli(recipe):
+    """phasing + getSeeds + correctSequence of the second pass == `Ratatosk correct -2 -O -c 8` (corrected_pass2.fastq.gz),
+    with the intermediate phasing() output checked on the way"""
+    d = os.path.join(GOLDEN, recipe)
+    g = rb.Graph.load(os.path.join(d, "index.k63.fasta.gz"), os.path.join(d, "index.k63.rtsk"), 63)
+    ctx = rb.Context(0)
+    ctx.upload(g)
+    raw, p1, ph = _phasing_inputs(recipe)
+    gold = read_fastq(os.path.join(d, "corrected_pass2.fastq.gz"))
+    out = ctx.phasing([r[1].upper() for r in raw], [r[1] for r in p1], [r[2] for r in p1])
+    bad = [i for i in range(len(p1)) if out[i] != (ph[i][1], ph[i][2])]
+    assert not bad, ("phasing", recipe, bad)
+    fin = ctx.correct([o[0] for o in out], [o[1] for o in out], pass_no=2)
+    bad = [i for i in range(len(p1)) if fin[i] != (gold[i][1], gold[i][2])]
+    assert not bad, ("two-pass", recipe, bad)
+    ctx.close()
+    g.close()
