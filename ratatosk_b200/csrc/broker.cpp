@@ -16,6 +16,9 @@
 
 namespace rtk {
 
+#ifndef RTK_HOSTSIM
+extern std::atomic<uint64_t> g_myers_prof[6];
+#endif
 static thread_local GpuBroker* tl_broker = nullptr;
 static thread_local GpuBroker::Worker* tl_worker = nullptr;
 GpuBroker* current_broker() { return tl_broker; }
@@ -39,30 +42,34 @@ void run_dist_batch(rtk_ctx* ctx, const std::vector<DistReq*>& reqs) {
     for (const DistReq* r : reqs)
         for (const AlignJob& j : *r->jobs) { qp += j.q; qo.push_back(qp.size()); tp += j.t; to.push_back(tp.size()); mode.push_back(j.mode); }
     const uint32_t n = (uint32_t)mode.size();
-    std::vector<int32_t> dist(n + 1, -1), kmax(n + 1, -1);
-    int32_t* ends = nullptr;
-    uint64_t* eoff = nullptr;
+    std::vector<int32_t> dist(n + 1, -1), first(n + 1, -1), last(n + 1, -1);
     uint64_t st[8] = {0};
     pt.lap(0, 0);
     if (n) {
         qp.push_back('\0'); tp.push_back('\0');
+#ifdef RTK_HOSTSIM   // the CPU simulator goes through the public entry (every end location) and keeps the two the callers use
+        std::vector<int32_t> kmax(n + 1, -1);
+        int32_t* ends = nullptr;
+        uint64_t* eoff = nullptr;
         if (rtk_edlib_batch(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), kmax.data(), dist.data(), &ends, &eoff, st) != RTK_OK)
             throw std::runtime_error(std::string("rtk_edlib_batch: ") + rtk_last_error());
+        for (uint32_t a = 0; a < n; ++a) if (eoff[a + 1] > eoff[a]) { first[a] = ends[eoff[a]]; last[a] = ends[eoff[a + 1] - 1]; }
+        rtk_free(ends);
+        rtk_free(eoff);
+#else
+        dist_batch_lean(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), dist.data(), first.data(), last.data(), st);
+#endif
     }
     pt.lap(0, 1);
     g_prof[0][3] += st[2];
     uint32_t a = 0;
     for (const DistReq* r : reqs) {
         const size_t m = r->jobs->size();
-        r->dist->assign(m, -1);
-        r->ends->assign(m, {});
-        for (size_t i = 0; i < m; ++i, ++a) {
-            (*r->dist)[i] = dist[a];
-            (*r->ends)[i].assign(ends + eoff[a], ends + eoff[a + 1]);
-        }
+        r->dist->assign(dist.begin() + a, dist.begin() + a + m);
+        r->first_end->assign(first.begin() + a, first.begin() + a + m);
+        r->last_end->assign(last.begin() + a, last.begin() + a + m);
+        a += (uint32_t)m;
     }
-    rtk_free(ends);
-    rtk_free(eoff);
     pt.lap(0, 2);
 }
 
@@ -443,6 +450,10 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
             fprintf(stderr, "[broker]   %s service host time: assemble %.1f ms, C-ABI call %.1f ms (GPU kernels %.1f ms), scatter %.1f ms\n", names[k],
                     prof[k][0] / 1e6, prof[k][1] / 1e6, prof[k][3] / 1e6, prof[k][2] / 1e6);
         }
+#ifndef RTK_HOSTSIM
+        fprintf(stderr, "[broker]   myers_run (all callers, cumulative): plan %.1f ms, H2D issue %.1f ms, launches %.1f ms, D2H + sync %.1f ms, ends phase %.1f ms\n",
+                g_myers_prof[0] / 1e6, g_myers_prof[1] / 1e6, g_myers_prof[2] / 1e6, g_myers_prof[3] / 1e6, g_myers_prof[4] / 1e6);
+#endif
     }
     for (int k = 0; k < 3; ++k) for (Service* s : services[k]) { s->batches = s->reqs = s->ns_busy = 0; }
     if (!task_error.empty()) throw std::runtime_error(task_error);

@@ -28,7 +28,8 @@ namespace rtk {
 struct DistReq {   // K4
     const std::vector<AlignJob>* jobs;
     std::vector<int32_t>* dist;
-    std::vector<std::vector<int32_t>>* ends;   // every end location, ascending
+    std::vector<int32_t>* first_end;   // smallest end column carrying the distance (edlib's endLocations[0]), -1 if none
+    std::vector<int32_t>* last_end;    // largest one (endLocations[numLocations-1])
 };
 struct PathReq {   // K5
     const std::vector<AlignJob>* jobs;

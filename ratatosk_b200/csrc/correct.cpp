@@ -747,13 +747,12 @@ ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::s
         std::vector<AlignJob> j(1);
         j[0].q = s.substr(v_s[i_s].pos, solid2_pos - v_s[i_s].pos + k);
         j[0].t = s_corrected; j[0].mode = 1;
-        // every end location is needed: keep the largest best end (:735-741)
-        std::vector<int32_t> dd;
-        std::vector<std::vector<int32_t>> ee;
-        gpu_distances_all(C.ctx, j, dd, ee);
-        if (dd[0] >= 0 && !ee[0].empty()) {
-            size_t end_location = (size_t)ee[0][0];  // size_t like the reference: an end of -1 wraps and is never exceeded
-            for (size_t x = 1; x < ee[0].size(); ++x) if ((size_t)ee[0][x] > end_location) end_location = (size_t)ee[0][x];
+        // the largest best end is kept (:735-741); the reference scans endLocations[] as size_t, so a first end of -1 (edlib's
+        // "position -1") wraps to the maximum and wins
+        std::vector<int32_t> dd, fe, le;
+        gpu_distances_fl(C.ctx, j, dd, fe, le);
+        if (dd[0] >= 0) {
+            const size_t end_location = (fe[0] < 0) ? (size_t)fe[0] : (size_t)le[0];
             s_corrected = s_corrected.substr(0, end_location + 1);
             q_corrected = q_corrected.substr(0, end_location + 1);
         }
@@ -994,8 +993,20 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
             jobs[r].s_fw = &out_seq[r]; jobs[r].q_fw = &out_qual[r]; jobs[r].solid = &solid[r]; jobs[r].weak = &weak[r];
             plan_read(g, l_opt, pass2, r, jobs[r], pieces);
         }
+        // longest regions first: a region is a chain of dependent GPU requests roughly proportional to its span, and the
+        // call ends when the longest chain does (the output order is restored below, so scheduling order is free)
+        std::vector<uint32_t> order(pieces.size());
+        std::vector<uint32_t> span(pieces.size());
+        for (size_t i = 0; i < pieces.size(); ++i) {
+            order[i] = (uint32_t)i;
+            const Piece& P = pieces[i];
+            const std::vector<rtk_hit>& vs = *jobs[P.read].solid;
+            const size_t len = jobs[P.read].s_fw->length();
+            span[i] = (P.kind == 0) ? vs[0].pos : (P.kind == 1) ? (vs[P.i_solid + 1].pos - vs[P.i_solid].pos) : (uint32_t)(len - vs[P.i_solid].pos);
+        }
+        if (!getenv("RTK_NO_LPT")) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return span[a] > span[b]; });
         GpuBroker broker(ctx);
-        broker.run(pieces.size(), correct_threads(), [&](size_t i) { run_piece(C, jobs[pieces[i].read], pieces[i]); });
+        broker.run(pieces.size(), correct_threads(), [&](size_t i) { run_piece(C, jobs[pieces[order[i]].read], pieces[order[i]]); });
         std::vector<std::string> ns(n_reads), nq(n_reads);
         for (const Piece& P : pieces) { ns[P.read] += P.s; nq[P.read] += P.q; }
         for (uint32_t r = 0; r < n_reads; ++r) {

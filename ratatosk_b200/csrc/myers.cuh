@@ -39,6 +39,13 @@ struct rtk_myers_params {
     const uint64_t* ends_off;
     int8_t* hbound;          // scratch: hb_off[a] .. + tlen, horizontal deltas between rounds
     const uint64_t* hb_off;
+    // lean mode (ends == nullptr): only the first and the last end column carrying the distance are reported
+    int32_t* first_end = nullptr;   // [alignment]
+    int32_t* last_end = nullptr;    // [alignment]
+    // fused launch (rtk_myers_fused_kernel): class c = lane groups of G = 32 >> c lanes; its blocks are
+    // [cls_blk[c], cls_blk[c+1]) and its alignment ids order[cls_ord[c] .. cls_ord[c+1])
+    uint32_t cls_blk[7] = {0, 0, 0, 0, 0, 0, 0};
+    uint32_t cls_ord[7] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 // IUPAC membership mask of a character: A1 C2 G4 T8, ambiguity codes = union (the index of the letter
@@ -62,15 +69,17 @@ RTK_HD bool rtk_iupac_eq(const char a, const char b) {
     return (base_a != base_b) && (ma & mb);  // exactly one side is a plain base and the code contains it
 }
 
+#if defined(__CUDACC__) || defined(__CUDACC_SIM__)
+// one alignment per group of G lanes; `order` / `n` = the alignments of this class, `blk` = block index within the class
 template <int G>
-__global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_kernel(const rtk_myers_params p) {
+__device__ __forceinline__ void rtk_myers_body(const rtk_myers_params& p, const uint32_t* __restrict__ order, const uint32_t n, const uint32_t blk) {
     const uint32_t lane = threadIdx.x & (G - 1);
-    const uint32_t grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-    if (grp >= p.n) return;  // whole groups drop out together; shuffles below are group-scoped
+    const uint32_t grp = (blk * blockDim.x + threadIdx.x) / G;
+    if (grp >= n) return;  // whole groups drop out together; shuffles below are group-scoped
     const uint32_t wl = threadIdx.x & 31;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(uint32_t)(G - 1)));
 
-    const uint32_t a = p.order[grp];
+    const uint32_t a = order[grp];
     const char* q = p.q_pool + p.q_beg[a];
     const char* t = p.t_pool + p.t_beg[a];
     const int qlen = (int)p.q_len[a];
@@ -80,7 +89,8 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_kernel(const rtk_
     const int nb = (qlen + 63) >> 6;
     const int rounds = (nb + G - 1) / G;
     int8_t* hb = p.hbound + p.hb_off[a];
-    int32_t* ends = p.ends + p.ends_off[a];
+    int32_t* ends = p.ends ? p.ends + p.ends_off[a] : nullptr;
+    int first = -1, last = -1;   // first / last end column with the best score (lean mode reports only these)
 
     // bottom-row score of the column before the first: D[m][-1] = m ; tracked by the lane owning the last block
     int score = qlen, best = 0x7fffffff, n_best = 0;
@@ -88,8 +98,12 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_kernel(const rtk_
     // The reference pads the query to a multiple of 64 with W wildcards and reads column c as position
     // c - W (src/edlib.cpp:658-692): when W > 0, "position -1" (the empty target prefix, score qlen) takes
     // part in the SHW/HW minimum and is reported first.  Only the reporting lane's copy is ever read.
-    if (mode != 0 && (qlen & 63) != 0) { best = qlen; n_best = 1; if ((int)lane == (nb - 1) % G) ends[0] = -1; }
+    if (mode != 0 && (qlen & 63) != 0) { best = qlen; n_best = 1; if (ends && (int)lane == (nb - 1) % G) ends[0] = -1; }
 
+    // does the target hold anything but A/C/G/T?  (group-cooperative scan; decides whether the step loop needs its slow path)
+    bool t_amb = false;
+    for (int i = (int)lane; i < tlen; i += G) { const char ch = t[i]; t_amb |= (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T'); }
+    t_amb = __any_sync(gmask, t_amb);
     for (int r = 0; r < rounds; ++r) {
         const int b = r * G + (int)lane;
         const bool has = b < nb;
@@ -108,61 +122,86 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_kernel(const rtk_
         int hout = 0;
         const bool is_last = has && (b == nb - 1);
         const bool spill = (lane == G - 1) && (r + 1 < rounds);
+        const bool top_spilled = (lane == 0) && (r != 0);            // this round's top lane reads the previous round's spill row
+        const int hin_top = (mode == 2) ? 0 : 1;                     // D[0][j] = 0 (HW) or j
+        const bool track = is_last && (mode != 0);                   // SHW / HW: remember the columns that carry the minimum
         const int steps = tlen + G - 1;
         char tc_next = (lane == 0 && tlen > 0) ? t[0] : (char)0;   // the target is read one step ahead of its use
+        // The step is STRAIGHT-LINE code: every decision is a select on values, never a branch.  One warp runs one to 32
+        // alignments with nothing else to hide latency, and the first version (an `if` around the active range, a `switch`
+        // on the target character, nested `if`s for the end columns) spent 42 % of its stall samples resolving branches
+        // (profiles/r1_myers_ncu_full.md).  Only loop-invariant, rare cases keep a branch: ambiguity codes in the target
+        // (`t_amb`), the spill row of multi-round queries, and the end-column store of the non-lean mode.
         for (int s = 0; s < steps; ++s) {
             const int from_left = __shfl_up_sync(gmask, hout, 1, G);
             const int col = s - (int)lane;
             const char tc = tc_next;
-            tc_next = (col + 1 >= 0 && col + 1 < tlen) ? t[col + 1] : (char)0;
-            hout = 0;
-            if (has && col >= 0 && col < tlen) {
-                int hin;
-                if (lane == 0) hin = (r == 0) ? ((mode == 2) ? 0 : 1) : (int)hb[col];  // D[0][j] = 0 (HW) or j
-                else hin = from_left;
-                uint64_t Eq;
-                switch (tc) {
-                    case 'A': Eq = PB0; break;
-                    case 'C': Eq = PB1; break;
-                    case 'G': Eq = PB2; break;
-                    case 'T': Eq = PB3; break;
-                    default: {  // ambiguity code (or foreign character) in the target: build the profile on the fly
-                        Eq = 0;
-                        const int lo = b << 6;
-                        const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
-                        for (int i = 0; i < n; ++i) Eq |= (uint64_t)(plain ? (q[lo + i] == tc) : rtk_iupac_eq(q[lo + i], tc)) << i;
-                    }
-                }
-                // one block of one column (Hyyro's formulation of Myers' recurrence)
-                const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
-                const uint64_t Xv = Eq | Mv;
-                Eq |= neg;
-                const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-                uint64_t Ph = Mv | ~(Xh | Pv);
-                uint64_t Mh = Pv & Xh;
-                hout = (int)(Ph >> 63) - (int)(Mh >> 63);
-                if (is_last) {
-                    score += (int)((Ph >> last_row) & 1) - (int)((Mh >> last_row) & 1);
-                    if (mode != 0) {  // SHW / HW: remember every column that carries the minimum
-                        if (score < best) { best = score; n_best = 0; }
-                        if (score == best) ends[n_best++] = col;
-                    }
-                }
-                Ph = (Ph << 1) | ((hin > 0) ? 1ULL : 0ULL);
-                Mh = (Mh << 1) | neg;
-                Pv = Mh | ~(Xv | Ph);
-                Mv = Ph & Xv;
-                if (spill) hb[col] = (int8_t)hout;
+            tc_next = ((unsigned)(col + 1) < (unsigned)tlen) ? t[col + 1] : (char)0;
+            const bool active = has && ((unsigned)col < (unsigned)tlen);
+            int hin = (lane == 0) ? hin_top : from_left;
+            if (top_spilled && active) hin = (int)hb[col];
+            uint64_t Eq = (tc == 'A') ? PB0 : (tc == 'C') ? PB1 : (tc == 'G') ? PB2 : (tc == 'T') ? PB3 : 0ULL;
+            if (t_amb && active && tc != 'A' && tc != 'C' && tc != 'G' && tc != 'T') {
+                // ambiguity code (or foreign character) in the target: build the profile on the fly
+                const int lo = b << 6;
+                const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+                for (int i = 0; i < n; ++i) Eq |= (uint64_t)(plain ? (q[lo + i] == tc) : rtk_iupac_eq(q[lo + i], tc)) << i;
             }
+            // one block of one column (Hyyro's formulation of Myers' recurrence)
+            const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
+            const uint64_t Xv = Eq | Mv;
+            Eq |= neg;
+            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            uint64_t Ph = Mv | ~(Xh | Pv);
+            uint64_t Mh = Pv & Xh;
+            hout = active ? ((int)(Ph >> 63) - (int)(Mh >> 63)) : 0;
+            const int dscore = (int)((Ph >> last_row) & 1) - (int)((Mh >> last_row) & 1);
+            Ph = (Ph << 1) | ((hin > 0) ? 1ULL : 0ULL);
+            Mh = (Mh << 1) | neg;
+            const uint64_t nPv = Mh | ~(Xv | Ph), nMv = Ph & Xv;
+            Pv = active ? nPv : Pv;
+            Mv = active ? nMv : Mv;
+            score += (active && is_last) ? dscore : 0;
+            const bool upd = active && track;
+            const bool better = upd && (score < best);
+            best = better ? score : best;
+            n_best = better ? 0 : n_best;
+            const bool eq = upd && (score == best);
+            if (ends != nullptr && eq) ends[n_best] = col;
+            first = (eq && n_best == 0) ? col : first;
+            last = eq ? col : last;
+            n_best += eq ? 1 : 0;
+            if (spill && active) hb[col] = (int8_t)hout;
         }
         __syncwarp(gmask);  // the next round's top lane reads what this round's bottom lane spilled
     }
     // the lane that owned the last block reports
     if ((int)lane == (nb - 1) % G) {
-        if (mode == 0) { best = score; ends[0] = tlen - 1; n_best = 1; }
-        const int kmax = p.kmax[a];
+        if (mode == 0) { best = score; if (ends) ends[0] = tlen - 1; first = last = tlen - 1; n_best = 1; }
+        const int kmax = p.kmax ? p.kmax[a] : -1;
         if (kmax >= 0 && best > kmax) { best = -1; n_best = 0; }
         p.dist[a] = best;
         p.n_ends[a] = n_best;
+        if (p.first_end) { p.first_end[a] = n_best ? first : -1; p.last_end[a] = n_best ? last : -1; }
     }
 }
+
+template <int G>
+__global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_kernel(const rtk_myers_params p) {
+    rtk_myers_body<G>(p, p.order, p.n, blockIdx.x);
+}
+
+// every lane-group class of a batch in ONE launch (classes in block order 32, 16, 8, 4, 2, 1 lanes: the longest queries
+// start first): one launch instead of six launches + twelve event calls per batch - the per-batch driver calls of all service
+// threads serialise on the context, which capped the whole correction step
+template <int UNUSED>   // a template so that the header can be included by several translation units
+__global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_fused_kernel(const rtk_myers_params p) {
+    const uint32_t b = blockIdx.x;
+    if (b < p.cls_blk[1]) rtk_myers_body<32>(p, p.order + p.cls_ord[0], p.cls_ord[1] - p.cls_ord[0], b - p.cls_blk[0]);
+    else if (b < p.cls_blk[2]) rtk_myers_body<16>(p, p.order + p.cls_ord[1], p.cls_ord[2] - p.cls_ord[1], b - p.cls_blk[1]);
+    else if (b < p.cls_blk[3]) rtk_myers_body<8>(p, p.order + p.cls_ord[2], p.cls_ord[3] - p.cls_ord[2], b - p.cls_blk[2]);
+    else if (b < p.cls_blk[4]) rtk_myers_body<4>(p, p.order + p.cls_ord[3], p.cls_ord[4] - p.cls_ord[3], b - p.cls_blk[3]);
+    else if (b < p.cls_blk[5]) rtk_myers_body<2>(p, p.order + p.cls_ord[4], p.cls_ord[5] - p.cls_ord[4], b - p.cls_blk[4]);
+    else rtk_myers_body<1>(p, p.order + p.cls_ord[5], p.cls_ord[6] - p.cls_ord[5], b - p.cls_blk[5]);
+}
+#endif  // __CUDACC__ || __CUDACC_SIM__

@@ -22,7 +22,7 @@ static inline double now_ns() {
 
 // ---------------------------------------------------------------- K1 driver
 uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint64_t* d_seq_off,
-                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms) {
+                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms, const char* h_seq) {
     if (!ctx->has_graph) throw std::invalid_argument("no graph uploaded to this context");
     if (n_reads >= (1u << RTK_HIT_READ_BITS)) throw std::invalid_argument("more than 2^24 reads in one batch");
     const uint32_t k = ctx->hdr.k;
@@ -33,7 +33,7 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
 
     const uint32_t tile = k1_tile_size(k, exact);
     std::vector<uint32_t> tiles;
-    build_tiles(n_reads, h_seq_off, k, tile, tiles);
+    build_tiles(n_reads, h_seq_off, k, tile, tiles, h_seq, exact ? k : k - 1);
     const uint32_t n_tiles = (uint32_t)(tiles.size() / 2);
     ctx->d_counters.reserve(64);
     RTK_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
@@ -106,7 +106,7 @@ void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, 
     }
     uint64_t probes = 0;
     float kms = 0.f;
-    const uint64_t n_raw = k1_launch(ctx, n_reads, d_seq, d_off, rel.data(), flags, &probes, &kms);
+    const uint64_t n_raw = k1_launch(ctx, n_reads, d_seq, d_off, rel.data(), flags, &probes, &kms, seq_pool + seq_off[0]);
     std::vector<RawHit> raw(n_raw);
     if (n_raw) {
         RTK_CUDA(counted_memcpy_async(raw.data(), ctx->d_hits.p, n_raw * sizeof(RawHit), cudaMemcpyDeviceToHost, ctx->stream));

@@ -52,15 +52,33 @@ inline void finish_host_graph(rtk_host_graph* g) {
 // read positions per K1 tile: one per thread
 inline uint32_t k1_tile_size(uint32_t, bool) { return RTK_K1_THREADS; }
 
-inline void build_tiles(uint32_t n_reads, const uint64_t* h_seq_off, uint32_t k, uint32_t tile, std::vector<uint32_t>& tiles) {
+// h_seq (optional): the reads on the host, h_seq + h_seq_off[r] = read r.  When given, a tile is emitted only if a window of
+// `need` consecutive A/C/G/T bases STARTS inside it (need = k for the exact sweep, k-1 = the shortest variant-string window of
+// the one-edit sweeps): the masked copies getSeeds sweeps inexactly are mostly 'N' (src/Graph.cpp:106-191), and a tile
+// without such a window can neither probe nor hit.
+inline void build_tiles(uint32_t n_reads, const uint64_t* h_seq_off, uint32_t k, uint32_t tile, std::vector<uint32_t>& tiles,
+                        const char* h_seq = nullptr, uint32_t need = 0) {
     tiles.clear();
+    std::vector<uint8_t> live;
     for (uint32_t r = 0; r < n_reads; ++r) {
         const uint64_t len = h_seq_off[r + 1] - h_seq_off[r];
         if (len >= (1ULL << RTK_HIT_POS_BITS)) throw std::invalid_argument("read longer than 2^30 bases");
         if (len < k) continue;
         // positions l with l + k - 1 <= len (one past the last full k-mer: insertion windows use k-1 read bases)
         const uint32_t npos = (uint32_t)(len - k + 2);
-        for (uint32_t t0 = 0; t0 < npos; t0 += tile) { tiles.push_back(r); tiles.push_back(t0); }
+        if (h_seq && need) {
+            live.assign((npos + tile - 1) / tile, 0);
+            const char* s = h_seq + h_seq_off[r];
+            uint32_t run = 0;
+            for (uint64_t i = 0; i < len; ++i) {
+                const char c = s[i];
+                run = (c == 'A' || c == 'C' || c == 'G' || c == 'T') ? run + 1 : 0;
+                if (run >= need) { const uint64_t start = i + 1 - need; if (start < npos) live[start / tile] = 1; }
+            }
+            for (uint32_t t0 = 0; t0 < npos; t0 += tile) if (live[t0 / tile]) { tiles.push_back(r); tiles.push_back(t0); }
+        } else {
+            for (uint32_t t0 = 0; t0 < npos; t0 += tile) { tiles.push_back(r); tiles.push_back(t0); }
+        }
     }
 }
 

@@ -5,7 +5,11 @@
 #endif
 #include <stdint.h>
 
+#include <sched.h>
+
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -109,7 +113,7 @@ struct rtk_ctx {
     rtk_host_graph host_graph_owned;
     // scratch
     rtk::DevBuf d_seq, d_seq_off, d_tiles, d_hits, d_counters, d_aux[8], d_sub[8];
-    rtk::PinBuf h_pin[4];
+    rtk::PinBuf h_pin[12];   // pinned landing zones of the D2H copies (one slot per copy site, see PinnedD2H)
     int sm_count = 148;
     // reads of the next exact sweep already resident in HBM (rtk_correct_batch_resident); consumed once
     const char* resident_seq = nullptr;
@@ -128,9 +132,46 @@ void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_p
 // K1 driver: runs the exact and/or inexact kernels over reads resident on the device and leaves the
 // raw labelled hits in ctx->d_hits.  Returns raw hit count; *n_probes / *kernel_ms optional.
 uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint64_t* d_seq_off,
-                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms);
+                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms, const char* h_seq = nullptr);
 
 #ifndef RTK_HOSTSIM
+// Wait for a stream without monopolising a core: the service threads of the correction broker outnumber the spare cores, and
+// a thread spinning inside cudaStreamSynchronize keeps a region worker off the CPU.  Poll + yield keeps the wake-up latency
+// of spinning (no interrupt round trip) but hands the core to any runnable worker.  RTK_SPIN_SYNC=1: plain spinning.
+inline void stream_wait(cudaStream_t st) {
+    static const bool spin = getenv("RTK_SPIN_SYNC") != nullptr;
+    if (spin) { RTK_CUDA(cudaStreamSynchronize(st)); return; }
+    for (;;) {
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e == cudaSuccess) return;
+        if (e != cudaErrorNotReady) RTK_CUDA(e);
+        sched_yield();
+    }
+}
+
+// Device -> host copies land in pinned memory and are copied out after the stream synchronisation.  A cudaMemcpyAsync
+// into PAGEABLE memory blocks inside the driver until the preceding kernels have finished; with five service threads
+// sharing one context that serialised the services on each other's kernel latency.
+struct PinnedD2H {
+    rtk_ctx* c;
+    cudaStream_t st;
+    struct Item { void* dst; const void* pin; size_t n; };
+    Item items[4];
+    int n_items = 0;
+    PinnedD2H(rtk_ctx* ctx, cudaStream_t s) : c(ctx), st(s) {}
+    void copy(int slot, void* dst, const void* src_dev, size_t n) {
+        if (!n) return;
+        c->h_pin[slot].reserve(n + 16);
+        RTK_CUDA(counted_memcpy_async(c->h_pin[slot].p, src_dev, n, cudaMemcpyDeviceToHost, st));
+        items[n_items++] = Item{dst, c->h_pin[slot].p, n};
+    }
+    void sync() {
+        stream_wait(st);
+        for (int i = 0; i < n_items; ++i) memcpy(items[i].dst, items[i].pin, items[i].n);
+        n_items = 0;
+    }
+};
+
 // everything enqueued on the side streams after fan_out sees the work enqueued on c->stream before it;
 // fan_in(k) makes c->stream wait for side stream k
 inline void fan_out(rtk_ctx* c) { RTK_CUDA(cudaEventRecord(c->ev_fork, c->stream)); }
@@ -150,6 +191,13 @@ struct MyersJobs {
 };
 void myers_run(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const MyersJobs& j, int32_t* dist, bool want_ends,
                int32_t** ends, uint64_t** ends_off, float* kernel_ms);
+// host pools in, distance + first / last best end out (the broker's K4 service); stats[2] += kernel ns
+void dist_batch_lean(rtk_ctx* c, uint32_t n, const char* q_pool, const uint64_t* q_off, const char* t_pool, const uint64_t* t_off,
+                     const uint8_t* mode, int32_t* dist, int32_t* first_end, int32_t* last_end, uint64_t* stats);
+// lean variant for internal callers: distance + first / last best end column; pools either resident (d_*) or on the host
+// (h_* != nullptr: packed into the same single upload as the descriptors).  kmax is unbounded.
+void myers_run_lean(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const char* h_qpool, uint64_t q_bytes, const char* h_tpool,
+                    uint64_t t_bytes, const MyersJobs& j, int32_t* dist, int32_t* first_end, int32_t* last_end, float* kernel_ms);
 #endif
 
 // full searchSequence for a host batch -> per read ordered hits

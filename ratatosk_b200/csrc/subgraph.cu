@@ -48,11 +48,12 @@ extern "C" int rtk_explore_subgraph_batch(rtk_ctx* c, uint32_t n_calls, const rt
         RTK_CUDA(cudaGetLastError());
         std::vector<uint64_t> nchars(n_calls);
         std::vector<uint32_t> ncand(n_calls + 1, 0);
+        PinnedD2H d2h(c, st);
         if (n_calls) {
-            RTK_CUDA(counted_memcpy_async(nchars.data(), d_nchars, (size_t)n_calls * 8, cudaMemcpyDeviceToHost, st));
-            RTK_CUDA(counted_memcpy_async(ncand.data(), d_ncand, (size_t)(n_calls + 1) * 4, cudaMemcpyDeviceToHost, st));
+            d2h.copy(2, nchars.data(), d_nchars, (size_t)n_calls * 8);
+            d2h.copy(3, ncand.data(), d_ncand, (size_t)(n_calls + 1) * 4);
         }
-        RTK_CUDA(cudaStreamSynchronize(st));
+        d2h.sync();
         if (ncand[n_calls]) throw std::runtime_error("exploreSubGraph: a burst exceeded the DFS capacity (RTK_DFS_MAX_NODES / RTK_DFS_STACK)");
         std::vector<uint64_t> cand_off(n_calls + 1, 0), char_off(n_calls + 1, 0);
         for (uint32_t i = 0; i < n_calls; ++i) { cand_off[i + 1] = cand_off[i] + ncand[i]; char_off[i + 1] = char_off[i] + nchars[i]; }
@@ -70,8 +71,8 @@ extern "C" int rtk_explore_subgraph_batch(rtk_ctx* c, uint32_t n_calls, const rt
         RTK_CUDA(cudaGetLastError());
         RTK_CUDA(cudaEventRecord(c->ev1, st));
         std::vector<rtk_cand> cands(n_cands);
-        if (n_cands) RTK_CUDA(counted_memcpy_async(cands.data(), S[4].p, n_cands * sizeof(rtk_cand), cudaMemcpyDeviceToHost, st));
-        RTK_CUDA(cudaStreamSynchronize(st));
+        if (n_cands) d2h.copy(4, cands.data(), S[4].p, n_cands * sizeof(rtk_cand));
+        d2h.sync();
         float dfs_ms = 0.f;
         RTK_CUDA(cudaEventElapsedTime(&dfs_ms, c->ev0, c->ev1));
         // K4 on every candidate
@@ -87,7 +88,7 @@ extern "C" int rtk_explore_subgraph_batch(rtk_ctx* c, uint32_t n_calls, const rt
         float my_ms = 0.f;
         if (n_cands) {
             MyersJobs j{(uint32_t)n_cands, qb.data(), ql.data(), tb.data(), tl.data(), md.data(), nullptr};
-            myers_run(c, S[5].as<char>(), S[5].as<char>(), j, ed.data(), false, nullptr, nullptr, &my_ms);
+            myers_run_lean(c, S[5].as<char>(), S[5].as<char>(), nullptr, 0, nullptr, 0, j, ed.data(), nullptr, nullptr, &my_ms);
         }
         fill_subgraph_out(n_calls, cands, cand_off, ed, plan, c->host_graph->view.unitig_off, c->hdr.k, out);
         if (stats) { stats[0] += n_cands; stats[1] += n_chars; stats[2] += (uint64_t)(dfs_ms * 1e6); stats[3] += (uint64_t)(my_ms * 1e6); }

@@ -100,10 +100,11 @@ struct CudaTbBackend : TbBackend {
         RTK_CUDA(cudaEventRecord(c->ev1, st));
         std::vector<uint32_t> h_len(n + 1);
         std::vector<uint8_t> h_ops(pl.ops_off[n] + 1);
-        RTK_CUDA(counted_memcpy_async(h_len.data(), tp.ops_len, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        RTK_CUDA(counted_memcpy_async(dist.data(), fp.dist, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        if (pl.ops_off[n]) RTK_CUDA(counted_memcpy_async(h_ops.data(), S[5].p, pl.ops_off[n], cudaMemcpyDeviceToHost, st));
-        RTK_CUDA(cudaStreamSynchronize(st));
+        PinnedD2H d2h(c, st);
+        d2h.copy(5, h_len.data(), tp.ops_len, (size_t)n * 4);
+        d2h.copy(6, dist.data(), fp.dist, (size_t)n * 4);
+        if (pl.ops_off[n]) d2h.copy(7, h_ops.data(), S[5].p, pl.ops_off[n]);
+        d2h.sync();
         float t = 0.f;
         RTK_CUDA(cudaEventElapsedTime(&t, c->ev0, c->ev1));
         ms += t;
@@ -126,9 +127,10 @@ struct CudaTbBackend : TbBackend {
         RTK_CUDA(cudaEventRecord(c->ev1, st));
         std::vector<uint64_t> cells(pl.cells * 2 + 2);
         std::vector<int32_t> anchor(pl.cells + 1);
-        RTK_CUDA(counted_memcpy_async(cells.data(), c->d_sub[3].p, pl.cells * 16, cudaMemcpyDeviceToHost, st));
-        RTK_CUDA(counted_memcpy_async(anchor.data(), c->d_sub[4].p, pl.cells * 4, cudaMemcpyDeviceToHost, st));
-        RTK_CUDA(cudaStreamSynchronize(st));
+        PinnedD2H d2h(c, st);
+        d2h.copy(8, cells.data(), c->d_sub[3].p, pl.cells * 16);
+        d2h.copy(9, anchor.data(), c->d_sub[4].p, pl.cells * 4);
+        d2h.sync();
         float t = 0.f;
         RTK_CUDA(cudaEventElapsedTime(&t, c->ev0, c->ev1));
         ms += t;
@@ -176,14 +178,13 @@ extern "C" int rtk_edlib_path_batch(rtk_ctx* c, uint32_t n, const char* q_pool, 
             std::vector<int32_t> d2(m);
             for (uint32_t i = 0; i < m; ++i) { qb2[i] = qrel[shw[i]]; tb2[i] = trel[shw[i]]; ql2[i] = qlen[shw[i]]; tl2[i] = tlen[shw[i]]; }
             MyersJobs j{m, qb2.data(), ql2.data(), tb2.data(), tl2.data(), md.data(), nullptr};
-            int32_t* e = nullptr; uint64_t* eo = nullptr;
-            myers_run(c, c->d_aux[0].as<char>(), c->d_aux[1].as<char>(), j, d2.data(), true, &e, &eo, nullptr);
+            std::vector<int32_t> fe(m, -1);
+            myers_run_lean(c, c->d_aux[0].as<char>(), c->d_aux[1].as<char>(), nullptr, 0, nullptr, 0, j, d2.data(), fe.data(), nullptr, nullptr);
             for (uint32_t i = 0; i < m; ++i) {
                 dist[shw[i]] = d2[i];
-                end_loc[shw[i]] = (eo[i + 1] > eo[i]) ? e[eo[i]] : -1;
+                end_loc[shw[i]] = fe[i];
                 teff[shw[i]] = (uint32_t)(end_loc[shw[i]] + 1);
             }
-            free(e); free(eo);
         }
         // 2. reversed copies (each query, each effective target prefix, reversed in place of its own range)
         std::string rq(qb + 1, 'N'), rt(tb + 1, 'N');

@@ -56,6 +56,9 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_fill_kernel(const
     const int nb = (qlen + 63) >> 6;
     const int rounds = (nb + G - 1) / G;
     int8_t* hb = p.hbound + p.hb_off[a];
+    bool t_amb = false;   // anything but A/C/G/T in the target?
+    for (int i = (int)lane; i < tlen; i += G) { const char ch = t[i]; t_amb |= (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T'); }
+    t_amb = __any_sync(gmask, t_amb);
     for (int r = 0; r < rounds; ++r) {
         const int b = r * G + (int)lane;
         const bool has = b < nb;
@@ -76,48 +79,44 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_fill_kernel(const
         const bool spill = (lane == G - 1) && (r + 1 < rounds);
         const int steps = tlen + G - 1;
         char tc_next = (lane == 0 && tlen > 0) ? t[0] : (char)0;   // the target is read one step ahead of its use
+        const bool top_spilled = (lane == 0) && (r != 0);
+        const bool is_last_blk = (b == nb - 1);
+        // straight-line step, selects instead of branches (see myers.cuh); the cell stores are predicated
         for (int s = 0; s < steps; ++s) {
             const int from_left = __shfl_up_sync(gmask, hout, 1, G);
             const int col = s - (int)lane;
             const char tc = tc_next;
-            tc_next = (col + 1 >= 0 && col + 1 < tlen) ? t[col + 1] : (char)0;
-            hout = 0;
-            if (has && col >= 0 && col < tlen) {
-                const int hin = (lane == 0) ? ((r == 0) ? 1 : (int)hb[col]) : from_left;   // NW: D[0][j] = j
-                uint64_t Eq;
-                switch (tc) {
-                    case 'A': Eq = PB0; break;
-                    case 'C': Eq = PB1; break;
-                    case 'G': Eq = PB2; break;
-                    case 'T': Eq = PB3; break;
-                    default: {
-                        Eq = 0;
-                        const int lo = b << 6;
-                        const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
-                        for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(q[lo + i], tc) << i;
-                    }
-                }
-                const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
-                const uint64_t Xv = Eq | Mv;
-                Eq |= neg;
-                const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-                uint64_t Ph = Mv | ~(Xh | Pv);
-                uint64_t Mh = Pv & Xh;
-                hout = (int)(Ph >> 63) - (int)(Mh >> 63);
-                score += (int)((Ph >> arow) & 1) - (int)((Mh >> arow) & 1);
-                Ph = (Ph << 1) | ((hin > 0) ? 1ULL : 0ULL);
-                Mh = (Mh << 1) | neg;
-                Pv = Mh | ~(Xv | Ph);
-                Mv = Ph & Xv;
-                if (!LASTCOL || col == tlen - 1) {
-                    ulonglong2 cell; cell.x = Pv; cell.y = Mv;
-                    const uint64_t idx = LASTCOL ? base : (base + col);
-                    p.mat[idx] = cell;
-                    p.anchor[idx] = score;
-                }
-                if (b == nb - 1 && col == tlen - 1) p.dist[a] = score;
-                if (spill) hb[col] = (int8_t)hout;
+            tc_next = ((unsigned)(col + 1) < (unsigned)tlen) ? t[col + 1] : (char)0;
+            const bool active = has && ((unsigned)col < (unsigned)tlen);
+            int hin = (lane == 0) ? 1 : from_left;   // NW: D[0][j] = j
+            if (top_spilled && active) hin = (int)hb[col];
+            uint64_t Eq = (tc == 'A') ? PB0 : (tc == 'C') ? PB1 : (tc == 'G') ? PB2 : (tc == 'T') ? PB3 : 0ULL;
+            if (t_amb && active && tc != 'A' && tc != 'C' && tc != 'G' && tc != 'T') {
+                const int lo = b << 6;
+                const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+                for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(q[lo + i], tc) << i;
             }
+            const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
+            const uint64_t Xv = Eq | Mv;
+            Eq |= neg;
+            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            uint64_t Ph = Mv | ~(Xh | Pv);
+            uint64_t Mh = Pv & Xh;
+            hout = active ? ((int)(Ph >> 63) - (int)(Mh >> 63)) : 0;
+            score += active ? ((int)((Ph >> arow) & 1) - (int)((Mh >> arow) & 1)) : 0;
+            Ph = (Ph << 1) | ((hin > 0) ? 1ULL : 0ULL);
+            Mh = (Mh << 1) | neg;
+            const uint64_t nPv = Mh | ~(Xv | Ph), nMv = Ph & Xv;
+            Pv = active ? nPv : Pv;
+            Mv = active ? nMv : Mv;
+            if (active && (!LASTCOL || col == tlen - 1)) {
+                ulonglong2 cell; cell.x = Pv; cell.y = Mv;
+                const uint64_t idx = LASTCOL ? base : (base + col);
+                p.mat[idx] = cell;
+                p.anchor[idx] = score;
+            }
+            if (active && is_last_blk && col == tlen - 1) p.dist[a] = score;
+            if (spill && active) hb[col] = (int8_t)hout;
         }
         __syncwarp(gmask);
     }

@@ -163,20 +163,20 @@ GPath GPath::from_compact(const rtk_graph_view& g, const PNode& um_start, const 
 
 // ---------------------------------------------------------------------------------------------- GPU services
 // A request is handed to the wave broker when this thread runs under one (broker.hpp), else executed at once.
-void gpu_distances_all(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<std::vector<int32_t>>& ends) {
+void gpu_distances_fl(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<int32_t>& first_end,
+                      std::vector<int32_t>& last_end) {
     dist.assign(jobs.size(), -1);
-    ends.assign(jobs.size(), {});
+    first_end.assign(jobs.size(), -1);
+    last_end.assign(jobs.size(), -1);
     if (jobs.empty()) return;
-    DistReq r{&jobs, &dist, &ends};
+    DistReq r{&jobs, &dist, &first_end, &last_end};
     if (GpuBroker* b = current_broker()) b->submit(&r);
     else run_dist_batch(ctx, std::vector<DistReq*>(1, &r));
 }
 
 void gpu_distances(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<int32_t>& first_end) {
-    std::vector<std::vector<int32_t>> ends;
-    gpu_distances_all(ctx, jobs, dist, ends);
-    first_end.assign(jobs.size(), -1);
-    for (size_t i = 0; i < jobs.size(); ++i) if (!ends[i].empty()) first_end[i] = ends[i][0];
+    std::vector<int32_t> last_end;
+    gpu_distances_fl(ctx, jobs, dist, first_end, last_end);
 }
 
 void gpu_paths(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<std::vector<uint8_t>>& ops) {

@@ -62,7 +62,9 @@ struct AlignJob {
     uint8_t mode;  // 0 NW, 1 SHW, 2 HW
 };
 void gpu_distances(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<int32_t>& first_end);
-void gpu_distances_all(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<std::vector<int32_t>>& ends);
+// + the largest end column carrying the distance (the end locations are ascending: first = endLocations[0], last = the final one)
+void gpu_distances_fl(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<int32_t>& first_end,
+                      std::vector<int32_t>& last_end);
 void gpu_paths(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<std::vector<uint8_t>>& ops);
 
 // selectors: first candidate wins ties (strict <), src/Alignment.cpp

@@ -95,6 +95,16 @@ template <typename T> static inline T __shfl_up_sync(unsigned mask, T v, int d, 
     memcpy(&r, &y, sizeof(T) <= 8 ? sizeof(T) : 8);
     return r;
 }
+// group-scoped vote (mask = the aligned sub-group the caller belongs to)
+static inline int __any_sync(unsigned mask, int pred) {
+    sim_warp_area& w = sim_warps[threadIdx.x >> 5];
+    w.slot[threadIdx.x & 31] = pred ? 1 : 0;
+    sim_mask_barrier(mask);
+    int r = 0;
+    for (int i = 0; i < 32; ++i) if ((mask >> i) & 1u) r |= (int)(w.slot[i] & 1);
+    sim_mask_barrier(mask);
+    return r;
+}
 template <typename T> static inline T __shfl_down_sync(unsigned m, T v, int d) {
     const int lane = threadIdx.x & 31;
     const T r = __shfl_sync(m, v, (lane + d) & 31);
