@@ -29,6 +29,10 @@ import time
 
 import numpy as np
 
+# the library's service contexts own ~20 CUDA streams: give them their own hardware work queues (default 8); must be set
+# before CUDA initialises in this process (torch does that first here)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -207,7 +211,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--bases-per-step", type=int, default=32 << 20)
+    ap.add_argument("--bases-per-step", type=int, default=64 << 20)
     ap.add_argument("--ref-sample-bases", type=int, default=3_000_000)
     ap.add_argument("--cpu-baseline-bases", type=int, default=8_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -137,6 +137,10 @@ extern "C" {
 
 int rtk_ctx_create(int device, rtk_ctx** out) {
     return guarded([&] {
+        // 32 hardware work queues instead of the default 8: the broker's service contexts own ~20 streams, and streams that
+        // alias onto one queue serialise on each other's (latency-bound) kernels.  Only effective before CUDA initialises in
+        // this process; a host program that initialises CUDA first (bench.py: torch) sets the variable itself.
+        setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
         if (e != cudaSuccess || n == 0) throw CudaError(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)");

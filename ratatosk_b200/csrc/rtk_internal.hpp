@@ -113,7 +113,7 @@ struct rtk_ctx {
     rtk_host_graph host_graph_owned;
     // scratch
     rtk::DevBuf d_seq, d_seq_off, d_tiles, d_hits, d_counters, d_aux[8], d_sub[8];
-    rtk::PinBuf h_pin[12];   // pinned landing zones of the D2H copies (one slot per copy site, see PinnedD2H)
+    rtk::PinBuf h_pin[16];   // pinned landing zones of the D2H copies (one slot per copy site, see PinnedD2H)
     int sm_count = 148;
     // reads of the next exact sweep already resident in HBM (rtk_correct_batch_resident); consumed once
     const char* resident_seq = nullptr;

@@ -29,8 +29,16 @@ extern "C" int rtk_explore_subgraph_batch(rtk_ctx* c, uint32_t n_calls, const rt
         S[1].reserve(n_pids * 4 + 16);
         S[2].reserve((size_t)n_calls * 12 + 32);
         S[3].reserve((size_t)(n_calls + 1) * 16 + 16);
-        RTK_CUDA(counted_memcpy_async(S[0].p, calls, (size_t)n_calls * sizeof(rtk_subgraph_call_t), cudaMemcpyHostToDevice, st));
-        if (n_pids) RTK_CUDA(counted_memcpy_async(S[1].p, pid_pool, n_pids * 4, cudaMemcpyHostToDevice, st));
+        // inputs through pinned staging (calls | pids | read windows): the uploads are then truly asynchronous
+        const uint64_t b_calls = (uint64_t)n_calls * sizeof(rtk_subgraph_call_t), b_pids = n_pids * 4;
+        PinBuf& H = c->h_pin[14];
+        H.reserve(b_calls + b_pids + ref_bytes + 64);
+        char* h_in = H.as<char>();
+        memcpy(h_in, calls, b_calls);
+        if (b_pids) memcpy(h_in + b_calls, pid_pool, b_pids);
+        memcpy(h_in + b_calls + b_pids, ref_pool, ref_bytes);
+        if (b_calls) RTK_CUDA(counted_memcpy_async(S[0].p, h_in, b_calls, cudaMemcpyHostToDevice, st));
+        if (b_pids) RTK_CUDA(counted_memcpy_async(S[1].p, h_in + b_calls, b_pids, cudaMemcpyHostToDevice, st));
         rtk_dfs_params p;
         const rtk_graph_view& g = c->dview;
         p.unitig_off = g.unitig_off; p.pool = g.pool; p.shared = g.shared; p.adj = g.adj; p.gset_of = g.gset_of;
@@ -62,9 +70,12 @@ extern "C" int rtk_explore_subgraph_batch(rtk_ctx* c, uint32_t n_calls, const rt
         S[4].reserve(n_cands * sizeof(rtk_cand) + 16);
         S[5].reserve(ref_bytes + n_chars + 16);
         uint64_t* d_off = S[3].as<uint64_t>();
-        RTK_CUDA(counted_memcpy_async(d_off, cand_off.data(), (size_t)(n_calls + 1) * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(counted_memcpy_async(d_off + (n_calls + 1), char_off.data(), (size_t)(n_calls + 1) * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(counted_memcpy_async(S[5].p, ref_pool, ref_bytes, cudaMemcpyHostToDevice, st));
+        PinBuf& H2 = c->h_pin[15];
+        H2.reserve((size_t)(n_calls + 1) * 16 + 64);
+        memcpy(H2.p, cand_off.data(), (size_t)(n_calls + 1) * 8);
+        memcpy(H2.as<char>() + (size_t)(n_calls + 1) * 8, char_off.data(), (size_t)(n_calls + 1) * 8);
+        RTK_CUDA(counted_memcpy_async(d_off, H2.p, (size_t)(n_calls + 1) * 16, cudaMemcpyHostToDevice, st));
+        if (ref_bytes) RTK_CUDA(counted_memcpy_async(S[5].p, h_in + b_calls + b_pids, ref_bytes, cudaMemcpyHostToDevice, st));
         p.cand_off = d_off; p.char_off = d_off + (n_calls + 1); p.cands = S[4].as<rtk_cand>(); p.chars = S[5].as<char>() + ref_bytes;
         if (n_calls) ++g_launches;
         if (n_calls) rtk_dfs_kernel<true><<<grid, RTK_DFS_WARPS * 32, 0, st>>>(p);

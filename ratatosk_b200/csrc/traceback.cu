@@ -12,21 +12,11 @@
 
 namespace rtk {
 
-template <int G, bool LC> static void launch_fill(rtk_ctx* c, int k, rtk_fill_params p, const uint32_t* d_order, uint32_t n) {
-    if (!n) return;
-    p.order = d_order;
-    p.n = n;
-    const uint64_t threads = (uint64_t)n * G;
-    ++g_launches;
-    rtk_myers_fill_kernel<G, LC><<<(uint32_t)((threads + RTK_MYERS_THREADS - 1) / RTK_MYERS_THREADS), RTK_MYERS_THREADS, 0, side_stream(c, k)>>>(p);
-    RTK_CUDA(cudaGetLastError());
-    fan_in(c, k);
-}
-
 // device pools: d_aux[0] queries, d_aux[1] targets (effective prefixes), d_sub[7] reversed queries | reversed targets
 struct CudaTbBackend : TbBackend {
     rtk_ctx* c;
     const char* d_q; const char* d_t; const char* d_rq; const char* d_rt;
+    const uint32_t* d_ids = nullptr;   // alignment ids of the current fill, device copy (class order G = 1 .. 32)
     float ms = 0.f;
 
     template <bool LC> void run_fill(const std::vector<TbItem>& items, const TbPlan& pl, rtk_fill_params& fp, uint64_t*& d_off, uint32_t*& d_len) {
@@ -45,38 +35,51 @@ struct CudaTbBackend : TbBackend {
             tb[i] = (uint64_t)((tp + items[i].t_beg) - d_t);
             ql[i] = items[i].q_len; tl[i] = items[i].t_len;
         }
-        S[0].reserve((size_t)(n + 1) * 8 * 5);
-        S[1].reserve((size_t)(n + 1) * 4 * 2);
-        S[2].reserve((size_t)(n + 1) * 4);
+        // one packed upload from pinned staging: u64 q_beg | t_beg | mat_off(n+1) | ops_off(n+1) | hb_off(n+1), u32 q_len | t_len | ids
+        const uint64_t o_qb = 0, o_tb = o_qb + 8ull * n, o_mat = o_tb + 8ull * n, o_ops = o_mat + 8ull * (n + 1), o_hb = o_ops + 8ull * (n + 1),
+                       o_ql = o_hb + 8ull * (n + 1), o_tl = o_ql + 4ull * (n + 1), o_ids = o_tl + 4ull * (n + 1), total = o_ids + 4ull * (n + 1);
+        PinBuf& H = c->h_pin[11];
+        H.reserve(total + 64);
+        char* h = H.as<char>();
+        memcpy(h + o_qb, qb.data(), 8ull * n);
+        memcpy(h + o_tb, tb.data(), 8ull * n);
+        memcpy(h + o_mat, pl.mat_off.data(), 8ull * (n + 1));
+        memcpy(h + o_ops, pl.ops_off.data(), 8ull * (n + 1));
+        memcpy(h + o_hb, pl.hb_off.data(), 8ull * (n + 1));
+        memcpy(h + o_ql, ql.data(), 4ull * n);
+        memcpy(h + o_tl, tl.data(), 4ull * n);
+        memcpy(h + o_ids, pl.ids.data(), pl.ids.size() * 4);
+        S[0].reserve(total + 64);
         S[3].reserve(pl.cells * 16 + 16);
         S[4].reserve(pl.cells * 4 + 16);
         S[5].reserve(pl.ops_off[n] + 16);
         S[6].reserve((size_t)(n + 1) * 8 + pl.hb_off[n] + 16);
-        d_off = S[0].as<uint64_t>();
-        d_len = S[1].as<uint32_t>();
-        RTK_CUDA(counted_memcpy_async(d_off, qb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(counted_memcpy_async(d_off + (n + 1), tb.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(counted_memcpy_async(d_off + 2 * (n + 1), pl.mat_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(counted_memcpy_async(d_off + 3 * (n + 1), pl.ops_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(counted_memcpy_async(d_off + 4 * (n + 1), pl.hb_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(counted_memcpy_async(d_len, ql.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(counted_memcpy_async(d_len + (n + 1), tl.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(counted_memcpy_async(S[2].p, pl.ids.data(), pl.ids.size() * 4, cudaMemcpyHostToDevice, st));
+        char* d = S[0].as<char>();
+        RTK_CUDA(counted_memcpy_async(d, h, total, cudaMemcpyHostToDevice, st));
+        d_off = (uint64_t*)d;                       // [q_beg | t_beg | mat_off | ops_off | hb_off]
+        d_len = (uint32_t*)(d + o_ql);              // [q_len (n+1) | t_len (n+1)]
+        d_ids = (const uint32_t*)(d + o_ids);
         uint32_t* d_opslen = S[6].as<uint32_t>();
         RTK_CUDA(cudaMemsetAsync(d_opslen, 0, (size_t)(n + 1) * 8, st));
-        fp.q_pool = d_q; fp.q_beg = d_off; fp.q_len = d_len; fp.t_pool = d_t; fp.t_beg = d_off + (n + 1); fp.t_len = d_len + (n + 1);
-        fp.order = nullptr; fp.n = 0; fp.mat_off = d_off + 2 * (n + 1); fp.mat = S[3].as<ulonglong2>(); fp.anchor = S[4].as<int32_t>();
-        fp.dist = (int32_t*)(d_opslen + (n + 1)); fp.hbound = (int8_t*)(d_opslen + 2 * (n + 1)); fp.hb_off = d_off + 4 * (n + 1);
+        fp.q_pool = d_q; fp.q_beg = d_off; fp.q_len = d_len; fp.t_pool = d_t; fp.t_beg = d_off + n; fp.t_len = d_len + (n + 1);
+        fp.order = d_ids; fp.n = n; fp.mat_off = (const uint64_t*)(d + o_mat); fp.mat = S[3].as<ulonglong2>(); fp.anchor = S[4].as<int32_t>();
+        fp.dist = (int32_t*)(d_opslen + (n + 1)); fp.hbound = (int8_t*)(d_opslen + 2 * (n + 1)); fp.hb_off = (const uint64_t*)(d + o_hb);
+        // pl.ids holds the classes in the order G = 1, 2, ..., 32; the fused kernel runs them 32 first
+        uint32_t off_c[7] = {0}, n_blocks = 0;
+        for (int k = 0; k < 6; ++k) off_c[k + 1] = off_c[k] + (uint32_t)pl.order[k].size();
+        for (int jx = 0; jx < 6; ++jx) {
+            const int k = 5 - jx;
+            const uint32_t G = 1u << k;
+            fp.cls_ord[jx] = off_c[k]; fp.cls_cnt[jx] = (uint32_t)pl.order[k].size(); fp.cls_blk[jx] = n_blocks;
+            n_blocks += (uint32_t)(((uint64_t)pl.order[k].size() * G + RTK_MYERS_THREADS - 1) / RTK_MYERS_THREADS);
+        }
+        fp.cls_blk[6] = n_blocks;
         RTK_CUDA(cudaEventRecord(c->ev0, st));
-        const uint32_t* d_ids = S[2].as<uint32_t>();
-        uint32_t o = 0;
-        fan_out(c);
-        launch_fill<1, LC>(c, 0, fp, d_ids + o, (uint32_t)pl.order[0].size()); o += (uint32_t)pl.order[0].size();
-        launch_fill<2, LC>(c, 1, fp, d_ids + o, (uint32_t)pl.order[1].size()); o += (uint32_t)pl.order[1].size();
-        launch_fill<4, LC>(c, 2, fp, d_ids + o, (uint32_t)pl.order[2].size()); o += (uint32_t)pl.order[2].size();
-        launch_fill<8, LC>(c, 3, fp, d_ids + o, (uint32_t)pl.order[3].size()); o += (uint32_t)pl.order[3].size();
-        launch_fill<16, LC>(c, 4, fp, d_ids + o, (uint32_t)pl.order[4].size()); o += (uint32_t)pl.order[4].size();
-        launch_fill<32, LC>(c, 5, fp, d_ids + o, (uint32_t)pl.order[5].size());
+        if (n_blocks) {
+            ++g_launches;
+            rtk_myers_fill_fused_kernel<LC><<<n_blocks, RTK_MYERS_THREADS, 0, st>>>(fp);
+            RTK_CUDA(cudaGetLastError());
+        }
     }
 
     void direct(const std::vector<TbItem>& items, std::vector<std::vector<uint8_t>>& ops, std::vector<int32_t>& dist) override {
@@ -91,8 +94,8 @@ struct CudaTbBackend : TbBackend {
         cudaStream_t st = c->stream;
         DevBuf* S = c->d_sub;
         rtk_tb_params tp;
-        tp.q_len = d_len; tp.t_len = d_len + (n + 1); tp.ids = S[2].as<uint32_t>(); tp.n = n; tp.mat_off = d_off + 2 * (n + 1);
-        tp.mat = S[3].as<ulonglong2>(); tp.anchor = S[4].as<int32_t>(); tp.dist = fp.dist; tp.ops_off = d_off + 3 * (n + 1);
+        tp.q_len = d_len; tp.t_len = d_len + (n + 1); tp.ids = d_ids; tp.n = n; tp.mat_off = d_off + 2 * (size_t)n;
+        tp.mat = S[3].as<ulonglong2>(); tp.anchor = S[4].as<int32_t>(); tp.dist = fp.dist; tp.ops_off = d_off + 2 * (size_t)n + (n + 1);
         tp.ops = S[5].as<uint8_t>(); tp.ops_len = S[6].as<uint32_t>();
         ++g_launches;
         rtk_traceback_kernel<<<(n + 127) / 128, 128, 0, st>>>(tp);
@@ -163,8 +166,14 @@ extern "C" int rtk_edlib_path_batch(rtk_ctx* c, uint32_t n, const char* q_pool, 
         for (uint32_t i = 0; i < n; ++i) { qlen[i] = (uint32_t)(q_off[i + 1] - q_off[i]); tlen[i] = (uint32_t)(t_off[i + 1] - t_off[i]); }
         c->d_aux[0].reserve(qb + 16);
         c->d_aux[1].reserve(tb + 16);
-        RTK_CUDA(counted_memcpy_async(c->d_aux[0].p, q_pool + q_off[0], qb, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(counted_memcpy_async(c->d_aux[1].p, t_pool + t_off[0], tb, cudaMemcpyHostToDevice, st));
+        {   // pools through pinned staging: the copies are then truly asynchronous
+            PinBuf& H = c->h_pin[12];
+            H.reserve(qb + tb + 64);
+            memcpy(H.as<char>(), q_pool + q_off[0], qb);
+            memcpy(H.as<char>() + qb, t_pool + t_off[0], tb);
+            if (qb) RTK_CUDA(counted_memcpy_async(c->d_aux[0].p, H.as<char>(), qb, cudaMemcpyHostToDevice, st));
+            if (tb) RTK_CUDA(counted_memcpy_async(c->d_aux[1].p, H.as<char>() + qb, tb, cudaMemcpyHostToDevice, st));
+        }
         // 1. SHW alignments: distance + first end column from K4
         std::vector<uint32_t> shw;
         for (uint32_t a = 0; a < n; ++a) if (mode[a] == 1) shw.push_back(a);
@@ -186,17 +195,26 @@ extern "C" int rtk_edlib_path_batch(rtk_ctx* c, uint32_t n, const char* q_pool, 
                 teff[shw[i]] = (uint32_t)(end_loc[shw[i]] + 1);
             }
         }
-        // 2. reversed copies (each query, each effective target prefix, reversed in place of its own range)
-        std::string rq(qb + 1, 'N'), rt(tb + 1, 'N');
-        for (uint32_t a = 0; a < n; ++a) {
-            const char* qs = q_pool + q_off[a];
-            for (uint32_t i = 0; i < qlen[a]; ++i) rq[qrel[a] + i] = qs[qlen[a] - 1 - i];
-            const char* ts = t_pool + t_off[a];
-            for (uint32_t i = 0; i < teff[a]; ++i) rt[trel[a] + i] = ts[teff[a] - 1 - i];
-        }
+        // 2. reversed copies (each query, each effective target prefix, reversed in place of its own range): only edlib's
+        //    divide-and-conquer reads them, i.e. only when some problem is above the 1 MiB switch
+        bool need_rev = false;
+        for (uint32_t a = 0; a < n && !need_rev; ++a) need_rev = qlen[a] != 0 && teff[a] != 0 && tb_needs_hirschberg(qlen[a], teff[a]);
         c->d_sub[7].reserve(qb + tb + 32);
-        RTK_CUDA(counted_memcpy_async(c->d_sub[7].p, rq.data(), qb, cudaMemcpyHostToDevice, st));
-        RTK_CUDA(counted_memcpy_async(c->d_sub[7].as<char>() + qb + 8, rt.data(), tb, cudaMemcpyHostToDevice, st));
+        if (need_rev) {
+            PinBuf& H = c->h_pin[13];
+            H.reserve(qb + tb + 64);
+            char* rq = H.as<char>();
+            char* rt = rq + qb;
+            memset(rq, 'N', qb + tb);
+            for (uint32_t a = 0; a < n; ++a) {
+                const char* qs = q_pool + q_off[a];
+                for (uint32_t i = 0; i < qlen[a]; ++i) rq[qrel[a] + i] = qs[qlen[a] - 1 - i];
+                const char* ts = t_pool + t_off[a];
+                for (uint32_t i = 0; i < teff[a]; ++i) rt[trel[a] + i] = ts[teff[a] - 1 - i];
+            }
+            if (qb) RTK_CUDA(counted_memcpy_async(c->d_sub[7].p, rq, qb, cudaMemcpyHostToDevice, st));
+            if (tb) RTK_CUDA(counted_memcpy_async(c->d_sub[7].as<char>() + qb + 8, rt, tb, cudaMemcpyHostToDevice, st));
+        }
         // 3. solve the non-trivial problems
         std::vector<uint32_t> ids;
         for (uint32_t a = 0; a < n; ++a) { flags[a] = 0; if (qlen[a] != 0 && tlen[a] != 0 && teff[a] != 0) ids.push_back(a); }

@@ -35,6 +35,11 @@ struct rtk_fill_params {
     int32_t* dist;             // [alignment] NW distance
     int8_t* hbound;            // scratch between rounds: hb_off[a] .. + t_len
     const uint64_t* hb_off;
+    // fused launch: slot j = lane groups of G = 32 >> j lanes; its blocks are [cls_blk[j], cls_blk[j+1]) and its alignment ids
+    // order[cls_ord[j] .. + cls_cnt[j])
+    uint32_t cls_blk[7] = {0, 0, 0, 0, 0, 0, 0};
+    uint32_t cls_ord[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t cls_cnt[6] = {0, 0, 0, 0, 0, 0};
 };
 
 #if defined(__CUDACC__) || defined(__CUDACC_SIM__)
@@ -43,13 +48,13 @@ struct rtk_fill_params {
 // column, at mat_off + block (Hirschberg's split needs one column of the forward and of the reversed problem).
 // Queries longer than 64*G rows are swept in rounds of G blocks like K4 (hbound spill between rounds).
 template <int G, bool LASTCOL>
-__global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_fill_kernel(const rtk_fill_params p) {
+__device__ __forceinline__ void rtk_myers_fill_body(const rtk_fill_params& p, const uint32_t* __restrict__ order, const uint32_t n, const uint32_t blk) {
     const uint32_t lane = threadIdx.x & (G - 1);
-    const uint32_t grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-    if (grp >= p.n) return;
+    const uint32_t grp = (blk * blockDim.x + threadIdx.x) / G;
+    if (grp >= n) return;
     const uint32_t wl = threadIdx.x & 31;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (wl & ~(uint32_t)(G - 1)));
-    const uint32_t a = p.order[grp];
+    const uint32_t a = order[grp];
     const char* q = p.q_pool + p.q_beg[a];
     const char* t = p.t_pool + p.t_beg[a];
     const int qlen = (int)p.q_len[a], tlen = (int)p.t_len[a];
@@ -120,6 +125,23 @@ __global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_fill_kernel(const
         }
         __syncwarp(gmask);
     }
+}
+
+template <int G, bool LASTCOL>
+__global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_fill_kernel(const rtk_fill_params p) {
+    rtk_myers_fill_body<G, LASTCOL>(p, p.order, p.n, blockIdx.x);
+}
+
+// every lane-group class of a batch in one launch, longest queries first (see rtk_myers_fused_kernel)
+template <bool LASTCOL>
+__global__ void __launch_bounds__(RTK_MYERS_THREADS) rtk_myers_fill_fused_kernel(const rtk_fill_params p) {
+    const uint32_t b = blockIdx.x;
+    if (b < p.cls_blk[1]) rtk_myers_fill_body<32, LASTCOL>(p, p.order + p.cls_ord[0], p.cls_cnt[0], b - p.cls_blk[0]);
+    else if (b < p.cls_blk[2]) rtk_myers_fill_body<16, LASTCOL>(p, p.order + p.cls_ord[1], p.cls_cnt[1], b - p.cls_blk[1]);
+    else if (b < p.cls_blk[3]) rtk_myers_fill_body<8, LASTCOL>(p, p.order + p.cls_ord[2], p.cls_cnt[2], b - p.cls_blk[2]);
+    else if (b < p.cls_blk[4]) rtk_myers_fill_body<4, LASTCOL>(p, p.order + p.cls_ord[3], p.cls_cnt[3], b - p.cls_blk[3]);
+    else if (b < p.cls_blk[5]) rtk_myers_fill_body<2, LASTCOL>(p, p.order + p.cls_ord[4], p.cls_cnt[4], b - p.cls_blk[4]);
+    else rtk_myers_fill_body<1, LASTCOL>(p, p.order + p.cls_ord[5], p.cls_cnt[5], b - p.cls_blk[5]);
 }
 
 struct rtk_tb_params {
