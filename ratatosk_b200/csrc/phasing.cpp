@@ -96,10 +96,13 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
         pos2rm[r].assign(clen + k + 1, 0);
         std::vector<Run> v_um;
         size_t max_nb_pids = 0;
-        const std::vector<rtk_hit>& h = hits[r];
+        // searchSequence lists the k-mers of a reverse-strand run in descending read position (Search.tcc:700): back to read order
+        std::vector<rtk_hit> h = hits[r];
+        std::sort(h.begin(), h.end(), [](const rtk_hit& x, const rtk_hit& y) { return x.pos < y.pos; });
         for (size_t i = 0; i < h.size();) {   // findUnitig() runs: consecutive k-mers of the read on consecutive k-mers of one unitig
             size_t j = i + 1;
-            while (j < h.size() && h[j].pos == h[j - 1].pos + 1 && h[j].unitig == h[i].unitig && h[j].strand == h[i].strand &&
+            const bool single = (g.unitig_off[h[i].unitig + 1] - g.unitig_off[h[i].unitig]) == k;   // short / abundant unitigs are never extended (CompactedDBG.tcc:4489)
+            while (!single && j < h.size() && h[j].pos == h[j - 1].pos + 1 && h[j].unitig == h[i].unitig && h[j].strand == h[i].strand &&
                    (h[i].strand ? h[j].dist == h[j - 1].dist + 1 : h[j].dist + 1 == h[j - 1].dist)) ++j;
             const uint32_t u = h[i].unitig;
             const uint64_t gs = (g.gset_of[u] == RTK_NONE32) ? 0 : (g.gset_off[g.gset_of[u] + 1] - g.gset_off[g.gset_of[u]]);

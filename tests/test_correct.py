@@ -152,3 +152,27 @@ def test_two_pass_cuda_matches_reference_cli(recipe):
     assert not bad, ("two-pass", recipe, bad)
     ctx.close()
     g.close()
+
+
+@pytest.mark.gpu
+def test_two_pass_cuda_matches_reference_cli_at_ecoli_scale():
+    """Second pass on the E. coli-scale k = 63 graph (bench_data/F3, 4.3 M k-mers): phasing + getSeeds + correctSequence of the
+    200 pass-1 corrected reads == `Ratatosk correct -2 -O -c 8` (whole-read NW paths of ~10 kb x 10 kb go through the
+    divide-and-conquer traceback; exploreSubGraphLong bursts on a real-size graph)."""
+    d = os.path.join(ROOT, "bench_data", "F3")
+    g = rb.Graph.load(os.path.join(d, "index.k63.fasta.gz"), os.path.join(d, "index.k63.rtsk"), 63)
+    ctx = rb.Context(0)
+    ctx.upload(g)
+    raw = read_fastq(os.path.join(d, "reads200.fastq.gz"))
+    p1 = read_fastq(os.path.join(d, "corrected200_pass1.fastq.gz"))
+    gold = read_fastq(os.path.join(d, "corrected200_pass2.fastq.gz"))
+    ph = ctx.phasing([r[1].upper() for r in raw], [r[1] for r in p1], [r[2] for r in p1])
+    gph = read_fastq(os.path.join(d, "phasing200.fastq.gz"))   # phasing() of the reference through the seam probe
+    bad = [i for i in range(len(p1)) if ph[i] != (gph[i][1], gph[i][2])]
+    assert not bad, ("phasing", bad[:10])
+    fin = ctx.correct([o[0] for o in ph], [o[1] for o in ph], pass_no=2)
+    bad = [i for i in range(len(p1)) if fin[i] != (gold[i][1], gold[i][2])]
+    assert not bad, bad[:10]
+    assert sum(1 for i in range(len(p1)) if fin[i] != (p1[i][1], p1[i][2])) > 10   # the second pass does change reads here
+    ctx.close()
+    g.close()
