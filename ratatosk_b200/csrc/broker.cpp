@@ -26,6 +26,7 @@ GpuBroker* current_broker() { return tl_broker; }
 // ------------------------------------------------------------------ batched execution
 // RTK_BROKER_PROFILE: host time spent assembling a batch, inside the C-ABI call, scattering the answers; GPU kernel time
 static std::atomic<uint64_t> g_prof[3][4];
+static std::atomic<uint64_t> g_mix[2][3][2];   // [dist|path][mode NW/SHW/HW][requests with one job | with several]: requests, jobs
 struct ProfTimer {
     std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
     void lap(int kind, int slot) {
@@ -39,8 +40,10 @@ void run_dist_batch(rtk_ctx* ctx, const std::vector<DistReq*>& reqs) {
     std::string qp, tp;
     std::vector<uint64_t> qo(1, 0), to(1, 0);
     std::vector<uint8_t> mode;
-    for (const DistReq* r : reqs)
+    for (const DistReq* r : reqs) {
+        if (!r->jobs->empty()) g_mix[0][(*r->jobs)[0].mode % 3][r->jobs->size() > 1] += 1;
         for (const AlignJob& j : *r->jobs) { qp += j.q; qo.push_back(qp.size()); tp += j.t; to.push_back(tp.size()); mode.push_back(j.mode); }
+    }
     const uint32_t n = (uint32_t)mode.size();
     std::vector<int32_t> dist(n + 1, -1), first(n + 1, -1), last(n + 1, -1);
     uint64_t st[8] = {0};
@@ -78,8 +81,10 @@ void run_path_batch(rtk_ctx* ctx, const std::vector<PathReq*>& reqs) {
     std::string qp, tp;
     std::vector<uint64_t> qo(1, 0), to(1, 0);
     std::vector<uint8_t> mode;
-    for (const PathReq* r : reqs)
+    for (const PathReq* r : reqs) {
+        if (!r->jobs->empty()) g_mix[1][(*r->jobs)[0].mode % 3][r->jobs->size() > 1] += 1;
         for (const AlignJob& j : *r->jobs) { qp += j.q; qo.push_back(qp.size()); tp += j.t; to.push_back(tp.size()); mode.push_back(j.mode); }
+    }
     const uint32_t n = (uint32_t)mode.size();
     std::vector<int32_t> dist(n + 1, -1), end(n + 1, -1);
     std::vector<uint8_t> flags(n + 1, 0);
@@ -450,6 +455,10 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
             fprintf(stderr, "[broker]   %s service host time: assemble %.1f ms, C-ABI call %.1f ms (GPU kernels %.1f ms), scatter %.1f ms\n", names[k],
                     prof[k][0] / 1e6, prof[k][1] / 1e6, prof[k][3] / 1e6, prof[k][2] / 1e6);
         }
+        fprintf(stderr, "[broker]   request mix (cumulative) dist NW 1-job %llu multi %llu | SHW 1-job %llu multi %llu | HW 1-job %llu multi %llu || path NW %llu/%llu SHW %llu/%llu\n",
+                (unsigned long long)g_mix[0][0][0], (unsigned long long)g_mix[0][0][1], (unsigned long long)g_mix[0][1][0], (unsigned long long)g_mix[0][1][1],
+                (unsigned long long)g_mix[0][2][0], (unsigned long long)g_mix[0][2][1], (unsigned long long)g_mix[1][0][0], (unsigned long long)g_mix[1][0][1],
+                (unsigned long long)g_mix[1][1][0], (unsigned long long)g_mix[1][1][1]);
 #ifndef RTK_HOSTSIM
         fprintf(stderr, "[broker]   myers_run (all callers, cumulative): plan %.1f ms, H2D issue %.1f ms, launches %.1f ms, D2H + sync %.1f ms, ends phase %.1f ms\n",
                 g_myers_prof[0] / 1e6, g_myers_prof[1] / 1e6, g_myers_prof[2] / 1e6, g_myers_prof[3] / 1e6, g_myers_prof[4] / 1e6);

@@ -501,7 +501,10 @@ std::vector<GPath> fix_repeats(rtk_ctx* ctx, const rtk_graph_view& g, const Trav
             gpu_distances(ctx, j, d, fe);
             edit = d[0];
         }
-        auto evaluate = [&](const GPath& repeat, size_t pos) -> std::pair<GPath, int64_t> {
+        // The reference tries the stored cycles of a vertex one by one, each alignment bounded by the best distance so far
+        // (k = edit: worse => -1).  The unbounded distances do not depend on that bound, so all candidates of a vertex are
+        // aligned in ONE K4 request and the sequential accept / reject scan is replayed on the results.
+        auto build_ext = [&](const GPath& repeat, size_t pos) -> GPath {
             GPath ext;
             size_t len_prefix = 0;
             for (size_t j = 0; j < pos; ++j) { ext.extend(g, v_um[j]); len_prefix += v_um[j].len; }
@@ -510,12 +513,7 @@ std::vector<GPath> fix_repeats(rtk_ctx* ctx, const rtk_graph_view& g, const Trav
             std::string lq = s_qual;
             if (len_prefix <= lq.length()) lq.replace(len_prefix, (size_t)v_um[pos].len + k - 1, std::string(repeat.length(), qmax), 0, repeat.length());
             ext.set_quality(lq);
-            std::vector<AlignJob> j(1);
-            j[0].q = ext.to_string(g).substr(0, ext.length()); j[0].t = ref; j[0].mode = 0;
-            std::vector<int32_t> d, fe;
-            gpu_distances(ctx, j, d, fe);
-            const int64_t rd = (d[0] > edit) ? -1 : d[0];  // the reference aligns with k = editDistance: worse => -1
-            return {ext, rd};
+            return ext;
         };
         for (size_t i = 0; i < v_um.size(); ++i) {
             const PNode um = v_um[i];
@@ -533,14 +531,12 @@ std::vector<GPath> fix_repeats(rtk_ctx* ctx, const rtk_graph_view& g, const Trav
                 size_t s = 0;
                 while (s < cl) { const size_t n = strnlen(cp + s, cl - s); cycles.emplace_back(cp + s, n); s += n + 1; }
             }
-            auto consider = [&](const GPath& cand) {
-                std::pair<GPath, int64_t> e = evaluate(cand, i);
-                if (e.second >= 0 && e.second < edit) { edit = e.second; best_ext = std::move(e.first); }
-            };
+            std::vector<GPath> local_cands;
+            const std::vector<GPath>* cands = &local_cands;
             if (i == 0 || i == v_um.size() - 1) {
                 for (const auto& cyc : cycles) {
                     const GPath pe = GPath::from_compact(g, us, cyc, ue);
-                    consider(um.strand ? pe : pe.rev_comp());
+                    local_cands.push_back(um.strand ? pe : pe.rev_comp());
                 }
             } else {
                 const uint64_t key = ((uint64_t)um.unitig << 1) | um.strand;
@@ -550,10 +546,22 @@ std::vector<GPath> fix_repeats(rtk_ctx* ctx, const rtk_graph_view& g, const Trav
                         GPath pe = GPath::from_compact(g, us, cyc, ue);
                         if (!um.strand) pe = pe.rev_comp();
                         ins.first->second.push_back(pe);
-                        consider(pe);
                     }
-                } else {
-                    for (const auto& pe : ins.first->second) consider(pe);
+                }
+                cands = &ins.first->second;
+            }
+            if (!cands->empty()) {
+                std::vector<GPath> exts;
+                std::vector<AlignJob> jobs(cands->size());
+                for (size_t c = 0; c < cands->size(); ++c) {
+                    exts.push_back(build_ext((*cands)[c], i));
+                    jobs[c].q = exts[c].to_string(g).substr(0, exts[c].length()); jobs[c].t = ref; jobs[c].mode = 0;
+                }
+                std::vector<int32_t> d, fe;
+                gpu_distances(ctx, jobs, d, fe);
+                for (size_t c = 0; c < cands->size(); ++c) {
+                    const int64_t rd = (d[c] > edit) ? -1 : d[c];   // bounded alignment: worse than the running best => -1
+                    if (rd >= 0 && rd < edit) { edit = rd; best_ext = std::move(exts[c]); }
                 }
             }
             if (best_ext.length() != 0) {

@@ -176,3 +176,48 @@ def test_two_pass_cuda_matches_reference_cli_at_ecoli_scale():
     assert sum(1 for i in range(len(p1)) if fin[i] != (p1[i][1], p1[i][2])) > 10   # the second pass does change reads here
     ctx.close()
     g.close()
+
+
+@pytest.mark.gpu
+def test_correction_cuda_matches_reference_library_on_fresh_reads():
+    """Differential test against the UNMODIFIED reference objects (oracle/_ref/libref_seams.so travels to the GPU box): a fresh
+    seeded batch of ONT-like reads drawn from the F3 genome with bench.py's generator (~1.5 Mbases, not a committed fixture),
+    corrected by both; skipped when the reference library was not built.  The reference breaks ties between colour sets of
+    equal cardinality by pointer hash (tests/ref_worker.py), so its output is collected from four processes and a read may
+    match any of them; at least 99 % of the reads must be identical in all."""
+    import pickle
+    import subprocess
+    import sys
+    import tempfile
+    sys.path.insert(0, ROOT)
+    import refseams as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libref_seams.so not built")
+    import bench
+    haps = bench.load_haplotypes()
+    seq, qual, off = bench.make_reads(haps, 1_500_000, seed=20261017)
+    reads = [(seq[int(off[i]):int(off[i + 1])].tobytes().decode(), qual[int(off[i]):int(off[i + 1])].tobytes().decode())
+             for i in range(len(off) - 1)]
+    d = os.path.join(ROOT, "bench_data", "F3")
+    fa, rt = os.path.join(d, "index.k31.fasta.gz"), os.path.join(d, "index.k31.rtsk")
+    tmp = tempfile.mkdtemp(prefix="rtk_ref_")
+    pickle.dump(reads, open(os.path.join(tmp, "reads.pkl"), "wb"))
+    variants = []
+    for i in range(4):
+        dst = os.path.join(tmp, "out%d.pkl" % i)
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "tests", "ref_worker.py"), fa, rt, "31", os.path.join(tmp, "reads.pkl"), dst])
+        variants.append(pickle.load(open(dst, "rb")))
+    g = rb.Graph.load(fa, rt, 31)
+    ctx = rb.Context(0)
+    ctx.upload(g)
+    got = ctx.correct([r[0] for r in reads], [r[1] for r in reads])
+    unstable = [i for i in range(len(reads)) if any(v[i] != variants[0][i] for v in variants)]
+    bad = [i for i in range(len(reads)) if all(got[i] != v[i] for v in variants)]
+    # A read whose tie the reference breaks by pointer order can come out in a variant none of the four runs happened to produce;
+    # the strict pins are the committed golden files above.  Here: at most 1 % of the reads may be of that kind.
+    if bad:
+        print("differs from every reference run:", bad[:10], "| reads on which the reference runs disagree:", unstable)
+    assert len(bad) <= max(1, len(reads) // 100), (bad[:10], unstable)
+    assert len(unstable) <= 0.03 * len(reads), unstable
+    ctx.close()
+    g.close()
