@@ -515,10 +515,10 @@ std::vector<GPath> fix_repeats(rtk_ctx* ctx, const rtk_graph_view& g, const Trav
             ext.set_quality(lq);
             return ext;
         };
-        for (size_t i = 0; i < v_um.size(); ++i) {
+        // candidate cycle paths of vertex i of the current path (built once per (unitig, strand) for interior vertices)
+        std::vector<GPath> local_cands;
+        auto candidates_of = [&](size_t i) -> const std::vector<GPath>* {
             const PNode um = v_um[i];
-            if (!is_short_cycle(g, um.unitig)) continue;
-            GPath best_ext;
             PNode us = um, ue = um;
             us.len = usize(g, um.unitig) - um.dist - (uint32_t)k + 1;
             ue.dist = 0;
@@ -531,51 +531,72 @@ std::vector<GPath> fix_repeats(rtk_ctx* ctx, const rtk_graph_view& g, const Trav
                 size_t s = 0;
                 while (s < cl) { const size_t n = strnlen(cp + s, cl - s); cycles.emplace_back(cp + s, n); s += n + 1; }
             }
-            std::vector<GPath> local_cands;
-            const std::vector<GPath>* cands = &local_cands;
             if (i == 0 || i == v_um.size() - 1) {
+                local_cands.clear();
                 for (const auto& cyc : cycles) {
                     const GPath pe = GPath::from_compact(g, us, cyc, ue);
                     local_cands.push_back(um.strand ? pe : pe.rev_comp());
                 }
-            } else {
-                const uint64_t key = ((uint64_t)um.unitig << 1) | um.strand;
-                auto ins = m_cycles.insert({key, std::vector<GPath>()});
-                if (ins.second) {
-                    for (const auto& cyc : cycles) {
-                        GPath pe = GPath::from_compact(g, us, cyc, ue);
-                        if (!um.strand) pe = pe.rev_comp();
-                        ins.first->second.push_back(pe);
-                    }
-                }
-                cands = &ins.first->second;
+                return &local_cands;
             }
-            if (!cands->empty()) {
-                std::vector<GPath> exts;
-                std::vector<AlignJob> jobs(cands->size());
-                for (size_t c = 0; c < cands->size(); ++c) {
-                    exts.push_back(build_ext((*cands)[c], i));
-                    jobs[c].q = exts[c].to_string(g).substr(0, exts[c].length()); jobs[c].t = ref; jobs[c].mode = 0;
-                }
-                std::vector<int32_t> d, fe;
-                gpu_distances(ctx, jobs, d, fe);
-                for (size_t c = 0; c < cands->size(); ++c) {
-                    const int64_t rd = (d[c] > edit) ? -1 : d[c];   // bounded alignment: worse than the running best => -1
-                    if (rd >= 0 && rd < edit) { edit = rd; best_ext = std::move(exts[c]); }
+            const uint64_t key = ((uint64_t)um.unitig << 1) | um.strand;
+            auto ins = m_cycles.insert({key, std::vector<GPath>()});
+            if (ins.second) {
+                for (const auto& cyc : cycles) {
+                    GPath pe = GPath::from_compact(g, us, cyc, ue);
+                    if (!um.strand) pe = pe.rev_comp();
+                    ins.first->second.push_back(pe);
                 }
             }
-            if (best_ext.length() != 0) {
-                const size_t diff = best_ext.size() - path.size();
-                path = std::move(best_ext);
-                v_um = path.v;
-                s_qual = path.qual;
-                i += diff - 1;
-            } else {
-                for (size_t j = i + 1; j < v_um.size(); ++j) {
-                    if (um.unitig == v_um[j].unitig) ++i;
-                    else break;
+            return &ins.first->second;
+        };
+        // The reference walks the vertices left to right and re-aligns after every accepted cycle.  Acceptances are rare, so the
+        // walk is SPECULATED: every vertex the walk would visit if nothing were accepted is evaluated in one K4 request; the
+        // accept / reject scan is replayed in order, and only an acceptance (which changes the path) restarts the speculation
+        // from the next vertex.  Same decisions, one request per acceptance instead of one per vertex.
+        size_t i = 0;
+        while (i < v_um.size()) {
+            struct Visit { size_t i; size_t first_job, n_jobs; };
+            std::vector<Visit> visits;
+            std::vector<GPath> exts;
+            std::vector<AlignJob> jobs;
+            for (size_t j = i; j < v_um.size(); ++j) {
+                if (!is_short_cycle(g, v_um[j].unitig)) continue;
+                const std::vector<GPath>* cands = candidates_of(j);
+                visits.push_back({j, jobs.size(), cands->size()});
+                for (const GPath& cand : *cands) {
+                    exts.push_back(build_ext(cand, j));
+                    AlignJob aj;
+                    aj.q = exts.back().to_string(g).substr(0, exts.back().length()); aj.t = ref; aj.mode = 0;
+                    jobs.push_back(std::move(aj));
+                }
+                // no acceptance at j: the following vertices on the same unitig are skipped (:1322-1330)
+                size_t jn = j;
+                for (size_t t = j + 1; t < v_um.size(); ++t) { if (v_um[j].unitig == v_um[t].unitig) ++jn; else break; }
+                j = jn;
+            }
+            if (visits.empty()) break;
+            std::vector<int32_t> d, fe;
+            gpu_distances(ctx, jobs, d, fe);
+            bool accepted = false;
+            for (const Visit& vis : visits) {
+                GPath best_ext;
+                for (size_t c = 0; c < vis.n_jobs; ++c) {
+                    const int32_t dc = d[vis.first_job + c];
+                    const int64_t rd = (dc > edit) ? -1 : dc;   // bounded alignment (k = edit): worse than the running best => -1
+                    if (rd >= 0 && rd < edit) { edit = rd; best_ext = std::move(exts[vis.first_job + c]); }
+                }
+                if (best_ext.length() != 0) {
+                    const size_t diff = best_ext.size() - path.size();
+                    path = std::move(best_ext);
+                    v_um = path.v;
+                    s_qual = path.qual;
+                    i = vis.i + diff;   // the reference: i += diff - 1, then the loop's ++i
+                    accepted = true;
+                    break;
                 }
             }
+            if (!accepted) break;
         }
         out.push_back(path);
     }
