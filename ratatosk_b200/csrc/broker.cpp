@@ -35,6 +35,26 @@ struct ProfTimer {
         t = n;
     }
 };
+// K4 over host pools: distance + first / last best end column (product: the lean fused path; CPU simulator: the public entry)
+static void dist_core(rtk_ctx* ctx, uint32_t n, std::string& qp, const std::vector<uint64_t>& qo, std::string& tp, const std::vector<uint64_t>& to,
+                      const std::vector<uint8_t>& mode, std::vector<int32_t>& dist, std::vector<int32_t>& first, std::vector<int32_t>& last, uint64_t* st) {
+    dist.assign(n + 1, -1); first.assign(n + 1, -1); last.assign(n + 1, -1);
+    if (!n) return;
+    qp.push_back('\0'); tp.push_back('\0');
+#ifdef RTK_HOSTSIM   // the CPU simulator goes through the public entry (every end location) and keeps the two the callers use
+    std::vector<int32_t> kmax(n + 1, -1);
+    int32_t* ends = nullptr;
+    uint64_t* eoff = nullptr;
+    if (rtk_edlib_batch(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), kmax.data(), dist.data(), &ends, &eoff, st) != RTK_OK)
+        throw std::runtime_error(std::string("rtk_edlib_batch: ") + rtk_last_error());
+    for (uint32_t a = 0; a < n; ++a) if (eoff[a + 1] > eoff[a]) { first[a] = ends[eoff[a]]; last[a] = ends[eoff[a + 1] - 1]; }
+    rtk_free(ends);
+    rtk_free(eoff);
+#else
+    dist_batch_lean(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), dist.data(), first.data(), last.data(), st);
+#endif
+}
+
 void run_dist_batch(rtk_ctx* ctx, const std::vector<DistReq*>& reqs) {
     ProfTimer pt;
     std::string qp, tp;
@@ -45,24 +65,10 @@ void run_dist_batch(rtk_ctx* ctx, const std::vector<DistReq*>& reqs) {
         for (const AlignJob& j : *r->jobs) { qp += j.q; qo.push_back(qp.size()); tp += j.t; to.push_back(tp.size()); mode.push_back(j.mode); }
     }
     const uint32_t n = (uint32_t)mode.size();
-    std::vector<int32_t> dist(n + 1, -1), first(n + 1, -1), last(n + 1, -1);
+    std::vector<int32_t> dist, first, last;
     uint64_t st[8] = {0};
     pt.lap(0, 0);
-    if (n) {
-        qp.push_back('\0'); tp.push_back('\0');
-#ifdef RTK_HOSTSIM   // the CPU simulator goes through the public entry (every end location) and keeps the two the callers use
-        std::vector<int32_t> kmax(n + 1, -1);
-        int32_t* ends = nullptr;
-        uint64_t* eoff = nullptr;
-        if (rtk_edlib_batch(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), kmax.data(), dist.data(), &ends, &eoff, st) != RTK_OK)
-            throw std::runtime_error(std::string("rtk_edlib_batch: ") + rtk_last_error());
-        for (uint32_t a = 0; a < n; ++a) if (eoff[a + 1] > eoff[a]) { first[a] = ends[eoff[a]]; last[a] = ends[eoff[a + 1] - 1]; }
-        rtk_free(ends);
-        rtk_free(eoff);
-#else
-        dist_batch_lean(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), dist.data(), first.data(), last.data(), st);
-#endif
-    }
+    dist_core(ctx, n, qp, qo, tp, to, mode, dist, first, last, st);
     pt.lap(0, 1);
     g_prof[0][3] += st[2];
     uint32_t a = 0;
@@ -117,22 +123,53 @@ void run_path_batch(rtk_ctx* ctx, const std::vector<PathReq*>& reqs) {
 void run_subgraph_batch(rtk_ctx* ctx, const std::vector<SubgraphReq*>& reqs) {
     if (reqs.empty()) return;
     ProfTimer pt;
+    // phase A: prefix alignments (SHW, first end location) of the requests that extend a non-trivial path
+    {
+        std::string qp, tp;
+        std::vector<uint64_t> qo(1, 0), to(1, 0);
+        std::vector<uint8_t> mode;
+        std::vector<size_t> who;
+        for (size_t i = 0; i < reqs.size(); ++i) {
+            reqs[i]->out->end_pos_ref = 0;
+            reqs[i]->out->explored = false;
+            if (reqs[i]->prefix && !reqs[i]->prefix->empty()) {
+                qp += *reqs[i]->prefix; qo.push_back(qp.size()); tp += *reqs[i]->ref; to.push_back(tp.size()); mode.push_back(1);
+                who.push_back(i);
+            }
+        }
+        if (!who.empty()) {
+            std::vector<int32_t> dist, first, last;
+            uint64_t st[8] = {0};
+            dist_core(ctx, (uint32_t)who.size(), qp, qo, tp, to, mode, dist, first, last, st);
+            g_prof[2][3] += st[2];
+            for (size_t x = 0; x < who.size(); ++x) reqs[who[x]]->out->end_pos_ref = (size_t)(first[x] + 1);
+        }
+    }
+    // phase B: the bursts, on the uncovered suffix of each window (:276)
+    std::vector<SubgraphReq*> live;
+    for (SubgraphReq* r : reqs) {
+        SubgraphResult& res = *r->out;
+        for (int s4 = 0; s4 < 4; ++s4) res.scores[s4] = 0.0;
+        res.terminal.clear(); res.nonterminal.clear();
+        if (res.end_pos_ref <= r->ref->size() && (r->ref->size() - res.end_pos_ref) != 0 && r->path_len < r->max_len_path_total) { res.explored = true; live.push_back(r); }
+    }
     // requests may carry different weak_region_len_factor values (multi-round correction): one call per value
-    std::vector<bool> done(reqs.size(), false);
-    for (size_t first = 0; first < reqs.size(); ++first) {
+    std::vector<bool> done(live.size(), false);
+    for (size_t first = 0; first < live.size(); ++first) {
         if (done[first]) continue;
-        const double wrlf = reqs[first]->wrlf;
+        const double wrlf = live[first]->wrlf;
         std::vector<size_t> idx;
-        for (size_t i = first; i < reqs.size(); ++i) if (!done[i] && reqs[i]->wrlf == wrlf) { idx.push_back(i); done[i] = true; }
+        for (size_t i = first; i < live.size(); ++i) if (!done[i] && live[i]->wrlf == wrlf) { idx.push_back(i); done[i] = true; }
         std::string refs;
         std::vector<uint32_t> pids;
         std::vector<rtk_subgraph_call_t> calls;
         for (size_t i : idx) {
-            rtk_subgraph_call_t c = reqs[i]->call;
-            c.ref_off = refs.size(); c.ref_len = (uint32_t)reqs[i]->ref->size();
-            c.pid_off = pids.size(); c.pid_len = (uint32_t)reqs[i]->pids->size();
-            refs += *reqs[i]->ref;
-            pids.insert(pids.end(), reqs[i]->pids->begin(), reqs[i]->pids->end());
+            rtk_subgraph_call_t c = live[i]->call;
+            const size_t e = live[i]->out->end_pos_ref;
+            c.ref_off = refs.size(); c.ref_len = (uint32_t)(live[i]->ref->size() - e);
+            c.pid_off = pids.size(); c.pid_len = (uint32_t)live[i]->pids->size();
+            refs.append(*live[i]->ref, e, std::string::npos);
+            pids.insert(pids.end(), live[i]->pids->begin(), live[i]->pids->end());
             calls.push_back(c);
         }
         rtk_subgraph_out out;
@@ -146,9 +183,8 @@ void run_subgraph_batch(rtk_ctx* ctx, const std::vector<SubgraphReq*>& reqs) {
         pt.lap(2, 1);
         g_prof[2][3] += st[2] + st[3];
         for (size_t ci = 0; ci < idx.size(); ++ci) {
-            SubgraphResult& res = *reqs[idx[ci]]->out;
+            SubgraphResult& res = *live[idx[ci]]->out;
             for (int s = 0; s < 4; ++s) res.scores[s] = out.scores[4 * ci + s];
-            res.terminal.clear(); res.nonterminal.clear();
             for (uint64_t pi = out.path_off[ci]; pi < out.path_off[ci + 1]; ++pi) {
                 std::vector<PNode> nodes;
                 for (uint64_t j = out.node_off[pi]; j < out.node_off[pi + 1]; ++j) {

@@ -39,10 +39,17 @@ struct PathReq {   // K5
 struct SubgraphResult {
     double scores[4];
     std::vector<std::vector<PNode>> terminal, nonterminal;
+    size_t end_pos_ref = 0;   // where the burst's read window starts in `ref` (after the prefix alignment, if any)
+    bool explored = false;    // false: the window was empty or the path already too long (no burst was run)
 };
-struct SubgraphReq {   // K2/K3 + K4
-    rtk_subgraph_call_t call;   // ref_off / pid_off are filled by the broker
-    const std::string* ref;
+// One step of the `explore` lambda of explorePathsBFS* (src/GraphTraversal.cpp:251-304) as ONE request: the SHW alignment of
+// the path's prefix against the read window (its first end location + 1 = where the uncovered part of the window starts), then,
+// if something is left to cover, the exploreSubGraph burst on that suffix of the window.
+struct SubgraphReq {   // K4 (prefix) + K2/K3 + K4 (leaves)
+    rtk_subgraph_call_t call;   // ref_off / ref_len / pid_off are filled by the service; max_len_path = the burst's own bound
+    const std::string* ref;     // the whole read window
+    const std::string* prefix;  // spelled prefix of the path being extended (nullptr / empty: the window is used from position 0)
+    size_t path_len = 0, max_len_path_total = 0;   // the burst runs only if path_len < max_len_path_total and the window is not used up
     const std::vector<uint32_t>* pids;
     double wrlf;
     SubgraphResult* out;

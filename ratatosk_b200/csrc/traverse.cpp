@@ -254,21 +254,28 @@ void set_qualities2(rtk_ctx* ctx, const rtk_graph_view& g, const TraverseOpt& op
     }
 }
 
+// One `explore` step (src/GraphTraversal.cpp:251-304) as a single GPU request: prefix alignment -> window start, burst on the
+// rest of the window (K2/K3 + leaf K4), then the qualities of the kept paths (K5).  `sub_out` = the part of the window the burst saw.
 Burst explore_subgraph(rtk_ctx* ctx, const rtk_graph_view& g, const TraverseOpt& opt, const std::vector<uint32_t>& pids,
-                       const std::string& ref, size_t max_len_path, const PNode& um, const PNode& um_e, uint32_t level) {
+                       const std::string& ref, const std::string& prefix, size_t path_len, size_t max_len_path_total, size_t l_max,
+                       const PNode& um, const PNode& um_e, uint32_t level, std::string& sub_out, bool& explored) {
     SubgraphReq rq;
     memset(&rq.call, 0, sizeof(rq.call));
     rq.call.start_unitig = um.unitig; rq.call.start_strand = um.strand;
     if (um_e.empty()) rq.call.end_unitig = RTK_NONE32;
     else { rq.call.end_unitig = um_e.unitig; rq.call.end_strand = um_e.strand; rq.call.end_dist = um_e.dist; }
-    rq.call.level = level; rq.call.max_len_path = (uint32_t)max_len_path; rq.call.min_cov = opt.min_cov_vertices;
+    rq.call.level = level; rq.call.max_len_path = (uint32_t)l_max; rq.call.min_cov = opt.min_cov_vertices;
     rq.call.max_len_subpath = opt.long_read_correct ? (uint32_t)opt.max_len_subpath() : 0u;
-    rq.ref = &ref; rq.pids = &pids; rq.wrlf = opt.weak_region_len_factor;
+    rq.ref = &ref; rq.prefix = &prefix; rq.path_len = path_len; rq.max_len_path_total = max_len_path_total;
+    rq.pids = &pids; rq.wrlf = opt.weak_region_len_factor;
     SubgraphResult res;
     rq.out = &res;
     if (GpuBroker* b = current_broker()) b->submit(&rq);
     else run_subgraph_batch(ctx, std::vector<SubgraphReq*>(1, &rq));
     Burst b;
+    explored = res.explored;
+    if (!res.explored) return b;
+    sub_out = ref.substr(res.end_pos_ref);
     b.t1 = res.scores[0]; b.nt1 = res.scores[2];
     for (int kind = 0; kind < 2; ++kind) {
         for (const auto& nodes : (kind == 0 ? res.terminal : res.nonterminal)) {
@@ -278,30 +285,24 @@ Burst explore_subgraph(rtk_ctx* ctx, const rtk_graph_view& g, const TraverseOpt&
         }
     }
     // both quality batches of the burst in one K5 request
-    set_qualities2(ctx, g, opt, b.terminal, b.t1, res.scores[1], b.nonterminal, b.nt1, res.scores[3], ref);
+    set_qualities2(ctx, g, opt, b.terminal, b.t1, res.scores[1], b.nonterminal, b.nt1, res.scores[3], sub_out);
     return b;
 }
 
 // the `explore` lambda shared by explorePathsBFS2 (:251-304) and explorePathsBFS (:43-94)
 Burst explore_step(rtk_ctx* ctx, const rtk_graph_view& g, const TraverseOpt& opt, const std::vector<uint32_t>& pids, const std::string& ref,
                    const PNode& um, const GPath& path, size_t max_len_path, uint32_t level, const PNode& um_e) {
-    const size_t k = g.k, ref_len = ref.length();
+    const size_t k = g.k;
     const size_t path_len = path.length();
     const bool non_empty_path = (path_len > ((size_t)um.len + k - 1)) && !um.empty();
     const size_t path_len_prefix = non_empty_path ? (path_len - um.len - k + 1) : 0;
-    size_t end_pos_ref = 0;
-    Burst b;
-    if (non_empty_path) {
-        std::vector<AlignJob> j(1);
-        j[0].q = path.to_string(g).substr(0, path_len_prefix); j[0].t = ref; j[0].mode = 1;
-        std::vector<int32_t> d, fe;
-        gpu_distances(ctx, j, d, fe);
-        end_pos_ref = (size_t)(fe[0] + 1);
-    }
-    if ((ref_len - end_pos_ref) != 0 && path_len < max_len_path) {
-        const size_t l_max = max_len_path - path_len_prefix;
-        const std::string sub = ref.substr(end_pos_ref);
-        b = explore_subgraph(ctx, g, opt, pids, sub, l_max, um, um_e, level - 1);
+    std::string prefix;
+    if (non_empty_path) prefix = path.to_string(g).substr(0, path_len_prefix);
+    const size_t l_max = max_len_path - path_len_prefix;
+    std::string sub;
+    bool explored = false;
+    Burst b = explore_subgraph(ctx, g, opt, pids, ref, prefix, path_len, max_len_path, l_max, um, um_e, level - 1, sub, explored);
+    if (explored) {
         if (!b.terminal.empty() && b.t1 < opt.min_score) b.terminal.clear();
         if (!b.nonterminal.empty() && b.nt1 < opt.min_score) b.nonterminal.clear();
         if (b.nonterminal.size() > 1) {
