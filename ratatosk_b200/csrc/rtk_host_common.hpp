@@ -52,12 +52,14 @@ inline void finish_host_graph(rtk_host_graph* g) {
 // read positions per K1 tile: one per thread
 inline uint32_t k1_tile_size(uint32_t, bool) { return RTK_K1_THREADS; }
 
-// h_seq (optional): the reads on the host, h_seq + h_seq_off[r] = read r.  When given, a tile is emitted only if a window of
-// `need` consecutive A/C/G/T bases STARTS inside it (need = k for the exact sweep, k-1 = the shortest variant-string window of
-// the one-edit sweeps): the masked copies getSeeds sweeps inexactly are mostly 'N' (src/Graph.cpp:106-191), and a tile
-// without such a window can neither probe nor hit.
+// h_seq (optional): the reads on the host, h_seq + h_seq_off[r] = read r.  When given, a tile is emitted only if some window
+// STARTING inside it can produce a k-mer: `need` A/C/G/T bases among the `span` read bases it draws from (exact sweep: k of
+// k; one-edit sweeps: at least k-1 of k+1 - a substitution / insertion window uses k or k-1 consecutive read bases, a
+// deletion window k of k+1 with the dropped base free to be anything, e.g. an 'N').  The masked copies getSeeds sweeps
+// inexactly are mostly 'N' (src/Graph.cpp:106-191); a tile without such a window can neither probe nor hit.  Conservative: a
+// live tile may still hold no valid window, the kernel decides per window.
 inline void build_tiles(uint32_t n_reads, const uint64_t* h_seq_off, uint32_t k, uint32_t tile, std::vector<uint32_t>& tiles,
-                        const char* h_seq = nullptr, uint32_t need = 0) {
+                        const char* h_seq = nullptr, uint32_t need = 0, uint32_t span = 0) {
     tiles.clear();
     std::vector<uint8_t> live;
     for (uint32_t r = 0; r < n_reads; ++r) {
@@ -66,14 +68,16 @@ inline void build_tiles(uint32_t n_reads, const uint64_t* h_seq_off, uint32_t k,
         if (len < k) continue;
         // positions l with l + k - 1 <= len (one past the last full k-mer: insertion windows use k-1 read bases)
         const uint32_t npos = (uint32_t)(len - k + 2);
-        if (h_seq && need) {
+        if (h_seq && need && span >= need) {
             live.assign((npos + tile - 1) / tile, 0);
             const char* s = h_seq + h_seq_off[r];
-            uint32_t run = 0;
-            for (uint64_t i = 0; i < len; ++i) {
-                const char c = s[i];
-                run = (c == 'A' || c == 'C' || c == 'G' || c == 'T') ? run + 1 : 0;
-                if (run >= need) { const uint64_t start = i + 1 - need; if (start < npos) live[start / tile] = 1; }
+            auto ok = [&](uint64_t i) { const char c = s[i]; return (uint32_t)(c == 'A' || c == 'C' || c == 'G' || c == 'T'); };
+            uint32_t cnt = 0;   // valid bases in [l, min(len, l + span))
+            for (uint64_t i = 0; i < std::min<uint64_t>(len, span); ++i) cnt += ok(i);
+            for (uint64_t l = 0; l < npos; ++l) {
+                if (cnt >= need) live[l / tile] = 1;
+                cnt -= ok(l);
+                if (l + span < len) cnt += ok(l + span);
             }
             for (uint32_t t0 = 0; t0 < npos; t0 += tile) if (live[t0 / tile]) { tiles.push_back(r); tiles.push_back(t0); }
         } else {

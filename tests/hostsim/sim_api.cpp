@@ -21,7 +21,7 @@ static uint64_t sim_k1(rtk_ctx* ctx, uint32_t n_reads, const char* seq, const ui
     if (exact && inexact) throw std::invalid_argument("exact and inexact search in one call is not a combination the reference path uses");
     const uint32_t tile = k1_tile_size(k, exact);
     std::vector<uint32_t> tiles;
-    build_tiles(n_reads, seq_off, k, tile, tiles, seq + seq_off[0] - seq_off[0], exact ? k : k - 1);
+    build_tiles(n_reads, seq_off, k, tile, tiles, seq, exact ? k : k - 1, exact ? k : k + 1);
     const uint32_t n_tiles = (uint32_t)(tiles.size() / 2);
     if (!n_tiles) return 0;
     const uint64_t total = seq_off[n_reads] - seq_off[0];

@@ -140,3 +140,18 @@ def test_single_edit_is_recovered(loaded):
     for u, h in zip(cands, ix):
         on_u = h[h[:, 1] == u]
         assert len(on_u) >= 20, (u, len(on_u))
+
+
+def test_masked_reads_with_isolated_n_keep_their_deletion_hits(loaded):
+    """tile skipping of the K1 driver (mostly-'N' masked copies) must keep windows whose deletion drops an isolated 'N'"""
+    recipe, g, ctx = loaded
+    n = g.info()["n_unitigs"]
+    u = max(range(min(n, 50)), key=lambda x: len(g.unitig_seq(x)))
+    s = g.unitig_seq(u)
+    pad = "N" * 700
+    reads = [pad + s[:20] + "N" + s[20:48] + pad, pad + s[:20] + "N" + s[20:48],
+             s[:20] + "N" + s[20:48] + pad + s[5:40] + pad, pad + s[:29] + pad]
+    got = ctx.search_sequence(reads, exact=False, insertion=True, deletion=True, substitution=True, or_exclusive_match=True)
+    for i, r in enumerate(reads):
+        assert np.array_equal(got[i], oracle_search(g, r, exact=False)), (recipe, i)
+    assert len(got[0]) > 0 and len(got[3]) == 0

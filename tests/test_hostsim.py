@@ -98,3 +98,24 @@ def test_slab_roundtrip(loaded, tmp_path, sim_lib):
     assert g2.info() == g.info()
     assert np.array_equal(g2.slab(), g.slab())
     g2.close()
+
+
+def test_masked_reads_with_isolated_n_keep_their_deletion_hits(loaded):
+    """The K1 driver skips tiles that cannot hold a valid window (the masked copies of getSeeds are mostly 'N').  A deletion
+    window may drop an 'N' that sits between two short valid stretches: such tiles must stay.  Checked against the CPU oracle."""
+    from common import oracle_search
+    recipe, g, ctx = loaded
+    n = g.info()["n_unitigs"]
+    u = max(range(min(n, 50)), key=lambda x: len(g.unitig_seq(x)))
+    s = g.unitig_seq(u)
+    assert len(s) >= 60
+    pad = "N" * 700
+    reads = [pad + s[:20] + "N" + s[20:48] + pad,            # valid stretches of 20 and 28 < k - 1, joined by deleting the N
+             pad + s[:20] + "N" + s[20:48],                   # the same at the end of the read
+             s[:20] + "N" + s[20:48] + pad + s[5:40] + pad,   # ... at the start, plus an ordinary stretch
+             pad + s[:29] + pad]                              # k - 2 valid bases: nothing can hit
+    got = ctx.search_sequence(reads, exact=False, insertion=True, deletion=True, substitution=True, or_exclusive_match=True)
+    for i, r in enumerate(reads):
+        want = oracle_search(g, r, exact=False)
+        assert np.array_equal(got[i], want), (recipe, i)
+    assert len(got[0]) > 0 and len(got[3]) == 0
