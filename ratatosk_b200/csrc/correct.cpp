@@ -33,17 +33,24 @@ typedef std::vector<uint32_t> IdSet;  // sorted, unique (PairID)
 // ------------------------------------------------------------------ small helpers
 inline bool is_dna(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'a' || c == 'c' || c == 'g' || c == 't'; }
 const char ambiguity_c[16] = {'.', 'A', 'C', 'M', 'G', 'R', 'S', 'V', 'T', 'W', 'Y', 'H', 'K', 'D', 'B', 'N'};  // src/Common.hpp:260
-inline uint8_t amb_index(char c) {
-    c &= 0xDF;
-    for (uint8_t i = 0; i < 16; ++i) if (ambiguity_c[i] == c) return i;
-    return 0;
-}
-inline char rc_char(char c) {  // reverse_complement(char), Bifrost/src/Common.hpp:61-90: IUPAC-aware
-    const uint8_t i = amb_index(c);
-    if (ambiguity_c[i] != (char)(c & 0xDF) || i == 0) return c;
-    const uint8_t r = (uint8_t)(((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3));
-    return ambiguity_c[r];
-}
+struct AmbTables {   // amb_index / reverse complement of every byte, built once (the linear scans were 3 % of the host time)
+    uint8_t idx[256];
+    char rc[256];
+    AmbTables() {
+        for (int b = 0; b < 256; ++b) {
+            const char c = (char)(b & 0xDF);
+            uint8_t i = 0;
+            for (uint8_t x = 0; x < 16; ++x) if (ambiguity_c[x] == c) { i = x; break; }
+            idx[b] = i;
+            // reverse_complement(char), Bifrost/src/Common.hpp:61-90: IUPAC-aware; anything else is returned unchanged
+            if (ambiguity_c[i] != c || i == 0) rc[b] = (char)b;
+            else rc[b] = ambiguity_c[(uint8_t)(((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3))];
+        }
+    }
+};
+static const AmbTables g_amb;
+inline uint8_t amb_index(char c) { return g_amb.idx[(unsigned char)c]; }
+inline char rc_char(char c) { return g_amb.rc[(unsigned char)c]; }
 std::string rc_string(const std::string& s) {
     std::string r(s.rbegin(), s.rend());
     for (auto& c : r) c = rc_char(c);

@@ -33,7 +33,7 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
 
     const uint32_t tile = k1_tile_size(k, exact);
     std::vector<uint32_t> tiles;
-    build_tiles(n_reads, h_seq_off, k, tile, tiles, h_seq, exact ? k : k - 1, exact ? k : k + 1);
+    build_tiles(n_reads, h_seq_off, k, tile, tiles, exact ? nullptr : h_seq, k - 1, k + 1);   // the exact sweep runs on whole reads: nothing to skip
     const uint32_t n_tiles = (uint32_t)(tiles.size() / 2);
     ctx->d_counters.reserve(64);
     RTK_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));

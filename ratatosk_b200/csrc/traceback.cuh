@@ -183,8 +183,9 @@ __device__ __forceinline__ int rtk_tb_row(const rtk_tb_cell& c, const int arow, 
     return c.A - __popcll(c.P & m) + __popcll(c.M & m);
 }
 
-// The walk keeps the blocks it can touch next in registers: (b, c) `cur`, (b, c-1) `left`, and prefetches
-// (b, c-2) so that a move to the left never waits for memory; only crossing into the block above reloads.
+// The walk keeps the blocks it can touch next in registers: (b, c) `cur`, (b, c-1) `left`, and prefetches (b, c-2) .. (b, c-5):
+// a thread walks ONE alignment, a step is ~60 cycles of dependent work and a cell load ~400 cycles from L2, so the loads are
+// issued four columns ahead of their use; only crossing into the block above reloads the window.
 __global__ void __launch_bounds__(128) rtk_traceback_kernel(const rtk_tb_params p) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= p.n) return;
@@ -199,6 +200,9 @@ __global__ void __launch_bounds__(128) rtk_traceback_kernel(const rtk_tb_params 
     rtk_tb_cell cur = rtk_tb_load(p, moff, tlen, nb, last_row, b, c);
     rtk_tb_cell left = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 1);
     rtk_tb_cell left2 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 2);
+    rtk_tb_cell left3 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 3);
+    rtk_tb_cell left4 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 4);
+    rtk_tb_cell left5 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 5);
     while (i >= 0 && c >= 0) {
         const int r = i & 63;
         const int arow = (b == nb - 1) ? last_row : 63;
@@ -218,14 +222,17 @@ __global__ void __launch_bounds__(128) rtk_traceback_kernel(const rtk_tb_params 
                 cur = rtk_tb_load(p, moff, tlen, nb, last_row, b, c);
                 left = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 1);
                 left2 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 2);
+                left3 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 3);
+                left4 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 4);
+                left5 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 5);
             }
             continue;
         }
         const int l = rtk_tb_row(left, arow, r);                   // D[i][c-1] (column -1 synthesised)
         if (l + 1 == cur_score) {                                   // left: target base unaligned
             out[--w] = 2; --c; cur_score = l;
-            cur = left; left = left2;
-            left2 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 2);
+            cur = left; left = left2; left2 = left3; left3 = left4; left4 = left5;
+            left5 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 5);
             continue;
         }
         // diagonal: D[i-1][c-1]
@@ -239,9 +246,12 @@ __global__ void __launch_bounds__(128) rtk_traceback_kernel(const rtk_tb_params 
             cur = rtk_tb_load(p, moff, tlen, nb, last_row, b, c);
             left = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 1);
             left2 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 2);
+            left3 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 3);
+            left4 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 4);
+            left5 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 5);
         } else {
-            cur = left; left = left2;
-            left2 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 2);
+            cur = left; left = left2; left2 = left3; left3 = left4; left4 = left5;
+            left5 = rtk_tb_load(p, moff, tlen, nb, last_row, b, c - 5);
         }
     }
     while (c >= 0) { out[--w] = 2; --c; }
