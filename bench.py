@@ -32,6 +32,7 @@ import numpy as np
 # the library's service contexts own ~20 CUDA streams: give them their own hardware work queues (default 8); must be set
 # before CUDA initialises in this process (torch does that first here)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout (one JSON line is the contract); an explicit setting wins
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -327,10 +328,10 @@ def main():
                 ev_ms += e0.elapsed_time(e1)
                 stats += np.asarray(st, dtype=np.float64)
         barrier()
-        return sum(step_s), stats, ev_ms, clk.summary()
+        return sum(step_s), stats, ev_ms, clk.summary(), [round(1e3 * x, 1) for x in step_s]
 
-    my_t, st_res, ev_ms, clocks = timed_loop(True, args.warmup)
-    my_e2e_t, st_e2e, ev_e2e_ms, _ = timed_loop(False, min(args.warmup, 1))
+    my_t, st_res, ev_ms, clocks, step_ms_res = timed_loop(True, args.warmup)
+    my_e2e_t, st_e2e, ev_e2e_ms, _, step_ms_e2e = timed_loop(False, args.warmup)
     my_b = sum(batches[s % n_batches]["bases"] for s in range(args.steps))
 
     if dist is not None:
@@ -376,13 +377,13 @@ def main():
                                  "candidate strings to the K2-K5 services in both arms",
                     "kmer_lookups_per_s_in_kernel": probes / (k1_ns * 1e-9) if k1_ns else None,
                     "kmer_lookups_per_step": probes,
-                    "ms_per_step_cuda_events": ev_ms / args.steps,
+                    "ms_per_step_cuda_events": ev_ms / args.steps, "step_ms_rank0": step_ms_res,
                     "stage_ms_per_step": {"getSeeds (K1 + host anchor logic)": st_res[10] / K_ / 1e6,
                                           "regions (host fibers + K2-K5 services)": st_res[11] / K_ / 1e6},
                     "gpu_service_calls_per_step": st_res[5] / K_, "gpu_requests_per_step": st_res[6] / K_}),
                 "clocks": clocks,
                 "e2e": {"value": tot_b / tot_e2e_t, "unit": "bases/s", "h2d_bytes_per_step": int(st_e2e[12] / K_),
-                        "d2h_bytes_per_step": int(st_e2e[13] / K_), "ms_per_step": 1e3 * tot_e2e_t / args.steps,
+                        "d2h_bytes_per_step": int(st_e2e[13] / K_), "ms_per_step": 1e3 * tot_e2e_t / args.steps, "step_ms_rank0": step_ms_e2e,
                         "note": "byte counts are the library's own tally of every cudaMemcpyAsync it issued in the step; the "
                                 "corrected reads are assembled in host memory (the D2H traffic is the services' answers)"},
                 "gpu_launches": int(st_res[14]),
