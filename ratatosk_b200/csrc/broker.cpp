@@ -35,40 +35,54 @@ struct ProfTimer {
         t = n;
     }
 };
-// K4 over host pools: distance + first / last best end column (product: the lean fused path; CPU simulator: the public entry)
-static void dist_core(rtk_ctx* ctx, uint32_t n, std::string& qp, const std::vector<uint64_t>& qo, std::string& tp, const std::vector<uint64_t>& to,
-                      const std::vector<uint8_t>& mode, std::vector<int32_t>& dist, std::vector<int32_t>& first, std::vector<int32_t>& last, uint64_t* st) {
+// K4 over host pools: distance + first / last best end column (product: the lean fused path; CPU simulator: the public entry).
+// Job i = qp[q_beg[i], +q_len[i]) vs tp[t_beg[i], +t_len[i]); several jobs may point at the same target bytes.
+static void dist_core(rtk_ctx* ctx, uint32_t n, std::string& qp, const std::vector<uint64_t>& q_beg, const std::vector<uint32_t>& q_len, std::string& tp,
+                      const std::vector<uint64_t>& t_beg, const std::vector<uint32_t>& t_len, const std::vector<uint8_t>& mode,
+                      std::vector<int32_t>& dist, std::vector<int32_t>& first, std::vector<int32_t>& last, uint64_t* st) {
     dist.assign(n + 1, -1); first.assign(n + 1, -1); last.assign(n + 1, -1);
     if (!n) return;
-    qp.push_back('\0'); tp.push_back('\0');
-#ifdef RTK_HOSTSIM   // the CPU simulator goes through the public entry (every end location) and keeps the two the callers use
+#ifdef RTK_HOSTSIM   // the CPU simulator goes through the public entry (contiguous pools, every end location) and keeps the two ends the callers use
+    std::string q2, t2;
+    std::vector<uint64_t> qo(1, 0), to(1, 0);
+    for (uint32_t a = 0; a < n; ++a) { q2.append(qp, q_beg[a], q_len[a]); qo.push_back(q2.size()); t2.append(tp, t_beg[a], t_len[a]); to.push_back(t2.size()); }
+    q2.push_back('\0'); t2.push_back('\0');
     std::vector<int32_t> kmax(n + 1, -1);
     int32_t* ends = nullptr;
     uint64_t* eoff = nullptr;
-    if (rtk_edlib_batch(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), kmax.data(), dist.data(), &ends, &eoff, st) != RTK_OK)
+    if (rtk_edlib_batch(ctx, n, q2.data(), qo.data(), t2.data(), to.data(), mode.data(), kmax.data(), dist.data(), &ends, &eoff, st) != RTK_OK)
         throw std::runtime_error(std::string("rtk_edlib_batch: ") + rtk_last_error());
     for (uint32_t a = 0; a < n; ++a) if (eoff[a + 1] > eoff[a]) { first[a] = ends[eoff[a]]; last[a] = ends[eoff[a + 1] - 1]; }
     rtk_free(ends);
     rtk_free(eoff);
 #else
-    dist_batch_lean(ctx, n, qp.data(), qo.data(), tp.data(), to.data(), mode.data(), dist.data(), first.data(), last.data(), st);
+    dist_batch_lean(ctx, n, qp.data(), qp.size(), q_beg.data(), q_len.data(), tp.data(), tp.size(), t_beg.data(), t_len.data(), mode.data(), dist.data(),
+                    first.data(), last.data(), st);
 #endif
 }
 
 void run_dist_batch(rtk_ctx* ctx, const std::vector<DistReq*>& reqs) {
     ProfTimer pt;
     std::string qp, tp;
-    std::vector<uint64_t> qo(1, 0), to(1, 0);
+    std::vector<uint64_t> qb, tb;
+    std::vector<uint32_t> ql, tl;
     std::vector<uint8_t> mode;
     for (const DistReq* r : reqs) {
         if (!r->jobs->empty()) g_mix[0][(*r->jobs)[0].mode % 3][r->jobs->size() > 1] += 1;
-        for (const AlignJob& j : *r->jobs) { qp += j.q; qo.push_back(qp.size()); tp += j.t; to.push_back(tp.size()); mode.push_back(j.mode); }
+        const std::string* prev = nullptr;   // consecutive jobs of a request that share one target string upload it once
+        for (const AlignJob& j : *r->jobs) {
+            qb.push_back(qp.size()); ql.push_back((uint32_t)j.q.size()); qp += j.q;
+            if (j.tref && j.tref == prev) { tb.push_back(tb.back()); tl.push_back(tl.back()); }
+            else { const std::string& t = j.target(); tb.push_back(tp.size()); tl.push_back((uint32_t)t.size()); tp += t; }
+            prev = j.tref;
+            mode.push_back(j.mode);
+        }
     }
     const uint32_t n = (uint32_t)mode.size();
     std::vector<int32_t> dist, first, last;
     uint64_t st[8] = {0};
     pt.lap(0, 0);
-    dist_core(ctx, n, qp, qo, tp, to, mode, dist, first, last, st);
+    dist_core(ctx, n, qp, qb, ql, tp, tb, tl, mode, dist, first, last, st);
     pt.lap(0, 1);
     g_prof[0][3] += st[2];
     uint32_t a = 0;
@@ -89,7 +103,7 @@ void run_path_batch(rtk_ctx* ctx, const std::vector<PathReq*>& reqs) {
     std::vector<uint8_t> mode;
     for (const PathReq* r : reqs) {
         if (!r->jobs->empty()) g_mix[1][(*r->jobs)[0].mode % 3][r->jobs->size() > 1] += 1;
-        for (const AlignJob& j : *r->jobs) { qp += j.q; qo.push_back(qp.size()); tp += j.t; to.push_back(tp.size()); mode.push_back(j.mode); }
+        for (const AlignJob& j : *r->jobs) { qp += j.q; qo.push_back(qp.size()); tp += j.target(); to.push_back(tp.size()); mode.push_back(j.mode); }
     }
     const uint32_t n = (uint32_t)mode.size();
     std::vector<int32_t> dist(n + 1, -1), end(n + 1, -1);
@@ -126,21 +140,24 @@ void run_subgraph_batch(rtk_ctx* ctx, const std::vector<SubgraphReq*>& reqs) {
     // phase A: prefix alignments (SHW, first end location) of the requests that extend a non-trivial path
     {
         std::string qp, tp;
-        std::vector<uint64_t> qo(1, 0), to(1, 0);
+        std::vector<uint64_t> qb, tb;
+        std::vector<uint32_t> ql, tl;
         std::vector<uint8_t> mode;
         std::vector<size_t> who;
         for (size_t i = 0; i < reqs.size(); ++i) {
             reqs[i]->out->end_pos_ref = 0;
             reqs[i]->out->explored = false;
             if (reqs[i]->prefix && !reqs[i]->prefix->empty()) {
-                qp += *reqs[i]->prefix; qo.push_back(qp.size()); tp += *reqs[i]->ref; to.push_back(tp.size()); mode.push_back(1);
+                qb.push_back(qp.size()); ql.push_back((uint32_t)reqs[i]->prefix->size()); qp += *reqs[i]->prefix;
+                tb.push_back(tp.size()); tl.push_back((uint32_t)reqs[i]->ref->size()); tp += *reqs[i]->ref;
+                mode.push_back(1);
                 who.push_back(i);
             }
         }
         if (!who.empty()) {
             std::vector<int32_t> dist, first, last;
             uint64_t st[8] = {0};
-            dist_core(ctx, (uint32_t)who.size(), qp, qo, tp, to, mode, dist, first, last, st);
+            dist_core(ctx, (uint32_t)who.size(), qp, qb, ql, tp, tb, tl, mode, dist, first, last, st);
             g_prof[2][3] += st[2];
             for (size_t x = 0; x < who.size(); ++x) reqs[who[x]]->out->end_pos_ref = (size_t)(first[x] + 1);
         }
@@ -200,8 +217,41 @@ void run_subgraph_batch(rtk_ctx* ctx, const std::vector<SubgraphReq*>& reqs) {
 }
 
 // ------------------------------------------------------------------ broker
+// Context switch between a worker's scheduler and its fibers.  glibc's swapcontext saves / restores the signal mask with a
+// system call on every switch (5 % of the host time in the sampling profile); the fibers never touch the mask, so on x86-64 a
+// switch only has to exchange the callee-saved registers and the stack pointer.  Other targets keep <ucontext.h>.
+#if defined(__x86_64__) && !defined(RTK_FIBER_UCONTEXT)
+#define RTK_FIBER_ASM 1
+extern "C" void rtk_fiber_switch(void** save_sp, void* new_sp);
+__asm__(
+    ".text\n"
+    ".globl rtk_fiber_switch\n"
+    ".type rtk_fiber_switch,@function\n"
+    "rtk_fiber_switch:\n"
+    "    pushq %rbp\n"
+    "    pushq %rbx\n"
+    "    pushq %r12\n"
+    "    pushq %r13\n"
+    "    pushq %r14\n"
+    "    pushq %r15\n"
+    "    movq %rsp, (%rdi)\n"
+    "    movq %rsi, %rsp\n"
+    "    popq %r15\n"
+    "    popq %r14\n"
+    "    popq %r13\n"
+    "    popq %r12\n"
+    "    popq %rbx\n"
+    "    popq %rbp\n"
+    "    ret\n"
+    ".size rtk_fiber_switch,.-rtk_fiber_switch\n");
+#endif
+
 struct GpuBroker::Fiber {
+#ifdef RTK_FIBER_ASM
+    void* sp = nullptr;               // saved stack pointer while the fiber is switched out
+#else
     ucontext_t uc;
+#endif
     char* stack = nullptr;
     size_t task = 0;
     bool done = false;
@@ -212,7 +262,11 @@ struct GpuBroker::Fiber {
 
 struct GpuBroker::Worker {
     std::thread th;
+#ifdef RTK_FIBER_ASM
+    void* sched_sp = nullptr;         // the worker thread's own context (scheduler loop), saved while a fiber runs
+#else
     ucontext_t sched;                 // the worker thread's own context (scheduler loop)
+#endif
     Fiber* current = nullptr;
     std::mutex mu;
     std::condition_variable cv;
@@ -288,7 +342,11 @@ void GpuBroker::park(int kind, void* req) {
         s->q.emplace_back(req, f);
     }
     s->cv.notify_one();
+#ifdef RTK_FIBER_ASM
+    rtk_fiber_switch(&f->sp, w->sched_sp);
+#else
     swapcontext(&f->uc, &w->sched);
+#endif
     if (!f->error.empty()) { std::string e; e.swap(f->error); throw std::runtime_error(e); }
 }
 void GpuBroker::submit(DistReq* r) { park(0, r); }
@@ -352,11 +410,24 @@ void GpuBroker::service_main(Service* s) {
     }
 }
 
+#ifdef RTK_FIBER_ASM
+// first activation of a fiber: reached by the `ret` of rtk_fiber_switch on a freshly prepared stack
+static void fiber_trampoline() {
+    GpuBroker::Worker* w = tl_worker;
+    GpuBroker::Fiber* f = w->current;
+    f->broker->fiber_body(f);
+    rtk_fiber_switch(&f->sp, w->sched_sp);   // done: back to the scheduler for good
+    __builtin_trap();
+}
+#endif
+
+#ifndef RTK_FIBER_ASM
 static void fiber_entry(unsigned lo, unsigned hi) {
     GpuBroker::Fiber* f = (GpuBroker::Fiber*)(((uintptr_t)hi << 32) | (uintptr_t)lo);
     f->broker->fiber_body(f);
     // returning switches to uc_link = the worker's scheduler context
 }
+#endif
 
 void GpuBroker::fiber_body(Fiber* f) {
     try {
@@ -382,7 +453,11 @@ void GpuBroker::worker_main(Worker* w) {
     size_t live = 0;
     auto enter = [&](Fiber* f) {
         w->current = f;
+#ifdef RTK_FIBER_ASM
+        rtk_fiber_switch(&w->sched_sp, f->sp);
+#else
         swapcontext(&w->sched, &f->uc);
+#endif
         w->current = nullptr;
         if (f->done) { w->pool.push_back(f); --live; }
     };
@@ -411,12 +486,22 @@ void GpuBroker::worker_main(Worker* w) {
                 f->stack = w->slab + (w->stacks_used++) * stack_bytes;
             }
             f->task = i; f->done = false; f->broker = this; f->owner = w; f->error.clear();
+#ifdef RTK_FIBER_ASM
+            {   // stack image rtk_fiber_switch pops: r15 r14 r13 r12 rbx rbp, then `ret` into the trampoline (rsp % 16 == 8 there)
+                void** sp = (void**)(((uintptr_t)f->stack + stack_bytes) & ~(uintptr_t)15);
+                *--sp = nullptr;                       // the trampoline's (never used) return address: ends unwinder walks
+                *--sp = (void*)&fiber_trampoline;
+                for (int r6 = 0; r6 < 6; ++r6) *--sp = nullptr;
+                f->sp = sp;
+            }
+#else
             getcontext(&f->uc);
             f->uc.uc_stack.ss_sp = f->stack;
             f->uc.uc_stack.ss_size = stack_bytes;
             f->uc.uc_link = &w->sched;
             const uintptr_t p = (uintptr_t)f;
             makecontext(&f->uc, (void (*)())fiber_entry, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
+#endif
             ++live; ++started;
             enter(f);
         }

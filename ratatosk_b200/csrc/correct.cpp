@@ -393,7 +393,7 @@ PathPair extract_semi_weak_paths(const Ctx& C, const std::string& s, const IdSet
 // selectBestPrefixAlignment(ref, len, vector<Path>, cut_threshold) (src/Alignment.cpp:47-97): {-1,-1} above the threshold
 std::pair<int, int> select_prefix_cut(const Ctx& C, const std::vector<GPath>& cands, const std::string& ref, double cut) {
     std::vector<AlignJob> jobs(cands.size());
-    for (size_t i = 0; i < cands.size(); ++i) { jobs[i].q = cands[i].to_string(C.g); jobs[i].t = ref; jobs[i].mode = 1; }
+    for (size_t i = 0; i < cands.size(); ++i) { jobs[i].q = cands[i].to_string(C.g); jobs[i].tref = &ref; jobs[i].mode = 1; }
     std::vector<int32_t> dist, fe;
     gpu_distances(C.ctx, jobs, dist, fe);
     double best = 0.0; int id = -1, endl = -1;
@@ -519,8 +519,8 @@ std::pair<std::string, std::string> generate_consensus(const Ctx& C, const Resul
     else if (fw_s->nb_corrected() + bw_s->nb_corrected() == 0) return {std::string(), std::string()};
     if (bw_s->nb_corrected() > fw_s->nb_corrected()) std::swap(fw_s, bw_s);
     std::vector<AlignJob> j(2);
-    j[0].q = fw_s->seq; j[0].t = ref_seq; j[0].mode = 0;
-    j[1].q = bw_s->seq; j[1].t = ref_seq; j[1].mode = 0;
+    j[0].q = fw_s->seq; j[0].tref = &ref_seq; j[0].mode = 0;
+    j[1].q = bw_s->seq; j[1].tref = &ref_seq; j[1].mode = 0;
     std::vector<int32_t> d;
     std::vector<std::vector<uint8_t>> ops;
     gpu_paths(C.ctx, j, d, ops);

@@ -233,19 +233,13 @@ void myers_run_lean(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const 
     }
 }
 
-void dist_batch_lean(rtk_ctx* c, uint32_t n, const char* q_pool, const uint64_t* q_off, const char* t_pool, const uint64_t* t_off,
-                     const uint8_t* mode, int32_t* dist, int32_t* first_end, int32_t* last_end, uint64_t* stats) {
+void dist_batch_lean(rtk_ctx* c, uint32_t n, const char* q_pool, uint64_t q_bytes, const uint64_t* q_beg, const uint32_t* q_len, const char* t_pool,
+                     uint64_t t_bytes, const uint64_t* t_beg, const uint32_t* t_len, const uint8_t* mode, int32_t* dist, int32_t* first_end,
+                     int32_t* last_end, uint64_t* stats) {
     RTK_CUDA(cudaSetDevice(c->device));
-    std::vector<uint64_t> qrel(n), trel(n);
-    std::vector<uint32_t> qlen(n), tlen(n);
-    for (uint32_t i = 0; i < n; ++i) {
-        qrel[i] = q_off[i] - q_off[0]; trel[i] = t_off[i] - t_off[0];
-        qlen[i] = (uint32_t)(q_off[i + 1] - q_off[i]); tlen[i] = (uint32_t)(t_off[i + 1] - t_off[i]);
-    }
-    MyersJobs j{n, qrel.data(), qlen.data(), trel.data(), tlen.data(), mode, nullptr};
+    MyersJobs j{n, q_beg, q_len, t_beg, t_len, mode, nullptr};
     float kms = 0.f;
-    myers_run_lean(c, nullptr, nullptr, q_pool + q_off[0], q_off[n] - q_off[0], t_pool + t_off[0], t_off[n] - t_off[0], j, dist, first_end, last_end,
-                   stats ? &kms : nullptr);
+    myers_run_lean(c, nullptr, nullptr, q_pool, q_bytes, t_pool, t_bytes, j, dist, first_end, last_end, stats ? &kms : nullptr);
     if (stats) stats[2] += (uint64_t)(kms * 1e6);
 }
 

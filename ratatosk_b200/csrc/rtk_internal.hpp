@@ -191,9 +191,11 @@ struct MyersJobs {
 };
 void myers_run(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const MyersJobs& j, int32_t* dist, bool want_ends,
                int32_t** ends, uint64_t** ends_off, float* kernel_ms);
-// host pools in, distance + first / last best end out (the broker's K4 service); stats[2] += kernel ns
-void dist_batch_lean(rtk_ctx* c, uint32_t n, const char* q_pool, const uint64_t* q_off, const char* t_pool, const uint64_t* t_off,
-                     const uint8_t* mode, int32_t* dist, int32_t* first_end, int32_t* last_end, uint64_t* stats);
+// host pools in, distance + first / last best end out (the broker's K4 service); job i = q_pool[q_beg[i], +q_len[i]) vs
+// t_pool[t_beg[i], +t_len[i]) (jobs may share target bytes); stats[2] += kernel ns
+void dist_batch_lean(rtk_ctx* c, uint32_t n, const char* q_pool, uint64_t q_bytes, const uint64_t* q_beg, const uint32_t* q_len, const char* t_pool,
+                     uint64_t t_bytes, const uint64_t* t_beg, const uint32_t* t_len, const uint8_t* mode, int32_t* dist, int32_t* first_end,
+                     int32_t* last_end, uint64_t* stats);
 // lean variant for internal callers: distance + first / last best end column; pools either resident (d_*) or on the host
 // (h_* != nullptr: packed into the same single upload as the descriptors).  kmax is unbounded.
 void myers_run_lean(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const char* h_qpool, uint64_t q_bytes, const char* h_tpool,

@@ -196,7 +196,7 @@ template <typename GetPath>
 static std::pair<int, int> select_generic(rtk_ctx* ctx, const rtk_graph_view& g, size_t n, GetPath get, const std::string& ref,
                                           uint8_t mode, bool norm_by_max) {
     std::vector<AlignJob> jobs(n);
-    for (size_t i = 0; i < n; ++i) { jobs[i].q = get(i).to_string(g); jobs[i].t = ref; jobs[i].mode = mode; }
+    for (size_t i = 0; i < n; ++i) { jobs[i].q = get(i).to_string(g); jobs[i].tref = &ref; jobs[i].mode = mode; }
     std::vector<int32_t> dist, fe;
     gpu_distances(ctx, jobs, dist, fe);
     double best = 0.0;
@@ -234,7 +234,7 @@ void set_qualities2(rtk_ctx* ctx, const rtk_graph_view& g, const TraverseOpt& op
     const size_t na = pa.size(), n = na + pb.size();
     if (!n) return;
     std::vector<AlignJob> jobs(n);
-    for (size_t i = 0; i < n; ++i) { jobs[i].q = (i < na ? pa[i] : pb[i - na]).to_string(g); jobs[i].t = ref; jobs[i].mode = 1; }
+    for (size_t i = 0; i < n; ++i) { jobs[i].q = (i < na ? pa[i] : pb[i - na]).to_string(g); jobs[i].tref = &ref; jobs[i].mode = 1; }
     std::vector<int32_t> dist;
     std::vector<std::vector<uint8_t>> ops;
     gpu_paths(ctx, jobs, dist, ops);
@@ -497,7 +497,7 @@ std::vector<GPath> fix_repeats(rtk_ctx* ctx, const rtk_graph_view& g, const Trav
         int64_t edit;
         {
             std::vector<AlignJob> j(1);
-            j[0].q = path.to_string(g).substr(0, path.length()); j[0].t = ref; j[0].mode = 0;
+            j[0].q = path.to_string(g).substr(0, path.length()); j[0].tref = &ref; j[0].mode = 0;
             std::vector<int32_t> d, fe;
             gpu_distances(ctx, j, d, fe);
             edit = d[0];
@@ -568,7 +568,7 @@ std::vector<GPath> fix_repeats(rtk_ctx* ctx, const rtk_graph_view& g, const Trav
                 for (const GPath& cand : *cands) {
                     exts.push_back(build_ext(cand, j));
                     AlignJob aj;
-                    aj.q = exts.back().to_string(g).substr(0, exts.back().length()); aj.t = ref; aj.mode = 0;
+                    aj.q = exts.back().to_string(g).substr(0, exts.back().length()); aj.tref = &ref; aj.mode = 0;
                     jobs.push_back(std::move(aj));
                 }
                 // no acceptance at j: the following vertices on the same unitig are skipped (:1322-1330)

@@ -60,6 +60,8 @@ struct TraverseOpt {
 struct AlignJob {
     std::string q, t;
     uint8_t mode;  // 0 NW, 1 SHW, 2 HW
+    const std::string* tref = nullptr;   // target shared by several jobs of a request (e.g. the read window): used instead of `t`, not copied
+    const std::string& target() const { return tref ? *tref : t; }
 };
 void gpu_distances(rtk_ctx* ctx, const std::vector<AlignJob>& jobs, std::vector<int32_t>& dist, std::vector<int32_t>& first_end);
 // + the largest end column carrying the distance (the end locations are ascending: first = endLocations[0], last = the final one)
