@@ -311,7 +311,7 @@ static void tune_allocator() {
 GpuBroker::GpuBroker(rtk_ctx* c) : ctx(c) {
     tune_allocator();
     // service threads per kind (each with its own forked context = stream + scratch): RTK_SERVICE_THREADS="d,p,s"
-    unsigned cnt[3] = {3, 3, 2};
+    unsigned cnt[3] = {2, 2, 3};
     if (const char* e = getenv("RTK_SERVICE_THREADS")) sscanf(e, "%u,%u,%u", &cnt[0], &cnt[1], &cnt[2]);
 #ifdef RTK_HOSTSIM   // the CPU simulator runs one launch at a time
     cnt[0] = cnt[1] = cnt[2] = 1;
