@@ -69,6 +69,48 @@ RTK_HD bool rtk_iupac_eq(const char a, const char b) {
     return (base_a != base_b) && (ma & mb);  // exactly one side is a plain base and the code contains it
 }
 
+// One wavefront sweep of a round (see rtk_myers_body): RARE = false drops the loop-invariant rare branches at compile time.
+#define RTK_MYERS_STEP_LOOP(RARE) \
+        for (int s = 0; s < steps; ++s) { \
+            const int from_left = __shfl_up_sync(gmask, hout, 1, G); \
+            const int col = s - (int)lane; \
+            const char tc = tc_next; \
+            tc_next = ((unsigned)(col + 1) < (unsigned)tlen) ? t[col + 1] : (char)0; \
+            const bool active = has && ((unsigned)col < (unsigned)tlen); \
+            int hin = (lane == 0) ? hin_top : from_left; \
+            if (RARE && top_spilled && active) hin = (int)hb[col]; \
+            uint64_t Eq = (tc == 'A') ? PB0 : (tc == 'C') ? PB1 : (tc == 'G') ? PB2 : (tc == 'T') ? PB3 : 0ULL; \
+            if (RARE && t_amb && active && tc != 'A' && tc != 'C' && tc != 'G' && tc != 'T') { \
+                const int lo = b << 6; \
+                const int n = (qlen - lo < 64) ? (qlen - lo) : 64; \
+                for (int i = 0; i < n; ++i) Eq |= (uint64_t)(plain ? (q[lo + i] == tc) : rtk_iupac_eq(q[lo + i], tc)) << i; \
+            } \
+            const uint64_t neg = (hin < 0) ? 1ULL : 0ULL; \
+            const uint64_t Xv = Eq | Mv; \
+            Eq |= neg; \
+            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq; \
+            uint64_t Ph = Mv | ~(Xh | Pv); \
+            uint64_t Mh = Pv & Xh; \
+            hout = active ? ((int)(Ph >> 63) - (int)(Mh >> 63)) : 0; \
+            const int dscore = (int)((Ph >> last_row) & 1) - (int)((Mh >> last_row) & 1); \
+            Ph = (Ph << 1) | ((hin > 0) ? 1ULL : 0ULL); \
+            Mh = (Mh << 1) | neg; \
+            const uint64_t nPv = Mh | ~(Xv | Ph), nMv = Ph & Xv; \
+            Pv = active ? nPv : Pv; \
+            Mv = active ? nMv : Mv; \
+            score += (active && is_last) ? dscore : 0; \
+            const bool upd = active && track; \
+            const bool better = upd && (score < best); \
+            best = better ? score : best; \
+            n_best = better ? 0 : n_best; \
+            const bool eq = upd && (score == best); \
+            if (RARE && ends != nullptr && eq) ends[n_best] = col; \
+            first = (eq && n_best == 0) ? col : first; \
+            last = eq ? col : last; \
+            n_best += eq ? 1 : 0; \
+            if (RARE && spill && active) hb[col] = (int8_t)hout; \
+        }
+
 #if defined(__CUDACC__) || defined(__CUDACC_SIM__)
 // one alignment per group of G lanes; `order` / `n` = the alignments of this class, `blk` = block index within the class
 template <int G>
@@ -132,47 +174,11 @@ __device__ __forceinline__ void rtk_myers_body(const rtk_myers_params& p, const 
         // on the target character, nested `if`s for the end columns) spent 42 % of its stall samples resolving branches
         // (profiles/r1_myers_ncu_full.md).  Only loop-invariant, rare cases keep a branch: ambiguity codes in the target
         // (`t_amb`), the spill row of multi-round queries, and the end-column store of the non-lean mode.
-        for (int s = 0; s < steps; ++s) {
-            const int from_left = __shfl_up_sync(gmask, hout, 1, G);
-            const int col = s - (int)lane;
-            const char tc = tc_next;
-            tc_next = ((unsigned)(col + 1) < (unsigned)tlen) ? t[col + 1] : (char)0;
-            const bool active = has && ((unsigned)col < (unsigned)tlen);
-            int hin = (lane == 0) ? hin_top : from_left;
-            if (top_spilled && active) hin = (int)hb[col];
-            uint64_t Eq = (tc == 'A') ? PB0 : (tc == 'C') ? PB1 : (tc == 'G') ? PB2 : (tc == 'T') ? PB3 : 0ULL;
-            if (t_amb && active && tc != 'A' && tc != 'C' && tc != 'G' && tc != 'T') {
-                // ambiguity code (or foreign character) in the target: build the profile on the fly
-                const int lo = b << 6;
-                const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
-                for (int i = 0; i < n; ++i) Eq |= (uint64_t)(plain ? (q[lo + i] == tc) : rtk_iupac_eq(q[lo + i], tc)) << i;
-            }
-            // one block of one column (Hyyro's formulation of Myers' recurrence)
-            const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
-            const uint64_t Xv = Eq | Mv;
-            Eq |= neg;
-            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-            uint64_t Ph = Mv | ~(Xh | Pv);
-            uint64_t Mh = Pv & Xh;
-            hout = active ? ((int)(Ph >> 63) - (int)(Mh >> 63)) : 0;
-            const int dscore = (int)((Ph >> last_row) & 1) - (int)((Mh >> last_row) & 1);
-            Ph = (Ph << 1) | ((hin > 0) ? 1ULL : 0ULL);
-            Mh = (Mh << 1) | neg;
-            const uint64_t nPv = Mh | ~(Xv | Ph), nMv = Ph & Xv;
-            Pv = active ? nPv : Pv;
-            Mv = active ? nMv : Mv;
-            score += (active && is_last) ? dscore : 0;
-            const bool upd = active && track;
-            const bool better = upd && (score < best);
-            best = better ? score : best;
-            n_best = better ? 0 : n_best;
-            const bool eq = upd && (score == best);
-            if (ends != nullptr && eq) ends[n_best] = col;
-            first = (eq && n_best == 0) ? col : first;
-            last = eq ? col : last;
-            n_best += eq ? 1 : 0;
-            if (spill && active) hb[col] = (int8_t)hout;
-        }
+        // two copies of the loop: the common one carries none of the loop-invariant rare branches (ambiguity codes in the
+        // target, spill rows of multi-round queries, the end-column store of the non-lean mode) - even a never-taken branch
+        // costs a warp with nothing else to run ~20 cycles per step to resolve
+        const bool rare = t_amb || (rounds > 1) || (ends != nullptr);   // uniform over the lane group: its lanes shuffle with each other inside the loop
+        if (!rare) { RTK_MYERS_STEP_LOOP(false) } else { RTK_MYERS_STEP_LOOP(true) }
         __syncwarp(gmask);  // the next round's top lane reads what this round's bottom lane spilled
     }
     // the lane that owned the last block reports
