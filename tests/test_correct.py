@@ -90,7 +90,7 @@ def test_pass2_correction_kernel_sources_match_reference_fastq(sim_lib):
     g = rb.Graph.load(os.path.join(d, "index.k63.fasta.gz"), os.path.join(d, "index.k63.rtsk"), 63, lib=sim_lib)
     ctx = rb.Context(0, lib=sim_lib)
     ctx.upload(g)
-    assert _run_pass2(ctx, "F2", [4]) == 1   # a read the second pass changes
+    assert _run_pass2(ctx, "F2", [15, 9]) == 2   # two (short) reads the second pass changes
     ctx.close()
     g.close()
 
