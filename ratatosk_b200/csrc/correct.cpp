@@ -963,12 +963,14 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
     const size_t max_km_cov = std::max<size_t>(ctx->host_graph->hdr.max_km_cov_graph, opt.max_km_cov);  // src/Ratatosk.cpp:625
     out_seq.assign(n_reads, std::string());
     out_qual.assign(n_reads, std::string());
-    for (uint32_t r = 0; r < n_reads; ++r) {
-        out_seq[r].assign(seq_pool + seq_off[r], seq_off[r + 1] - seq_off[r]);
-        for (auto& c : out_seq[r]) c = (char)toupper((unsigned char)c);  // :814
-        if (qual_pool && qual_off) out_qual[r].assign(qual_pool + qual_off[r], qual_off[r + 1] - qual_off[r]);
-        if (!pass2) for (auto& c : out_qual[r]) { if (c < (char)33) c = (char)33; if (c > (char)(33 + opt.max_qual)) c = (char)(33 + opt.max_qual); }  // getStdQual
-    }
+    parallel_for(n_reads, [&](size_t rb, size_t re) {
+        for (size_t r = rb; r < re; ++r) {
+            out_seq[r].assign(seq_pool + seq_off[r], seq_off[r + 1] - seq_off[r]);
+            for (auto& c : out_seq[r]) if (c >= 'a' && c <= 'z') c = (char)(c - 'a' + 'A');  // :814 (::toupper in the "C" locale)
+            if (qual_pool && qual_off) out_qual[r].assign(qual_pool + qual_off[r], qual_off[r + 1] - qual_off[r]);
+            if (!pass2) for (auto& c : out_qual[r]) { if (c < (char)33) c = (char)33; if (c > (char)(33 + opt.max_qual)) c = (char)(33 + opt.max_qual); }  // getStdQual
+        }
+    });
     const size_t rounds = pass2 ? 1 : std::max<uint32_t>(1, opt.nb_correction_rounds);
     const double step_min_score = 1.00 / static_cast<double>(rounds);
     const double step_wrlf = (rounds == 1) ? 0.0 : ((opt.weak_region_len_factor - 0.10) / static_cast<double>(rounds - 1));
@@ -980,10 +982,10 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
             l_opt.weak_region_len_factor = opt.weak_region_len_factor - (rounds - j - 1) * step_wrlf;
             l_opt.max_len_weak_region1 = (uint32_t)((j + 1) * step_mlwr1);
         }
-        std::string pool;
-        std::vector<uint64_t> off(1, 0);
-        for (uint32_t r = 0; r < n_reads; ++r) { pool += out_seq[r]; off.push_back(pool.size()); }
-        pool.push_back('\0');
+        std::vector<uint64_t> off(n_reads + 1, 0);
+        for (uint32_t r = 0; r < n_reads; ++r) off[r + 1] = off[r] + out_seq[r].size();
+        std::string pool(off[n_reads] + 1, '\0');
+        parallel_for(n_reads, [&](size_t rb, size_t re) { for (size_t r = rb; r < re; ++r) memcpy(&pool[off[r]], out_seq[r].data(), out_seq[r].size()); });
         std::vector<std::vector<rtk_hit>> solid, weak;
         const auto t_seeds = std::chrono::steady_clock::now();
         get_seeds_host(ctx, l_opt, pass, n_reads, pool.data(), off.data(), solid, weak, stats);
@@ -1014,13 +1016,24 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
         if (!getenv("RTK_NO_LPT")) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return span[a] > span[b]; });
         GpuBroker broker(ctx);
         broker.run(pieces.size(), correct_threads(), [&](size_t i) { run_piece(C, jobs[pieces[order[i]].read], pieces[order[i]]); });
-        std::vector<std::string> ns(n_reads), nq(n_reads);
-        for (const Piece& P : pieces) { ns[P.read] += P.s; nq[P.read] += P.q; }
-        for (uint32_t r = 0; r < n_reads; ++r) {
-            if (jobs[r].trivial) { ns[r] = jobs[r].trivial_out.first; nq[r] = jobs[r].trivial_out.second; }
-            out_seq[r] = std::move(ns[r]);
-            out_qual[r] = std::move(nq[r]);
-        }
+        // pieces were planned read by read: [first_piece[r], first_piece[r + 1]) belong to read r, in order
+        std::vector<size_t> first_piece(n_reads + 1, 0);
+        for (const Piece& P : pieces) ++first_piece[P.read + 1];
+        for (uint32_t r = 0; r < n_reads; ++r) first_piece[r + 1] += first_piece[r];
+        parallel_for(n_reads, [&](size_t rb, size_t re) {
+            for (size_t r = rb; r < re; ++r) {
+                std::string ns, nq;
+                if (jobs[r].trivial) { ns = jobs[r].trivial_out.first; nq = jobs[r].trivial_out.second; }
+                else {
+                    size_t tot = 0;
+                    for (size_t x = first_piece[r]; x < first_piece[r + 1]; ++x) tot += pieces[x].s.size();
+                    ns.reserve(tot); nq.reserve(tot);
+                    for (size_t x = first_piece[r]; x < first_piece[r + 1]; ++x) { ns += pieces[x].s; nq += pieces[x].q; }
+                }
+                out_seq[r] = std::move(ns);
+                out_qual[r] = std::move(nq);
+            }
+        });
         if (stats) {
             stats[5] += broker.waves; stats[6] += broker.jobs;
             for (int s3 = 0; s3 < 3; ++s3) stats[7 + s3] += broker.kernel_ns[s3];
@@ -1055,10 +1068,12 @@ extern "C" int rtk_correct_batch(rtk_ctx* ctx, const rtk_opt* opt, int pass, uin
         for (uint32_t r = 0; r < n_reads; ++r) {
             (*out_off)[r] = t;
             if (os[r].size() != oq[r].size()) throw std::runtime_error("corrected sequence and quality lengths differ");
-            memcpy(*out_seq_pool + t, os[r].data(), os[r].size());
-            memcpy(*out_qual_pool + t, oq[r].data(), oq[r].size());
             t += os[r].size();
         }
         (*out_off)[n_reads] = t;
+        char* sp = *out_seq_pool; char* qp = *out_qual_pool; const uint64_t* oo = *out_off;
+        parallel_for(n_reads, [&](size_t rb, size_t re) {
+            for (size_t r = rb; r < re; ++r) { memcpy(sp + oo[r], os[r].data(), os[r].size()); memcpy(qp + oo[r], oq[r].data(), oq[r].size()); }
+        });
     });
 }
