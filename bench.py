@@ -312,7 +312,7 @@ def main():
         for w in range(warmup):
             correct_step(batches[w % n_batches], resident)
         barrier()
-        step_s, stats, ev_ms = [], np.zeros(16, dtype=np.float64), 0.0
+        step_s, stats, ev_ms, seeds_ms = [], np.zeros(16, dtype=np.float64), 0.0, []
         with ClockSampler(local_rank) as clk:
             for s in range(args.steps):
                 bt = batches[s % n_batches]
@@ -327,8 +327,9 @@ def main():
                 step_s.append(time.perf_counter() - t0)
                 ev_ms += e0.elapsed_time(e1)
                 stats += np.asarray(st, dtype=np.float64)
+                seeds_ms.append(round(st[10] / 1e6, 1))
         barrier()
-        return sum(step_s), stats, ev_ms, clk.summary(), [round(1e3 * x, 1) for x in step_s]
+        return sum(step_s), stats, ev_ms, clk.summary(), {"step": [round(1e3 * x, 1) for x in step_s], "getSeeds_stage": seeds_ms}
 
     my_t, st_res, ev_ms, clocks, step_ms_res = timed_loop(True, args.warmup)
     my_e2e_t, st_e2e, ev_e2e_ms, _, step_ms_e2e = timed_loop(False, args.warmup)

@@ -107,7 +107,7 @@ void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, 
     uint64_t probes = 0;
     float kms = 0.f;
     const uint64_t n_raw = k1_launch(ctx, n_reads, d_seq, d_off, rel.data(), flags, &probes, &kms, seq_pool + seq_off[0]);
-    std::vector<RawHit> raw(n_raw);
+    RawHitVec raw(n_raw);
     if (n_raw) {
         RTK_CUDA(counted_memcpy_async(raw.data(), ctx->d_hits.p, n_raw * sizeof(RawHit), cudaMemcpyDeviceToHost, ctx->stream));
         RTK_CUDA(cudaStreamSynchronize(ctx->stream));

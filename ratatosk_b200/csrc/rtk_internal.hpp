@@ -127,7 +127,7 @@ namespace rtk {
 
 // sorted raw hits of a batch -> per-read hit lists in reference order (shared by product and hostsim)
 void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
-                   std::vector<RawHit>& raw, std::vector<std::vector<rtk_hit>>& per_read);
+                   RawHitVec& raw, std::vector<std::vector<rtk_hit>>& per_read);
 
 // K1 driver: runs the exact and/or inexact kernels over reads resident on the device and leaves the
 // raw labelled hits in ctx->d_hits.  Returns raw hit count; *n_probes / *kernel_ms optional.

@@ -134,7 +134,7 @@ void resolve_inexact(const rtk_graph_view& g, const char* s, uint32_t slen, bool
 }
 
 void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
-                   std::vector<RawHit>& raw, std::vector<std::vector<rtk_hit>>& per_read) {
+                   RawHitVec& raw, std::vector<std::vector<rtk_hit>>& per_read) {
     per_read.assign(n_reads, {});
     // bucket the raw hits by read (counting sort on the read id), then sort + replay each read independently
     const int sh = RTK_HIT_VAR_BITS + RTK_HIT_POS_BITS;
@@ -145,7 +145,7 @@ void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_p
         ++start[r + 1];
     }
     for (uint32_t r = 0; r < n_reads; ++r) start[r + 1] += start[r];
-    std::vector<RawHit> by_read(raw.size());
+    RawHitVec by_read(raw.size());
     {
         std::vector<uint64_t> fill(start.begin(), start.end() - 1);
         for (const RawHit& h : raw) by_read[fill[(uint32_t)(h.a >> sh)]++] = h;

@@ -14,6 +14,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <memory>
+#include <utility>
 #include <vector>
 
 #include "../../include/rtk.h"
@@ -25,6 +27,15 @@ struct RawHit {
     uint64_t a;  // read(24) | variant(10) | pos_s(30)
     uint64_t b;  // P(40) | strand<<40
 };
+
+// vector whose resize / sized constructor leaves trivially-constructible elements uninitialised: the hit lists of a batch are
+// hundreds of MB that are about to be overwritten by a device-to-host copy or a counting sort
+template <typename T> struct DefaultInitAlloc : std::allocator<T> {
+    template <typename U> struct rebind { typedef DefaultInitAlloc<U> other; };
+    template <typename U> void construct(U* p) { ::new ((void*)p) U; }
+    template <typename U, typename... A> void construct(U* p, A&&... a) { ::new ((void*)p) U(std::forward<A>(a)...); }
+};
+typedef std::vector<RawHit, DefaultInitAlloc<RawHit>> RawHitVec;
 
 // raw: hits of ONE read, sorted ascending by `a`. Appends to out in reference order.
 void resolve_exact(const rtk_graph_view& g, const RawHit* raw, size_t n, std::vector<rtk_hit>& out);

@@ -13,7 +13,7 @@
 namespace rtk {
 
 static uint64_t sim_k1(rtk_ctx* ctx, uint32_t n_reads, const char* seq, const uint64_t* seq_off, uint32_t flags,
-                       std::vector<RawHit>& raw, uint64_t* n_probes) {
+                       RawHitVec& raw, uint64_t* n_probes) {
     const rtk_graph_view& g = ctx->host_graph->view;
     const uint32_t k = g.k;
     const bool exact = flags & RTK_SEARCH_EXACT;
@@ -53,7 +53,7 @@ static uint64_t sim_k1(rtk_ctx* ctx, uint32_t n_reads, const char* seq, const ui
 void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                           std::vector<std::vector<rtk_hit>>& per_read, uint64_t* stats) {
     if (!ctx->has_graph || !ctx->host_graph) throw std::invalid_argument("no graph uploaded to this context");
-    std::vector<RawHit> raw;
+    RawHitVec raw;
     uint64_t probes = 0;
     const uint64_t n_raw = sim_k1(ctx, n_reads, seq_pool, seq_off, flags, raw, &probes);
     resolve_batch(ctx->host_graph->view, n_reads, seq_pool, seq_off, flags, raw, per_read);
