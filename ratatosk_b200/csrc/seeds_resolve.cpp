@@ -136,19 +136,47 @@ void resolve_inexact(const rtk_graph_view& g, const char* s, uint32_t slen, bool
 void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                    RawHitVec& raw, std::vector<std::vector<rtk_hit>>& per_read) {
     per_read.assign(n_reads, {});
-    // bucket the raw hits by read (counting sort on the read id), then sort + replay each read independently
+    // bucket the raw hits by read (parallel counting sort on the read id: per-chunk histograms, one prefix pass, parallel
+    // scatter), then sort + replay each read independently
     const int sh = RTK_HIT_VAR_BITS + RTK_HIT_POS_BITS;
+    const size_t n_raw = raw.size();
+    const size_t n_chunks = std::max<size_t>(1, std::min<size_t>(host_threads(), n_raw / 65536 + 1));
+    const size_t chunk = (n_raw + n_chunks - 1) / n_chunks;
+    std::vector<std::vector<uint32_t>> cnt(n_chunks);
+    parallel_for(n_chunks, [&](size_t cb, size_t ce) {
+        for (size_t c = cb; c < ce; ++c) {
+            std::vector<uint32_t>& h = cnt[c];
+            h.assign(n_reads, 0);
+            const size_t lo = c * chunk, hi = std::min(n_raw, lo + chunk);
+            for (size_t i = lo; i < hi; ++i) {
+                const uint32_t r = (uint32_t)(raw[i].a >> sh);
+                if (r >= n_reads) throw std::runtime_error("corrupt hit record");
+                ++h[r];
+            }
+        }
+    });
     std::vector<uint64_t> start(n_reads + 1, 0);
-    for (const RawHit& h : raw) {
-        const uint32_t r = (uint32_t)(h.a >> sh);
-        if (r >= n_reads) throw std::runtime_error("corrupt hit record");
-        ++start[r + 1];
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        uint64_t t = 0;
+        for (size_t c = 0; c < n_chunks; ++c) t += cnt[c][r];
+        start[r + 1] = start[r] + t;
     }
-    for (uint32_t r = 0; r < n_reads; ++r) start[r + 1] += start[r];
-    RawHitVec by_read(raw.size());
+    RawHitVec by_read(n_raw);
     {
-        std::vector<uint64_t> fill(start.begin(), start.end() - 1);
-        for (const RawHit& h : raw) by_read[fill[(uint32_t)(h.a >> sh)]++] = h;
+        // write cursor of chunk c for read r = start[r] + hits of r in the chunks before c
+        std::vector<std::vector<uint64_t>> cur(n_chunks);
+        for (size_t c = 0; c < n_chunks; ++c) cur[c].resize(n_reads);
+        for (uint32_t r = 0; r < n_reads; ++r) {
+            uint64_t t = start[r];
+            for (size_t c = 0; c < n_chunks; ++c) { cur[c][r] = t; t += cnt[c][r]; }
+        }
+        parallel_for(n_chunks, [&](size_t cb, size_t ce) {
+            for (size_t c = cb; c < ce; ++c) {
+                std::vector<uint64_t>& w = cur[c];
+                const size_t lo = c * chunk, hi = std::min(n_raw, lo + chunk);
+                for (size_t i = lo; i < hi; ++i) by_read[w[(uint32_t)(raw[i].a >> sh)]++] = raw[i];
+            }
+        });
     }
     const bool exact = flags & RTK_SEARCH_EXACT;
     parallel_for(n_reads, [&](size_t b, size_t e) {
