@@ -226,6 +226,12 @@ def main():
         run_reference(args, rank)
         return
 
+    # exactly ONE line on stdout: NCCL / driver banners written to file descriptor 1 by native code go to stderr instead;
+    # the descriptor is restored just before the JSON line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import ratatosk_b200 as rb
     if not torch.cuda.is_available():
@@ -405,7 +411,10 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(args, haps)
             except Exception as e:
                 line["cpu_baseline"] = {"unavailable": str(e).splitlines()[0]}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
