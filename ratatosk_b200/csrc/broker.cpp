@@ -289,6 +289,7 @@ struct GpuBroker::Service {
     uint64_t batches = 0, reqs = 0, ns_busy = 0;
 };
 
+static const size_t kGuardBytes = 4096;   // one inaccessible page below every fiber stack
 static size_t fiber_stack_bytes() {
     const char* e = getenv("RTK_FIBER_STACK_KB");
     const long kb = e ? atol(e) : 256;
@@ -386,6 +387,7 @@ void GpuBroker::service_main(Service* s) {
             else if (s->kind == 1) { std::vector<PathReq*> v; for (auto& b : batch) v.push_back((PathReq*)b.first); run_path_batch(s->ctx, v); }
             else { std::vector<SubgraphReq*> v; for (auto& b : batch) v.push_back((SubgraphReq*)b.first); run_subgraph_batch(s->ctx, v); }
         } catch (const std::exception& e) { err = e.what(); if (err.empty()) err = "GPU service failed"; }
+        catch (...) { err = "GPU service failed (unknown exception)"; }
         s->ns_busy += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         ++s->batches; s->reqs += batch.size();
         if (!err.empty()) {   // no new tasks after a service error
@@ -483,7 +485,11 @@ void GpuBroker::worker_main(Worker* w) {
             if (!w->pool.empty()) { f = w->pool.back(); w->pool.pop_back(); }
             else {
                 f = new Fiber();
-                f->stack = w->slab + (w->stacks_used++) * stack_bytes;
+                // stacks are carved from one mapping with a PROT_NONE guard page below each: an overflow faults instead of
+                // silently overwriting the neighbouring fiber's saved registers
+                char* base = w->slab + (w->stacks_used++) * (stack_bytes + kGuardBytes);
+                mprotect(base, kGuardBytes, PROT_NONE);
+                f->stack = base + kGuardBytes;
             }
             f->task = i; f->done = false; f->broker = this; f->owner = w; f->error.clear();
 #ifdef RTK_FIBER_ASM
@@ -534,7 +540,7 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
     for (int k = 0; k < 3; ++k) for (int j = 0; j < 4; ++j) prof0[k][j] = g_prof[k][j];
     for (unsigned t = 0; t < n_workers; ++t) {
         Worker* w = new Worker();
-        w->slab_bytes = cap_per_worker * stack_bytes;
+        w->slab_bytes = cap_per_worker * (stack_bytes + kGuardBytes);
         w->slab = (char*)mmap(nullptr, w->slab_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (w->slab == (char*)MAP_FAILED) { delete w; for (Worker* x : workers) { munmap(x->slab, x->slab_bytes); delete x; } workers.clear(); throw std::bad_alloc(); }
         w->rr = t;

@@ -1056,6 +1056,7 @@ extern "C" int rtk_correct_batch(rtk_ctx* ctx, const rtk_opt* opt, int pass, uin
     return guarded([&] {
         if (!ctx || !opt || !seq_pool || !seq_off || !out_seq_pool || !out_qual_pool || !out_off) throw std::invalid_argument("null argument");
         if (pass != 1 && pass != 2) throw std::invalid_argument("pass must be 1 (k1 graph, short-read colours) or 2 (k2 graph, long-read colours)");
+        DeviceBind bind(ctx);
         std::vector<std::string> os, oq;
         correct_batch_host(ctx, *opt, pass, n_reads, seq_pool, seq_off, qual_pool, qual_off, os, oq, stats);
         uint64_t total = 0;

@@ -251,6 +251,7 @@ extern "C" int rtk_phasing_batch(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_re
             throw std::invalid_argument("null argument");
         for (uint32_t r = 0; r < n_reads; ++r)
             if (qual_off[r + 1] - qual_off[r] != corr_off[r + 1] - corr_off[r]) throw std::invalid_argument("corrected read and quality lengths differ");
+        DeviceBind bind(ctx);
         std::vector<std::string> os, oq;
         phasing_batch_host(ctx, *opt, n_reads, raw_pool, raw_off, corr_pool, corr_off, qual_pool, qual_off, os, oq);
         uint64_t total = 0;

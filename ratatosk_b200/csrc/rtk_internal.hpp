@@ -125,6 +125,24 @@ struct rtk_ctx {
 
 namespace rtk {
 
+// Make ctx's GPU the calling thread's current device for the lifetime of the guard and restore the caller's device
+// afterwards (several contexts may live in one process; an entry point may be called from any host thread).  No-op on
+// the CPU simulator.
+struct DeviceBind {
+#ifndef RTK_HOSTSIM
+    int prev = -1;
+    explicit DeviceBind(const rtk_ctx* c) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != c->device) RTK_CUDA(cudaSetDevice(c->device)); else prev = -1;
+    }
+    ~DeviceBind() { if (prev >= 0) cudaSetDevice(prev); }
+#else
+    explicit DeviceBind(const rtk_ctx*) {}
+#endif
+    DeviceBind(const DeviceBind&) = delete;
+    DeviceBind& operator=(const DeviceBind&) = delete;
+};
+
 // sorted raw hits of a batch -> per-read hit lists in reference order (shared by product and hostsim)
 void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                    RawHitVec& raw, std::vector<std::vector<rtk_hit>>& per_read);

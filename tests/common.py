@@ -91,16 +91,20 @@ class OracleGraph:
             self.h = None
 
 
-_ograph_cache = {}
+_ograph_cache = []   # [(graph, OracleGraph)]: the strong reference keeps the Graph alive, so its identity cannot be recycled
 
 
 def oracle_graph_for(graph):
-    """OracleGraph over the unitigs of a loaded product Graph (unitig ids coincide)."""
-    key = id(graph)
-    if key not in _ograph_cache:
-        n = graph.info()["n_unitigs"]
-        _ograph_cache[key] = OracleGraph([graph.unitig_seq(u) for u in range(n)], graph.info()["k"])
-    return _ograph_cache[key]
+    """OracleGraph over the unitigs of a loaded product Graph (unitig ids coincide).  Cached per Graph OBJECT: the
+    cache holds the graph itself (an `id()` key could be reused by a later Graph once the first one is collected,
+    which is what made round 1's F2 parity test compare against the F1 oracle)."""
+    for g, og in _ograph_cache:
+        if g is graph:
+            return og
+    n = graph.info()["n_unitigs"]
+    og = OracleGraph([graph.unitig_seq(u) for u in range(n)], graph.info()["k"])
+    _ograph_cache.append((graph, og))
+    return og
 
 
 def oracle_search(graph, s, exact=True):
