@@ -285,7 +285,7 @@ def main():
     def correct_step(bt, resident):
         """one batch through getSeeds + correctSequence; returns (library stats, corrected bases out)"""
         os_, oq_, oo = C.c_void_p(), C.c_void_p(), u64p()
-        st = (C.c_uint64 * 16)()
+        st = (C.c_uint64 * 24)()
         seq_p = C.cast(bt["h_seq"].data_ptr(), C.c_char_p)
         qual_p = C.cast(bt["h_qual"].data_ptr(), C.c_char_p)
         off_p = C.cast(bt["h_off"].data_ptr(), u64p)

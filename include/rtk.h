@@ -197,14 +197,60 @@ int rtk_explore_paths(rtk_ctx* ctx, const rtk_opt* opt, const rtk_hit* um_s, con
                       uint32_t ref_len, const uint32_t* pids, uint32_t n_pids, rtk_path_node** nodes, uint32_t* n_nodes,
                       char** qual, uint32_t* path_len);
 
+/* ---- device-resident region engine: extractSemiWeakPaths (src/Correction.cpp:3-157) with explorePathsBFS2 / explorePathsBFS
+ * (src/GraphTraversal.cpp:212-454, :3-210), exploreSubGraph(Long) (:456-720), getScorePath (:722-772, :867-909) and the
+ * selectors (src/Alignment.cpp:3-147, :967-1015) chained on the GPU, one warp per call, no host round trips.  A call is the
+ * path search of one weak region: from the left anchor `start` over the weak anchors of the region to the right anchor
+ * `end` (or to the open end of the read).  Positions are read positions as in the reference.  Output per call: status 0 =
+ * the path reached the end (paths.first), 1 = it dead-ended at a weak anchor (paths.second), 2 = the engine declined the
+ * call (`bail` says why: fixRepeats on short-cycle unitigs, the 512 / 1024 list collapses, alignments above edlib's 1 MiB
+ * traceback switch, scratch capacity) and the caller must use rtk_explore_paths-level entries instead.  rtk_correct_batch
+ * uses this engine internally and falls back per call. */
+typedef struct rtk_region_call_t {
+    uint64_t win_off;        /* window = win_pool[win_off, +win_len) = s[start_pos, pos_um_solid2 + k) */
+    uint64_t weak_off;       /* weak anchors from i_weak on: weak_pool[weak_off, +n_weak), ascending pos */
+    uint64_t pid_off;        /* WeightsPairID::all_pids, sorted: pid_pool[pid_off, +pid_len) */
+    uint32_t win_len;
+    uint32_t n_weak;
+    uint32_t pid_len;
+    uint32_t start_pos;      /* um_start.first */
+    uint32_t start_unitig, start_dist, start_strand;
+    uint32_t has_end;
+    uint32_t end_pos;        /* pos_um_solid2 when has_end */
+    uint32_t end_unitig, end_dist, end_strand;
+    uint32_t s_len;          /* read length (open end: pos_um_solid2 = s_len - k) */
+    uint32_t reserved;
+} rtk_region_call_t;
+
+typedef struct rtk_region_result_t {
+    uint32_t status, bail;
+    uint32_t n_nodes, len;   /* path vertices / spelled length */
+    uint64_t node_off;       /* nodes[node_off, +n_nodes) */
+    uint64_t str_off;        /* chars[str_off, +len) = spelled path; chars[str_off + pad8(len), +len) = its quality string */
+    uint32_t n_hops, n_pops, n_cands, n_aligns;   /* work done: BFS calls, queue pops, candidates scored, alignments */
+} rtk_region_result_t;
+
+typedef struct rtk_region_out {
+    rtk_region_result_t* results;   /* n_calls */
+    rtk_path_node* nodes;
+    char* chars;
+    uint64_t n_nodes, n_chars;
+} rtk_region_out;
+
+int rtk_region_paths_batch(rtk_ctx* ctx, const rtk_opt* opt, int pass, uint32_t n_calls, const rtk_region_call_t* calls,
+                           const char* win_pool, uint64_t win_bytes, const rtk_hit* weak_pool, uint64_t n_weak,
+                           const uint32_t* pid_pool, uint64_t n_pids, rtk_region_out* out, uint64_t* stats);
+void rtk_region_out_free(rtk_region_out* out);
+
 /* ---- the per-read body of search() (src/Ratatosk.cpp:808-867): getSeeds + correctSequence for a ticket of reads ----
  * Pass 1 (k = 31 graph coloured by short reads).  Inputs: reads and their qualities (qual_pool may be NULL).
  * Output: corrected read i = out_seq_pool[out_off[i], out_off[i+1]) with its quality string at the same
  * offsets of out_qual_pool - the exact bytes the reference writes to the FASTQ (library-allocated).
- * stats (optional, 16 x u64, accumulated): [0] K1 probes, [1] K1 raw hits, [2] K1 kernel ns, [3] K1 stage ns (copies +
+ * stats (optional, 24 x u64, accumulated): [0] K1 probes, [1] K1 raw hits, [2] K1 kernel ns, [3] K1 stage ns (copies +
  * host replay), [5] batched GPU service calls, [6] GPU requests served, [7] K4 / [8] K5 / [9] K2+K3+K4 kernel ns (CUDA
  * events on the launching streams; the services overlap), [10] getSeeds stage ns, [11] region stage ns, [12] bytes copied host->device, [13] device->host, [14] kernels launched
- * (process-wide tallies: exact when one batch runs at a time). */
+ * (process-wide tallies: exact when one batch runs at a time), [16] region-engine kernel ns, [17] region-engine calls, [18] calls
+ * the engine declined (served by the request-at-a-time path instead). */
 int rtk_correct_batch(rtk_ctx* ctx, const rtk_opt* opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
                       const char* qual_pool, const uint64_t* qual_off, char** out_seq_pool, char** out_qual_pool,
                       uint64_t** out_off, uint64_t* stats);

@@ -69,6 +69,25 @@ class RtkSubgraphOut(C.Structure):
                 ("path_ed", C.POINTER(C.c_int32))]
 
 
+class RtkRegionCall(C.Structure):
+    _fields_ = [("win_off", C.c_uint64), ("weak_off", C.c_uint64), ("pid_off", C.c_uint64), ("win_len", C.c_uint32),
+                ("n_weak", C.c_uint32), ("pid_len", C.c_uint32), ("start_pos", C.c_uint32), ("start_unitig", C.c_uint32),
+                ("start_dist", C.c_uint32), ("start_strand", C.c_uint32), ("has_end", C.c_uint32), ("end_pos", C.c_uint32),
+                ("end_unitig", C.c_uint32), ("end_dist", C.c_uint32), ("end_strand", C.c_uint32), ("s_len", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class RtkRegionResult(C.Structure):
+    _fields_ = [("status", C.c_uint32), ("bail", C.c_uint32), ("n_nodes", C.c_uint32), ("len", C.c_uint32),
+                ("node_off", C.c_uint64), ("str_off", C.c_uint64), ("n_hops", C.c_uint32), ("n_pops", C.c_uint32),
+                ("n_cands", C.c_uint32), ("n_aligns", C.c_uint32)]
+
+
+class RtkRegionOut(C.Structure):
+    _fields_ = [("results", C.POINTER(RtkRegionResult)), ("nodes", C.POINTER(RtkPathNode)), ("chars", C.c_void_p),
+                ("n_nodes", C.c_uint64), ("n_chars", C.c_uint64)]
+
+
 HIT_DTYPE = np.dtype([("pos", "<u4"), ("unitig", "<u4"), ("dist", "<u4"), ("strand", "<u4")])
 
 _libs = {}
@@ -129,6 +148,10 @@ def load_library(path=None):
     L.rtk_explore_paths.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.POINTER(RtkHit), C.POINTER(RtkHit), C.c_char_p, C.c_uint32,
                                     C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.POINTER(RtkPathNode)), C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_char_p), C.POINTER(C.c_uint32)]
+    L.rtk_region_paths_batch.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_int, C.c_uint32, C.POINTER(RtkRegionCall), C.c_char_p,
+                                         C.c_uint64, C.POINTER(RtkHit), C.c_uint64, C.POINTER(C.c_uint32), C.c_uint64,
+                                         C.POINTER(RtkRegionOut), C.POINTER(C.c_uint64)]
+    L.rtk_region_out_free.argtypes = [C.POINTER(RtkRegionOut)]
     L.rtk_edlib_path_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.c_char_p,
                                        C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), C.POINTER(C.POINTER(C.c_uint8)),
@@ -332,7 +355,7 @@ class Context:
             qp, qo = None, None
         os_, oq_ = C.c_void_p(), C.c_void_p()
         oo = C.POINTER(C.c_uint64)()
-        st = (C.c_uint64 * 16)()
+        st = (C.c_uint64 * 24)()
         _check(self.L, self.L.rtk_correct_batch(self.h, C.byref(opt), pass_no, len(reads), pool, off.ctypes.data_as(C.POINTER(C.c_uint64)),
                                                 qp, qo, C.byref(os_), C.byref(oq_), C.byref(oo), st))
         n = len(reads)
@@ -388,6 +411,57 @@ class Context:
                "qual": q.value.decode("latin1"), "length": pl.value}
         self.L.rtk_free(C.cast(pn, C.c_void_p))
         self.L.rtk_free(C.cast(q, C.c_void_p))
+        return res
+
+    def region_paths(self, calls, opt=None, pass_no=1, stats=None):
+        """Device-resident region engine (extractSemiWeakPaths and everything below it, one warp per call).
+        calls: dicts with window (str = s[start_pos, pos2 + k)), start=(pos, unitig, strand, dist),
+        end=(pos, unitig, strand, dist) or None (open end: s_len required), weak=[(pos, unitig, strand, dist)], pids (sorted).
+        -> per call dict(status, bail, nodes=[(unitig, strand, dist, len)], seq, qual, hops, pops, cands, aligns)"""
+        opt = opt or default_opt(pass_no)
+        n = len(calls)
+        arr = (RtkRegionCall * max(n, 1))()
+        wins, weak, pids = [], [], []
+        wo = 0
+        for i, c in enumerate(calls):
+            w = c["window"].encode()
+            a = arr[i]
+            a.win_off, a.win_len = wo, len(w)
+            a.weak_off, a.n_weak = len(weak), len(c.get("weak", []))
+            a.pid_off, a.pid_len = len(pids), len(c["pids"])
+            a.start_pos, a.start_unitig, a.start_strand, a.start_dist = c["start"]
+            if c.get("end") is None:
+                a.has_end, a.s_len = 0, c["s_len"]
+            else:
+                a.has_end = 1
+                a.end_pos, a.end_unitig, a.end_strand, a.end_dist = c["end"]
+                a.s_len = c.get("s_len", a.end_pos + opt.k)
+            wins.append(w); wo += len(w)
+            weak.extend(c.get("weak", []))
+            pids.extend(c["pids"])
+        win_pool = b"".join(wins)
+        weak_arr = (RtkHit * max(len(weak), 1))(*[RtkHit(w[0], w[1], w[3], w[2]) for w in weak])
+        pid_arr = (C.c_uint32 * max(len(pids), 1))(*pids)
+        out = RtkRegionOut()
+        st = (C.c_uint64 * 8)()
+        _check(self.L, self.L.rtk_region_paths_batch(self.h, C.byref(opt), pass_no, n, arr, win_pool, len(win_pool), weak_arr, len(weak),
+                                                     pid_arr, len(pids), C.byref(out), st))
+        chars = C.string_at(out.chars, out.n_chars) if out.n_chars else b""
+        res = []
+        for i in range(n):
+            r = out.results[i]
+            d = {"status": r.status, "bail": r.bail, "nodes": [], "seq": "", "qual": "", "hops": r.n_hops, "pops": r.n_pops,
+                 "cands": r.n_cands, "aligns": r.n_aligns}
+            if r.status != 2:
+                d["nodes"] = [(out.nodes[j].unitig, out.nodes[j].strand, out.nodes[j].dist, out.nodes[j].len)
+                              for j in range(r.node_off, r.node_off + r.n_nodes)]
+                pad = (r.len + 7) & ~7
+                d["seq"] = chars[r.str_off:r.str_off + r.len].decode("latin1")
+                d["qual"] = chars[r.str_off + pad:r.str_off + pad + r.len].decode("latin1")
+            res.append(d)
+        self.L.rtk_region_out_free(C.byref(out))
+        if stats is not None:
+            stats.extend(list(st))
         return res
 
     def edlib_path_batch(self, queries, targets, modes, stats=None):

@@ -25,7 +25,8 @@ GpuBroker* current_broker() { return tl_broker; }
 
 // ------------------------------------------------------------------ batched execution
 // RTK_BROKER_PROFILE: host time spent assembling a batch, inside the C-ABI call, scattering the answers; GPU kernel time
-static std::atomic<uint64_t> g_prof[3][4];
+static std::atomic<uint64_t> g_prof[4][4];
+static std::atomic<uint64_t> g_region_stats[18];   // [0] calls, [1] bails, [2 + reason] bails by reason
 static std::atomic<uint64_t> g_mix[2][3][2];   // [dist|path][mode NW/SHW/HW][requests with one job | with several]: requests, jobs
 struct ProfTimer {
     std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
@@ -216,6 +217,66 @@ void run_subgraph_batch(rtk_ctx* ctx, const std::vector<SubgraphReq*>& reqs) {
     }
 }
 
+void run_region_batch(rtk_ctx* ctx, const std::vector<RegionReq*>& reqs, uint64_t* kernel_ns) {
+    if (reqs.empty()) return;
+    ProfTimer pt;
+    // requests of one broker share the options of their correction round; split defensively if they do not
+    std::vector<bool> done(reqs.size(), false);
+    for (size_t first = 0; first < reqs.size(); ++first) {
+        if (done[first]) continue;
+        const rtk_opt* opt = reqs[first]->opt;
+        const int pass = reqs[first]->pass;
+        std::vector<size_t> idx;
+        for (size_t i = first; i < reqs.size(); ++i) if (!done[i] && reqs[i]->opt == opt && reqs[i]->pass == pass) { idx.push_back(i); done[i] = true; }
+        const uint32_t k = opt->k;
+        std::vector<rtk_region_call_t> calls(idx.size());
+        std::string wins;
+        std::vector<rtk_hit> weak;
+        std::vector<uint32_t> pids;
+        for (size_t x = 0; x < idx.size(); ++x) {
+            const RegionReq& r = *reqs[idx[x]];
+            rtk_region_call_t& c = calls[x];
+            memset(&c, 0, sizeof(c));
+            const size_t pos2 = r.has_end ? r.end_pos : r.s->length() - k;
+            c.win_off = wins.size(); c.win_len = (uint32_t)(pos2 - r.um_start.pos + k);
+            wins.append(*r.s, r.um_start.pos, c.win_len);
+            c.weak_off = weak.size();
+            for (size_t i = r.i_weak; i < r.v_w->size(); ++i) weak.push_back((*r.v_w)[i]);
+            c.n_weak = (uint32_t)(weak.size() - c.weak_off);
+            c.pid_off = pids.size(); c.pid_len = (uint32_t)r.pids->size();
+            pids.insert(pids.end(), r.pids->begin(), r.pids->end());
+            c.start_pos = r.um_start.pos; c.start_unitig = r.um_start.unitig; c.start_dist = r.um_start.dist; c.start_strand = r.um_start.strand;
+            c.has_end = r.has_end ? 1u : 0u;
+            if (r.has_end) { c.end_pos = (uint32_t)r.end_pos; c.end_unitig = r.um_end.unitig; c.end_dist = r.um_end.dist; c.end_strand = r.um_end.strand; }
+            c.s_len = (uint32_t)r.s->length();
+        }
+        pt.lap(3, 0);
+        RegionBatchOut out;
+        region_batch_run(ctx, *opt, pass, (uint32_t)calls.size(), calls.data(), wins.data(), wins.size(), weak.data(), weak.size(), pids.data(), pids.size(), out);
+        pt.lap(3, 1);
+        g_prof[3][3] += (uint64_t)(out.kernel_ms * 1e6);
+        if (kernel_ns) *kernel_ns += (uint64_t)(out.kernel_ms * 1e6);
+        for (size_t x = 0; x < idx.size(); ++x) {
+            RegionReq& r = *reqs[idx[x]];
+            const rtk_region_result_t& R = out.results[x];
+            r.status = R.status; r.bail = R.bail;
+            g_region_stats[0] += 1;
+            if (R.status == 2) { g_region_stats[1] += 1; g_region_stats[2 + std::min<uint32_t>(R.bail, 15u)] += 1; continue; }
+            r.path.clear();
+            r.path.v.resize(R.n_nodes);
+            for (uint32_t i = 0; i < R.n_nodes; ++i) {
+                const rtk_path_node& n = out.nodes[R.node_off + i];
+                r.path.v[i].unitig = n.unitig; r.path.v[i].strand = n.strand; r.path.v[i].dist = n.dist; r.path.v[i].len = n.len;
+            }
+            r.path.l = R.len;
+            const uint64_t pad = ((uint64_t)R.len + 7) & ~7ull;
+            r.seq.assign(out.chars.data() + R.str_off, R.len);
+            r.path.qual.assign(out.chars.data() + R.str_off + pad, R.len);
+        }
+        pt.lap(3, 2);
+    }
+}
+
 // ------------------------------------------------------------------ broker
 // Context switch between a worker's scheduler and its fibers.  glibc's swapcontext saves / restores the signal mask with a
 // system call on every switch (5 % of the host time in the sampling profile); the fibers never touch the mask, so on x86-64 a
@@ -312,12 +373,12 @@ static void tune_allocator() {
 GpuBroker::GpuBroker(rtk_ctx* c) : ctx(c) {
     tune_allocator();
     // service threads per kind (each with its own forked context = stream + scratch): RTK_SERVICE_THREADS="d,p,s"
-    unsigned cnt[3] = {2, 2, 3};
-    if (const char* e = getenv("RTK_SERVICE_THREADS")) sscanf(e, "%u,%u,%u", &cnt[0], &cnt[1], &cnt[2]);
+    unsigned cnt[4] = {2, 2, 2, 2};
+    if (const char* e = getenv("RTK_SERVICE_THREADS")) sscanf(e, "%u,%u,%u,%u", &cnt[0], &cnt[1], &cnt[2], &cnt[3]);
 #ifdef RTK_HOSTSIM   // the CPU simulator runs one launch at a time
-    cnt[0] = cnt[1] = cnt[2] = 1;
+    cnt[0] = cnt[1] = cnt[2] = cnt[3] = 1;
 #endif
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 4; ++k)
         for (unsigned i = 0; i < std::max(1u, std::min(cnt[k], 8u)); ++i) {
             Service* s = new Service();
             s->kind = k;
@@ -326,7 +387,7 @@ GpuBroker::GpuBroker(rtk_ctx* c) : ctx(c) {
         }
 }
 GpuBroker::~GpuBroker() {
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 4; ++k)
         for (Service* s : services[k]) { rtk_ctx_destroy(s->ctx); delete s; }
 }
 
@@ -353,6 +414,7 @@ void GpuBroker::park(int kind, void* req) {
 void GpuBroker::submit(DistReq* r) { park(0, r); }
 void GpuBroker::submit(PathReq* r) { park(1, r); }
 void GpuBroker::submit(SubgraphReq* r) { park(2, r); }
+void GpuBroker::submit(RegionReq* r) { park(3, r); }
 
 #ifdef RTK_HOSTSIM
 static std::mutex g_sim_launch_mu;   // the CPU simulator runs one launch at a time
@@ -385,7 +447,8 @@ void GpuBroker::service_main(Service* s) {
 #endif
             if (s->kind == 0) { std::vector<DistReq*> v; for (auto& b : batch) v.push_back((DistReq*)b.first); run_dist_batch(s->ctx, v); }
             else if (s->kind == 1) { std::vector<PathReq*> v; for (auto& b : batch) v.push_back((PathReq*)b.first); run_path_batch(s->ctx, v); }
-            else { std::vector<SubgraphReq*> v; for (auto& b : batch) v.push_back((SubgraphReq*)b.first); run_subgraph_batch(s->ctx, v); }
+            else if (s->kind == 2) { std::vector<SubgraphReq*> v; for (auto& b : batch) v.push_back((SubgraphReq*)b.first); run_subgraph_batch(s->ctx, v); }
+            else { std::vector<RegionReq*> v; for (auto& b : batch) v.push_back((RegionReq*)b.first); run_region_batch(s->ctx, v, nullptr); }
         } catch (const std::exception& e) { err = e.what(); if (err.empty()) err = "GPU service failed"; }
         catch (...) { err = "GPU service failed (unknown exception)"; }
         s->ns_busy += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
@@ -536,8 +599,9 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
     n_tasks = n; next_task = 0; task_fn = &task; task_error.clear();
     cap_per_worker = std::max<size_t>(1, (std::min<size_t>(std::max(1u, inflight), n) + n_workers - 1) / n_workers);
     const auto t_begin = std::chrono::steady_clock::now();
-    uint64_t prof0[3][4];
-    for (int k = 0; k < 3; ++k) for (int j = 0; j < 4; ++j) prof0[k][j] = g_prof[k][j];
+    uint64_t prof0[4][4], rs0[18];
+    for (int k = 0; k < 4; ++k) for (int j = 0; j < 4; ++j) prof0[k][j] = g_prof[k][j];
+    for (int j = 0; j < 18; ++j) rs0[j] = g_region_stats[j];
     for (unsigned t = 0; t < n_workers; ++t) {
         Worker* w = new Worker();
         w->slab_bytes = cap_per_worker * (stack_bytes + kGuardBytes);
@@ -546,7 +610,7 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
         w->rr = t;
         workers.push_back(w);
     }
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 4; ++k)
         for (Service* s : services[k]) { s->stop = false; s->th = std::thread([this, s] { service_main(s); }); }
     for (Worker* w : workers) w->th = std::thread([this, w] { worker_main(w); });
     uint64_t idle_ns = 0, resumes = 0;
@@ -558,7 +622,7 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
         delete w;
     }
     workers.clear();
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < 4; ++k)
         for (Service* s : services[k]) {
             { std::lock_guard<std::mutex> lk(s->mu); s->stop = true; }
             s->cv.notify_one();
@@ -566,19 +630,26 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
             waves += s->batches; jobs += s->reqs;
         }
     task_fn = nullptr;
-    uint64_t prof[3][4];
-    for (int k = 0; k < 3; ++k) for (int j = 0; j < 4; ++j) prof[k][j] = g_prof[k][j] - prof0[k][j];
-    for (int k = 0; k < 3; ++k) kernel_ns[k] += prof[k][3];
+    uint64_t prof[4][4];
+    for (int k = 0; k < 4; ++k) for (int j = 0; j < 4; ++j) prof[k][j] = g_prof[k][j] - prof0[k][j];
+    for (int k = 0; k < 4; ++k) kernel_ns[k] += prof[k][3];
+    region_calls += g_region_stats[0] - rs0[0]; region_bails += g_region_stats[1] - rs0[1];
+    for (int j = 0; j < 16; ++j) region_bail_reason[j] += g_region_stats[2 + j] - rs0[2 + j];
     if (getenv("RTK_BROKER_PROFILE")) {
         const double total_ms = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count() / 1e6;
-        static const char* names[3] = {"dist", "path", "subgraph"};
+        static const char* names[4] = {"dist", "path", "subgraph", "region"};
         fprintf(stderr, "[broker] tasks=%zu workers=%u inflight/worker=%zu total %.1f ms, workers idle %.1f%% |", n, n_workers, cap_per_worker, total_ms,
                 100.0 * (idle_ns / 1e6) / (total_ms * n_workers));
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < 4; ++k)
             for (Service* s : services[k])
                 fprintf(stderr, " %s: %llu reqs in %llu batches, busy %.1f ms |", names[k], (unsigned long long)s->reqs, (unsigned long long)s->batches, s->ns_busy / 1e6);
         fprintf(stderr, "\n");
-        for (int k = 0; k < 3; ++k) {
+        fprintf(stderr, "[broker]   region engine: %llu calls, %llu declined (cycle %llu queue %llu vlist %llu arena %llu strcap %llu hirschberg %llu dfs %llu chain %llu logic %llu)\n",
+                (unsigned long long)region_calls, (unsigned long long)region_bails, (unsigned long long)region_bail_reason[1], (unsigned long long)region_bail_reason[2],
+                (unsigned long long)region_bail_reason[3], (unsigned long long)region_bail_reason[4], (unsigned long long)region_bail_reason[5],
+                (unsigned long long)region_bail_reason[6], (unsigned long long)region_bail_reason[7], (unsigned long long)region_bail_reason[8],
+                (unsigned long long)region_bail_reason[9]);
+        for (int k = 0; k < 4; ++k) {
             fprintf(stderr, "[broker]   %s service host time: assemble %.1f ms, C-ABI call %.1f ms (GPU kernels %.1f ms), scatter %.1f ms\n", names[k],
                     prof[k][0] / 1e6, prof[k][1] / 1e6, prof[k][3] / 1e6, prof[k][2] / 1e6);
         }
@@ -591,7 +662,7 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
                 g_myers_prof[0] / 1e6, g_myers_prof[1] / 1e6, g_myers_prof[2] / 1e6, g_myers_prof[3] / 1e6, g_myers_prof[4] / 1e6);
 #endif
     }
-    for (int k = 0; k < 3; ++k) for (Service* s : services[k]) { s->batches = s->reqs = s->ns_busy = 0; }
+    for (int k = 0; k < 4; ++k) for (Service* s : services[k]) { s->batches = s->reqs = s->ns_busy = 0; }
     if (!task_error.empty()) throw std::runtime_error(task_error);
 }
 

@@ -55,10 +55,28 @@ struct SubgraphReq {   // K4 (prefix) + K2/K3 + K4 (leaves)
     SubgraphResult* out;
 };
 
+// One extractSemiWeakPaths call (src/Correction.cpp:3-157) served by the device-resident region engine (region.cuh): the whole
+// chain of hops, BFS queues, bursts, leaf alignments and path qualities of a weak region in ONE request.
+struct RegionReq {
+    const rtk_opt* opt; int pass;       // options of the correction round this request belongs to
+    const std::string* s;               // the read, in the orientation the region is corrected in
+    rtk_hit um_start, um_end;
+    bool has_end;
+    size_t end_pos;                     // pos_um_solid2 when has_end
+    const std::vector<rtk_hit>* v_w;    // weak anchors of the region
+    size_t i_weak;                      // first weak anchor to consider
+    const std::vector<uint32_t>* pids;  // WeightsPairID::all_pids
+    // answer
+    uint32_t status = 2, bail = 0;      // 0 complete path, 1 dead-end path, 2 declined (use the request-at-a-time path)
+    GPath path;
+    std::string seq;                    // the path spelled (Path::toString)
+};
+
 // direct (un-brokered) execution of a set of requests: one batched call per kind
 void run_dist_batch(rtk_ctx* ctx, const std::vector<DistReq*>& reqs);
 void run_path_batch(rtk_ctx* ctx, const std::vector<PathReq*>& reqs);
 void run_subgraph_batch(rtk_ctx* ctx, const std::vector<SubgraphReq*>& reqs);
+void run_region_batch(rtk_ctx* ctx, const std::vector<RegionReq*>& reqs, uint64_t* kernel_ns);
 
 class GpuBroker {
 public:
@@ -71,8 +89,10 @@ public:
     void submit(DistReq* r);
     void submit(PathReq* r);
     void submit(SubgraphReq* r);
+    void submit(RegionReq* r);
     uint64_t waves = 0, jobs = 0;   // batched service calls issued / requests served
-    uint64_t kernel_ns[3] = {0, 0, 0};   // GPU kernel time (CUDA events) of the dist / path / subgraph services
+    uint64_t kernel_ns[4] = {0, 0, 0, 0};   // GPU kernel time (CUDA events) of the dist / path / subgraph / region services
+    uint64_t region_calls = 0, region_bails = 0, region_bail_reason[16] = {0};
 
     struct Worker;    // one host thread: scheduler context, live fibers, ready list
     struct Fiber;
@@ -84,7 +104,7 @@ private:
     void worker_main(Worker* w);
     void service_main(Service* s);
     rtk_ctx* ctx;
-    std::vector<Service*> services[3];   // 0 dist (K4), 1 path (K5), 2 subgraph (K2/K3+K4)
+    std::vector<Service*> services[4];   // 0 dist (K4), 1 path (K5), 2 subgraph (K2/K3+K4), 3 region engine
     std::vector<Worker*> workers;
     std::string task_error;    // first exception that escaped a task
     // per run()

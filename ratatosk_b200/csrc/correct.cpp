@@ -241,6 +241,7 @@ struct Ctx {
     TraverseOpt topt;
     bool pass2;
     size_t max_km_cov;
+    bool device_regions = true;   // extractSemiWeakPaths through the device-resident region engine (region.cuh)
 };
 
 // ------------------------------------------------------------------ chooseColors (src/Correction.cpp:215-429)
@@ -388,6 +389,27 @@ PathPair extract_semi_weak_paths(const Ctx& C, const std::string& s, const IdSet
     }
     for (auto& p : paths1) paths.first.push_back(std::move(p.first));
     return paths;
+}
+
+// extractSemiWeakPaths as ONE request to the device-resident region engine; calls the engine declines (short-cycle unitigs ->
+// fixRepeats, list collapses, alignments above edlib's traceback switch, scratch capacity) run through the request-at-a-time
+// orchestration above, which yields the same bytes
+PathPair region_paths(const Ctx& C, const std::string& s, const IdSet& all_pids, const rtk_hit& um_start, bool has_end, const rtk_hit& um_end,
+                      size_t end_pos, const std::vector<rtk_hit>& v_w, size_t i_weak) {
+    GpuBroker* b = C.device_regions ? current_broker() : nullptr;
+    if (b) {
+        RegionReq r;
+        r.opt = &C.opt; r.pass = C.pass2 ? 2 : 1;
+        r.s = &s; r.um_start = um_start; r.um_end = um_end; r.has_end = has_end; r.end_pos = end_pos;
+        r.v_w = &v_w; r.i_weak = i_weak; r.pids = &all_pids;
+        b->submit(&r);
+        if (r.status != 2) {
+            PathPair pp;
+            (r.status == 0 ? pp.first : pp.second).push_back(std::move(r.path));
+            return pp;
+        }
+    }
+    return extract_semi_weak_paths(C, s, all_pids, um_start, has_end, um_end, end_pos, v_w, i_weak);
 }
 
 // selectBestPrefixAlignment(ref, len, vector<Path>, cut_threshold) (src/Alignment.cpp:47-97): {-1,-1} above the threshold
@@ -682,7 +704,7 @@ ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::s
     }
     const size_t card_pids = all_pids.size();
     PathPair paths1;
-    if (card_pids >= opt.min_cov_vertices) paths1 = extract_semi_weak_paths(C, s, all_pids, um_solid1, has_end_pt, um_solid2, solid2_pos, l_v_w, 0);
+    if (card_pids >= opt.min_cov_vertices) paths1 = region_paths(C, s, all_pids, um_solid1, has_end_pt, um_solid2, solid2_pos, l_v_w, 0);
     auto emit_path = [&](const GPath& p, bool offset_amb) {
         const std::vector<std::pair<size_t, char>> v_amb = ambiguity_vector(g, p.v);
         for (const auto& a : v_amb) v_ambiguity.push_back({(offset_amb ? s_corrected.length() : 0) + a.first, a.second});
@@ -707,10 +729,11 @@ ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::s
             res.add_range(um_solid1.pos - v_s[i_s].pos, um_solid1.pos + align.second + 1 - v_s[i_s].pos);
             um_solid1 = l_v_w[i_w_s];
             len_weak_region = solid2_pos - um_solid1.pos + k;
-            paths1 = extract_semi_weak_paths(C, s, all_pids, um_solid1, has_end_pt, um_solid2, solid2_pos, l_v_w, i_w_s);
+            paths1 = region_paths(C, s, all_pids, um_solid1, has_end_pt, um_solid2, solid2_pos, l_v_w, i_w_s);
         }
         if (!paths1.first.empty()) {
-            const std::pair<int, int> pa = select_best_alignment(C.ctx, g, paths1.first, s.substr(um_solid1.pos, len_weak_region));
+            // a single candidate wins whatever its distance (and the end location is not used here): no alignment needed
+            const std::pair<int, int> pa = paths1.first.size() == 1 ? std::pair<int, int>(0, -1) : select_best_alignment(C.ctx, g, paths1.first, s.substr(um_solid1.pos, len_weak_region));
             const GPath& po = paths1.first[(size_t)pa.first];
             emit_path(po, true);
             s_corrected += po.to_string(g);
@@ -732,7 +755,7 @@ ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::s
         } else if (!s_corrected.empty()) add_uncorrected(um_solid1.pos, len_weak_region, q_min);
         else set_uncorrected(v_s[i_s].pos, len_weak_region, q_min);
     } else {
-        const std::pair<int, int> pa = select_best_alignment(C.ctx, g, paths1.first, s.substr(um_solid1.pos, len_weak_region));
+        const std::pair<int, int> pa = paths1.first.size() == 1 ? std::pair<int, int>(0, -1) : select_best_alignment(C.ctx, g, paths1.first, s.substr(um_solid1.pos, len_weak_region));
         const GPath& po = paths1.first[(size_t)pa.first];
         emit_path(po, false);
         s_corrected = po.to_string(g);
@@ -996,6 +1019,7 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
         C.topt.k = g.k; C.topt.min_cov_vertices = l_opt.min_cov_vertices; C.topt.out_qual = l_opt.out_qual; C.topt.max_qual = l_opt.max_qual;
         C.topt.weak_region_len_factor = l_opt.weak_region_len_factor; C.topt.large_k_factor = l_opt.large_k_factor; C.topt.min_score = l_opt.min_score;
         C.topt.long_read_correct = pass2;
+        C.device_regions = getenv("RTK_NO_REGION_ENGINE") == nullptr;
         std::vector<ReadJob> jobs(n_reads);
         std::vector<Piece> pieces;
         for (uint32_t r = 0; r < n_reads; ++r) {
@@ -1037,6 +1061,7 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
         if (stats) {
             stats[5] += broker.waves; stats[6] += broker.jobs;
             for (int s3 = 0; s3 < 3; ++s3) stats[7 + s3] += broker.kernel_ns[s3];
+            stats[16] += broker.kernel_ns[3]; stats[17] += broker.region_calls; stats[18] += broker.region_bails;
             stats[10] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_broker - t_seeds).count();
             stats[11] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_broker).count();
         }

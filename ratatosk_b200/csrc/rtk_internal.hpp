@@ -114,6 +114,8 @@ struct rtk_ctx {
     // scratch
     rtk::DevBuf d_seq, d_seq_off, d_tiles, d_hits, d_counters, d_aux[8], d_sub[8];
     rtk::PinBuf h_pin[16];   // pinned landing zones of the D2H copies (one slot per copy site, see PinnedD2H)
+    rtk::DevBuf d_rg[6];     // region engine: [0] packed inputs, [1] results, [2] out vertices, [3] out chars, [4] counters, [5] per-warp scratch
+    rtk::PinBuf h_rg[3];     // region engine: [0] packed upload, [1] results + counters, [2] output pools
     int sm_count = 148;
     // reads of the next exact sweep already resident in HBM (rtk_correct_batch_resident); consumed once
     const char* resident_seq = nullptr;
@@ -219,6 +221,16 @@ void dist_batch_lean(rtk_ctx* c, uint32_t n, const char* q_pool, uint64_t q_byte
 void myers_run_lean(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const char* h_qpool, uint64_t q_bytes, const char* h_tpool,
                     uint64_t t_bytes, const MyersJobs& j, int32_t* dist, int32_t* first_end, int32_t* last_end, float* kernel_ms);
 #endif
+
+// device-resident region engine (region.cu / tests/hostsim/sim_region.cpp): n extractSemiWeakPaths calls in one launch
+struct RegionBatchOut {
+    std::vector<rtk_region_result_t> results;
+    std::vector<rtk_path_node> nodes;
+    std::vector<char> chars;
+    float kernel_ms = 0.f;
+};
+void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls, const rtk_region_call_t* calls, const char* win_pool,
+                      uint64_t win_bytes, const rtk_hit* weak_pool, uint64_t n_weak, const uint32_t* pid_pool, uint64_t n_pids, RegionBatchOut& out);
 
 // full searchSequence for a host batch -> per read ordered hits
 void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,

@@ -1,9 +1,11 @@
 // cuda_sim.h — TEST INFRASTRUCTURE: runs the repo's CUDA kernel SOURCE on the CPU.
 //
 // There is no GPU in the build container, so the `-m "not gpu"` tests compile the very same
-// .cuh kernel sources with g++ against this shim and execute them with one host thread per
-// CUDA thread (blocks run one after another; __syncthreads is a pthread barrier; warp
-// collectives go through a per-warp exchange area).  This is a debugging vehicle for index
+// .cuh kernel sources with g++ against this shim and execute them with one FIBER per CUDA
+// thread: a block's fibers are multiplexed on one host thread and switch at every collective
+// (__syncthreads, __syncwarp, shuffles, votes), so a barrier costs a few user-level context
+// switches instead of futex round trips; blocks run in parallel on a small pool of host
+// threads (`__shared__` variables are thread_local statics = one copy per simulated block).  This is a debugging vehicle for index
 // arithmetic and bit manipulation, NOT a product path: nothing here is linked into
 // librtk_b200.so, and the product fails loudly without a CUDA device (rtk_ctx_create).
 #pragma once
@@ -22,32 +24,44 @@ struct ulonglong2 { unsigned long long x, y; };
 
 extern thread_local sim_dim3 threadIdx, blockIdx;
 extern sim_dim3 blockDim, gridDim;
-extern pthread_barrier_t sim_block_barrier;
+// cooperative barrier among the fibers of one block (single host thread: no atomics needed)
+struct sim_bar { unsigned count = 0, gen = 0; };
+void sim_yield();                       // switch to the block's scheduler (cuda_sim.cpp)
+extern thread_local unsigned long long sim_progress;
+static inline void sim_bar_wait(sim_bar& b, unsigned n) {
+    if (n <= 1) return;
+    const unsigned gen = b.gen;
+    ++sim_progress;   // an arrival is progress (the deadlock detector looks for rounds without any)
+    if (++b.count == n) { b.count = 0; ++b.gen; return; }
+    while (b.gen == gen) sim_yield();
+}
+extern thread_local sim_bar sim_block_barrier;
 struct sim_warp_area {
-    pthread_barrier_t bar;            // all lanes of the warp
-    pthread_barrier_t gbar[5][32];    // aligned sub-groups of width 1<<w (w = 0..4), indexed by first lane
+    sim_bar bar;                      // all lanes of the warp
+    sim_bar gbar[5][32];              // aligned sub-groups of width 1<<w (w = 0..4), indexed by first lane
     unsigned long long slot[32];
+    unsigned nl = 32;                 // live lanes of this warp (the last warp of a block may be partial)
 };
-extern sim_warp_area* sim_warps;
+extern thread_local sim_warp_area* sim_warps;
 
 #define __global__
 #define __device__
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
-#define __shared__ static
+#define __shared__ static thread_local
 #define __launch_bounds__(...)
 #define __CUDACC_SIM__ 1
 
-static inline void __syncthreads() { pthread_barrier_wait(&sim_block_barrier); }
+static inline void __syncthreads() { sim_bar_wait(sim_block_barrier, blockDim.x); }
 // barrier over the lanes named by `mask` (full warp or one aligned power-of-two sub-group)
 static inline void sim_mask_barrier(unsigned mask) {
     sim_warp_area& w = sim_warps[threadIdx.x >> 5];
-    if (mask == 0xffffffffu) { pthread_barrier_wait(&w.bar); return; }
+    if (mask == 0xffffffffu) { sim_bar_wait(w.bar, w.nl); return; }
     const int n = __builtin_popcount(mask);
     const int first = __builtin_ctz(mask);
     if (n == 1) return;
-    pthread_barrier_wait(&w.gbar[__builtin_ctz((unsigned)n)][first]);
+    sim_bar_wait(w.gbar[__builtin_ctz((unsigned)n)][first], (unsigned)n);
 }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { sim_mask_barrier(mask); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
@@ -60,11 +74,10 @@ static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned lo
 static inline unsigned __ballot_sync(unsigned, int pred) {
     sim_warp_area& w = sim_warps[threadIdx.x >> 5];
     w.slot[threadIdx.x & 31] = pred ? 1 : 0;
-    pthread_barrier_wait(&w.bar);
+    sim_bar_wait(w.bar, w.nl);
     unsigned m = 0;
-    const unsigned nl = ((threadIdx.x >> 5) * 32 + 32 <= blockDim.x) ? 32 : (blockDim.x & 31);
-    for (unsigned i = 0; i < nl; ++i) m |= (unsigned)(w.slot[i] & 1) << i;
-    pthread_barrier_wait(&w.bar);
+    for (unsigned i = 0; i < w.nl; ++i) m |= (unsigned)(w.slot[i] & 1) << i;
+    sim_bar_wait(w.bar, w.nl);
     return m;
 }
 template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
@@ -72,9 +85,9 @@ template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
     unsigned long long x = 0;
     memcpy(&x, &v, sizeof(T) <= 8 ? sizeof(T) : 8);
     w.slot[threadIdx.x & 31] = x;
-    pthread_barrier_wait(&w.bar);
+    sim_bar_wait(w.bar, w.nl);
     const unsigned long long y = w.slot[src & 31];
-    pthread_barrier_wait(&w.bar);
+    sim_bar_wait(w.bar, w.nl);
     T r;
     memcpy(&r, &y, sizeof(T) <= 8 ? sizeof(T) : 8);
     return r;
