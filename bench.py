@@ -318,7 +318,7 @@ def main():
         for w in range(warmup):
             correct_step(batches[w % n_batches], resident)
         barrier()
-        step_s, stats, ev_ms, seeds_ms = [], np.zeros(16, dtype=np.float64), 0.0, []
+        step_s, stats, ev_ms, seeds_ms = [], np.zeros(24, dtype=np.float64), 0.0, []
         with ClockSampler(local_rank) as clk:
             for s in range(args.steps):
                 bt = batches[s % n_batches]

@@ -63,7 +63,7 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     RTK_CUDA(cudaMemsetAsync(c->d_rg[4].p, 0, 64, st));
     const rtk_graph_view& g = c->dview;
     p.unitig_off = g.unitig_off; p.pool = g.pool; p.shared = g.shared; p.adj = g.adj; p.gset_of = g.gset_of;
-    p.gset_off = g.gset_off; p.gset_ids = g.gset_ids; p.loc_off = g.loc_off; p.loc_ids = g.loc_ids; p.k = c->hdr.k;
+    p.gset_off = g.gset_off; p.gset_ids = g.gset_ids; p.loc_off = g.loc_off; p.loc_ids = g.loc_ids; p.cyc_off = g.cyc_off; p.cyc_pool = g.cyc_pool; p.k = c->hdr.k;
     p.tasks = (const rtk_rg_task*)(d + o_tasks); p.order = (const uint32_t*)(d + o_order); p.n_tasks = n_calls;
     p.win_pool = d + o_win; p.weak_pool = (const rtk_hit*)(d + o_weak); p.pid_pool = (const uint32_t*)(d + o_pids);
     p.results = c->d_rg[1].as<rtk_rg_result>();

@@ -63,6 +63,8 @@ struct rtk_rg_params {
     const uint32_t* gset_ids;
     const uint64_t* loc_off;
     const uint32_t* loc_ids;
+    const uint64_t* cyc_off;     // UnitigData::compactedCycles: NUL-separated successor strings per unitig
+    const char* cyc_pool;
     uint32_t k;
     // work
     const rtk_rg_task* tasks;
@@ -623,6 +625,147 @@ __device__ __forceinline__ uint32_t rg_extend_with(rg_ctx& C, const uint32_t par
     return off;
 }
 
+// ------------------------------------------------------------------------------------------------ fixRepeats
+// spell a vertex list and cut it at `l` bases (Path::toString().substr(0, length()): after fixRepeats' re-extension a last
+// vertex may be recorded whole while the path length still counts its partial mapping); returns the length, 0xFFFFFFFF on overflow
+__device__ __forceinline__ uint32_t rg_spell_cut(rg_ctx& C, const rtk_rg_node* nd, const uint32_t n, const uint32_t l, char* out) {
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) total += (i == 0) ? ((uint64_t)nd[i].len + C.p->k - 1) : (uint64_t)nd[i].len;
+    if (total + 8 > (uint64_t)C.p->str_cap) { C.bail = RTK_RG_BAIL_STRCAP; return 0xFFFFFFFFu; }
+    const uint32_t sp = rg_spell_nodes(C, nd, n, out);
+    return sp < l ? sp : l;
+}
+
+// fixRepeats (src/GraphTraversal.cpp:1149-1334) on the winning path of a hop: walk its vertices left to right; at a vertex
+// on a short-cycle unitig try every stored cycle (UnitigData::getCompactCycles) spliced in at that vertex, each NW-aligned
+// against the window with the running best distance as bound; the last strictly improving one is accepted, the walk resumes
+// behind the inserted vertices; without an acceptance the following vertices on the same unitig are skipped.
+__device__ __forceinline__ uint32_t rg_fix_repeats(rg_ctx& C, const uint32_t path_off, const char* __restrict__ ref, const uint32_t ref_len) {
+    const rtk_rg_params& p = *C.p;
+    const uint32_t k = p.k, lane = C.lane;
+    uint32_t cur = path_off;
+    {
+        rg_path* Q = rg_at(C, cur);
+        const rtk_rg_node* nd = rg_nodes(Q);
+        bool cyc = false;
+        for (uint32_t i = lane; i < Q->n; i += 32) cyc |= rg_short_cycle(C, nd[i].unitig);
+        if (!__any_sync(0xffffffffu, cyc)) return cur;
+    }
+    int edit;
+    {
+        rg_path* Q = rg_at(C, cur);
+        const uint32_t ql = rg_spell_cut(C, rg_nodes(Q), Q->n, Q->l, C.sB);
+        if (C.bail) return RTK_NONE32;
+        edit = rg_myers(C, C.sB, (int)ql, ref, (int)ref_len, 0).dist;
+    }
+    const char qmax = rg_get_qual(1.0, 0, p.max_qual);
+    uint32_t i = 0;
+    while (!C.bail) {
+        rg_path* Q = rg_at(C, cur);
+        const uint32_t n = Q->n;
+        if (i >= n) break;
+        const rtk_rg_node* nd = rg_nodes(Q);
+        const rtk_rg_node um = nd[i];
+        if (!rg_short_cycle(C, um.unitig)) { ++i; continue; }
+        const char* cp = p.cyc_pool + p.cyc_off[um.unitig];
+        const uint32_t cl = (uint32_t)(p.cyc_off[um.unitig + 1] - p.cyc_off[um.unitig]);
+        uint32_t best_ext = RTK_NONE32;
+        uint32_t len_prefix = 0;
+        for (uint32_t j = 0; j < i; ++j) len_prefix += nd[j].len;
+        uint32_t sidx = 0;
+        while (sidx < cl && !C.bail) {
+            uint32_t clen = 0;
+            while (sidx + clen < cl && cp[sidx + clen] != 0) ++clen;
+            const char* cyc = cp + sidx;
+            sidx += clen + 1;
+            // Path(us, cyc, ue): us = the unitig from the vertex's first k-mer to its end, `cyc` successors, ue = the unitig from
+            // its start to the vertex's last k-mer (forward strand); reverse-complemented when the vertex is traversed in reverse
+            const uint32_t m = clen + 2;                         // vertices of the repeat
+            const uint32_t usz = rg_usize(C, um.unitig);
+            rtk_rg_node us = um, ue = um;
+            us.len = usz - um.dist - k + 1; us.strand = 1;
+            ue.dist = 0; ue.len = um.dist + um.len; ue.strand = 1;
+            // the extension: vertices [0, i) + repeat + (i, n)
+            const uint32_t en = (n - 1) + m;
+            // lengths first (the walk below may fail)
+            uint32_t rep_l = us.len + k - 1 + ue.len;
+            bool ok = true;
+            {
+                uint32_t cu = um.unitig, cs = 1;
+                for (uint32_t c = 0; c < clen; ++c) {
+                    const uint32_t b = rtk_base_code(cyc[c]);
+                    uint32_t slot = RTK_NONE32;
+                    if (b < 4) slot = cs ? p.adj[8 * (uint64_t)cu + b] : p.adj[8 * (uint64_t)cu + 4 + (3 - b)];
+                    if (slot == RTK_NONE32) { ok = false; break; }
+                    const uint32_t v = slot & 0x7fffffffu;
+                    cs = cs ? (slot >> 31) : (1u - (slot >> 31));
+                    cu = v;
+                    rep_l += rg_ufull(C, v);
+                }
+            }
+            if (!ok) { C.bail = RTK_RG_BAIL_LOGIC; break; }   // a stored cycle the adjacency cannot follow: host path decides
+            const uint32_t new_l = Q->l - (um.len + k - 1) + rep_l;
+            if ((uint64_t)len_prefix + um.len + k - 1 > (uint64_t)Q->l) { C.bail = RTK_RG_BAIL_LOGIC; break; }
+            const uint32_t eoff = rg_alloc_path(C, en, new_l);
+            if (eoff == RTK_NONE32) break;
+            Q = rg_at(C, cur); nd = rg_nodes(Q);
+            rg_path* E = rg_at(C, eoff);
+            rtk_rg_node* ev = rg_nodes(E);
+            if (lane == 0) {
+                for (uint32_t j = 0; j < i; ++j) ev[j] = nd[j];
+                // repeat vertices in traversal order
+                rtk_rg_node* rv = ev + i;
+                rv[0] = us;
+                uint32_t cu = um.unitig, cs = 1;
+                for (uint32_t c = 0; c < clen; ++c) {
+                    const uint32_t b = rtk_base_code(cyc[c]);
+                    const uint32_t slot = cs ? p.adj[8 * (uint64_t)cu + b] : p.adj[8 * (uint64_t)cu + 4 + (3 - b)];
+                    const uint32_t v = slot & 0x7fffffffu;
+                    cs = cs ? (slot >> 31) : (1u - (slot >> 31));
+                    cu = v;
+                    rtk_rg_node x; x.unitig = v; x.strand = cs; x.dist = 0; x.len = rg_ufull(C, v);
+                    rv[1 + c] = x;
+                }
+                rv[m - 1] = ue;
+                if (!um.strand) {   // Path::rev_comp: reversed order, flipped strands
+                    for (uint32_t a = 0, z = m - 1; a < z; ++a, --z) { const rtk_rg_node t = rv[a]; rv[a] = rv[z]; rv[z] = t; }
+                    for (uint32_t a = 0; a < m; ++a) rv[a].strand = 1u - rv[a].strand;
+                }
+                for (uint32_t j = i + 1; j < n; ++j) ev[m + j - 1] = nd[j];
+                // Path::extend re-walk: every vertex but the first and the last is recorded whole
+                for (uint32_t j = 1; j + 1 < en; ++j) { ev[j].dist = 0; ev[j].len = rg_ufull(C, ev[j].unitig); }
+            }
+            // quality: the vertex's stretch replaced by max-quality bases for the whole repeat
+            {
+                char* eq = rg_qual(E);
+                const char* oq = rg_qual(Q);
+                const uint32_t cut = len_prefix + um.len + k - 1;
+                for (uint32_t x = lane; x < len_prefix; x += 32) eq[x] = oq[x];
+                for (uint32_t x = lane; x < rep_l; x += 32) eq[len_prefix + x] = qmax;
+                for (uint32_t x = lane; x < Q->l - cut; x += 32) eq[len_prefix + rep_l + x] = oq[cut + x];
+            }
+            __syncwarp();
+            const uint32_t ql = rg_spell_cut(C, ev, en, new_l, C.sB);
+            if (C.bail) break;
+            const int d = rg_myers(C, C.sB, (int)ql, ref, (int)ref_len, 0).dist;
+            const int rd = (d > edit) ? -1 : d;       // edlib bounded by k = edit: worse than the running best => -1
+            if (rd >= 0 && rd < edit) { edit = rd; best_ext = eoff; }
+        }
+        if (C.bail) break;
+        if (best_ext != RTK_NONE32) {
+            const uint32_t diff = rg_at(C, best_ext)->n - n;
+            cur = best_ext;
+            i = i + diff;
+        } else {
+            uint32_t jn = i;
+            for (uint32_t t = i + 1; t < n; ++t) { if (nd[i].unitig == nd[t].unitig) ++jn; else break; }
+            i = jn + 1;
+        }
+    }
+    if (C.bail) return RTK_NONE32;
+    return cur;
+}
+
 // ------------------------------------------------------------------------------------------------ one hop
 // explorePathsBFS2 (has_end) / explorePathsBFS (open end) on the window ref[0, ref_len) from vertex um_s; returns the arena
 // offset of the winning path (before fixRepeats, which bails) or RTK_NONE32 when there is none.
@@ -826,14 +969,9 @@ __device__ __forceinline__ uint32_t rg_hop(rg_ctx& C, const char* __restrict__ r
         }
         if (C.bail) return RTK_NONE32;
     }
-    // fixRepeats (:1149-1334) only acts on paths crossing short-cycle unitigs: those regions go back to the host path
-    {
-        rg_path* Q = rg_at(C, best_off);
-        const rtk_rg_node* nd = rg_nodes(Q);
-        bool cyc = false;
-        for (uint32_t i = lane; i < Q->n; i += 32) cyc |= rg_short_cycle(C, nd[i].unitig);
-        if (__any_sync(0xffffffffu, cyc)) { C.bail = RTK_RG_BAIL_CYCLE; return RTK_NONE32; }
-    }
+    // fixRepeats (:1149-1334): stored short cycles spliced into the winner where that lowers its distance to the window
+    best_off = rg_fix_repeats(C, best_off, ref, ref_len);
+    if (C.bail) return RTK_NONE32;
     return best_off;
 }
 

@@ -12,7 +12,7 @@ mkdir -p "$WORK" "$OUT"
 cd "$WORK"
 if [ ! -f i.index.k31.rtsk ]; then
   [ -f sr.fastq ] || python "$ROOT/scripts/make_f4.py" --out-dir "$WORK" --genome-len "$GLEN" --long-bases 3
-  /usr/bin/time -v "$REF" index -1 -v -c "$THREADS" -s sr.fastq -l lr_sample.fastq -o i > index1.log 2>&1
+  "$REF" index -1 -v -c "$THREADS" -s sr.fastq -l lr_sample.fastq -o i > index1.log 2>&1
   rm -f sr.fastq
 fi
 cp genome.npz "$OUT/genome.npz"
@@ -23,8 +23,8 @@ head -n 800 lr_sample.fastq > reads200.fastq
 "$REF" correct -1 -v -c "$THREADS" -g i.index.k31.fasta.gz -d i.index.k31.rtsk -l reads200.fastq -o g200 > correct1_200.log 2>&1
 gzip -c reads200.fastq > "$OUT/reads200.fastq.gz"; gzip -c g200.2.fastq > "$OUT/corrected200_pass1.fastq.gz"
 # pass-1 correction of the whole long-read sample (colours of the k = 63 graph), then the pass-2 index and goldens
-/usr/bin/time -v "$REF" correct -1 -v -c "$THREADS" -g i.index.k31.fasta.gz -d i.index.k31.rtsk -l lr_sample.fastq -o p1 > correct1_all.log 2>&1
-/usr/bin/time -v "$REF" index -2 -v -c "$THREADS" -g i.index.k63.fasta.gz -l p1.2.fastq -o j > index2.log 2>&1
+"$REF" correct -1 -v -c "$THREADS" -g i.index.k31.fasta.gz -d i.index.k31.rtsk -l lr_sample.fastq -o p1 > correct1_all.log 2>&1
+"$REF" index -2 -v -c "$THREADS" -g i.index.k63.fasta.gz -l p1.2.fastq -o j > index2.log 2>&1
 cp j.index.k63.rtsk "$OUT/index.k63.rtsk"
 "$REF" correct -2 -O -v -c "$THREADS" -g i.index.k63.fasta.gz -d j.index.k63.rtsk -l g200.2.fastq -L reads200.fastq -o g200b > correct2_200.log 2>&1
 gzip -c g200b.fastq > "$OUT/corrected200_pass2.fastq.gz"

@@ -34,7 +34,7 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     const rtk_hit no_weak = {0, 0, 0, 0};
     const uint32_t no_pid = 0;
     p.unitig_off = g.unitig_off; p.pool = g.pool; p.shared = g.shared; p.adj = g.adj; p.gset_of = g.gset_of;
-    p.gset_off = g.gset_off; p.gset_ids = g.gset_ids; p.loc_off = g.loc_off; p.loc_ids = g.loc_ids; p.k = g.k;
+    p.gset_off = g.gset_off; p.gset_ids = g.gset_ids; p.loc_off = g.loc_off; p.loc_ids = g.loc_ids; p.cyc_off = g.cyc_off; p.cyc_pool = g.cyc_pool; p.k = g.k;
     p.tasks = calls; p.order = order.data(); p.n_tasks = n_calls;
     p.win_pool = win_pool; p.weak_pool = n_weak ? weak_pool : &no_weak; p.pid_pool = n_pids ? pid_pool : &no_pid;
     p.results = out.results.data();
