@@ -378,11 +378,13 @@ GpuBroker::GpuBroker(rtk_ctx* c) : ctx(c) {
 #ifdef RTK_HOSTSIM   // the CPU simulator runs one launch at a time
     cnt[0] = cnt[1] = cnt[2] = cnt[3] = 1;
 #endif
+    bulk_regions = getenv("RTK_NO_BULK_REGIONS") == nullptr;
+    if (bulk_regions) cnt[3] = 1;   // one bulk launch per wave: a single region service thread
     for (int k = 0; k < 4; ++k)
         for (unsigned i = 0; i < std::max(1u, std::min(cnt[k], 8u)); ++i) {
             Service* s = new Service();
             s->kind = k;
-            if (rtk_ctx_fork(ctx, &s->ctx) != RTK_OK) { delete s; throw std::runtime_error(std::string("rtk_ctx_fork: ") + rtk_last_error()); }
+            if (ctx_fork_priority(ctx, /*high=*/k != 3, &s->ctx) != RTK_OK) { delete s; throw std::runtime_error(std::string("rtk_ctx_fork: ") + rtk_last_error()); }
             services[k].push_back(s);
         }
 }
@@ -428,7 +430,26 @@ void GpuBroker::service_main(Service* s) {
     const long linger_us = e_lg ? atol(e_lg) : 150;
     for (;;) {
         batch.clear();
-        {
+        if (s->kind == 3 && bulk_regions) {
+            // Bulk mode of the region engine: a launch is efficient when it holds thousands of regions (one warp each; its
+            // duration is set by the longest region, not by the count).  Regions of a gang reach their region request in
+            // waves (first the forward regions of all pieces, then the backward regions of the uncorrected ones, then the
+            // restarts after dead ends), so the service waits until EVERY live fiber is parked here - nothing else can make
+            // progress - and serves the whole wave with one launch.
+            std::unique_lock<std::mutex> lk(s->mu);
+            for (;;) {
+                if (s->stop && s->q.empty()) break;
+                if (!s->q.empty()) {
+                    const size_t live = live_total.load(std::memory_order_acquire);
+                    bool none_to_start;
+                    { std::lock_guard<std::mutex> g(mu_task); none_to_start = next_task >= n_tasks; }
+                    if (s->q.size() >= live && (none_to_start || live >= cap_total)) break;
+                }
+                s->cv.wait_for(lk, std::chrono::microseconds(500));
+            }
+            if (s->q.empty()) break;
+            batch.swap(s->q);
+        } else {
             std::unique_lock<std::mutex> lk(s->mu);
             s->cv.wait(lk, [&] { return s->stop || !s->q.empty(); });
             if (s->q.empty()) break;   // stop requested and nothing left
@@ -439,6 +460,7 @@ void GpuBroker::service_main(Service* s) {
             }
             batch.swap(s->q);
         }
+        if (batch.empty()) break;
         const auto t0 = std::chrono::steady_clock::now();
         std::string err;
         try {
@@ -524,7 +546,7 @@ void GpuBroker::worker_main(Worker* w) {
         swapcontext(&w->sched, &f->uc);
 #endif
         w->current = nullptr;
-        if (f->done) { w->pool.push_back(f); --live; }
+        if (f->done) { w->pool.push_back(f); --live; live_total.fetch_sub(1, std::memory_order_acq_rel); }
     };
     std::vector<Fiber*> resume;
     bool tasks_left = true;
@@ -551,7 +573,7 @@ void GpuBroker::worker_main(Worker* w) {
                 // stacks are carved from one mapping with a PROT_NONE guard page below each: an overflow faults instead of
                 // silently overwriting the neighbouring fiber's saved registers
                 char* base = w->slab + (w->stacks_used++) * (stack_bytes + kGuardBytes);
-                mprotect(base, kGuardBytes, PROT_NONE);
+                if (cap_total <= 16384) mprotect(base, kGuardBytes, PROT_NONE);   // every guard page is a mapping of its own: only below the kernel's map-count limit
                 f->stack = base + kGuardBytes;
             }
             f->task = i; f->done = false; f->broker = this; f->owner = w; f->error.clear();
@@ -572,6 +594,7 @@ void GpuBroker::worker_main(Worker* w) {
             makecontext(&f->uc, (void (*)())fiber_entry, 2, (unsigned)(p & 0xffffffffu), (unsigned)(p >> 32));
 #endif
             ++live; ++started;
+            live_total.fetch_add(1, std::memory_order_acq_rel);
             enter(f);
         }
         if (!resume.empty() || started) continue;
@@ -594,10 +617,12 @@ void GpuBroker::worker_main(Worker* w) {
 
 void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t)>& task) {
     if (n == 0) return;
-    const unsigned n_workers = (unsigned)std::min<size_t>(std::max(1u, host_threads()), n);
+    const unsigned n_workers = (unsigned)std::min<size_t>(std::max(1u, thread_budget()), n);
     const size_t stack_bytes = fiber_stack_bytes();
     n_tasks = n; next_task = 0; task_fn = &task; task_error.clear();
     cap_per_worker = std::max<size_t>(1, (std::min<size_t>(std::max(1u, inflight), n) + n_workers - 1) / n_workers);
+    cap_total = cap_per_worker * n_workers;
+    live_total.store(0);
     const auto t_begin = std::chrono::steady_clock::now();
     uint64_t prof0[4][4], rs0[18];
     for (int k = 0; k < 4; ++k) for (int j = 0; j < 4; ++j) prof0[k][j] = g_prof[k][j];

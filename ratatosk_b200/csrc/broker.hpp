@@ -14,6 +14,7 @@
 // per-region logic is untouched (and stays byte-identical to the reference).  Fibers never migrate between
 // worker threads, so thread-local state (current_broker) stays valid across a park.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -108,6 +109,9 @@ private:
     std::vector<Worker*> workers;
     std::string task_error;    // first exception that escaped a task
     // per run()
+    std::atomic<size_t> live_total{0};   // fibers started and not finished, all workers
+    size_t cap_total = 1;                // in-flight cap, all workers
+    bool bulk_regions = true;            // the region service launches when every live fiber waits for it (one bulk launch per wave)
     size_t n_tasks = 0, cap_per_worker = 1;
     size_t next_task = 0;      // guarded by mu_task (tasks are handed out in index order)
     std::mutex mu_task;

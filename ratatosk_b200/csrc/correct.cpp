@@ -12,6 +12,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -968,24 +969,17 @@ void run_piece(const Ctx& C, const ReadJob& J, Piece& P) {
 // weak regions in flight per batch (= fibers parked on the GPU broker); RTK_CORRECT_INFLIGHT overrides
 static unsigned correct_threads() {
     const char* e = getenv("RTK_CORRECT_INFLIGHT");
-    const int v = e ? atoi(e) : 32768;
+    const int v = e ? atoi(e) : 131072;
     return (unsigned)std::max(1, std::min(v, 1 << 20));
 }
 
 // ------------------------------------------------------------------ batch driver: the per-read body of search() (src/Ratatosk.cpp:808-867)
-void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
-                        const char* qual_pool, const uint64_t* qual_off, std::vector<std::string>& out_seq, std::vector<std::string>& out_qual,
-                        uint64_t* stats) {
-    if (!ctx->has_graph || !ctx->host_graph) throw std::invalid_argument("no graph uploaded to this context");
+// one gang: reads [0, n_reads) of its own pools through every correction round, on its own context
+static void correct_range(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
+                          const char* qual_pool, const uint64_t* qual_off, std::string* out_seq, std::string* out_qual, uint64_t* stats) {
     const rtk_graph_view& g = ctx->host_graph->view;
-    if (opt.k != g.k) throw std::invalid_argument("rtk_opt.k does not match the graph's k");
     const bool pass2 = (pass == 2);
-#ifndef RTK_HOSTSIM
-    const uint64_t launches0 = g_launches, h2d0 = g_h2d_bytes, d2h0 = g_d2h_bytes;
-#endif
     const size_t max_km_cov = std::max<size_t>(ctx->host_graph->hdr.max_km_cov_graph, opt.max_km_cov);  // src/Ratatosk.cpp:625
-    out_seq.assign(n_reads, std::string());
-    out_qual.assign(n_reads, std::string());
     parallel_for(n_reads, [&](size_t rb, size_t re) {
         for (size_t r = rb; r < re; ++r) {
             out_seq[r].assign(seq_pool + seq_off[r], seq_off[r + 1] - seq_off[r]);
@@ -1064,6 +1058,85 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
             stats[16] += broker.kernel_ns[3]; stats[17] += broker.region_calls; stats[18] += broker.region_bails;
             stats[10] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_broker - t_seeds).count();
             stats[11] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_broker).count();
+        }
+    }
+}
+
+// Reads of a batch are independent: the batch is split into GANGS (contiguous read ranges of about equal size in bases),
+// each running the whole pipeline (K1 sweeps -> anchors -> regions) on its own forked context and its own share of the host
+// threads.  While one gang's regions run on the device as one bulk launch (broker.hpp: the region service launches when every
+// live region of the gang is waiting for it), another gang's host stages (anchor logic, colour selection, stitching) run:
+// device and host overlap without any cross-gang dependency.  RTK_GANGS overrides the default of 2.
+void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
+                        const char* qual_pool, const uint64_t* qual_off, std::vector<std::string>& out_seq, std::vector<std::string>& out_qual,
+                        uint64_t* stats) {
+    if (!ctx->has_graph || !ctx->host_graph) throw std::invalid_argument("no graph uploaded to this context");
+    if (opt.k != ctx->host_graph->view.k) throw std::invalid_argument("rtk_opt.k does not match the graph's k");
+#ifndef RTK_HOSTSIM
+    const uint64_t launches0 = g_launches, h2d0 = g_h2d_bytes, d2h0 = g_d2h_bytes;
+#endif
+    out_seq.assign(n_reads, std::string());
+    out_qual.assign(n_reads, std::string());
+    const char* e = getenv("RTK_GANGS");
+    unsigned n_gangs = e ? (unsigned)std::max(1, atoi(e)) : 2u;
+    const uint64_t total_bases = n_reads ? seq_off[n_reads] - seq_off[0] : 0;
+    if (total_bases < (4u << 20) || n_reads < 2 * n_gangs) n_gangs = 1;   // small batches: not worth splitting
+    n_gangs = std::min(n_gangs, std::max(1u, host_threads()));
+    if (n_gangs == 1) {
+        correct_range(ctx, opt, pass, n_reads, seq_pool, seq_off, qual_pool, qual_off, out_seq.data(), out_qual.data(), stats);
+    } else {
+        // contiguous ranges of about equal bases
+        std::vector<uint32_t> cut(n_gangs + 1, n_reads);
+        cut[0] = 0;
+        for (unsigned gi = 1; gi < n_gangs; ++gi) {
+            const uint64_t want = seq_off[0] + total_bases * gi / n_gangs;
+            cut[gi] = (uint32_t)(std::lower_bound(seq_off, seq_off + n_reads + 1, want) - seq_off);
+            cut[gi] = std::max(cut[gi], cut[gi - 1]);
+        }
+        std::vector<std::vector<uint64_t>> gstats(n_gangs, std::vector<uint64_t>(24, 0));
+        std::vector<std::string> errors(n_gangs);
+        std::vector<rtk_ctx*> gctx(n_gangs, nullptr);
+        for (unsigned gi = 0; gi < n_gangs; ++gi) {
+            if (rtk_ctx_fork(ctx, &gctx[gi]) != RTK_OK) {
+                for (rtk_ctx* c : gctx) if (c) rtk_ctx_destroy(c);
+                throw std::runtime_error(std::string("rtk_ctx_fork: ") + rtk_last_error());
+            }
+#ifndef RTK_HOSTSIM
+            if (ctx->resident_seq && ctx->resident_n == n_reads) {   // the caller's resident copy of the reads, this gang's slice
+                gctx[gi]->resident_seq = ctx->resident_seq; gctx[gi]->resident_off = ctx->resident_off + cut[gi];
+                gctx[gi]->resident_n = cut[gi + 1] - cut[gi]; gctx[gi]->resident_total = seq_off[cut[gi + 1]] - seq_off[cut[gi]];
+            }
+#endif
+        }
+        const unsigned budget = std::max(1u, host_threads() / n_gangs);
+        std::vector<std::thread> th;
+        for (unsigned gi = 0; gi < n_gangs; ++gi) {
+            th.emplace_back([&, gi] {
+                set_thread_budget(budget);
+                try {
+#ifndef RTK_HOSTSIM
+                    DeviceBind bind(gctx[gi]);
+#endif
+                    const uint32_t r0 = cut[gi], n = cut[gi + 1] - cut[gi];
+                    if (n) correct_range(gctx[gi], opt, pass, n, seq_pool, seq_off + r0, qual_pool, qual_off ? qual_off + r0 : nullptr, out_seq.data() + r0,
+                                         out_qual.data() + r0, gstats[gi].data());
+                } catch (const std::exception& ex) { errors[gi] = ex.what(); if (errors[gi].empty()) errors[gi] = "correction gang failed"; }
+                catch (...) { errors[gi] = "correction gang failed (unknown exception)"; }
+            });
+        }
+        for (auto& t : th) t.join();
+        for (rtk_ctx* c : gctx) rtk_ctx_destroy(c);
+#ifndef RTK_HOSTSIM
+        ctx->resident_seq = nullptr;
+#endif
+        for (const std::string& er : errors) if (!er.empty()) throw std::runtime_error(er);
+        if (stats) {
+            // counters add up; stage times are wall-clock per gang (the gangs run concurrently): report the slowest gang
+            for (int i = 0; i < 24; ++i) {
+                uint64_t sum = 0, mx = 0;
+                for (unsigned gi = 0; gi < n_gangs; ++gi) { sum += gstats[gi][i]; mx = std::max(mx, gstats[gi][i]); }
+                stats[i] += (i == 3 || i == 10 || i == 11) ? mx : sum;
+            }
         }
     }
 #ifndef RTK_HOSTSIM

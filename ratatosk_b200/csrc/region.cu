@@ -1,5 +1,5 @@
 // region.cu — launcher and C ABI entry of the device-resident region engine (region.cuh): one packed upload, ONE kernel
-// launch for all calls of the batch (persistent warps pulling regions from an atomic counter), results + the used part of
+// launch for all calls of the batch (one warp per region, longest first), results + the used part of
 // the output pools back.  Compiled with -fmad=false: the engine's few double-precision score / quality expressions must
 // round like the host's (no FMA contraction), see rg_get_qual / rg_min_max.
 #include <cstring>
@@ -11,14 +11,17 @@
 
 namespace rtk {
 
-static uint32_t region_slots(const rtk_ctx* c, uint32_t n_calls) {
-    // resident warps: 8 per SM by default (RTK_RG_WARPS_PER_SM overrides); a warp holds ~2 MB of scratch
-    const char* e = getenv("RTK_RG_WARPS_PER_SM");
-    const uint32_t per_sm = e ? (uint32_t)std::max(1, atoi(e)) : 8u;
-    const uint32_t max_slots = (uint32_t)c->sm_count * per_sm;
-    uint32_t slots = std::min(max_slots, n_calls);
-    slots = ((slots + RTK_RG_WARPS - 1) / RTK_RG_WARPS) * RTK_RG_WARPS;
-    return std::max<uint32_t>(slots, RTK_RG_WARPS);
+// scratch slots = CTAs that can be resident at once (RTK_RG_CTAS_PER_SM overrides the occupancy query); a CTA holds
+// RTK_RG_WARPS x ~2 MB
+static uint32_t region_slots(const rtk_ctx* c) {
+    static int per_sm = [] {
+        const char* e = getenv("RTK_RG_CTAS_PER_SM");
+        if (e) return std::max(1, atoi(e));
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rtk_region_kernel, RTK_RG_WARPS * 32, 0) != cudaSuccess || n < 1) n = 4;
+        return n;
+    }();
+    return (uint32_t)c->sm_count * (uint32_t)per_sm;
 }
 
 void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls, const rtk_region_call_t* calls, const char* win_pool,
@@ -57,10 +60,10 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     c->d_rg[1].reserve((uint64_t)n_calls * sizeof(rtk_region_result_t));
     c->d_rg[2].reserve(nodes_cap * sizeof(rtk_path_node));
     c->d_rg[3].reserve(chars_cap);
-    c->d_rg[4].reserve(64);
-    const uint32_t slots = region_slots(c, n_calls);
-    c->d_rg[5].reserve((uint64_t)slots * p.scratch_per_warp);
-    RTK_CUDA(cudaMemsetAsync(c->d_rg[4].p, 0, 64, st));
+    const uint32_t n_slots = region_slots(c);
+    c->d_rg[4].reserve(64 + (uint64_t)n_slots * 4);
+    c->d_rg[5].reserve((uint64_t)n_slots * RTK_RG_WARPS * p.scratch_per_warp);
+    RTK_CUDA(cudaMemsetAsync(c->d_rg[4].p, 0, 64 + (uint64_t)n_slots * 4, st));
     const rtk_graph_view& g = c->dview;
     p.unitig_off = g.unitig_off; p.pool = g.pool; p.shared = g.shared; p.adj = g.adj; p.gset_of = g.gset_of;
     p.gset_off = g.gset_off; p.gset_ids = g.gset_ids; p.loc_off = g.loc_off; p.loc_ids = g.loc_ids; p.cyc_off = g.cyc_off; p.cyc_pool = g.cyc_pool; p.k = c->hdr.k;
@@ -68,12 +71,12 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     p.win_pool = d + o_win; p.weak_pool = (const rtk_hit*)(d + o_weak); p.pid_pool = (const uint32_t*)(d + o_pids);
     p.results = c->d_rg[1].as<rtk_rg_result>();
     p.out_nodes = c->d_rg[2].as<rtk_rg_node>(); p.out_chars = c->d_rg[3].as<char>();
-    p.out_top = c->d_rg[4].as<unsigned long long>(); p.next_task = (uint32_t*)(c->d_rg[4].as<unsigned long long>() + 2);
+    p.out_top = c->d_rg[4].as<unsigned long long>(); p.slot_flags = (uint32_t*)(c->d_rg[4].as<char>() + 64); p.n_slots = n_slots;
     p.out_nodes_cap = nodes_cap; p.out_chars_cap = chars_cap;
     p.scratch = c->d_rg[5].as<unsigned char>();
     RTK_CUDA(cudaEventRecord(c->ev0, st));
     ++g_launches;
-    rtk_region_kernel<<<slots / RTK_RG_WARPS, RTK_RG_WARPS * 32, 0, st>>>(p);
+    rtk_region_kernel<<<(n_calls + RTK_RG_WARPS - 1) / RTK_RG_WARPS, RTK_RG_WARPS * 32, 0, st>>>(p);
     RTK_CUDA(cudaGetLastError());
     RTK_CUDA(cudaEventRecord(c->ev1, st));
     // ---- results + counters, then the used part of the pools

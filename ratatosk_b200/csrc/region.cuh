@@ -18,8 +18,8 @@
 //     place, writing qualities instead of an op string.
 // Rare shapes the kernel does not handle (short-cycle unitigs -> fixRepeats, queue / result-list collapses at 512 / 1024
 // entries, alignments above edlib's 1 MiB traceback switch, arena overflow) set a BAIL code; the host then re-runs that one
-// call through the request-at-a-time path (traverse.cpp), which produces the same bytes.  Regions are independent, so a
-// launch is a persistent grid of warps pulling region ids from an atomic counter (longest first).
+// call through the request-at-a-time path (traverse.cpp), which produces the same bytes.  Regions are independent: a launch
+// is one warp per region, longest first (see rtk_region_kernel).
 #pragma once
 #ifndef RTK_HOSTSIM
 #include <cuda_runtime.h>
@@ -79,7 +79,8 @@ struct rtk_rg_params {
     char* out_chars;
     unsigned long long* out_top;
     uint64_t out_nodes_cap, out_chars_cap;
-    uint32_t* next_task;         // atomic work counter
+    uint32_t* slot_flags;        // n_slots flags: scratch slots (one per resident CTA) handed out by atomic compare-and-swap
+    uint32_t n_slots;
     // per-warp scratch
     unsigned char* scratch;
     uint64_t scratch_per_warp;
@@ -243,7 +244,7 @@ __device__ __forceinline__ rg_dist rg_myers(rg_ctx& C, const char* __restrict__ 
         const bool top_spilled = (lane == 0) && (r != 0);
         const int hin_top = (mode == 2) ? 0 : 1;
         const bool track = is_last && (mode != 0);
-        const int steps = tlen + G - 1;
+        const int steps = tlen + (nb < G ? nb : G) - 1;   // lanes beyond the query's last block never work: no fill / drain steps for them
         char tc_next = (lane == 0 && tlen > 0) ? t[0] : (char)0;
         const bool rare = t_amb || (rounds > 1);
         if (!rare) { RTK_MYERS_STEP_LOOP(false) } else { RTK_MYERS_STEP_LOOP(true) }
@@ -331,7 +332,7 @@ __device__ __forceinline__ void rg_path_quality(rg_ctx& C, const char* __restric
         int score = (b << 6) + arow + 1;
         const uint64_t base = (uint64_t)b * (uint64_t)tlen;
         const bool spill = (lane == G - 1) && (r + 1 < rounds);
-        const int steps = tlen + G - 1;
+        const int steps = tlen + (nb < G ? nb : G) - 1;   // lanes beyond the query's last block never work: no fill / drain steps for them
         char tc_next = (lane == 0 && tlen > 0) ? t[0] : (char)0;
         const bool top_spilled = (lane == 0) && (r != 0);
         const bool is_last_blk = (b == nb - 1);
@@ -1066,32 +1067,42 @@ __device__ __forceinline__ void rg_region(rg_ctx& C, const rtk_rg_task& T, rtk_r
     R.status = alive ? 0u : 1u; R.bail = 0; R.n_nodes = cn; R.len = cl; R.node_off = no; R.str_off = so;
 }
 
+// One region per warp, RTK_RG_WARPS regions per CTA, grid = all regions of the batch (longest first).  The grid is NOT
+// persistent: a CTA retires as soon as its regions are done, so the SM slots it held go back to the scheduler every few
+// milliseconds and the small high-priority kernels of the other services (K4 / K5 batches) never wait behind a whole batch of
+// regions.  Scratch is a pool of per-CTA slots (one per CTA that can be resident), acquired on entry and released on exit.
 __global__ void __launch_bounds__(RTK_RG_WARPS * 32) rtk_region_kernel(const rtk_rg_params p) {
+    __shared__ uint32_t s_slot;
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint64_t slot = (uint64_t)blockIdx.x * RTK_RG_WARPS + w;
-    const rtk_rg_layout L = rtk_rg_make_layout(p.str_cap, p.mat_cells, p.tmp_cap, p.arena_cap, p.chain_nodes_cap, p.chain_len_cap);
-    unsigned char* S = p.scratch + slot * p.scratch_per_warp;
-    rg_ctx C;
-    C.p = &p; C.lane = lane;
-    C.sA = (char*)(S + L.sA); C.sB = (char*)(S + L.sB); C.sC = (char*)(S + L.sC); C.hb = (int8_t*)(S + L.hb);
-    C.mat = (ulonglong2*)(S + L.mat); C.anc = (int32_t*)(S + L.anc);
-    C.dfs = (rtk_dfs_frame*)(S + L.dfs); C.dfs_cur = (rtk_dfs_frame*)(S + L.dfs_cur);
-    C.tmpT = S + L.tmpT; C.tmpN = S + L.tmpN; C.arena = S + L.arena;
-    C.q_items = (uint32_t*)(S + L.q_items); C.v_items = (uint32_t*)(S + L.v_items); C.vt_items = (uint32_t*)(S + L.vt_items);
-    C.ch_nodes = (rtk_rg_node*)(S + L.ch_nodes); C.ch_qual = (char*)(S + L.ch_qual);
-    for (;;) {
-        uint32_t ti = 0;
-        if (lane == 0) ti = atomicAdd(p.next_task, 1u);
-        ti = __shfl_sync(0xffffffffu, ti, 0);
-        if (ti >= p.n_tasks) break;
+    if (threadIdx.x == 0) {
+        uint32_t s = blockIdx.x % p.n_slots;
+        while (atomicCAS(&p.slot_flags[s], 0u, 1u) != 0u) s = (s + 1 == p.n_slots) ? 0u : s + 1;
+        __threadfence();
+        s_slot = s;
+    }
+    __syncthreads();
+    const uint64_t slot = (uint64_t)s_slot * RTK_RG_WARPS + w;
+    const uint32_t ti = blockIdx.x * RTK_RG_WARPS + w;
+    if (ti < p.n_tasks) {
+        const rtk_rg_layout L = rtk_rg_make_layout(p.str_cap, p.mat_cells, p.tmp_cap, p.arena_cap, p.chain_nodes_cap, p.chain_len_cap);
+        unsigned char* S = p.scratch + slot * p.scratch_per_warp;
+        rg_ctx C;
+        C.p = &p; C.lane = lane;
+        C.sA = (char*)(S + L.sA); C.sB = (char*)(S + L.sB); C.sC = (char*)(S + L.sC); C.hb = (int8_t*)(S + L.hb);
+        C.mat = (ulonglong2*)(S + L.mat); C.anc = (int32_t*)(S + L.anc);
+        C.dfs = (rtk_dfs_frame*)(S + L.dfs); C.dfs_cur = (rtk_dfs_frame*)(S + L.dfs_cur);
+        C.tmpT = S + L.tmpT; C.tmpN = S + L.tmpN; C.arena = S + L.arena;
+        C.q_items = (uint32_t*)(S + L.q_items); C.v_items = (uint32_t*)(S + L.v_items); C.vt_items = (uint32_t*)(S + L.vt_items);
+        C.ch_nodes = (rtk_rg_node*)(S + L.ch_nodes); C.ch_qual = (char*)(S + L.ch_qual);
         const uint32_t id = p.order ? p.order[ti] : ti;
         C.arena_top = 0; C.bail = 0; C.n_hops = C.n_pops = C.n_cands = C.n_aligns = 0;
         rtk_rg_result R;
         rg_region(C, p.tasks[id], R);
         __syncwarp();
         if (lane == 0) p.results[id] = R;
-        __syncwarp();
     }
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicExch(&p.slot_flags[s_slot], 0u); }
 }
 
 #endif  // __CUDACC__ || __CUDACC_SIM__

@@ -125,10 +125,10 @@ void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, 
 
 using namespace rtk;
 
-static void create_side_streams(rtk_ctx* c) {
+static void create_side_streams(rtk_ctx* c, int prio = 0) {
     RTK_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     for (int k = 0; k < 6; ++k) {
-        RTK_CUDA(cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking));
+        RTK_CUDA(cudaStreamCreateWithPriority(&c->side[k], cudaStreamNonBlocking, prio));
         RTK_CUDA(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
     }
 }
@@ -161,16 +161,25 @@ int rtk_ctx_create(int device, rtk_ctx** out) {
     });
 }
 
-int rtk_ctx_fork(const rtk_ctx* parent, rtk_ctx** out) {
+int rtk_ctx_fork(const rtk_ctx* parent, rtk_ctx** out) { return rtk::ctx_fork_priority(parent, false, out); }
+
+}  // extern "C"
+
+// fork whose streams run at the device's highest (high = true) or lowest stream priority: the short K4 / K5 batches of the
+// correction broker must not queue behind the long region-engine launches
+int rtk::ctx_fork_priority(const rtk_ctx* parent, bool high, rtk_ctx** out) {
     return guarded([&] {
         if (!parent || !out) throw std::invalid_argument("null argument");
         RTK_CUDA(cudaSetDevice(parent->device));
+        int lo = 0, hi = 0;   // numerically lowest = highest priority
+        RTK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const int prio = high ? hi : lo;
         rtk_ctx* c = new rtk_ctx();
         c->device = parent->device;
-        RTK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        RTK_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio));
         RTK_CUDA(cudaEventCreate(&c->ev0));
         RTK_CUDA(cudaEventCreate(&c->ev1));
-        create_side_streams(c);
+        create_side_streams(c, prio);
         c->sm_count = parent->sm_count;
         // the graph is shared, never owned: the parent must outlive the fork
         c->d_slab = parent->d_slab; c->owns_slab = false; c->has_graph = parent->has_graph;
@@ -178,6 +187,8 @@ int rtk_ctx_fork(const rtk_ctx* parent, rtk_ctx** out) {
         *out = c;
     });
 }
+
+extern "C" {
 
 void rtk_ctx_destroy(rtk_ctx* c) {
     if (!c) return;

@@ -29,8 +29,14 @@ unsigned host_threads() {
     return n;
 }
 
+// per-thread override of the host thread count: a correction gang (correct.cpp) owns a share of the cores, and everything
+// it starts (parallel_for, the broker's workers) inherits that share through this thread-local
+static thread_local unsigned tl_thread_budget = 0;
+void set_thread_budget(unsigned n) { tl_thread_budget = n; }
+unsigned thread_budget() { return tl_thread_budget ? tl_thread_budget : host_threads(); }
+
 void parallel_for(size_t n, const std::function<void(size_t, size_t)>& body) {
-    const unsigned nt = (unsigned)std::min<size_t>(host_threads(), n);
+    const unsigned nt = (unsigned)std::min<size_t>(thread_budget(), n);
     if (nt <= 1) { if (n) body(0, n); return; }
     // dynamic chunks: reads differ in length by orders of magnitude
     const size_t chunk = std::max<size_t>(1, n / (nt * 8));

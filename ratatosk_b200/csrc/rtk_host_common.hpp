@@ -59,6 +59,8 @@ inline uint32_t k1_tile_size(uint32_t, bool) { return RTK_K1_THREADS; }
 // inexactly are mostly 'N' (src/Graph.cpp:106-191); a tile without such a window can neither probe nor hit.  Conservative: a
 // live tile may still hold no valid window, the kernel decides per window.
 unsigned host_threads();
+void set_thread_budget(unsigned n);   // thread-local share of the host threads (0 = all); inherited by parallel_for / the broker
+unsigned thread_budget();
 void parallel_for(size_t n, const std::function<void(size_t, size_t)>& body);  // body(begin, end) on chunks
 
 inline void build_tiles(uint32_t n_reads, const uint64_t* h_seq_off, uint32_t k, uint32_t tile, std::vector<uint32_t>& tiles,

@@ -222,6 +222,9 @@ void myers_run_lean(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const 
                     uint64_t t_bytes, const MyersJobs& j, int32_t* dist, int32_t* first_end, int32_t* last_end, float* kernel_ms);
 #endif
 
+// rtk_ctx_fork with the streams at the highest / lowest priority of the device (no-op distinction on the CPU simulator)
+int ctx_fork_priority(const rtk_ctx* parent, bool high, rtk_ctx** out);
+
 // device-resident region engine (region.cu / tests/hostsim/sim_region.cpp): n extractSemiWeakPaths calls in one launch
 struct RegionBatchOut {
     std::vector<rtk_region_result_t> results;

@@ -29,8 +29,9 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     std::vector<rtk_path_node> nodes(nodes_cap);
     std::vector<char> chars(chars_cap);
     unsigned long long counters[4] = {0, 0, 0, 0};
-    const unsigned slots = RTK_RG_WARPS;   // one CTA at a time on the simulator
-    std::vector<unsigned char> scratch((size_t)slots * p.scratch_per_warp);
+    const unsigned n_slots = 16;           // CTA scratch slots (the simulator runs at most 16 blocks at a time)
+    std::vector<unsigned char> scratch((size_t)n_slots * RTK_RG_WARPS * p.scratch_per_warp);
+    std::vector<uint32_t> slot_flags(n_slots, 0);
     const rtk_hit no_weak = {0, 0, 0, 0};
     const uint32_t no_pid = 0;
     p.unitig_off = g.unitig_off; p.pool = g.pool; p.shared = g.shared; p.adj = g.adj; p.gset_of = g.gset_of;
@@ -38,10 +39,10 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     p.tasks = calls; p.order = order.data(); p.n_tasks = n_calls;
     p.win_pool = win_pool; p.weak_pool = n_weak ? weak_pool : &no_weak; p.pid_pool = n_pids ? pid_pool : &no_pid;
     p.results = out.results.data();
-    p.out_nodes = nodes.data(); p.out_chars = chars.data(); p.out_top = counters; p.next_task = (uint32_t*)(counters + 2);
+    p.out_nodes = nodes.data(); p.out_chars = chars.data(); p.out_top = counters; p.slot_flags = slot_flags.data(); p.n_slots = n_slots;
     p.out_nodes_cap = nodes_cap; p.out_chars_cap = chars_cap;
     p.scratch = scratch.data();
-    sim_launch(1, RTK_RG_WARPS * 32, [&] { rtk_region_kernel(p); });
+    sim_launch((n_calls + RTK_RG_WARPS - 1) / RTK_RG_WARPS, RTK_RG_WARPS * 32, [&] { rtk_region_kernel(p); });
     const uint64_t un = std::min<uint64_t>(counters[0], nodes_cap), uc = std::min<uint64_t>(counters[1], chars_cap);
     out.nodes.assign(nodes.begin(), nodes.begin() + un);
     out.chars.assign(chars.begin(), chars.begin() + uc);
