@@ -11,14 +11,14 @@
 
 namespace rtk {
 
-// scratch slots = CTAs that can be resident at once (RTK_RG_CTAS_PER_SM overrides the occupancy query); a CTA holds
-// RTK_RG_WARPS x ~2 MB
+// scratch slots = CTAs (= warps = regions) that can be resident at once (RTK_RG_CTAS_PER_SM overrides the occupancy query);
+// a slot is ~2 MB
 static uint32_t region_slots(const rtk_ctx* c) {
     static int per_sm = [] {
         const char* e = getenv("RTK_RG_CTAS_PER_SM");
         if (e) return std::max(1, atoi(e));
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rtk_region_kernel, RTK_RG_WARPS * 32, 0) != cudaSuccess || n < 1) n = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, rtk_region_kernel, RTK_RG_WARPS * 32, 0) != cudaSuccess || n < 1) n = 12;
         return n;
     }();
     return (uint32_t)c->sm_count * (uint32_t)per_sm;

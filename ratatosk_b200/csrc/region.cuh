@@ -32,7 +32,12 @@
 #include "myers.cuh"
 #include "subgraph.cuh"
 
-#define RTK_RG_WARPS 4          /* warps (= regions in flight) per CTA */
+#define RTK_RG_WARPS 1          /* one region = one warp = one CTA */
+#if defined(__CUDACC__)
+#define RTK_RG_NOINLINE __noinline__
+#else
+#define RTK_RG_NOINLINE
+#endif
 #define RTK_RG_QCAP 512         /* max_sz_stck of the reference: reaching it collapses the queue (bail) */
 #define RTK_RG_VCAP 1024        /* max_paths of the reference */
 #define RTK_RG_DROPPED 0xFFFFFFFEu /* queue marker: a path that is dropped when popped (already >= max_len_path) */
@@ -190,7 +195,7 @@ __device__ __forceinline__ uint32_t rg_spell_node(const rg_ctx& C, const uint32_
     return mlen > skip ? mlen - skip : 0;
 }
 // Path::toString of a vertex list (interior vertices overlap their predecessor by k-1 bases)
-__device__ __forceinline__ uint32_t rg_spell_nodes(const rg_ctx& C, const rtk_rg_node* nd, const uint32_t n, char* out) {
+__device__ RTK_RG_NOINLINE uint32_t rg_spell_nodes(const rg_ctx& C, const rtk_rg_node* nd, const uint32_t n, char* out) {
     uint32_t o = 0;
     for (uint32_t i = 0; i < n; ++i) o += rg_spell_node(C, nd[i].unitig, nd[i].strand, nd[i].dist, nd[i].len, i == 0 ? 0u : C.p->k - 1, out + o);
     __syncwarp();
@@ -202,7 +207,7 @@ struct rg_dist { int dist, first, last; };
 
 // edlibAlign distance (modes 0 NW / 1 SHW / 2 HW, IUPAC equalities) of q against t by all 32 lanes: the wavefront sweep of
 // myers.cuh with G = 32; returns the distance and the first / last end column carrying it (edlib's endLocations[0] / [n-1])
-__device__ __forceinline__ rg_dist rg_myers(rg_ctx& C, const char* __restrict__ q, const int qlen, const char* __restrict__ t, const int tlen, const int mode) {
+__device__ RTK_RG_NOINLINE rg_dist rg_myers(rg_ctx& C, const char* __restrict__ q, const int qlen, const char* __restrict__ t, const int tlen, const int mode) {
     rg_dist R;
     ++C.n_aligns;
     if (qlen == 0 || tlen == 0) {   // edlibAlign's special case (src/edlib.cpp:160-176)
@@ -291,7 +296,7 @@ __device__ __forceinline__ int rg_tb_row(const rg_tb_cell& c, const int arow, co
 // distance sweep, then the NW path against that target prefix, src/edlib.cpp:262-279); every path base that sits on an exact
 // match of an M run gets `best_q`, the others `base_q`.  The traceback (move priority up > left > diagonal,
 // src/edlib.cpp:1023-1134) is walked in place by lane 0 over the stored sweep.
-__device__ __forceinline__ void rg_path_quality(rg_ctx& C, const char* __restrict__ ps, const int qlen, const char* __restrict__ t, const int tlen_full,
+__device__ RTK_RG_NOINLINE void rg_path_quality(rg_ctx& C, const char* __restrict__ ps, const int qlen, const char* __restrict__ t, const int tlen_full,
                                                 const char base_q, const char best_q, char* __restrict__ qual_out) {
     const uint32_t lane = C.lane;
     for (int i = (int)lane; i < qlen; i += 32) qual_out[i] = base_q;
@@ -444,7 +449,7 @@ __device__ __forceinline__ rg_cand* rg_cand_next(rg_cand* c) { return (rg_cand*)
 // exploreSubGraph / exploreSubGraphLong from vertex (cu, cs) on the window sub[0, sub_len): enumeration as rtk_dfs_kernel
 // (subgraph.cuh), each candidate spelled and scored the moment it is found (getScorePath :867-909), the reference's
 // selection (`>=` keeps ties in discovery order, `>` restarts the list; :511-523, :536-548) applied to the stream.
-__device__ __forceinline__ void rg_burst(rg_ctx& C, const uint32_t cu0, const uint32_t cs0, const bool has_end, const uint32_t end_unitig,
+__device__ RTK_RG_NOINLINE void rg_burst(rg_ctx& C, const uint32_t cu0, const uint32_t cs0, const bool has_end, const uint32_t end_unitig,
                                          const uint32_t end_strand, const uint32_t end_dist, const uint32_t level, const uint32_t max_len_path,
                                          const char* __restrict__ sub, const uint32_t sub_len, const uint32_t* __restrict__ P, const uint32_t pid_len,
                                          rg_burst_out& B) {
@@ -591,7 +596,7 @@ __device__ __forceinline__ uint32_t rg_alloc_path(rg_ctx& C, const uint32_t n, c
 
 // p_ext = parent + the first `take` vertices of a burst candidate with their slice of the burst's quality string
 // (extend loop of explorePathsBFS*, src/GraphTraversal.cpp:377-412 / :140-170; Path::extend src/Path.hpp)
-__device__ __forceinline__ uint32_t rg_extend_with(rg_ctx& C, const uint32_t parent_off, rg_cand* cd, const uint32_t take) {
+__device__ RTK_RG_NOINLINE uint32_t rg_extend_with(rg_ctx& C, const uint32_t parent_off, rg_cand* cd, const uint32_t take) {
     rg_path* par = rg_at(C, parent_off);
     const uint32_t k = C.p->k;
     const uint32_t pn = par->n, pl = par->l;
@@ -641,7 +646,7 @@ __device__ __forceinline__ uint32_t rg_spell_cut(rg_ctx& C, const rtk_rg_node* n
 // on a short-cycle unitig try every stored cycle (UnitigData::getCompactCycles) spliced in at that vertex, each NW-aligned
 // against the window with the running best distance as bound; the last strictly improving one is accepted, the walk resumes
 // behind the inserted vertices; without an acceptance the following vertices on the same unitig are skipped.
-__device__ __forceinline__ uint32_t rg_fix_repeats(rg_ctx& C, const uint32_t path_off, const char* __restrict__ ref, const uint32_t ref_len) {
+__device__ RTK_RG_NOINLINE uint32_t rg_fix_repeats(rg_ctx& C, const uint32_t path_off, const char* __restrict__ ref, const uint32_t ref_len) {
     const rtk_rg_params& p = *C.p;
     const uint32_t k = p.k, lane = C.lane;
     uint32_t cur = path_off;
@@ -770,7 +775,7 @@ __device__ __forceinline__ uint32_t rg_fix_repeats(rg_ctx& C, const uint32_t pat
 // ------------------------------------------------------------------------------------------------ one hop
 // explorePathsBFS2 (has_end) / explorePathsBFS (open end) on the window ref[0, ref_len) from vertex um_s; returns the arena
 // offset of the winning path (before fixRepeats, which bails) or RTK_NONE32 when there is none.
-__device__ __forceinline__ uint32_t rg_hop(rg_ctx& C, const char* __restrict__ ref, const uint32_t ref_len, const rtk_rg_node um_s, const bool has_end,
+__device__ RTK_RG_NOINLINE uint32_t rg_hop(rg_ctx& C, const char* __restrict__ ref, const uint32_t ref_len, const rtk_rg_node um_s, const bool has_end,
                                            const uint32_t e_unitig, const uint32_t e_strand, const uint32_t e_dist, const uint32_t* __restrict__ P,
                                            const uint32_t pid_len) {
     const rtk_rg_params& p = *C.p;
@@ -1067,25 +1072,25 @@ __device__ __forceinline__ void rg_region(rg_ctx& C, const rtk_rg_task& T, rtk_r
     R.status = alive ? 0u : 1u; R.bail = 0; R.n_nodes = cn; R.len = cl; R.node_off = no; R.str_off = so;
 }
 
-// One region per warp, RTK_RG_WARPS regions per CTA, grid = all regions of the batch (longest first).  The grid is NOT
-// persistent: a CTA retires as soon as its regions are done, so the SM slots it held go back to the scheduler every few
-// milliseconds and the small high-priority kernels of the other services (K4 / K5 batches) never wait behind a whole batch of
-// regions.  Scratch is a pool of per-CTA slots (one per CTA that can be resident), acquired on entry and released on exit.
-__global__ void __launch_bounds__(RTK_RG_WARPS * 32) rtk_region_kernel(const rtk_rg_params p) {
-    __shared__ uint32_t s_slot;
-    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        uint32_t s = blockIdx.x % p.n_slots;
-        while (atomicCAS(&p.slot_flags[s], 0u, 1u) != 0u) s = (s + 1 == p.n_slots) ? 0u : s + 1;
+// One region per warp, ONE WARP PER CTA, grid = all regions of the batch (longest first).  The grid is not persistent and a
+// CTA is a single warp: a region that finishes gives its SM slot back at once (regions differ 100x in duration; with several
+// regions per CTA the finished warps sat at the final barrier - 39 % of the stall samples of the first bulk launches,
+// profiles/r2_region_bulk_a.md), and the short high-priority kernels of the other services never wait behind a batch of
+// regions.  Scratch is a pool of per-warp slots (one per warp that can be resident), acquired on entry, released on exit.
+__global__ void __launch_bounds__(32) rtk_region_kernel(const rtk_rg_params p) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ti = blockIdx.x;
+    if (ti >= p.n_tasks) return;
+    uint32_t slot = 0;
+    if (lane == 0) {
+        slot = blockIdx.x % p.n_slots;
+        while (atomicCAS(&p.slot_flags[slot], 0u, 1u) != 0u) slot = (slot + 1 == p.n_slots) ? 0u : slot + 1;
         __threadfence();
-        s_slot = s;
     }
-    __syncthreads();
-    const uint64_t slot = (uint64_t)s_slot * RTK_RG_WARPS + w;
-    const uint32_t ti = blockIdx.x * RTK_RG_WARPS + w;
-    if (ti < p.n_tasks) {
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    {
         const rtk_rg_layout L = rtk_rg_make_layout(p.str_cap, p.mat_cells, p.tmp_cap, p.arena_cap, p.chain_nodes_cap, p.chain_len_cap);
-        unsigned char* S = p.scratch + slot * p.scratch_per_warp;
+        unsigned char* S = p.scratch + (uint64_t)slot * p.scratch_per_warp;
         rg_ctx C;
         C.p = &p; C.lane = lane;
         C.sA = (char*)(S + L.sA); C.sB = (char*)(S + L.sB); C.sC = (char*)(S + L.sC); C.hb = (int8_t*)(S + L.hb);
@@ -1101,8 +1106,8 @@ __global__ void __launch_bounds__(RTK_RG_WARPS * 32) rtk_region_kernel(const rtk
         __syncwarp();
         if (lane == 0) p.results[id] = R;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) { __threadfence(); atomicExch(&p.slot_flags[s_slot], 0u); }
+    __syncwarp();
+    if (lane == 0) { __threadfence(); atomicExch(&p.slot_flags[slot], 0u); }
 }
 
 #endif  // __CUDACC__ || __CUDACC_SIM__

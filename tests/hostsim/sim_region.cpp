@@ -29,7 +29,7 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     std::vector<rtk_path_node> nodes(nodes_cap);
     std::vector<char> chars(chars_cap);
     unsigned long long counters[4] = {0, 0, 0, 0};
-    const unsigned n_slots = 16;           // CTA scratch slots (the simulator runs at most 16 blocks at a time)
+    const unsigned n_slots = 16;           // scratch slots (the simulator runs at most 16 blocks at a time)
     std::vector<unsigned char> scratch((size_t)n_slots * RTK_RG_WARPS * p.scratch_per_warp);
     std::vector<uint32_t> slot_flags(n_slots, 0);
     const rtk_hit no_weak = {0, 0, 0, 0};
