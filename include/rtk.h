@@ -219,8 +219,18 @@ typedef struct rtk_region_call_t {
     uint32_t end_pos;        /* pos_um_solid2 when has_end */
     uint32_t end_unitig, end_dist, end_strand;
     uint32_t s_len;          /* read length (open end: pos_um_solid2 = s_len - k) */
-    uint32_t reserved;
+    uint32_t reserved;       /* bit 0: follow dead ends like the `correct` lambda (src/Correction.cpp:619-651): best prefix alignment of
+                                the dead-end path, restart from the next weak anchor behind it; one segment per restart */
 } rtk_region_call_t;
+
+/* one extractSemiWeakPaths call of a region (a region has several when dead ends are followed) */
+typedef struct rtk_region_seg_t {
+    uint32_t status;         /* 0 complete path, 1 dead-end path */
+    uint32_t start_weak;     /* index (in the call's weak list) of the weak anchor this segment starts from; 0xFFFFFFFF: the left anchor */
+    uint32_t n_nodes, len;
+    uint64_t node_off, str_off;
+    int32_t shw_dist, shw_first_end;   /* dead ends followed: SHW distance / first end location of the path against the rest of the window */
+} rtk_region_seg_t;
 
 typedef struct rtk_region_result_t {
     uint32_t status, bail;
@@ -228,13 +238,17 @@ typedef struct rtk_region_result_t {
     uint64_t node_off;       /* nodes[node_off, +n_nodes) */
     uint64_t str_off;        /* chars[str_off, +len) = spelled path; chars[str_off + pad8(len), +len) = its quality string */
     uint32_t n_hops, n_pops, n_cands, n_aligns;   /* work done: BFS calls, queue pops, candidates scored, alignments */
+    uint64_t seg_off;        /* segs[seg_off, +n_segs): every extractSemiWeakPaths call of the region, in order; the fields above */
+    uint32_t n_segs;         /* describe the last one */
+    uint32_t reserved;
 } rtk_region_result_t;
 
 typedef struct rtk_region_out {
     rtk_region_result_t* results;   /* n_calls */
     rtk_path_node* nodes;
     char* chars;
-    uint64_t n_nodes, n_chars;
+    rtk_region_seg_t* segs;
+    uint64_t n_nodes, n_chars, n_segs;
 } rtk_region_out;
 
 int rtk_region_paths_batch(rtk_ctx* ctx, const rtk_opt* opt, int pass, uint32_t n_calls, const rtk_region_call_t* calls,

@@ -80,12 +80,18 @@ class RtkRegionCall(C.Structure):
 class RtkRegionResult(C.Structure):
     _fields_ = [("status", C.c_uint32), ("bail", C.c_uint32), ("n_nodes", C.c_uint32), ("len", C.c_uint32),
                 ("node_off", C.c_uint64), ("str_off", C.c_uint64), ("n_hops", C.c_uint32), ("n_pops", C.c_uint32),
-                ("n_cands", C.c_uint32), ("n_aligns", C.c_uint32)]
+                ("n_cands", C.c_uint32), ("n_aligns", C.c_uint32), ("seg_off", C.c_uint64), ("n_segs", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class RtkRegionSeg(C.Structure):
+    _fields_ = [("status", C.c_uint32), ("start_weak", C.c_uint32), ("n_nodes", C.c_uint32), ("len", C.c_uint32),
+                ("node_off", C.c_uint64), ("str_off", C.c_uint64), ("shw_dist", C.c_int32), ("shw_first_end", C.c_int32)]
 
 
 class RtkRegionOut(C.Structure):
     _fields_ = [("results", C.POINTER(RtkRegionResult)), ("nodes", C.POINTER(RtkPathNode)), ("chars", C.c_void_p),
-                ("n_nodes", C.c_uint64), ("n_chars", C.c_uint64)]
+                ("segs", C.POINTER(RtkRegionSeg)), ("n_nodes", C.c_uint64), ("n_chars", C.c_uint64), ("n_segs", C.c_uint64)]
 
 
 HIT_DTYPE = np.dtype([("pos", "<u4"), ("unitig", "<u4"), ("dist", "<u4"), ("strand", "<u4")])
@@ -430,6 +436,7 @@ class Context:
             a.weak_off, a.n_weak = len(weak), len(c.get("weak", []))
             a.pid_off, a.pid_len = len(pids), len(c["pids"])
             a.start_pos, a.start_unitig, a.start_strand, a.start_dist = c["start"]
+            a.reserved = 1 if c.get("follow_dead_ends") else 0
             if c.get("end") is None:
                 a.has_end, a.s_len = 0, c["s_len"]
             else:
@@ -458,6 +465,9 @@ class Context:
                 pad = (r.len + 7) & ~7
                 d["seq"] = chars[r.str_off:r.str_off + r.len].decode("latin1")
                 d["qual"] = chars[r.str_off + pad:r.str_off + pad + r.len].decode("latin1")
+                d["segments"] = [{"status": out.segs[j].status, "start_weak": out.segs[j].start_weak, "len": out.segs[j].len,
+                                  "shw_dist": out.segs[j].shw_dist, "shw_first_end": out.segs[j].shw_first_end}
+                                 for j in range(r.seg_off, r.seg_off + r.n_segs)]
             res.append(d)
         self.L.rtk_region_out_free(C.byref(out))
         if stats is not None:

@@ -249,6 +249,7 @@ void run_region_batch(rtk_ctx* ctx, const std::vector<RegionReq*>& reqs, uint64_
             c.has_end = r.has_end ? 1u : 0u;
             if (r.has_end) { c.end_pos = (uint32_t)r.end_pos; c.end_unitig = r.um_end.unitig; c.end_dist = r.um_end.dist; c.end_strand = r.um_end.strand; }
             c.s_len = (uint32_t)r.s->length();
+            c.reserved = r.follow_dead_ends ? 1u : 0u;
         }
         pt.lap(3, 0);
         RegionBatchOut out;
@@ -262,16 +263,22 @@ void run_region_batch(rtk_ctx* ctx, const std::vector<RegionReq*>& reqs, uint64_
             r.status = R.status; r.bail = R.bail;
             g_region_stats[0] += 1;
             if (R.status == 2) { g_region_stats[1] += 1; g_region_stats[2 + std::min<uint32_t>(R.bail, 15u)] += 1; continue; }
-            r.path.clear();
-            r.path.v.resize(R.n_nodes);
-            for (uint32_t i = 0; i < R.n_nodes; ++i) {
-                const rtk_path_node& n = out.nodes[R.node_off + i];
-                r.path.v[i].unitig = n.unitig; r.path.v[i].strand = n.strand; r.path.v[i].dist = n.dist; r.path.v[i].len = n.len;
+            r.segs.resize(R.n_segs);
+            for (uint32_t si = 0; si < R.n_segs; ++si) {
+                const rtk_region_seg_t& S = out.segs[R.seg_off + si];
+                RegionReq::Seg& D = r.segs[si];
+                D.status = S.status; D.start_weak = S.start_weak; D.shw_dist = S.shw_dist; D.shw_first_end = S.shw_first_end;
+                D.path.clear();
+                D.path.v.resize(S.n_nodes);
+                for (uint32_t i = 0; i < S.n_nodes; ++i) {
+                    const rtk_path_node& n = out.nodes[S.node_off + i];
+                    D.path.v[i].unitig = n.unitig; D.path.v[i].strand = n.strand; D.path.v[i].dist = n.dist; D.path.v[i].len = n.len;
+                }
+                D.path.l = S.len;
+                const uint64_t pad = ((uint64_t)S.len + 7) & ~7ull;
+                D.seq.assign(out.chars.data() + S.str_off, S.len);
+                D.path.qual.assign(out.chars.data() + S.str_off + pad, S.len);
             }
-            r.path.l = R.len;
-            const uint64_t pad = ((uint64_t)R.len + 7) & ~7ull;
-            r.seq.assign(out.chars.data() + R.str_off, R.len);
-            r.path.qual.assign(out.chars.data() + R.str_off + pad, R.len);
         }
         pt.lap(3, 2);
     }
@@ -346,6 +353,7 @@ struct GpuBroker::Service {
     std::mutex mu;
     std::condition_variable cv;
     std::vector<std::pair<void*, Fiber*>> q;
+    size_t n_riders = 0;   // queued requests that carry no fiber (extra requests of a task that parked once)
     bool stop = false;
     uint64_t batches = 0, reqs = 0, ns_busy = 0;
 };
@@ -379,6 +387,7 @@ GpuBroker::GpuBroker(rtk_ctx* c) : ctx(c) {
     cnt[0] = cnt[1] = cnt[2] = cnt[3] = 1;
 #endif
     bulk_regions = getenv("RTK_NO_BULK_REGIONS") == nullptr;
+    bulk_all = getenv("RTK_BULK_ALL") != nullptr;
     if (bulk_regions) cnt[3] = 1;   // one bulk launch per wave: a single region service thread
     for (int k = 0; k < 4; ++k)
         for (unsigned i = 0; i < std::max(1u, std::min(cnt[k], 8u)); ++i) {
@@ -405,6 +414,7 @@ void GpuBroker::park(int kind, void* req) {
         std::lock_guard<std::mutex> lk(s->mu);
         s->q.emplace_back(req, f);
     }
+    parked_total.fetch_add(1, std::memory_order_acq_rel);
     s->cv.notify_one();
 #ifdef RTK_FIBER_ASM
     rtk_fiber_switch(&f->sp, w->sched_sp);
@@ -417,6 +427,29 @@ void GpuBroker::submit(DistReq* r) { park(0, r); }
 void GpuBroker::submit(PathReq* r) { park(1, r); }
 void GpuBroker::submit(SubgraphReq* r) { park(2, r); }
 void GpuBroker::submit(RegionReq* r) { park(3, r); }
+// all requests go to one region service; the fiber rides on the last one and is resumed when the batch that holds them all is done
+void GpuBroker::submit(const std::vector<RegionReq*>& rs) {
+    if (rs.empty()) return;
+    Worker* w = tl_worker;
+    if (!w || !w->current) throw std::logic_error("GpuBroker::submit called outside a broker task");
+    if (rs.size() > 1) {
+        Service* s = services[3][0];
+        std::lock_guard<std::mutex> lk(s->mu);
+        for (size_t i = 0; i + 1 < rs.size(); ++i) s->q.emplace_back((void*)rs[i], (Fiber*)nullptr);
+        s->q.emplace_back((void*)rs.back(), w->current);
+        parked_total.fetch_add(1, std::memory_order_acq_rel);
+        s->n_riders += rs.size() - 1;
+    } else { park(3, rs[0]); return; }
+    Service* s = services[3][0];
+    s->cv.notify_one();
+    Fiber* f = w->current;
+#ifdef RTK_FIBER_ASM
+    rtk_fiber_switch(&f->sp, w->sched_sp);
+#else
+    swapcontext(&f->uc, &w->sched);
+#endif
+    if (!f->error.empty()) { std::string e; e.swap(f->error); throw std::runtime_error(e); }
+}
 
 #ifdef RTK_HOSTSIM
 static std::mutex g_sim_launch_mu;   // the CPU simulator runs one launch at a time
@@ -430,7 +463,23 @@ void GpuBroker::service_main(Service* s) {
     const long linger_us = e_lg ? atol(e_lg) : 150;
     for (;;) {
         batch.clear();
-        if (s->kind == 3 && bulk_regions) {
+        if (bulk_all) {
+            // global waves: a service launches when every live fiber is parked somewhere (this queue or another service's)
+            std::unique_lock<std::mutex> lk(s->mu);
+            for (;;) {
+                if (s->stop && s->q.empty()) break;
+                if (!s->q.empty()) {
+                    const size_t live = live_total.load(std::memory_order_acquire);
+                    bool none_to_start;
+                    { std::lock_guard<std::mutex> g(mu_task); none_to_start = next_task >= n_tasks; }
+                    if (parked_total.load(std::memory_order_acquire) >= live && (none_to_start || live >= cap_total)) break;
+                }
+                s->cv.wait_for(lk, std::chrono::microseconds(200));
+            }
+            if (s->q.empty()) break;
+            batch.swap(s->q);
+            s->n_riders = 0;
+        } else if (s->kind == 3 && bulk_regions) {
             // Bulk mode of the region engine: a launch is efficient when it holds thousands of regions (one warp each; its
             // duration is set by the longest region, not by the count).  Regions of a gang reach their region request in
             // waves (first the forward regions of all pieces, then the backward regions of the uncorrected ones, then the
@@ -443,12 +492,13 @@ void GpuBroker::service_main(Service* s) {
                     const size_t live = live_total.load(std::memory_order_acquire);
                     bool none_to_start;
                     { std::lock_guard<std::mutex> g(mu_task); none_to_start = next_task >= n_tasks; }
-                    if (s->q.size() >= live && (none_to_start || live >= cap_total)) break;
+                    if (s->q.size() - s->n_riders >= live && (none_to_start || live >= cap_total)) break;
                 }
                 s->cv.wait_for(lk, std::chrono::microseconds(500));
             }
             if (s->q.empty()) break;
             batch.swap(s->q);
+            s->n_riders = 0;
         } else {
             std::unique_lock<std::mutex> lk(s->mu);
             s->cv.wait(lk, [&] { return s->stop || !s->q.empty(); });
@@ -459,6 +509,7 @@ void GpuBroker::service_main(Service* s) {
                 s->cv.wait_until(lk, deadline, [&] { return s->stop || s->q.size() >= min_batch; });
             }
             batch.swap(s->q);
+            s->n_riders = 0;
         }
         if (batch.empty()) break;
         const auto t0 = std::chrono::steady_clock::now();
@@ -479,6 +530,16 @@ void GpuBroker::service_main(Service* s) {
             std::lock_guard<std::mutex> g(mu_task);
             next_task = n_tasks;
         }
+        if (getenv("RTK_WAVE_LOG") && (s->kind == 3 || bulk_all))
+            fprintf(stderr, "[wave] broker %p kind %d: %zu requests, t = %.1f ms, service call %.1f ms\n", (void*)this, s->kind, batch.size(),
+                    std::chrono::duration_cast<std::chrono::microseconds>(t0 - t_run_begin).count() / 1e3,
+                    std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() / 1e3);
+        {   // requests without a fiber belong to a task that rides on another request of the same batch
+            size_t w2 = 0;
+            for (size_t i = 0; i < batch.size(); ++i) if (batch[i].second) batch[w2++] = batch[i];
+            batch.resize(w2);
+        }
+        parked_total.fetch_sub(batch.size(), std::memory_order_acq_rel);
         // hand the fibers back, grouped per owner so that each worker is locked / woken once
         std::sort(batch.begin(), batch.end(), [](const std::pair<void*, Fiber*>& a, const std::pair<void*, Fiber*>& b) { return a.second->owner < b.second->owner; });
         for (size_t i = 0; i < batch.size();) {
@@ -624,6 +685,8 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
     cap_total = cap_per_worker * n_workers;
     live_total.store(0);
     const auto t_begin = std::chrono::steady_clock::now();
+    t_run_begin = t_begin;
+    parked_total.store(0);
     uint64_t prof0[4][4], rs0[18];
     for (int k = 0; k < 4; ++k) for (int j = 0; j < 4; ++j) prof0[k][j] = g_prof[k][j];
     for (int j = 0; j < 18; ++j) rs0[j] = g_region_stats[j];

@@ -15,6 +15,7 @@
 // worker threads, so thread-local state (current_broker) stays valid across a park.
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -67,10 +68,16 @@ struct RegionReq {
     const std::vector<rtk_hit>* v_w;    // weak anchors of the region
     size_t i_weak;                      // first weak anchor to consider
     const std::vector<uint32_t>* pids;  // WeightsPairID::all_pids
+    bool follow_dead_ends = false;      // run the dead-end restarts of the `correct` lambda on the device too (one segment each)
     // answer
-    uint32_t status = 2, bail = 0;      // 0 complete path, 1 dead-end path, 2 declined (use the request-at-a-time path)
-    GPath path;
-    std::string seq;                    // the path spelled (Path::toString)
+    uint32_t status = 2, bail = 0;      // of the last segment: 0 complete path, 1 dead-end path; 2 = declined (use the request-at-a-time path)
+    struct Seg {
+        uint32_t status, start_weak;    // start_weak: index into v_w (from i_weak = 0) of the anchor the segment starts from, RTK_NONE32 = um_start
+        GPath path;
+        std::string seq;                // the path spelled (Path::toString)
+        int32_t shw_dist, shw_first_end;
+    };
+    std::vector<Seg> segs;
 };
 
 // direct (un-brokered) execution of a set of requests: one batched call per kind
@@ -91,6 +98,7 @@ public:
     void submit(PathReq* r);
     void submit(SubgraphReq* r);
     void submit(RegionReq* r);
+    void submit(const std::vector<RegionReq*>& rs);   // several region requests of one task, one park
     uint64_t waves = 0, jobs = 0;   // batched service calls issued / requests served
     uint64_t kernel_ns[4] = {0, 0, 0, 0};   // GPU kernel time (CUDA events) of the dist / path / subgraph / region services
     uint64_t region_calls = 0, region_bails = 0, region_bail_reason[16] = {0};
@@ -112,6 +120,9 @@ private:
     std::atomic<size_t> live_total{0};   // fibers started and not finished, all workers
     size_t cap_total = 1;                // in-flight cap, all workers
     bool bulk_regions = true;            // the region service launches when every live fiber waits for it (one bulk launch per wave)
+    bool bulk_all = false;               // every service launches only when all live fibers are parked (global waves)
+    std::atomic<size_t> parked_total{0}; // fibers parked at any service and not yet handed back
+    std::chrono::steady_clock::time_point t_run_begin;
     size_t n_tasks = 0, cap_per_worker = 1;
     size_t next_task = 0;      // guarded by mu_task (tasks are handed out in index order)
     std::mutex mu_task;

@@ -404,9 +404,9 @@ PathPair region_paths(const Ctx& C, const std::string& s, const IdSet& all_pids,
         r.s = &s; r.um_start = um_start; r.um_end = um_end; r.has_end = has_end; r.end_pos = end_pos;
         r.v_w = &v_w; r.i_weak = i_weak; r.pids = &all_pids;
         b->submit(&r);
-        if (r.status != 2) {
+        if (r.status != 2 && r.segs.size() == 1) {
             PathPair pp;
-            (r.status == 0 ? pp.first : pp.second).push_back(std::move(r.path));
+            (r.status == 0 ? pp.first : pp.second).push_back(std::move(r.segs[0].path));
             return pp;
         }
     }
@@ -429,26 +429,40 @@ std::pair<int, int> select_prefix_cut(const Ctx& C, const std::vector<GPath>& ca
 }
 
 // ------------------------------------------------------------------ fixAmbiguity (src/Alignment.cpp:527-844), hap_id undetermined
-void fix_ambiguity(const Ctx& C, std::string& query, std::string& quality, const char* ref_seq, size_t ref_len,
-                   const std::vector<std::pair<size_t, char>>& v_ambiguity) {
-    if (v_ambiguity.empty()) return;
+// In two steps around its one alignment (SHW + path of the query with the ambiguity codes filled in against the read window), so
+// that a caller can batch the alignments of several regions into one GPU request.
+struct FixAmbiguity {
+    std::string query_tmp;
+    std::unordered_map<size_t, char> safe, all;
+    bool active = false;
+    // step 1: returns true and fills `job` when an alignment is needed
+    bool begin(const Ctx& C, const std::string& query, const std::string& quality, const char* ref_seq, size_t ref_len,
+               const std::vector<std::pair<size_t, char>>& v_ambiguity, AlignJob& job) {
+        active = false;
+        if (v_ambiguity.empty()) return false;
+        const char q_min_conf_corr = rtk_get_qual(C.opt.min_confidence_snp_corr, 0, C.opt.max_qual);
+        query_tmp = query;
+        safe.clear(); all.clear();
+        for (const auto& p : v_ambiguity) {
+            if (quality[p.first] < q_min_conf_corr) { safe.insert(p); query_tmp[p.first] = p.second; }
+        }
+        all = safe;
+        job.q = query_tmp.substr(0, query.length()); job.t = std::string(ref_seq, ref_len); job.mode = 1; job.tref = nullptr;
+        active = true;
+        return true;
+    }
+    void finish(const Ctx& C, std::string& query, std::string& quality, const char* ref_seq, const std::vector<uint8_t>& ops0);
+};
+
+void FixAmbiguity::finish(const Ctx& C, std::string& query, std::string& quality, const char* ref_seq, const std::vector<uint8_t>& ops0) {
+    if (!active) return;
     const rtk_graph_view& g = C.g;
     const size_t query_len = query.length(), k = g.k;
     const char q_max_corr = rtk_get_qual(1.0, C.opt.out_qual, C.opt.max_qual);
     const char q_min_corr = rtk_get_qual(0.0, C.opt.out_qual, C.opt.max_qual);
     const char q_min_conf_corr = rtk_get_qual(C.opt.min_confidence_snp_corr, 0, C.opt.max_qual);
     const char c_noCorrect = 'X';
-    std::string query_tmp = query;
-    std::unordered_map<size_t, char> safe, all;
-    for (const auto& p : v_ambiguity) {
-        if (quality[p.first] < q_min_conf_corr) { safe.insert(p); query_tmp[p.first] = p.second; }
-    }
-    all = safe;
-    std::vector<AlignJob> j(1);
-    j[0].q = query_tmp.substr(0, query_len); j[0].t = std::string(ref_seq, ref_len); j[0].mode = 1;
-    std::vector<int32_t> d;
-    std::vector<std::vector<uint8_t>> ops;
-    gpu_paths(C.ctx, j, d, ops);
+    std::vector<std::vector<uint8_t>> ops(1, ops0);
     size_t query_pos = 0, target_pos = 0;  // SHW: startLocations[0] == 0
     auto rev = [](char c, bool* a) { const uint8_t i = amb_index(c); a[0] = i & 1; a[1] = i & 2; a[2] = i & 4; a[3] = i & 8; };
     for (const Run& r : runs_of(ops[0])) {
@@ -617,45 +631,63 @@ std::pair<std::string, std::string> generate_consensus(const Ctx& C, const Resul
 }
 
 // ------------------------------------------------------------------ the `correct` lambda (src/Correction.cpp:431-753)
-ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::string& q, const std::vector<rtk_hit>& v_s,
-                                const std::vector<rtk_hit>& v_w, size_t i_s, size_t i_w, const ResultCorrection* rc) {
-    const rtk_graph_view& g = C.g;
-    const rtk_opt& opt = C.opt;
-    const size_t k = g.k;
-    const bool lrc = C.pass2;
-    const bool has_end_pt = (i_s + 1) < v_s.size();
-    const size_t max_len_weak_anchors = lrc ? opt.max_len_weak_region2 : opt.max_len_weak_region1;
-    const char q_min = rtk_get_qual(0.0, 0, opt.max_qual);
-    rtk_hit um_solid1 = v_s[i_s];
-    rtk_hit um_solid2;
-    memset(&um_solid2, 0, sizeof(um_solid2));
-    size_t solid2_pos;
-    if (has_end_pt) { um_solid2 = v_s[i_s + 1]; solid2_pos = um_solid2.pos; }
-    else solid2_pos = s.length() - k;
-    size_t len_weak_region = solid2_pos - um_solid1.pos + k;
-    const int64_t min_start = (int64_t)((size_t)um_solid1.pos - (size_t)opt.insert_sz);
-    const int64_t min_end = (int64_t)(solid2_pos + opt.insert_sz);
-    const char* s_start = s.c_str() + um_solid1.pos;
-    ResultCorrection res(len_weak_region);
+// One call of the lambda as a job in stages, each stage ending where the reference needs a GPU answer:
+//   prepare()  colour selection (chooseColors) and the region's weak anchors            -> `req`, one region-engine request
+//   paths()    the path phase on the engine's segments (or, declined, request by request) -> s_corrected / q_corrected / ranges
+//   amb_begin() / amb_finish()   fixAmbiguity around its one SHW path alignment
+//   trim_begin() / trim_finish() the SHW cut of a not fully corrected region
+// A caller may run the stages of several jobs side by side and batch their alignments (run_piece does so for the forward
+// and backward attempts of a gap); correct_region() runs one job start to end.
+struct InconsistentSegments {};   // thrown when the engine's segments do not replay like the host loop (never seen; kept as a guard)
+
+struct RegionJob {
+    const Ctx& C; const std::string& s; const std::string& q; const std::vector<rtk_hit>& v_s; const std::vector<rtk_hit>& v_w;
+    const size_t i_s, i_w;
+    bool has_end_pt = false;
+    rtk_hit um_solid1, um_solid2;
+    size_t solid2_pos = 0, len_weak_region = 0;
+    const char* s_start = nullptr;
+    ResultCorrection res;
     std::string s_corrected, q_corrected;
     std::vector<std::pair<size_t, char>> v_ambiguity;
     std::vector<rtk_hit> l_v_w;
     IdSet all_pids;
-    // NB: the reference fills q_corrected with len_weak_region (captured by reference, so its CURRENT value) copies of qual
-    auto set_uncorrected = [&](size_t pos, size_t len, char qual) {
-        s_corrected = s.substr(pos, len);
-        q_corrected = lrc ? q.substr(pos, len) : std::string(len_weak_region, qual);
-    };
-    auto add_uncorrected = [&](size_t pos, size_t len, char qual) {
-        s_corrected += s.substr(pos, len);
-        q_corrected += lrc ? q.substr(pos, len) : std::string(len_weak_region, qual);
-    };
+    RegionReq req;
+    bool has_req = false;
+    FixAmbiguity amb;
+    RegionJob(const Ctx& C_, const std::string& s_, const std::string& q_, const std::vector<rtk_hit>& v_s_, const std::vector<rtk_hit>& v_w_, size_t i_s_, size_t i_w_)
+        : C(C_), s(s_), q(q_), v_s(v_s_), v_w(v_w_), i_s(i_s_), i_w(i_w_), res(0) {}
+    void prepare(const IdSet* rc_pids);
+    void paths();
+    void paths_impl(bool use_device);
+    bool amb_begin(AlignJob& j) { return amb.begin(C, s_corrected, q_corrected, s_start, res.old_seq_len, v_ambiguity, j); }
+    void amb_finish(const std::vector<uint8_t>& ops) { amb.finish(C, s_corrected, q_corrected, s_start, ops); }
+    bool trim_begin(AlignJob& j);
+    void trim_finish(int32_t dd, int32_t fe, int32_t le);
+    ResultCorrection& done() { res.seq = std::move(s_corrected); res.qual = std::move(q_corrected); return res; }
+};
+
+void RegionJob::prepare(const IdSet* rc_pids) {
+    const rtk_graph_view& g = C.g;
+    const rtk_opt& opt = C.opt;
+    const size_t k = g.k;
+    has_end_pt = (i_s + 1) < v_s.size();
+    um_solid1 = v_s[i_s];
+    memset(&um_solid2, 0, sizeof(um_solid2));
+    if (has_end_pt) { um_solid2 = v_s[i_s + 1]; solid2_pos = um_solid2.pos; }
+    else solid2_pos = s.length() - k;
+    len_weak_region = solid2_pos - um_solid1.pos + k;
+    const int64_t min_start = (int64_t)((size_t)um_solid1.pos - (size_t)opt.insert_sz);
+    const int64_t min_end = (int64_t)(solid2_pos + opt.insert_sz);
+    s_start = s.c_str() + um_solid1.pos;
+    res = ResultCorrection(len_weak_region);
+    const bool rc = rc_pids != nullptr;
     // `v[i].first > min_start` etc. compare a size_t with an int64_t: the signed side converts to unsigned (a negative
     // min_start becomes huge and the loop body never runs) - reproduced with explicit casts
     const uint64_t u_min_start = (uint64_t)min_start, u_min_end = (uint64_t)min_end;
     auto usable = [&](uint32_t u) { return kmer_coverage(g, u) < (double)C.max_km_cov; };
     const size_t v_w_sz = v_w.size();
-    if (rc == nullptr) {
+    if (!rc) {
         ColorSide s_l, s_m, s_r;
         {
             size_t nb_branching = 0;
@@ -701,11 +733,75 @@ ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::s
             while (i_w_s < v_w_sz && v_w[i_w_s].pos < v_s[i_s].pos) ++i_w_s;
             for (; i_w_s < v_w_sz && v_w[i_w_s].pos < pos_end; ++i_w_s) l_v_w.push_back(v_w[i_w_s]);
         }
-        all_pids = rc->all_pids;
+        all_pids = *rc_pids;
     }
+    // the region-engine request of the path phase (dead ends followed on the device)
+    has_req = false;
+    if (all_pids.size() >= opt.min_cov_vertices && C.device_regions && current_broker()) {
+        req = RegionReq();
+        req.opt = &C.opt; req.pass = C.pass2 ? 2 : 1;
+        req.s = &s; req.um_start = um_solid1; req.um_end = um_solid2; req.has_end = has_end_pt; req.end_pos = solid2_pos;
+        req.v_w = &l_v_w; req.i_weak = 0; req.pids = &all_pids; req.follow_dead_ends = true;
+        has_req = true;
+    }
+}
+
+void RegionJob::paths() {
+    if (has_req && req.status != 2) {
+        const rtk_hit saved1 = um_solid1;
+        const size_t saved_len = len_weak_region;
+        try { paths_impl(true); return; }
+        catch (const InconsistentSegments&) {   // replay the region request by request
+            um_solid1 = saved1; len_weak_region = saved_len;
+            s_corrected.clear(); q_corrected.clear(); v_ambiguity.clear();
+            res = ResultCorrection(saved_len); res.all_pids = all_pids;
+        }
+    }
+    paths_impl(false);
+}
+
+void RegionJob::paths_impl(const bool use_device) {
+    const rtk_graph_view& g = C.g;
+    const rtk_opt& opt = C.opt;
+    const size_t k = g.k;
+    const bool lrc = C.pass2;
+    const size_t max_len_weak_anchors = lrc ? opt.max_len_weak_region2 : opt.max_len_weak_region1;
+    const char q_min = rtk_get_qual(0.0, 0, opt.max_qual);
+    // NB: the reference fills q_corrected with len_weak_region (captured by reference, so its CURRENT value) copies of qual
+    auto set_uncorrected = [&](size_t pos, size_t len, char qual) {
+        s_corrected = s.substr(pos, len);
+        q_corrected = lrc ? q.substr(pos, len) : std::string(len_weak_region, qual);
+    };
+    auto add_uncorrected = [&](size_t pos, size_t len, char qual) {
+        s_corrected += s.substr(pos, len);
+        q_corrected += lrc ? q.substr(pos, len) : std::string(len_weak_region, qual);
+    };
+    // the two GPU-backed steps of the loop: extractSemiWeakPaths and the prefix alignment of a dead-end path.  With the engine's
+    // answer they read its segments (one per extractSemiWeakPaths call, in order); otherwise they are requests of their own.
+    size_t seg = 0;
+    std::vector<std::string> seg_str;   // spelled path of the current segment (the engine spells it)
+    auto eswp = [&](size_t i_weak_arg, bool initial) -> PathPair {
+        if (!use_device) return region_paths(C, s, all_pids, um_solid1, has_end_pt, um_solid2, solid2_pos, l_v_w, i_weak_arg);
+        if (!initial) ++seg;
+        if (seg >= req.segs.size()) throw InconsistentSegments();
+        RegionReq::Seg& S = req.segs[seg];
+        if (S.start_weak != (initial ? RTK_NONE32 : (uint32_t)i_weak_arg)) throw InconsistentSegments();
+        PathPair pp;
+        (S.status == 0 ? pp.first : pp.second).push_back(std::move(S.path));
+        return pp;
+    };
+    auto spelled = [&](const GPath& po) -> std::string { return use_device ? req.segs[seg].seq : po.to_string(g); };
+    auto prefix_cut = [&](const std::vector<GPath>& cands, const std::string& ref) -> std::pair<int, int> {
+        if (!use_device) return select_prefix_cut(C, cands, ref, opt.weak_region_len_factor);
+        const RegionReq::Seg& S = req.segs[seg];
+        if (cands.size() != 1 || S.status != 1) throw InconsistentSegments();
+        const double best = static_cast<double>(S.shw_dist) / cands[0].length();
+        if (opt.weak_region_len_factor > 0.0 && best > opt.weak_region_len_factor) return {-1, -1};
+        return {0, S.shw_first_end};
+    };
     const size_t card_pids = all_pids.size();
     PathPair paths1;
-    if (card_pids >= opt.min_cov_vertices) paths1 = region_paths(C, s, all_pids, um_solid1, has_end_pt, um_solid2, solid2_pos, l_v_w, 0);
+    if (card_pids >= opt.min_cov_vertices) paths1 = eswp(0, true);
     auto emit_path = [&](const GPath& p, bool offset_amb) {
         const std::vector<std::pair<size_t, char>> v_amb = ambiguity_vector(g, p.v);
         for (const auto& a : v_amb) v_ambiguity.push_back({(offset_amb ? s_corrected.length() : 0) + a.first, a.second});
@@ -713,7 +809,7 @@ ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::s
     if (paths1.first.empty()) {
         size_t i_w_s = 0;
         while (paths1.first.empty() && !paths1.second.empty() && !l_v_w.empty() && card_pids >= opt.min_cov_vertices) {
-            const std::pair<int, int> align = select_prefix_cut(C, paths1.second, s.substr(um_solid1.pos, len_weak_region), opt.weak_region_len_factor);
+            const std::pair<int, int> align = prefix_cut(paths1.second, s.substr(um_solid1.pos, len_weak_region));
             if (align.first == -1) break;
             {
                 const size_t next_pos = um_solid1.pos + align.second + k;
@@ -723,31 +819,31 @@ ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::s
             const GPath& po = paths1.second[(size_t)align.first];
             emit_path(po, true);
             const size_t gap = l_v_w[i_w_s].pos - um_solid1.pos - align.second - 1;
-            s_corrected += po.to_string(g) + s.substr(um_solid1.pos + align.second + 1, gap);
+            s_corrected += spelled(po) + s.substr(um_solid1.pos + align.second + 1, gap);
             q_corrected += po.qual;
             if (lrc) q_corrected += q.substr(um_solid1.pos + align.second + 1, gap);
             else q_corrected += std::string(gap, q_min);
             res.add_range(um_solid1.pos - v_s[i_s].pos, um_solid1.pos + align.second + 1 - v_s[i_s].pos);
             um_solid1 = l_v_w[i_w_s];
             len_weak_region = solid2_pos - um_solid1.pos + k;
-            paths1 = region_paths(C, s, all_pids, um_solid1, has_end_pt, um_solid2, solid2_pos, l_v_w, i_w_s);
+            paths1 = eswp(i_w_s, false);
         }
         if (!paths1.first.empty()) {
             // a single candidate wins whatever its distance (and the end location is not used here): no alignment needed
             const std::pair<int, int> pa = paths1.first.size() == 1 ? std::pair<int, int>(0, -1) : select_best_alignment(C.ctx, g, paths1.first, s.substr(um_solid1.pos, len_weak_region));
             const GPath& po = paths1.first[(size_t)pa.first];
             emit_path(po, true);
-            s_corrected += po.to_string(g);
+            s_corrected += spelled(po);
             q_corrected += po.qual;
             res.add_range(um_solid1.pos - v_s[i_s].pos, solid2_pos - v_s[i_s].pos + k);
         } else if (!paths1.second.empty()) {
-            const std::pair<int, int> align = select_prefix_cut(C, paths1.second, s.substr(um_solid1.pos, len_weak_region), opt.weak_region_len_factor);
+            const std::pair<int, int> align = prefix_cut(paths1.second, s.substr(um_solid1.pos, len_weak_region));
             if (align.first == -1) add_uncorrected(um_solid1.pos, len_weak_region, q_min);
             else {
                 const GPath& po = paths1.second[(size_t)align.first];
                 emit_path(po, true);
                 const size_t gap = len_weak_region - align.second - 1;
-                s_corrected += po.to_string(g) + s.substr(um_solid1.pos + align.second + 1, gap);
+                s_corrected += spelled(po) + s.substr(um_solid1.pos + align.second + 1, gap);
                 q_corrected += po.qual;
                 if (lrc) q_corrected += q.substr(um_solid1.pos + align.second + 1, gap);
                 else q_corrected += std::string(gap, q_min);
@@ -759,11 +855,16 @@ ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::s
         const std::pair<int, int> pa = paths1.first.size() == 1 ? std::pair<int, int>(0, -1) : select_best_alignment(C.ctx, g, paths1.first, s.substr(um_solid1.pos, len_weak_region));
         const GPath& po = paths1.first[(size_t)pa.first];
         emit_path(po, false);
-        s_corrected = po.to_string(g);
+        s_corrected = spelled(po);
         q_corrected = po.qual;
         res.add_range(0, len_weak_region);
     }
-    fix_ambiguity(C, s_corrected, q_corrected, s_start, res.old_seq_len, v_ambiguity);
+    if (use_device && seg + 1 != req.segs.size()) throw InconsistentSegments();
+}
+
+// after fixAmbiguity: fully corrected?  else the SHW alignment of the raw window against the correction that trims it (:727-747)
+bool RegionJob::trim_begin(AlignJob& job) {
+    const size_t k = C.g.k;
     if (res.nb_corrected() == res.old_seq_len) {
         // Kmer(end of s) == Kmer(end of s_corrected): Kmer::set_kmer maps characters through bit tricks, compare the same way
         bool same = s_corrected.length() >= k;
@@ -774,23 +875,59 @@ ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::s
         }
         if (same) res.is_corrected = true;
     }
-    if (!res.is_corrected) {
-        std::vector<AlignJob> j(1);
-        j[0].q = s.substr(v_s[i_s].pos, solid2_pos - v_s[i_s].pos + k);
-        j[0].t = s_corrected; j[0].mode = 1;
-        // the largest best end is kept (:735-741); the reference scans endLocations[] as size_t, so a first end of -1 (edlib's
-        // "position -1") wraps to the maximum and wins
-        std::vector<int32_t> dd, fe, le;
-        gpu_distances_fl(C.ctx, j, dd, fe, le);
-        if (dd[0] >= 0) {
-            const size_t end_location = (fe[0] < 0) ? (size_t)fe[0] : (size_t)le[0];
-            s_corrected = s_corrected.substr(0, end_location + 1);
-            q_corrected = q_corrected.substr(0, end_location + 1);
+    if (res.is_corrected) return false;
+    job.q = s.substr(v_s[i_s].pos, solid2_pos - v_s[i_s].pos + k);
+    job.t = s_corrected; job.mode = 1; job.tref = nullptr;
+    return true;
+}
+
+void RegionJob::trim_finish(const int32_t dd, const int32_t fe, const int32_t le) {
+    // the largest best end is kept (:735-741); the reference scans endLocations[] as size_t, so a first end of -1 (edlib's
+    // "position -1") wraps to the maximum and wins
+    if (dd >= 0) {
+        const size_t end_location = (fe < 0) ? (size_t)fe : (size_t)le;
+        s_corrected = s_corrected.substr(0, end_location + 1);
+        q_corrected = q_corrected.substr(0, end_location + 1);
+    }
+}
+
+// the stages of up to two jobs side by side: ONE region-engine request (both path searches), one K5 request (both fixAmbiguity
+// alignments), one K4 request (both trims)
+void run_region_jobs(const Ctx& C, RegionJob* a, RegionJob* b) {
+    RegionJob* jobs[2] = {a, b};
+    std::vector<RegionReq*> reqs;
+    for (RegionJob* j : jobs) if (j && j->has_req) reqs.push_back(&j->req);
+    if (!reqs.empty()) current_broker()->submit(reqs);
+    for (RegionJob* j : jobs) if (j) j->paths();
+    {
+        std::vector<AlignJob> aj;
+        RegionJob* who[2]; size_t n = 0;
+        for (RegionJob* j : jobs) if (j) { AlignJob x; if (j->amb_begin(x)) { aj.push_back(std::move(x)); who[n++] = j; } }
+        if (n) {
+            std::vector<int32_t> d;
+            std::vector<std::vector<uint8_t>> ops;
+            gpu_paths(C.ctx, aj, d, ops);
+            for (size_t i = 0; i < n; ++i) who[i]->amb_finish(ops[i]);
         }
     }
-    res.seq = std::move(s_corrected);
-    res.qual = std::move(q_corrected);
-    return res;
+    {
+        std::vector<AlignJob> aj;
+        RegionJob* who[2]; size_t n = 0;
+        for (RegionJob* j : jobs) if (j) { AlignJob x; if (j->trim_begin(x)) { aj.push_back(std::move(x)); who[n++] = j; } }
+        if (n) {
+            std::vector<int32_t> dd, fe, le;
+            gpu_distances_fl(C.ctx, aj, dd, fe, le);
+            for (size_t i = 0; i < n; ++i) who[i]->trim_finish(dd[i], fe[i], le[i]);
+        }
+    }
+}
+
+ResultCorrection correct_region(const Ctx& C, const std::string& s, const std::string& q, const std::vector<rtk_hit>& v_s,
+                                const std::vector<rtk_hit>& v_w, size_t i_s, size_t i_w, const ResultCorrection* rc) {
+    RegionJob job(C, s, q, v_s, v_w, i_s, i_w);
+    job.prepare(rc ? &rc->all_pids : nullptr);
+    run_region_jobs(C, &job, nullptr);
+    return std::move(job.done());
 }
 
 inline bool has_min_qual(const std::string& s, const std::string& q, size_t start, size_t end, char min_q) {
@@ -901,7 +1038,19 @@ void run_piece(const Ctx& C, const ReadJob& J, Piece& P) {
                         } else corrected_q += std::string((p0 - prev_pos) + (s_um_sub.length() - k), q_max);
                     } else isUncorrected = true;
                 } else if (p1 >= p0 + k) {
-                    const ResultCorrection fw = correct_region(C, s_fw, q_fw, v_um_solid, v_um_weak, i_solid, i_weak, nullptr);
+                    // The backward attempt only runs when the forward one leaves the region not fully corrected - which is the common
+                    // case on noisy reads (9 in 10 regions here) - and depends on the forward attempt through its colour set alone, known
+                    // before any path search.  Both attempts are therefore prepared together and share every GPU request; a backward
+                    // result the forward attempt makes unnecessary is dropped.
+                    const size_t i_solid_bw = solid_rev.size() - i_solid - 2;
+                    size_t i_weak_bw = weak_rev.size() - i_weak;
+                    while (i_weak_bw > 0 && weak_rev[i_weak_bw - 1].pos > solid_rev[i_solid_bw].pos) --i_weak_bw;
+                    RegionJob jf(C, s_fw, q_fw, v_um_solid, v_um_weak, i_solid, i_weak);
+                    jf.prepare(nullptr);
+                    RegionJob jb(C, s_bw, q_bw, solid_rev, weak_rev, i_solid_bw, i_weak_bw);
+                    jb.prepare(&jf.all_pids);
+                    run_region_jobs(C, &jf, &jb);
+                    const ResultCorrection fw = std::move(jf.done());
                     if (fw.is_corrected) {
                         const size_t l_solid = p0 - prev_pos;
                         const std::string sub = s_fw.substr(prev_pos, l_solid) + fw.seq;
@@ -909,10 +1058,7 @@ void run_piece(const Ctx& C, const ReadJob& J, Piece& P) {
                         corrected_s += sub.substr(0, sub.length() - k);
                         corrected_q += subq.substr(0, subq.length() - k);
                     } else {
-                        const size_t i_solid_bw = solid_rev.size() - i_solid - 2;
-                        size_t i_weak_bw = weak_rev.size() - i_weak;
-                        while (i_weak_bw > 0 && weak_rev[i_weak_bw - 1].pos > solid_rev[i_solid_bw].pos) --i_weak_bw;
-                        ResultCorrection bw = correct_region(C, s_bw, q_bw, solid_rev, weak_rev, i_solid_bw, i_weak_bw, &fw);
+                        ResultCorrection bw = std::move(jb.done());
                         bw.reverse_complement();
                         if (bw.is_corrected) {
                             const size_t l_solid = (s_bw.length() - solid_rev[i_solid_bw + 1].pos - k) - prev_pos;

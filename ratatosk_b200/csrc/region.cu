@@ -27,7 +27,7 @@ static uint32_t region_slots(const rtk_ctx* c) {
 void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls, const rtk_region_call_t* calls, const char* win_pool,
                       uint64_t win_bytes, const rtk_hit* weak_pool, uint64_t n_weak, const uint32_t* pid_pool, uint64_t n_pids, RegionBatchOut& out) {
     out.results.assign(n_calls, rtk_region_result_t());
-    out.nodes.clear(); out.chars.clear(); out.kernel_ms = 0.f;
+    out.nodes.clear(); out.chars.clear(); out.segs.clear(); out.kernel_ms = 0.f;
     if (!n_calls) return;
     if (!c->has_graph) throw std::invalid_argument("no graph uploaded to this context");
     if (opt.k != c->hdr.k) throw std::invalid_argument("rtk_opt.k does not match the graph's k");
@@ -55,8 +55,9 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     char* d = c->d_rg[0].as<char>();
     RTK_CUDA(counted_memcpy_async(d, h, total, cudaMemcpyHostToDevice, st));
     // ---- outputs and scratch
-    uint64_t nodes_cap, chars_cap;
-    region_out_caps(n_calls, calls, nodes_cap, chars_cap);
+    uint64_t nodes_cap, chars_cap, segs_cap;
+    region_out_caps(n_calls, calls, nodes_cap, chars_cap, segs_cap);
+    c->d_rg[6].reserve(segs_cap * sizeof(rtk_region_seg_t));
     c->d_rg[1].reserve((uint64_t)n_calls * sizeof(rtk_region_result_t));
     c->d_rg[2].reserve(nodes_cap * sizeof(rtk_path_node));
     c->d_rg[3].reserve(chars_cap);
@@ -72,7 +73,7 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     p.results = c->d_rg[1].as<rtk_rg_result>();
     p.out_nodes = c->d_rg[2].as<rtk_rg_node>(); p.out_chars = c->d_rg[3].as<char>();
     p.out_top = c->d_rg[4].as<unsigned long long>(); p.slot_flags = (uint32_t*)(c->d_rg[4].as<char>() + 64); p.n_slots = n_slots;
-    p.out_nodes_cap = nodes_cap; p.out_chars_cap = chars_cap;
+    p.out_nodes_cap = nodes_cap; p.out_chars_cap = chars_cap; p.out_segs = c->d_rg[6].as<rtk_region_seg_t>(); p.out_segs_cap = segs_cap;
     p.scratch = c->d_rg[5].as<unsigned char>();
     RTK_CUDA(cudaEventRecord(c->ev0, st));
     ++g_launches;
@@ -84,21 +85,26 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     PinBuf& HR = c->h_rg[1];
     HR.reserve(b_res + 64);
     RTK_CUDA(counted_memcpy_async(HR.p, c->d_rg[1].p, b_res, cudaMemcpyDeviceToHost, st));
-    RTK_CUDA(counted_memcpy_async(HR.as<char>() + b_res, c->d_rg[4].p, 16, cudaMemcpyDeviceToHost, st));
+    RTK_CUDA(counted_memcpy_async(HR.as<char>() + b_res, c->d_rg[4].p, 24, cudaMemcpyDeviceToHost, st));
     stream_wait(st);
     memcpy(out.results.data(), HR.p, b_res);
-    unsigned long long tops[2];
-    memcpy(tops, HR.as<char>() + b_res, 16);
-    const uint64_t used_nodes = std::min<uint64_t>(tops[0], nodes_cap), used_chars = std::min<uint64_t>(tops[1], chars_cap);
+    unsigned long long tops[3];
+    memcpy(tops, HR.as<char>() + b_res, 24);
+    const uint64_t used_nodes = std::min<uint64_t>(tops[0], nodes_cap), used_chars = std::min<uint64_t>(tops[1], chars_cap),
+                   used_segs = std::min<uint64_t>(tops[2], segs_cap);
+    const uint64_t b_nodes = used_nodes * sizeof(rtk_path_node), b_segs = used_segs * sizeof(rtk_region_seg_t);
     PinBuf& HO = c->h_rg[2];
-    HO.reserve(used_nodes * sizeof(rtk_path_node) + used_chars + 64);
-    if (used_nodes) RTK_CUDA(counted_memcpy_async(HO.p, c->d_rg[2].p, used_nodes * sizeof(rtk_path_node), cudaMemcpyDeviceToHost, st));
-    if (used_chars) RTK_CUDA(counted_memcpy_async(HO.as<char>() + used_nodes * sizeof(rtk_path_node), c->d_rg[3].p, used_chars, cudaMemcpyDeviceToHost, st));
+    HO.reserve(b_nodes + b_segs + used_chars + 64);
+    if (used_nodes) RTK_CUDA(counted_memcpy_async(HO.p, c->d_rg[2].p, b_nodes, cudaMemcpyDeviceToHost, st));
+    if (used_segs) RTK_CUDA(counted_memcpy_async(HO.as<char>() + b_nodes, c->d_rg[6].p, b_segs, cudaMemcpyDeviceToHost, st));
+    if (used_chars) RTK_CUDA(counted_memcpy_async(HO.as<char>() + b_nodes + b_segs, c->d_rg[3].p, used_chars, cudaMemcpyDeviceToHost, st));
     stream_wait(st);
     out.nodes.resize(used_nodes);
+    out.segs.resize(used_segs);
     out.chars.resize(used_chars);
-    if (used_nodes) memcpy(out.nodes.data(), HO.p, used_nodes * sizeof(rtk_path_node));
-    if (used_chars) memcpy(out.chars.data(), HO.as<char>() + used_nodes * sizeof(rtk_path_node), used_chars);
+    if (used_nodes) memcpy(out.nodes.data(), HO.p, b_nodes);
+    if (used_segs) memcpy(out.segs.data(), HO.as<char>() + b_nodes, b_segs);
+    if (used_chars) memcpy(out.chars.data(), HO.as<char>() + b_nodes + b_segs, used_chars);
     RTK_CUDA(cudaEventElapsedTime(&out.kernel_ms, c->ev0, c->ev1));
 }
 
@@ -120,17 +126,19 @@ extern "C" int rtk_region_paths_batch(rtk_ctx* c, const rtk_opt* opt, int pass, 
         out->results = (rtk_region_result_t*)malloc(sizeof(rtk_region_result_t) * ((size_t)n_calls + 1));
         out->nodes = (rtk_path_node*)malloc(sizeof(rtk_path_node) * (r.nodes.size() + 1));
         out->chars = (char*)malloc(r.chars.size() + 1);
-        if (!out->results || !out->nodes || !out->chars) { free(out->results); free(out->nodes); free(out->chars); memset(out, 0, sizeof(*out)); throw std::bad_alloc(); }
+        out->segs = (rtk_region_seg_t*)malloc(sizeof(rtk_region_seg_t) * (r.segs.size() + 1));
+        if (!out->results || !out->nodes || !out->chars || !out->segs) { free(out->results); free(out->nodes); free(out->chars); free(out->segs); memset(out, 0, sizeof(*out)); throw std::bad_alloc(); }
         if (n_calls) memcpy(out->results, r.results.data(), sizeof(rtk_region_result_t) * (size_t)n_calls);
         if (!r.nodes.empty()) memcpy(out->nodes, r.nodes.data(), sizeof(rtk_path_node) * r.nodes.size());
         if (!r.chars.empty()) memcpy(out->chars, r.chars.data(), r.chars.size());
-        out->n_nodes = r.nodes.size(); out->n_chars = r.chars.size();
+        if (!r.segs.empty()) memcpy(out->segs, r.segs.data(), sizeof(rtk_region_seg_t) * r.segs.size());
+        out->n_nodes = r.nodes.size(); out->n_chars = r.chars.size(); out->n_segs = r.segs.size();
         if (stats) { stats[0] += n_calls; stats[2] += (uint64_t)(r.kernel_ms * 1e6); }
     });
 }
 
 extern "C" void rtk_region_out_free(rtk_region_out* o) {
     if (!o) return;
-    free(o->results); free(o->nodes); free(o->chars);
+    free(o->results); free(o->nodes); free(o->chars); free(o->segs);
     memset(o, 0, sizeof(*o));
 }

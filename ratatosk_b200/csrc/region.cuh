@@ -40,6 +40,7 @@
 #endif
 #define RTK_RG_QCAP 512         /* max_sz_stck of the reference: reaching it collapses the queue (bail) */
 #define RTK_RG_VCAP 1024        /* max_paths of the reference */
+#define RTK_RG_MAX_SEGS 32       /* extractSemiWeakPaths restarts of one region (dead ends followed) */
 #define RTK_RG_DROPPED 0xFFFFFFFEu /* queue marker: a path that is dropped when popped (already >= max_len_path) */
 
 // why a region was handed back to the host path
@@ -79,11 +80,12 @@ struct rtk_rg_params {
     const rtk_hit* weak_pool;
     const uint32_t* pid_pool;
     rtk_rg_result* results;
-    // outputs, bump-allocated by the finishing warps: out_top[0] nodes used, out_top[1] chars used
+    // outputs, bump-allocated by the finishing warps: out_top[0] nodes used, out_top[1] chars used, out_top[2] segments
     rtk_rg_node* out_nodes;
     char* out_chars;
+    rtk_region_seg_t* out_segs;  // out_top[2]
     unsigned long long* out_top;
-    uint64_t out_nodes_cap, out_chars_cap;
+    uint64_t out_nodes_cap, out_chars_cap, out_segs_cap;
     uint32_t* slot_flags;        // n_slots flags: scratch slots (one per resident CTA) handed out by atomic compare-and-swap
     uint32_t n_slots;
     // per-warp scratch
@@ -108,7 +110,7 @@ struct rtk_rg_params {
 // bytes of per-warp scratch for the capacities in p (shared by the host launcher and the kernel's carve-up)
 RTK_HD uint64_t rtk_rg_align16(const uint64_t x) { return (x + 15ull) & ~15ull; }
 struct rtk_rg_layout {
-    uint64_t sA, sB, sC, hb, mat, anc, dfs, dfs_cur, tmpT, tmpN, arena, q_items, v_items, vt_items, ch_nodes, ch_qual, total;
+    uint64_t sA, sB, sC, hb, mat, anc, dfs, dfs_cur, segs, tmpT, tmpN, arena, q_items, v_items, vt_items, ch_nodes, ch_qual, total;
 };
 RTK_HD rtk_rg_layout rtk_rg_make_layout(const uint32_t str_cap, const uint32_t mat_cells, const uint32_t tmp_cap, const uint32_t arena_cap,
                                         const uint32_t chain_nodes_cap, const uint32_t chain_len_cap) {
@@ -122,6 +124,7 @@ RTK_HD rtk_rg_layout rtk_rg_make_layout(const uint32_t str_cap, const uint32_t m
     L.anc = o; o += rtk_rg_align16((uint64_t)mat_cells * 4);
     L.dfs = o; o += rtk_rg_align16((uint64_t)RTK_DFS_STACK * sizeof(rtk_dfs_frame));
     L.dfs_cur = o; o += rtk_rg_align16(sizeof(rtk_dfs_frame));
+    L.segs = o; o += rtk_rg_align16((uint64_t)RTK_RG_MAX_SEGS * sizeof(rtk_region_seg_t));
     L.tmpT = o; o += rtk_rg_align16(tmp_cap);
     L.tmpN = o; o += rtk_rg_align16(tmp_cap);
     L.arena = o; o += rtk_rg_align16(arena_cap);
@@ -152,6 +155,7 @@ struct rg_ctx {
     int8_t* hb;
     ulonglong2* mat; int32_t* anc;
     rtk_dfs_frame* dfs; rtk_dfs_frame* dfs_cur;
+    rtk_region_seg_t* segs;
     unsigned char* tmpT; unsigned char* tmpN; unsigned char* arena;
     uint32_t* q_items; uint32_t* v_items; uint32_t* vt_items;
     rtk_rg_node* ch_nodes; char* ch_qual;
@@ -982,10 +986,12 @@ __device__ RTK_RG_NOINLINE uint32_t rg_hop(rg_ctx& C, const char* __restrict__ r
 }
 
 // ------------------------------------------------------------------------------------------------ the region chain
-// extractSemiWeakPaths (src/Correction.cpp:3-157).  Every hop returns at most one path, so the reference's path lists never
-// hold more than one entry: the chain is a single accumulated path (Path::merge) that either reaches the right anchor / the
-// end of the read (status 0) or dead-ends at a weak anchor (status 1).
-__device__ __forceinline__ void rg_region(rg_ctx& C, const rtk_rg_task& T, rtk_rg_result& R) {
+// extractSemiWeakPaths (src/Correction.cpp:3-157) from the anchor (s_pos, s_unitig, s_dist, s_strand), weak anchors considered
+// from index i_weak0 on.  Every hop returns at most one path, so the reference's path lists never hold more than one entry:
+// the chain is a single accumulated path (Path::merge) in C.ch_nodes / C.ch_qual that either reaches the right anchor / the
+// end of the read (returns 0) or dead-ends at a weak anchor (returns 1).  cn / cl = its vertices / spelled length.
+__device__ __forceinline__ uint32_t rg_eswp(rg_ctx& C, const rtk_rg_task& T, const uint32_t s_pos, const uint32_t s_unitig, const uint32_t s_dist,
+                                            const uint32_t s_strand, const uint64_t i_weak0, uint32_t& cn, uint32_t& cl) {
     const rtk_rg_params& p = *C.p;
     const uint32_t k = p.k, lane = C.lane;
     const char* win = p.win_pool + T.win_off;
@@ -995,17 +1001,18 @@ __device__ __forceinline__ void rg_region(rg_ctx& C, const rtk_rg_task& T, rtk_r
     const uint64_t pos_um_solid2 = no_end ? (uint64_t)T.s_len - k : (uint64_t)T.end_pos;
     const uint64_t max_len_weak_region = p.max_len_weak_region;
     const uint64_t n_weak = T.n_weak;
-    uint64_t i_weak = 0, next_weak_pos = 0;
+    uint64_t i_weak = i_weak0, next_weak_pos = 0;
     bool begin = true, end = false, alive = true;
     // chain = the start anchor's k-mer
-    uint32_t cn = 1, cl = k;
-    uint64_t chain_pos = T.start_pos;
+    cn = 1; cl = k;
+    uint64_t chain_pos = s_pos;
     const char qmax = rg_get_qual(1.0, 0, p.max_qual);
-    if (lane == 0) { rtk_rg_node s; s.unitig = T.start_unitig; s.strand = T.start_strand; s.dist = T.start_dist; s.len = 1; C.ch_nodes[0] = s; }
+    __syncwarp();
+    if (lane == 0) { rtk_rg_node s; s.unitig = s_unitig; s.strand = s_strand; s.dist = s_dist; s.len = 1; C.ch_nodes[0] = s; }
     for (uint32_t i = lane; i < k; i += 32) C.ch_qual[i] = qmax;
     __syncwarp();
-    while (i_weak < n_weak && (uint64_t)vw[i_weak].pos < (uint64_t)T.start_pos) ++i_weak;
-    if (i_weak < n_weak) { const uint64_t a = vw[i_weak].pos, b = (uint64_t)T.start_pos + k; next_weak_pos = a > b ? a : b; }
+    while (i_weak < n_weak && (uint64_t)vw[i_weak].pos < (uint64_t)s_pos) ++i_weak;
+    if (i_weak < n_weak) { const uint64_t a = vw[i_weak].pos, b = (uint64_t)s_pos + k; next_weak_pos = a > b ? a : b; }
     while (alive && !end && !C.bail) {
         if (i_weak < n_weak) {
             while (i_weak < n_weak && (uint64_t)vw[i_weak].pos < (pos_um_solid2 - k) && (uint64_t)vw[i_weak].pos < next_weak_pos) ++i_weak;
@@ -1015,7 +1022,7 @@ __device__ __forceinline__ void rg_region(rg_ctx& C, const rtk_rg_task& T, rtk_r
         if (target_pos < chain_pos) { C.bail = RTK_RG_BAIL_LOGIC; break; }
         const uint64_t l_len = (target_pos - chain_pos) + k;
         rtk_rg_node um_s = C.ch_nodes[cn - 1];
-        if (begin) { um_s.unitig = T.start_unitig; um_s.strand = T.start_strand; um_s.dist = T.start_dist; um_s.len = 1; }
+        if (begin) { um_s.unitig = s_unitig; um_s.strand = s_strand; um_s.dist = s_dist; um_s.len = 1; }
         const uint64_t woff = chain_pos - T.start_pos;
         if (woff + l_len > (uint64_t)T.win_len) { C.bail = RTK_RG_BAIL_LOGIC; break; }
         const char* ref = win + woff;
@@ -1051,25 +1058,89 @@ __device__ __forceinline__ void rg_region(rg_ctx& C, const rtk_rg_task& T, rtk_r
         if (!end) next_weak_pos = (uint64_t)vw[i_weak].pos + k;
         begin = false;
     }
+    return alive ? 0u : 1u;
+}
+
+// The path phase of the `correct` lambda (src/Correction.cpp:613-651): extractSemiWeakPaths from the left anchor; when it
+// dead-ends (and the call asks for it: rtk_region_call_t::reserved bit 0), the best prefix alignment of the dead-end path
+// against the rest of the window (selectBestPrefixAlignment with the weak_region_len_factor cut, src/Alignment.cpp:47-97)
+// says how far the path is trusted; the search restarts from the next weak anchor behind that point, until a path reaches
+// the end, no anchor is left or a prefix fails the cut.  Each extractSemiWeakPaths call yields one SEGMENT (path, status,
+// prefix alignment); the host stitches them exactly like the reference loop.
+__device__ __forceinline__ void rg_region(rg_ctx& C, const rtk_rg_task& T, rtk_rg_result& R) {
+    const rtk_rg_params& p = *C.p;
+    const uint32_t k = p.k, lane = C.lane;
+    const rtk_hit* vw = p.weak_pool + T.weak_off;
+    const uint64_t pos_um_solid2 = T.has_end ? (uint64_t)T.end_pos : (uint64_t)T.s_len - k;
+    const bool follow = (T.reserved & 1u) != 0;
+    uint32_t s_pos = T.start_pos, s_unitig = T.start_unitig, s_dist = T.start_dist, s_strand = T.start_strand;
+    uint32_t start_idx = RTK_NONE32;   // weak-anchor index the current segment starts from (none: the left anchor)
+    uint64_t i_w_s = 0;
+    uint32_t n_segs = 0;
+    rtk_region_seg_t last;
+    last.status = 2; last.start_weak = RTK_NONE32; last.n_nodes = 0; last.len = 0; last.node_off = 0; last.str_off = 0; last.shw_dist = -1; last.shw_first_end = -1;
+    while (!C.bail) {
+        uint32_t cn = 0, cl = 0;
+        const uint32_t status = rg_eswp(C, T, s_pos, s_unitig, s_dist, s_strand, start_idx == RTK_NONE32 ? 0ull : i_w_s, cn, cl);
+        if (C.bail) break;
+        if (n_segs >= RTK_RG_MAX_SEGS) { C.bail = RTK_RG_BAIL_CHAIN; break; }
+        // publish the segment's path: vertices + spelled string + quality string, bump-allocated from the output pools
+        unsigned long long no = 0, so = 0;
+        if (lane == 0) {
+            no = atomicAdd(&p.out_top[0], (unsigned long long)cn);
+            so = atomicAdd(&p.out_top[1], (unsigned long long)(2ull * rg_pad8(cl)));
+        }
+        no = __shfl_sync(0xffffffffu, no, 0);
+        so = __shfl_sync(0xffffffffu, so, 0);
+        if (no + cn > p.out_nodes_cap || so + 2ull * rg_pad8(cl) > p.out_chars_cap) { C.bail = RTK_RG_BAIL_CHAIN; break; }
+        for (uint32_t i = lane; i < cn; i += 32) p.out_nodes[no + i] = C.ch_nodes[i];
+        char* ostr = p.out_chars + so;
+        rg_spell_nodes(C, C.ch_nodes, cn, ostr);
+        char* oq = ostr + rg_pad8(cl);
+        for (uint32_t i = lane; i < cl; i += 32) oq[i] = C.ch_qual[i];
+        __syncwarp();
+        last.status = status; last.start_weak = start_idx; last.n_nodes = cn; last.len = cl; last.node_off = no; last.str_off = so;
+        last.shw_dist = -1; last.shw_first_end = -1;
+        bool again = false;
+        if (status == 1 && follow) {
+            // select_prefix_cut: SHW of the dead-end path against the window from this segment's start (first end location)
+            const uint64_t woff = (uint64_t)s_pos - T.start_pos;
+            const uint32_t wlen = (uint32_t)(pos_um_solid2 - s_pos + k);
+            if ((uint64_t)cl + 8 > p.str_cap || (uint64_t)wlen + 8 > p.str_cap) { C.bail = RTK_RG_BAIL_STRCAP; break; }
+            const rg_dist d = rg_myers(C, ostr, (int)cl, p.win_pool + T.win_off + woff, (int)wlen, 1);
+            last.shw_dist = d.dist; last.shw_first_end = d.first;
+            const double dn = (double)d.dist / (double)cl;
+            const bool cut_fail = (p.wrlf > 0.0) && (dn > p.wrlf);
+            if (!cut_fail && T.n_weak != 0) {
+                const uint64_t next_pos = (uint64_t)s_pos + (uint64_t)(int64_t)d.first + k;
+                while (i_w_s < T.n_weak && (uint64_t)vw[i_w_s].pos < next_pos) ++i_w_s;
+                if (!(i_w_s >= T.n_weak || (uint64_t)vw[i_w_s].pos >= pos_um_solid2 - k || ((uint64_t)vw[i_w_s].pos - s_pos) >= (uint64_t)p.max_len_weak_region)) {
+                    again = true;
+                }
+            }
+        }
+        if (lane == 0) C.segs[n_segs] = last;
+        ++n_segs;
+        if (!again) break;
+        start_idx = (uint32_t)i_w_s;
+        s_pos = vw[i_w_s].pos; s_unitig = vw[i_w_s].unitig; s_dist = vw[i_w_s].dist; s_strand = vw[i_w_s].strand;
+    }
     R.n_hops = C.n_hops; R.n_pops = C.n_pops; R.n_cands = C.n_cands; R.n_aligns = C.n_aligns;
+    R.seg_off = 0; R.n_segs = 0; R.reserved = 0;
+    if (!C.bail) {   // the segment descriptors, contiguous
+        unsigned long long seg_base = 0;
+        if (lane == 0) seg_base = atomicAdd(&p.out_top[2], (unsigned long long)n_segs);
+        seg_base = __shfl_sync(0xffffffffu, seg_base, 0);
+        if (seg_base + n_segs > p.out_segs_cap) C.bail = RTK_RG_BAIL_CHAIN;
+        else {
+            __syncwarp();
+            for (uint32_t i = lane; i < n_segs; i += 32) p.out_segs[seg_base + i] = C.segs[i];
+            R.seg_off = seg_base;
+        }
+    }
     if (C.bail) { R.status = 2; R.bail = C.bail; R.n_nodes = 0; R.len = 0; R.node_off = 0; R.str_off = 0; return; }
-    // publish: vertices + spelled string + quality string, bump-allocated from the output pools
-    unsigned long long no = 0, so = 0;
-    if (lane == 0) {
-        no = atomicAdd(&p.out_top[0], (unsigned long long)cn);
-        so = atomicAdd(&p.out_top[1], (unsigned long long)(2ull * rg_pad8(cl)));
-    }
-    no = __shfl_sync(0xffffffffu, no, 0);
-    so = __shfl_sync(0xffffffffu, so, 0);
-    if (no + cn > p.out_nodes_cap || so + 2ull * rg_pad8(cl) > p.out_chars_cap) {
-        R.status = 2; R.bail = RTK_RG_BAIL_CHAIN; R.n_nodes = 0; R.len = 0; R.node_off = 0; R.str_off = 0;
-        return;
-    }
-    for (uint32_t i = lane; i < cn; i += 32) p.out_nodes[no + i] = C.ch_nodes[i];
-    rg_spell_nodes(C, C.ch_nodes, cn, p.out_chars + so);
-    char* oq = p.out_chars + so + rg_pad8(cl);
-    for (uint32_t i = lane; i < cl; i += 32) oq[i] = C.ch_qual[i];
-    R.status = alive ? 0u : 1u; R.bail = 0; R.n_nodes = cn; R.len = cl; R.node_off = no; R.str_off = so;
+    R.status = last.status; R.bail = 0; R.n_nodes = last.n_nodes; R.len = last.len; R.node_off = last.node_off; R.str_off = last.str_off;
+    R.n_segs = n_segs;
 }
 
 // One region per warp, ONE WARP PER CTA, grid = all regions of the batch (longest first).  The grid is not persistent and a
@@ -1095,7 +1166,7 @@ __global__ void __launch_bounds__(32) rtk_region_kernel(const rtk_rg_params p) {
         C.p = &p; C.lane = lane;
         C.sA = (char*)(S + L.sA); C.sB = (char*)(S + L.sB); C.sC = (char*)(S + L.sC); C.hb = (int8_t*)(S + L.hb);
         C.mat = (ulonglong2*)(S + L.mat); C.anc = (int32_t*)(S + L.anc);
-        C.dfs = (rtk_dfs_frame*)(S + L.dfs); C.dfs_cur = (rtk_dfs_frame*)(S + L.dfs_cur);
+        C.dfs = (rtk_dfs_frame*)(S + L.dfs); C.dfs_cur = (rtk_dfs_frame*)(S + L.dfs_cur); C.segs = (rtk_region_seg_t*)(S + L.segs);
         C.tmpT = S + L.tmpT; C.tmpN = S + L.tmpN; C.arena = S + L.arena;
         C.q_items = (uint32_t*)(S + L.q_items); C.v_items = (uint32_t*)(S + L.v_items); C.vt_items = (uint32_t*)(S + L.vt_items);
         C.ch_nodes = (rtk_rg_node*)(S + L.ch_nodes); C.ch_qual = (char*)(S + L.ch_qual);

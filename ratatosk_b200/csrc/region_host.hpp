@@ -66,9 +66,10 @@ inline std::vector<uint32_t> region_order(uint32_t n_calls, const rtk_region_cal
 }
 
 // output pools: vertices and characters (spelled path + quality, 8-byte padded each) all calls may publish
-inline void region_out_caps(uint32_t n_calls, const rtk_region_call_t* calls, uint64_t& nodes_cap, uint64_t& chars_cap) {
+inline void region_out_caps(uint32_t n_calls, const rtk_region_call_t* calls, uint64_t& nodes_cap, uint64_t& chars_cap, uint64_t& segs_cap) {
     uint64_t w = 0;
     for (uint32_t i = 0; i < n_calls; ++i) w += calls[i].win_len;
+    segs_cap = 4ull * n_calls + 1024;
     chars_cap = 2 * (2 * w + 80ull * n_calls) + 1024;   // a path is at most ~1.6 x its window (1.25 x + 10 per hop) + k
     nodes_cap = w / 2 + 64ull * n_calls + 1024;               // vertices: far fewer than bases in practice; overflow bails
 }

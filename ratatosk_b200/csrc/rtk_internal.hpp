@@ -114,7 +114,7 @@ struct rtk_ctx {
     // scratch
     rtk::DevBuf d_seq, d_seq_off, d_tiles, d_hits, d_counters, d_aux[8], d_sub[8];
     rtk::PinBuf h_pin[16];   // pinned landing zones of the D2H copies (one slot per copy site, see PinnedD2H)
-    rtk::DevBuf d_rg[6];     // region engine: [0] packed inputs, [1] results, [2] out vertices, [3] out chars, [4] counters, [5] per-warp scratch
+    rtk::DevBuf d_rg[7];     // region engine: [0] packed inputs, [1] results, [2] out vertices, [3] out chars, [4] counters, [5] per-warp scratch, [6] out segments
     rtk::PinBuf h_rg[3];     // region engine: [0] packed upload, [1] results + counters, [2] output pools
     int sm_count = 148;
     // reads of the next exact sweep already resident in HBM (rtk_correct_batch_resident); consumed once
@@ -230,6 +230,7 @@ struct RegionBatchOut {
     std::vector<rtk_region_result_t> results;
     std::vector<rtk_path_node> nodes;
     std::vector<char> chars;
+    std::vector<rtk_region_seg_t> segs;
     float kernel_ms = 0.f;
 };
 void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls, const rtk_region_call_t* calls, const char* win_pool,

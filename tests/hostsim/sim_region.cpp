@@ -13,7 +13,7 @@ namespace rtk {
 void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls, const rtk_region_call_t* calls, const char* win_pool,
                       uint64_t win_bytes, const rtk_hit* weak_pool, uint64_t n_weak, const uint32_t* pid_pool, uint64_t n_pids, RegionBatchOut& out) {
     out.results.assign(n_calls, rtk_region_result_t());
-    out.nodes.clear(); out.chars.clear(); out.kernel_ms = 0.f;
+    out.nodes.clear(); out.chars.clear(); out.segs.clear(); out.kernel_ms = 0.f;
     if (!n_calls) return;
     if (!c->has_graph) throw std::invalid_argument("no graph uploaded to this context");
     const rtk_graph_view& g = c->host_graph->view;
@@ -24,8 +24,9 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     memset(&p, 0, sizeof(p));
     region_fill_params(p, opt, pass, caps);
     const std::vector<uint32_t> order = region_order(n_calls, calls);
-    uint64_t nodes_cap, chars_cap;
-    region_out_caps(n_calls, calls, nodes_cap, chars_cap);
+    uint64_t nodes_cap, chars_cap, segs_cap;
+    region_out_caps(n_calls, calls, nodes_cap, chars_cap, segs_cap);
+    std::vector<rtk_region_seg_t> segs(segs_cap);
     std::vector<rtk_path_node> nodes(nodes_cap);
     std::vector<char> chars(chars_cap);
     unsigned long long counters[4] = {0, 0, 0, 0};
@@ -40,12 +41,13 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     p.win_pool = win_pool; p.weak_pool = n_weak ? weak_pool : &no_weak; p.pid_pool = n_pids ? pid_pool : &no_pid;
     p.results = out.results.data();
     p.out_nodes = nodes.data(); p.out_chars = chars.data(); p.out_top = counters; p.slot_flags = slot_flags.data(); p.n_slots = n_slots;
-    p.out_nodes_cap = nodes_cap; p.out_chars_cap = chars_cap;
+    p.out_nodes_cap = nodes_cap; p.out_chars_cap = chars_cap; p.out_segs = segs.data(); p.out_segs_cap = segs_cap;
     p.scratch = scratch.data();
     sim_launch((n_calls + RTK_RG_WARPS - 1) / RTK_RG_WARPS, RTK_RG_WARPS * 32, [&] { rtk_region_kernel(p); });
     const uint64_t un = std::min<uint64_t>(counters[0], nodes_cap), uc = std::min<uint64_t>(counters[1], chars_cap);
     out.nodes.assign(nodes.begin(), nodes.begin() + un);
     out.chars.assign(chars.begin(), chars.begin() + uc);
+    out.segs.assign(segs.begin(), segs.begin() + std::min<uint64_t>(counters[2], segs_cap));
 }
 
 }  // namespace rtk
@@ -64,17 +66,19 @@ extern "C" int rtk_region_paths_batch(rtk_ctx* c, const rtk_opt* opt, int pass, 
         out->results = (rtk_region_result_t*)malloc(sizeof(rtk_region_result_t) * ((size_t)n_calls + 1));
         out->nodes = (rtk_path_node*)malloc(sizeof(rtk_path_node) * (r.nodes.size() + 1));
         out->chars = (char*)malloc(r.chars.size() + 1);
-        if (!out->results || !out->nodes || !out->chars) throw std::bad_alloc();
+        out->segs = (rtk_region_seg_t*)malloc(sizeof(rtk_region_seg_t) * (r.segs.size() + 1));
+        if (!out->results || !out->nodes || !out->chars || !out->segs) throw std::bad_alloc();
         if (n_calls) memcpy(out->results, r.results.data(), sizeof(rtk_region_result_t) * (size_t)n_calls);
         if (!r.nodes.empty()) memcpy(out->nodes, r.nodes.data(), sizeof(rtk_path_node) * r.nodes.size());
         if (!r.chars.empty()) memcpy(out->chars, r.chars.data(), r.chars.size());
-        out->n_nodes = r.nodes.size(); out->n_chars = r.chars.size();
+        if (!r.segs.empty()) memcpy(out->segs, r.segs.data(), sizeof(rtk_region_seg_t) * r.segs.size());
+        out->n_nodes = r.nodes.size(); out->n_chars = r.chars.size(); out->n_segs = r.segs.size();
         if (stats) stats[0] += n_calls;
     });
 }
 
 extern "C" void rtk_region_out_free(rtk_region_out* o) {
     if (!o) return;
-    free(o->results); free(o->nodes); free(o->chars);
+    free(o->results); free(o->nodes); free(o->chars); free(o->segs);
     memset(o, 0, sizeof(*o));
 }
