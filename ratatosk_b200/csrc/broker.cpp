@@ -229,57 +229,74 @@ void run_region_batch(rtk_ctx* ctx, const std::vector<RegionReq*>& reqs, uint64_
         std::vector<size_t> idx;
         for (size_t i = first; i < reqs.size(); ++i) if (!done[i] && reqs[i]->opt == opt && reqs[i]->pass == pass) { idx.push_back(i); done[i] = true; }
         const uint32_t k = opt->k;
-        std::vector<rtk_region_call_t> calls(idx.size());
-        std::string wins;
-        std::vector<rtk_hit> weak;
-        std::vector<uint32_t> pids;
-        for (size_t x = 0; x < idx.size(); ++x) {
+        const size_t n = idx.size();
+        std::vector<rtk_region_call_t> calls(n);
+        // pool offsets first (serial prefix sums), then the pools are filled in parallel: a bulk wave holds 10^5 regions
+        std::vector<uint64_t> wo(n + 1, 0), ko(n + 1, 0), po(n + 1, 0);
+        for (size_t x = 0; x < n; ++x) {
             const RegionReq& r = *reqs[idx[x]];
-            rtk_region_call_t& c = calls[x];
-            memset(&c, 0, sizeof(c));
             const size_t pos2 = r.has_end ? r.end_pos : r.s->length() - k;
-            c.win_off = wins.size(); c.win_len = (uint32_t)(pos2 - r.um_start.pos + k);
-            wins.append(*r.s, r.um_start.pos, c.win_len);
-            c.weak_off = weak.size();
-            for (size_t i = r.i_weak; i < r.v_w->size(); ++i) weak.push_back((*r.v_w)[i]);
-            c.n_weak = (uint32_t)(weak.size() - c.weak_off);
-            c.pid_off = pids.size(); c.pid_len = (uint32_t)r.pids->size();
-            pids.insert(pids.end(), r.pids->begin(), r.pids->end());
-            c.start_pos = r.um_start.pos; c.start_unitig = r.um_start.unitig; c.start_dist = r.um_start.dist; c.start_strand = r.um_start.strand;
-            c.has_end = r.has_end ? 1u : 0u;
-            if (r.has_end) { c.end_pos = (uint32_t)r.end_pos; c.end_unitig = r.um_end.unitig; c.end_dist = r.um_end.dist; c.end_strand = r.um_end.strand; }
-            c.s_len = (uint32_t)r.s->length();
-            c.reserved = r.follow_dead_ends ? 1u : 0u;
+            wo[x + 1] = wo[x] + (pos2 - r.um_start.pos + k);
+            ko[x + 1] = ko[x] + (r.v_w->size() - std::min(r.i_weak, r.v_w->size()));
+            po[x + 1] = po[x] + r.pids->size();
         }
+        std::string wins(wo[n], '\0');
+        std::vector<rtk_hit> weak(ko[n]);
+        std::vector<uint32_t> pids(po[n]);
+        parallel_for(n, [&](size_t xb, size_t xe) {
+            for (size_t x = xb; x < xe; ++x) {
+                const RegionReq& r = *reqs[idx[x]];
+                rtk_region_call_t& c = calls[x];
+                memset(&c, 0, sizeof(c));
+                c.win_off = wo[x]; c.win_len = (uint32_t)(wo[x + 1] - wo[x]);
+                memcpy(&wins[wo[x]], r.s->data() + r.um_start.pos, c.win_len);
+                c.weak_off = ko[x]; c.n_weak = (uint32_t)(ko[x + 1] - ko[x]);
+                if (c.n_weak) memcpy(&weak[ko[x]], r.v_w->data() + r.i_weak, (size_t)c.n_weak * sizeof(rtk_hit));
+                c.pid_off = po[x]; c.pid_len = (uint32_t)r.pids->size();
+                if (c.pid_len) memcpy(&pids[po[x]], r.pids->data(), (size_t)c.pid_len * 4);
+                c.start_pos = r.um_start.pos; c.start_unitig = r.um_start.unitig; c.start_dist = r.um_start.dist; c.start_strand = r.um_start.strand;
+                c.has_end = r.has_end ? 1u : 0u;
+                if (r.has_end) { c.end_pos = (uint32_t)r.end_pos; c.end_unitig = r.um_end.unitig; c.end_dist = r.um_end.dist; c.end_strand = r.um_end.strand; }
+                c.s_len = (uint32_t)r.s->length();
+                c.reserved = r.follow_dead_ends ? 1u : 0u;
+            }
+        });
         pt.lap(3, 0);
         RegionBatchOut out;
         region_batch_run(ctx, *opt, pass, (uint32_t)calls.size(), calls.data(), wins.data(), wins.size(), weak.data(), weak.size(), pids.data(), pids.size(), out);
         pt.lap(3, 1);
         g_prof[3][3] += (uint64_t)(out.kernel_ms * 1e6);
         if (kernel_ns) *kernel_ns += (uint64_t)(out.kernel_ms * 1e6);
-        for (size_t x = 0; x < idx.size(); ++x) {
-            RegionReq& r = *reqs[idx[x]];
-            const rtk_region_result_t& R = out.results[x];
-            r.status = R.status; r.bail = R.bail;
-            g_region_stats[0] += 1;
-            if (R.status == 2) { g_region_stats[1] += 1; g_region_stats[2 + std::min<uint32_t>(R.bail, 15u)] += 1; continue; }
-            r.segs.resize(R.n_segs);
-            for (uint32_t si = 0; si < R.n_segs; ++si) {
-                const rtk_region_seg_t& S = out.segs[R.seg_off + si];
-                RegionReq::Seg& D = r.segs[si];
-                D.status = S.status; D.start_weak = S.start_weak; D.shw_dist = S.shw_dist; D.shw_first_end = S.shw_first_end;
-                D.path.clear();
-                D.path.v.resize(S.n_nodes);
-                for (uint32_t i = 0; i < S.n_nodes; ++i) {
-                    const rtk_path_node& n = out.nodes[S.node_off + i];
-                    D.path.v[i].unitig = n.unitig; D.path.v[i].strand = n.strand; D.path.v[i].dist = n.dist; D.path.v[i].len = n.len;
+        std::atomic<uint64_t> n_bail(0);
+        std::atomic<uint64_t> by_reason[16];
+        for (auto& a : by_reason) a = 0;
+        parallel_for(n, [&](size_t xb, size_t xe) {
+            for (size_t x = xb; x < xe; ++x) {
+                RegionReq& r = *reqs[idx[x]];
+                const rtk_region_result_t& R = out.results[x];
+                r.status = R.status; r.bail = R.bail;
+                if (R.status == 2) { n_bail += 1; by_reason[std::min<uint32_t>(R.bail, 15u)] += 1; continue; }
+                r.segs.resize(R.n_segs);
+                for (uint32_t si = 0; si < R.n_segs; ++si) {
+                    const rtk_region_seg_t& S = out.segs[R.seg_off + si];
+                    RegionReq::Seg& D = r.segs[si];
+                    D.status = S.status; D.start_weak = S.start_weak; D.shw_dist = S.shw_dist; D.shw_first_end = S.shw_first_end;
+                    D.path.clear();
+                    D.path.v.resize(S.n_nodes);
+                    for (uint32_t i = 0; i < S.n_nodes; ++i) {
+                        const rtk_path_node& nd = out.nodes[S.node_off + i];
+                        D.path.v[i].unitig = nd.unitig; D.path.v[i].strand = nd.strand; D.path.v[i].dist = nd.dist; D.path.v[i].len = nd.len;
+                    }
+                    D.path.l = S.len;
+                    const uint64_t pad = ((uint64_t)S.len + 7) & ~7ull;
+                    D.seq.assign(out.chars.data() + S.str_off, S.len);
+                    D.path.qual.assign(out.chars.data() + S.str_off + pad, S.len);
                 }
-                D.path.l = S.len;
-                const uint64_t pad = ((uint64_t)S.len + 7) & ~7ull;
-                D.seq.assign(out.chars.data() + S.str_off, S.len);
-                D.path.qual.assign(out.chars.data() + S.str_off + pad, S.len);
             }
-        }
+        });
+        g_region_stats[0] += n;
+        g_region_stats[1] += n_bail.load();
+        for (int j = 0; j < 16; ++j) g_region_stats[2 + j] += by_reason[j].load();
         pt.lap(3, 2);
     }
 }
@@ -456,6 +473,7 @@ static std::mutex g_sim_launch_mu;   // the CPU simulator runs one launch at a t
 #endif
 
 void GpuBroker::service_main(Service* s) {
+    set_thread_budget(run_budget);   // parallel_for inside a service (bulk pack / unpack) stays within the gang's share of the cores
     std::vector<std::pair<void*, Fiber*>> batch;
     const char* e_mb = getenv("RTK_SERVICE_MIN_BATCH");
     const char* e_lg = getenv("RTK_SERVICE_LINGER_US");
@@ -683,6 +701,7 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
     n_tasks = n; next_task = 0; task_fn = &task; task_error.clear();
     cap_per_worker = std::max<size_t>(1, (std::min<size_t>(std::max(1u, inflight), n) + n_workers - 1) / n_workers);
     cap_total = cap_per_worker * n_workers;
+    run_budget = thread_budget();
     live_total.store(0);
     const auto t_begin = std::chrono::steady_clock::now();
     t_run_begin = t_begin;

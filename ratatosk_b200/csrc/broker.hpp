@@ -119,6 +119,7 @@ private:
     // per run()
     std::atomic<size_t> live_total{0};   // fibers started and not finished, all workers
     size_t cap_total = 1;                // in-flight cap, all workers
+    unsigned run_budget = 0;             // host threads of the gang that runs this broker
     bool bulk_regions = true;            // the region service launches when every live fiber waits for it (one bulk launch per wave)
     bool bulk_all = false;               // every service launches only when all live fibers are parked (global waves)
     std::atomic<size_t> parked_total{0}; // fibers parked at any service and not yet handed back

@@ -781,7 +781,10 @@ void RegionJob::paths_impl(const bool use_device) {
     size_t seg = 0;
     std::vector<std::string> seg_str;   // spelled path of the current segment (the engine spells it)
     auto eswp = [&](size_t i_weak_arg, bool initial) -> PathPair {
-        if (!use_device) return region_paths(C, s, all_pids, um_solid1, has_end_pt, um_solid2, solid2_pos, l_v_w, i_weak_arg);
+        // declined by the engine (or no engine): the request-at-a-time orchestration; not another engine request, which would
+        // wait for the next bulk wave only to be declined again
+        if (!use_device) return has_req ? extract_semi_weak_paths(C, s, all_pids, um_solid1, has_end_pt, um_solid2, solid2_pos, l_v_w, i_weak_arg)
+                                        : region_paths(C, s, all_pids, um_solid1, has_end_pt, um_solid2, solid2_pos, l_v_w, i_weak_arg);
         if (!initial) ++seg;
         if (seg >= req.segs.size()) throw InconsistentSegments();
         RegionReq::Seg& S = req.segs[seg];

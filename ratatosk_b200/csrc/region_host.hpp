@@ -25,8 +25,8 @@ inline RegionCaps region_caps() {
     RegionCaps c;
     c.str_cap = env("RTK_RG_STR_CAP", 16384);
     c.mat_cells = env("RTK_RG_MAT_CELLS", (1u << 20) / 20 + 64);   // edlib's direct traceback holds < 1 MiB of state (20 B per cell)
-    c.tmp_cap = env("RTK_RG_TMP_CAP", 64u << 10);
-    c.arena_cap = env("RTK_RG_ARENA_CAP", 512u << 10);
+    c.tmp_cap = env("RTK_RG_TMP_CAP", 192u << 10);
+    c.arena_cap = env("RTK_RG_ARENA_CAP", 1536u << 10);
     c.chain_nodes_cap = env("RTK_RG_CHAIN_NODES", 4096);
     c.chain_len_cap = env("RTK_RG_CHAIN_LEN", 32768);
     return c;
