@@ -340,6 +340,7 @@ struct GpuBroker::Fiber {
     char* stack = nullptr;
     size_t task = 0;
     bool done = false;
+    bool express = false;
     GpuBroker* broker = nullptr;
     Worker* owner = nullptr;
     std::string error;   // set by the service that failed this fiber's request
@@ -370,6 +371,7 @@ struct GpuBroker::Service {
     std::mutex mu;
     std::condition_variable cv;
     std::vector<std::pair<void*, Fiber*>> q;
+    bool is_express = false;
     size_t n_riders = 0;   // queued requests that carry no fiber (extra requests of a task that parked once)
     bool stop = false;
     uint64_t batches = 0, reqs = 0, ns_busy = 0;
@@ -410,13 +412,21 @@ GpuBroker::GpuBroker(rtk_ctx* c) : ctx(c) {
         for (unsigned i = 0; i < std::max(1u, std::min(cnt[k], 8u)); ++i) {
             Service* s = new Service();
             s->kind = k;
-            if (ctx_fork_priority(ctx, /*high=*/k != 3, &s->ctx) != RTK_OK) { delete s; throw std::runtime_error(std::string("rtk_ctx_fork: ") + rtk_last_error()); }
+            try { s->ctx = fork_acquire(ctx, /*high=*/k != 3); } catch (...) { delete s; throw; }
             services[k].push_back(s);
         }
+    for (int k = 0; k < 3; ++k) {
+        Service* s = new Service();
+        s->kind = k; s->is_express = true;
+        try { s->ctx = fork_acquire(ctx, true); } catch (...) { delete s; throw; }
+        express[k].push_back(s);
+    }
 }
 GpuBroker::~GpuBroker() {
     for (int k = 0; k < 4; ++k)
-        for (Service* s : services[k]) { rtk_ctx_destroy(s->ctx); delete s; }
+        for (Service* s : services[k]) { fork_release(ctx, s->ctx, /*high=*/k != 3); delete s; }
+    for (int k = 0; k < 3; ++k)
+        for (Service* s : express[k]) { fork_release(ctx, s->ctx, true); delete s; }
 }
 
 // called on a fiber: queue the request at a service thread and hand control back to the worker's scheduler.  The
@@ -426,7 +436,7 @@ void GpuBroker::park(int kind, void* req) {
     Worker* w = tl_worker;
     if (!w || !w->current) throw std::logic_error("GpuBroker::submit called outside a broker task");
     Fiber* f = w->current;
-    Service* s = services[kind][(w->rr++) % services[kind].size()];
+    Service* s = (f->express && kind < 3) ? express[kind][0] : services[kind][(w->rr++) % services[kind].size()];
     {
         std::lock_guard<std::mutex> lk(s->mu);
         s->q.emplace_back(req, f);
@@ -439,6 +449,10 @@ void GpuBroker::park(int kind, void* req) {
     swapcontext(&f->uc, &w->sched);
 #endif
     if (!f->error.empty()) { std::string e; e.swap(f->error); throw std::runtime_error(e); }
+}
+void GpuBroker::set_express() {
+    Worker* w = tl_worker;
+    if (w && w->current) w->current->express = true;
 }
 void GpuBroker::submit(DistReq* r) { park(0, r); }
 void GpuBroker::submit(PathReq* r) { park(1, r); }
@@ -481,7 +495,7 @@ void GpuBroker::service_main(Service* s) {
     const long linger_us = e_lg ? atol(e_lg) : 150;
     for (;;) {
         batch.clear();
-        if (bulk_all) {
+        if (bulk_all && !s->is_express) {
             // global waves: a service launches when every live fiber is parked somewhere (this queue or another service's)
             std::unique_lock<std::mutex> lk(s->mu);
             for (;;) {
@@ -522,7 +536,7 @@ void GpuBroker::service_main(Service* s) {
             s->cv.wait(lk, [&] { return s->stop || !s->q.empty(); });
             if (s->q.empty()) break;   // stop requested and nothing left
             // a batch costs a fixed launch + copy latency: linger briefly for more requests when only a few are queued
-            if (s->q.size() < min_batch && linger_us > 0) {
+            if (!s->is_express && s->q.size() < min_batch && linger_us > 0) {
                 const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(linger_us);
                 s->cv.wait_until(lk, deadline, [&] { return s->stop || s->q.size() >= min_batch; });
             }
@@ -655,7 +669,7 @@ void GpuBroker::worker_main(Worker* w) {
                 if (cap_total <= 16384) mprotect(base, kGuardBytes, PROT_NONE);   // every guard page is a mapping of its own: only below the kernel's map-count limit
                 f->stack = base + kGuardBytes;
             }
-            f->task = i; f->done = false; f->broker = this; f->owner = w; f->error.clear();
+            f->task = i; f->done = false; f->express = false; f->broker = this; f->owner = w; f->error.clear();
 #ifdef RTK_FIBER_ASM
             {   // stack image rtk_fiber_switch pops: r15 r14 r13 r12 rbx rbp, then `ret` into the trampoline (rsp % 16 == 8 there)
                 void** sp = (void**)(((uintptr_t)f->stack + stack_bytes) & ~(uintptr_t)15);
@@ -719,6 +733,8 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
     }
     for (int k = 0; k < 4; ++k)
         for (Service* s : services[k]) { s->stop = false; s->th = std::thread([this, s] { service_main(s); }); }
+    for (int k = 0; k < 3; ++k)
+        for (Service* s : express[k]) { s->stop = false; s->th = std::thread([this, s] { service_main(s); }); }
     for (Worker* w : workers) w->th = std::thread([this, w] { worker_main(w); });
     uint64_t idle_ns = 0, resumes = 0;
     for (Worker* w : workers) {
@@ -735,6 +751,14 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
             s->cv.notify_one();
             s->th.join();
             waves += s->batches; jobs += s->reqs;
+        }
+    for (int k = 0; k < 3; ++k)
+        for (Service* s : express[k]) {
+            { std::lock_guard<std::mutex> lk(s->mu); s->stop = true; }
+            s->cv.notify_one();
+            s->th.join();
+            waves += s->batches; jobs += s->reqs;
+            s->batches = s->reqs = s->ns_busy = 0;
         }
     task_fn = nullptr;
     uint64_t prof[4][4];

@@ -99,6 +99,10 @@ public:
     void submit(SubgraphReq* r);
     void submit(RegionReq* r);
     void submit(const std::vector<RegionReq*>& rs);   // several region requests of one task, one park
+    // From now on the calling task's K2-K5 requests go to the express services (own threads and streams, served at once in
+    // small batches).  For the rare region the engine declines: it falls back to hundreds of DEPENDENT requests, which must
+    // not queue behind the bulk batches of the other regions.
+    void set_express();
     uint64_t waves = 0, jobs = 0;   // batched service calls issued / requests served
     uint64_t kernel_ns[4] = {0, 0, 0, 0};   // GPU kernel time (CUDA events) of the dist / path / subgraph / region services
     uint64_t region_calls = 0, region_bails = 0, region_bail_reason[16] = {0};
@@ -114,6 +118,7 @@ private:
     void service_main(Service* s);
     rtk_ctx* ctx;
     std::vector<Service*> services[4];   // 0 dist (K4), 1 path (K5), 2 subgraph (K2/K3+K4), 3 region engine
+    std::vector<Service*> express[3];    // low-latency twins of services 0-2 for declined regions
     std::vector<Worker*> workers;
     std::string task_error;    // first exception that escaped a task
     // per run()

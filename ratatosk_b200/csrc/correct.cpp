@@ -757,6 +757,7 @@ void RegionJob::paths() {
             res = ResultCorrection(saved_len); res.all_pids = all_pids;
         }
     }
+    if (has_req) { if (GpuBroker* b = current_broker()) b->set_express(); }   // declined: hundreds of dependent requests follow
     paths_impl(false);
 }
 
@@ -1246,10 +1247,8 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
         std::vector<std::string> errors(n_gangs);
         std::vector<rtk_ctx*> gctx(n_gangs, nullptr);
         for (unsigned gi = 0; gi < n_gangs; ++gi) {
-            if (rtk_ctx_fork(ctx, &gctx[gi]) != RTK_OK) {
-                for (rtk_ctx* c : gctx) if (c) rtk_ctx_destroy(c);
-                throw std::runtime_error(std::string("rtk_ctx_fork: ") + rtk_last_error());
-            }
+            try { gctx[gi] = fork_acquire(ctx, false); }
+            catch (...) { for (rtk_ctx* c : gctx) fork_release(ctx, c, false); throw; }
 #ifndef RTK_HOSTSIM
             if (ctx->resident_seq && ctx->resident_n == n_reads) {   // the caller's resident copy of the reads, this gang's slice
                 gctx[gi]->resident_seq = ctx->resident_seq; gctx[gi]->resident_off = ctx->resident_off + cut[gi];
@@ -1274,7 +1273,7 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
             });
         }
         for (auto& t : th) t.join();
-        for (rtk_ctx* c : gctx) rtk_ctx_destroy(c);
+        for (rtk_ctx* c : gctx) fork_release(ctx, c, false);
 #ifndef RTK_HOSTSIM
         ctx->resident_seq = nullptr;
 #endif

@@ -133,6 +133,30 @@ static void create_side_streams(rtk_ctx* c, int prio = 0) {
     }
 }
 
+rtk_ctx* rtk::fork_acquire(rtk_ctx* parent, bool high) {
+    {
+        std::lock_guard<std::mutex> lk(parent->fork_mu);
+        auto& v = parent->fork_cache[high ? 1 : 0];
+        if (!v.empty()) { rtk_ctx* c = v.back(); v.pop_back(); return c; }
+    }
+    rtk_ctx* c = nullptr;
+    if (ctx_fork_priority(parent, high, &c) != RTK_OK) throw std::runtime_error(std::string("rtk_ctx_fork: ") + rtk_last_error());
+    return c;
+}
+void rtk::fork_release(rtk_ctx* parent, rtk_ctx* child, bool high) {
+    if (!child) return;
+    std::lock_guard<std::mutex> lk(parent->fork_mu);
+    parent->fork_cache[high ? 1 : 0].push_back(child);
+}
+static void drop_fork_cache(rtk_ctx* c) {
+    std::vector<rtk_ctx*> all;
+    {
+        std::lock_guard<std::mutex> lk(c->fork_mu);
+        for (auto& v : c->fork_cache) { all.insert(all.end(), v.begin(), v.end()); v.clear(); }
+    }
+    for (rtk_ctx* f : all) rtk_ctx_destroy(f);
+}
+
 extern "C" {
 
 int rtk_ctx_create(int device, rtk_ctx** out) {
@@ -192,6 +216,7 @@ extern "C" {
 
 void rtk_ctx_destroy(rtk_ctx* c) {
     if (!c) return;
+    drop_fork_cache(c);
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->owns_slab && c->d_slab) cudaFree((void*)c->d_slab);
@@ -217,6 +242,7 @@ int rtk_graph_upload(rtk_ctx* c, const rtk_host_graph* g) {
     return guarded([&] {
         if (!c || !g) throw std::invalid_argument("null argument");
         RTK_CUDA(cudaSetDevice(c->device));
+        drop_fork_cache(c);   // cached forks share the previous graph
         if (c->owns_slab && c->d_slab) RTK_CUDA(cudaFree((void*)c->d_slab));
         void* d = nullptr;
         RTK_CUDA(cudaMalloc(&d, g->slab.bytes));
@@ -236,6 +262,7 @@ int rtk_graph_adopt_device(rtk_ctx* c, const void* dev_slab, uint64_t bytes) {
         if (!c || !dev_slab) throw std::invalid_argument("null argument");
         RTK_CUDA(cudaSetDevice(c->device));
         if (bytes < sizeof(rtk_slab_header)) throw std::invalid_argument("slab too small");
+        drop_fork_cache(c);   // cached forks share the previous graph
         // the host-side anchor logic needs a host mirror: copy the slab back once
         if (c->host_copy.data) { free(c->host_copy.data); c->host_copy.data = nullptr; }
         c->host_copy.data = (unsigned char*)aligned_alloc(256, (bytes + 255) & ~(uint64_t)255);

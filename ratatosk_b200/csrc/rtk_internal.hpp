@@ -8,6 +8,7 @@
 #include <sched.h>
 
 #include <atomic>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -117,6 +118,11 @@ struct rtk_ctx {
     rtk::DevBuf d_rg[7];     // region engine: [0] packed inputs, [1] results, [2] out vertices, [3] out chars, [4] counters, [5] per-warp scratch, [6] out segments
     rtk::PinBuf h_rg[3];     // region engine: [0] packed upload, [1] results + counters, [2] output pools
     int sm_count = 148;
+    // forked contexts kept for re-use (fork_acquire / fork_release): the broker's service contexts and the correction gangs are
+    // needed again by every batch; re-creating them per call means re-growing their device / pinned buffers every time, and a
+    // cudaMalloc / cudaFree / cudaMallocHost synchronises with whatever the device is running (a bulk region launch: 0.5 s)
+    std::vector<rtk_ctx*> fork_cache[2];   // [0] default / low-priority streams, [1] high priority
+    std::mutex fork_mu;
     // reads of the next exact sweep already resident in HBM (rtk_correct_batch_resident); consumed once
     const char* resident_seq = nullptr;
     const uint64_t* resident_off = nullptr;
@@ -224,6 +230,11 @@ void myers_run_lean(rtk_ctx* c, const char* d_qpool, const char* d_tpool, const 
 
 // rtk_ctx_fork with the streams at the highest / lowest priority of the device (no-op distinction on the CPU simulator)
 int ctx_fork_priority(const rtk_ctx* parent, bool high, rtk_ctx** out);
+
+// a fork of `parent` from its cache (created on first use) / back into the cache; cached forks die with the parent and are
+// dropped when the parent's graph changes.  On the CPU simulator: plain fork / destroy.
+rtk_ctx* fork_acquire(rtk_ctx* parent, bool high);
+void fork_release(rtk_ctx* parent, rtk_ctx* child, bool high);
 
 // device-resident region engine (region.cu / tests/hostsim/sim_region.cpp): n extractSemiWeakPaths calls in one launch
 struct RegionBatchOut {

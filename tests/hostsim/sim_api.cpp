@@ -71,6 +71,8 @@ void rtk_ctx_destroy(rtk_ctx* c) { delete c; }
 int rtk_ctx_fork(const rtk_ctx* parent, rtk_ctx** out) { *out = new rtk_ctx(*parent); return RTK_OK; }
 }
 int rtk::ctx_fork_priority(const rtk_ctx* parent, bool, rtk_ctx** out) { *out = new rtk_ctx(*parent); return RTK_OK; }
+rtk_ctx* rtk::fork_acquire(rtk_ctx* parent, bool) { return new rtk_ctx(*parent); }
+void rtk::fork_release(rtk_ctx*, rtk_ctx* child, bool) { delete child; }
 extern "C" {
 int rtk_graph_upload(rtk_ctx* c, const rtk_host_graph* g) {
     c->host_graph = g; c->hdr = g->hdr; c->has_graph = true;
