@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -1126,7 +1127,8 @@ static unsigned correct_threads() {
 // ------------------------------------------------------------------ batch driver: the per-read body of search() (src/Ratatosk.cpp:808-867)
 // one gang: reads [0, n_reads) of its own pools through every correction round, on its own context
 static void correct_range(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
-                          const char* qual_pool, const uint64_t* qual_off, std::string* out_seq, std::string* out_qual, uint64_t* stats) {
+                          const char* qual_pool, const uint64_t* qual_off, std::string* out_seq, std::string* out_qual, uint64_t* stats,
+                          std::mutex* seeds_turn = nullptr) {
     const rtk_graph_view& g = ctx->host_graph->view;
     const bool pass2 = (pass == 2);
     const size_t max_km_cov = std::max<size_t>(ctx->host_graph->hdr.max_km_cov_graph, opt.max_km_cov);  // src/Ratatosk.cpp:625
@@ -1154,8 +1156,17 @@ static void correct_range(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n
         std::string pool(off[n_reads] + 1, '\0');
         parallel_for(n_reads, [&](size_t rb, size_t re) { for (size_t r = rb; r < re; ++r) memcpy(&pool[off[r]], out_seq[r].data(), out_seq[r].size()); });
         std::vector<std::vector<rtk_hit>> solid, weak;
-        const auto t_seeds = std::chrono::steady_clock::now();
-        get_seeds_host(ctx, l_opt, pass, n_reads, pool.data(), off.data(), solid, weak, stats);
+        auto t_seeds = std::chrono::steady_clock::now();
+        if (seeds_turn) {
+            // The gangs take turns at the anchor stage, each with ALL host threads: the stage is short and host-heavy, and taking
+            // turns staggers the gangs - while one gang's regions are on the device, the next gang's anchors are computed.
+            std::lock_guard<std::mutex> turn(*seeds_turn);
+            const unsigned mine = thread_budget();
+            set_thread_budget(host_threads());
+            t_seeds = std::chrono::steady_clock::now();
+            get_seeds_host(ctx, l_opt, pass, n_reads, pool.data(), off.data(), solid, weak, stats);
+            set_thread_budget(mine);
+        } else get_seeds_host(ctx, l_opt, pass, n_reads, pool.data(), off.data(), solid, weak, stats);
         const auto t_broker = std::chrono::steady_clock::now();
         // every region of every read is one broker task: regions run concurrently on host threads, their GPU requests
         // are served in waves (broker.hpp); pieces are concatenated in read order afterwards
@@ -1216,7 +1227,7 @@ static void correct_range(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n
 // each running the whole pipeline (K1 sweeps -> anchors -> regions) on its own forked context and its own share of the host
 // threads.  While one gang's regions run on the device as one bulk launch (broker.hpp: the region service launches when every
 // live region of the gang is waiting for it), another gang's host stages (anchor logic, colour selection, stitching) run:
-// device and host overlap without any cross-gang dependency.  RTK_GANGS overrides the default of 2.
+// device and host overlap without any cross-gang dependency.  RTK_GANGS overrides the default of 3.
 void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
                         const char* qual_pool, const uint64_t* qual_off, std::vector<std::string>& out_seq, std::vector<std::string>& out_qual,
                         uint64_t* stats) {
@@ -1228,7 +1239,7 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
     out_seq.assign(n_reads, std::string());
     out_qual.assign(n_reads, std::string());
     const char* e = getenv("RTK_GANGS");
-    unsigned n_gangs = e ? (unsigned)std::max(1, atoi(e)) : 2u;
+    unsigned n_gangs = e ? (unsigned)std::max(1, atoi(e)) : 3u;
     const uint64_t total_bases = n_reads ? seq_off[n_reads] - seq_off[0] : 0;
     if (total_bases < (4u << 20) || n_reads < 2 * n_gangs) n_gangs = 1;   // small batches: not worth splitting
     n_gangs = std::min(n_gangs, std::max(1u, host_threads()));
@@ -1257,6 +1268,7 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
 #endif
         }
         const unsigned budget = std::max(1u, host_threads() / n_gangs);
+        std::mutex seeds_turn;
         std::vector<std::thread> th;
         for (unsigned gi = 0; gi < n_gangs; ++gi) {
             th.emplace_back([&, gi] {
@@ -1267,7 +1279,7 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
 #endif
                     const uint32_t r0 = cut[gi], n = cut[gi + 1] - cut[gi];
                     if (n) correct_range(gctx[gi], opt, pass, n, seq_pool, seq_off + r0, qual_pool, qual_off ? qual_off + r0 : nullptr, out_seq.data() + r0,
-                                         out_qual.data() + r0, gstats[gi].data());
+                                         out_qual.data() + r0, gstats[gi].data(), &seeds_turn);
                 } catch (const std::exception& ex) { errors[gi] = ex.what(); if (errors[gi].empty()) errors[gi] = "correction gang failed"; }
                 catch (...) { errors[gi] = "correction gang failed (unknown exception)"; }
             });

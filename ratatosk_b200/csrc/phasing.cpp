@@ -157,18 +157,39 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
     }
     });
 
-    // 3. whole-read NW paths raw (query) vs corrected (target)
+    // 3. whole-read NW paths raw (query) vs corrected (target).  The walk below only ever departs from the corrected read at
+    // positions marked in pos2rm: a read without any marked position comes out as its corrected self whatever the alignment
+    // is, so its (10 kb x 10 kb) alignment is not computed.  (The reference aligns every read, :1001; with one side empty it
+    // gets no alignment and emits nothing, which the unaligned walk below reproduces.)
+    std::vector<uint8_t> need(n, 0);
+    parallel_for(n, [&](size_t rb, size_t re) {
+        for (size_t r = rb; r < re; ++r) {
+            const bool empty_side = (raw_off[r + 1] == raw_off[r]) || (corr_off[r + 1] == corr_off[r]);
+            bool any = false;
+            for (const uint8_t x : pos2rm[r]) if (x) { any = true; break; }
+            need[r] = (any && !empty_side) ? 1 : 0;
+        }
+    });
     std::vector<AlignJob> jobs(n);
+    std::vector<AlignJob> ajobs;
+    std::vector<uint32_t> aidx;
     for (uint32_t r = 0; r < n; ++r) {
         jobs[r].q.assign(raw_pool + raw_off[r], (size_t)(raw_off[r + 1] - raw_off[r]));
         jobs[r].t.assign(corr_pool + corr_off[r], (size_t)(corr_off[r + 1] - corr_off[r]));
         jobs[r].mode = 0;
+        if (need[r]) { ajobs.push_back(jobs[r]); aidx.push_back(r); }
     }
-    std::vector<int32_t> dist;
-    std::vector<std::vector<uint8_t>> ops;
-    {
-        PathReq rq{&jobs, &dist, &ops};
+    std::vector<std::vector<uint8_t>> ops(n);
+    if (!ajobs.empty()) {
+        std::vector<int32_t> dist;
+        std::vector<std::vector<uint8_t>> aops;
+        PathReq rq{&ajobs, &dist, &aops};
         run_path_batch(ctx, std::vector<PathReq*>(1, &rq));
+        for (size_t i = 0; i < aidx.size(); ++i) ops[aidx[i]] = std::move(aops[i]);
+    }
+    for (uint32_t r = 0; r < n; ++r) {
+        // not aligned: an all-match walk over the corrected read (no position is marked) / nothing when a side is empty
+        if (!need[r] && raw_off[r + 1] != raw_off[r] && corr_off[r + 1] != corr_off[r]) ops[r].assign(jobs[r].t.size(), 2);
     }
 
     // walk the alignment (:1001-1052) and collect the reverted neighbourhoods

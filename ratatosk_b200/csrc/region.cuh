@@ -41,6 +41,7 @@
 #define RTK_RG_QCAP 512         /* max_sz_stck of the reference: reaching it collapses the queue (bail) */
 #define RTK_RG_VCAP 1024        /* max_paths of the reference */
 #define RTK_RG_MAX_SEGS 32       /* extractSemiWeakPaths restarts of one region (dead ends followed) */
+#define RTK_RG_HSTACK 64         /* open quadrants of edlib's divide-and-conquer traceback */
 #define RTK_RG_DROPPED 0xFFFFFFFEu /* queue marker: a path that is dropped when popped (already >= max_len_path) */
 
 // why a region was handed back to the host path
@@ -105,12 +106,13 @@ struct rtk_rg_params {
     int32_t out_qual, max_qual;
     double wrlf;                 // weak_region_len_factor
     double min_score;
+    uint64_t tb_limit;           // edlib's direct-traceback limit in bytes of alignment state (1 MiB)
 };
 
 // bytes of per-warp scratch for the capacities in p (shared by the host launcher and the kernel's carve-up)
 RTK_HD uint64_t rtk_rg_align16(const uint64_t x) { return (x + 15ull) & ~15ull; }
 struct rtk_rg_layout {
-    uint64_t sA, sB, sC, hb, mat, anc, dfs, dfs_cur, segs, tmpT, tmpN, arena, q_items, v_items, vt_items, ch_nodes, ch_qual, total;
+    uint64_t sA, sB, sC, hb, mat, anc, dfs, dfs_cur, segs, hstack, tmpT, tmpN, arena, q_items, v_items, vt_items, ch_nodes, ch_qual, total;
 };
 RTK_HD rtk_rg_layout rtk_rg_make_layout(const uint32_t str_cap, const uint32_t mat_cells, const uint32_t tmp_cap, const uint32_t arena_cap,
                                         const uint32_t chain_nodes_cap, const uint32_t chain_len_cap) {
@@ -125,6 +127,7 @@ RTK_HD rtk_rg_layout rtk_rg_make_layout(const uint32_t str_cap, const uint32_t m
     L.dfs = o; o += rtk_rg_align16((uint64_t)RTK_DFS_STACK * sizeof(rtk_dfs_frame));
     L.dfs_cur = o; o += rtk_rg_align16(sizeof(rtk_dfs_frame));
     L.segs = o; o += rtk_rg_align16((uint64_t)RTK_RG_MAX_SEGS * sizeof(rtk_region_seg_t));
+    L.hstack = o; o += rtk_rg_align16((uint64_t)RTK_RG_HSTACK * 16);
     L.tmpT = o; o += rtk_rg_align16(tmp_cap);
     L.tmpN = o; o += rtk_rg_align16(tmp_cap);
     L.arena = o; o += rtk_rg_align16(arena_cap);
@@ -156,6 +159,7 @@ struct rg_ctx {
     ulonglong2* mat; int32_t* anc;
     rtk_dfs_frame* dfs; rtk_dfs_frame* dfs_cur;
     rtk_region_seg_t* segs;
+    uint4* hstack;
     unsigned char* tmpT; unsigned char* tmpN; unsigned char* arena;
     uint32_t* q_items; uint32_t* v_items; uint32_t* vt_items;
     rtk_rg_node* ch_nodes; char* ch_qual;
@@ -270,9 +274,9 @@ __device__ RTK_RG_NOINLINE rg_dist rg_myers(rg_ctx& C, const char* __restrict__ 
 
 // ------------------------------------------------------------------------------------------------ K5 in the warp
 // edlib's direct traceback is used below 1 MiB of state (src/edlib.cpp:1191-1193), Hirschberg above
-__device__ __forceinline__ bool rg_needs_hirschberg(const uint64_t qlen, const uint64_t tlen) {
+__device__ __forceinline__ bool rg_needs_hirschberg(const rg_ctx& C, const uint64_t qlen, const uint64_t tlen) {
     const uint64_t nb = (qlen + 63) / 64;
-    return (2ull * 8 + 4) * nb * tlen + 2ull * 4 * tlen >= 1024ull * 1024ull;
+    return (2ull * 8 + 4) * nb * tlen + 2ull * 4 * tlen >= C.p->tb_limit;
 }
 
 struct rg_tb_cell { uint64_t P, M; int32_t A; };
@@ -295,25 +299,15 @@ __device__ __forceinline__ int rg_tb_row(const rg_tb_cell& c, const int arow, co
     return c.A - __popcll(c.P & m) + __popcll(c.M & m);
 }
 
-// getScorePath(opt, path, ref, ref_len, best, second) (src/GraphTraversal.cpp:722-772): per-base quality of a kept path.
-// SHW alignment of the spelled path `ps` against the window `t` (edlib PATH task = distance + first end column from the
-// distance sweep, then the NW path against that target prefix, src/edlib.cpp:262-279); every path base that sits on an exact
-// match of an M run gets `best_q`, the others `base_q`.  The traceback (move priority up > left > diagonal,
-// src/edlib.cpp:1023-1134) is walked in place by lane 0 over the stored sweep.
-__device__ RTK_RG_NOINLINE void rg_path_quality(rg_ctx& C, const char* __restrict__ ps, const int qlen, const char* __restrict__ t, const int tlen_full,
-                                                const char base_q, const char best_q, char* __restrict__ qual_out) {
+// NW traceback of ps[0, qlen) against t[0, tlen) below edlib's 1 MiB switch: matrix-storing sweep (rtk_myers_fill_body<32, false>
+// with the matrix in the warp's scratch) + the walk of rtk_traceback_kernel (move priority up > left > diagonal,
+// src/edlib.cpp:1023-1134) by lane 0; every diagonal move onto identical characters sets qual_out[i] = best_q.
+__device__ RTK_RG_NOINLINE void rg_quality_direct(rg_ctx& C, const char* __restrict__ ps, const int qlen, const char* __restrict__ t, const int tlen,
+                                                  const char best_q, char* __restrict__ qual_out) {
     const uint32_t lane = C.lane;
-    for (int i = (int)lane; i < qlen; i += 32) qual_out[i] = base_q;
-    __syncwarp();
-    if (qlen == 0 || tlen_full == 0) return;
-    const rg_dist d = rg_myers(C, ps, qlen, t, tlen_full, 1);
-    const int tlen = d.first + 1;       // SHW ending "before the target starts" (position -1): every path base unaligned
-    if (tlen <= 0) return;
-    if (rg_needs_hirschberg((uint64_t)qlen, (uint64_t)tlen)) { C.bail = RTK_RG_BAIL_HIRSCH; return; }
     const int nb = (qlen + 63) >> 6;
     if ((uint64_t)nb * (uint64_t)tlen > (uint64_t)C.p->mat_cells) { C.bail = RTK_RG_BAIL_HIRSCH; return; }
     ++C.n_aligns;
-    // ---- matrix-storing sweep (rtk_myers_fill_body<32, false> with the matrix in the warp's scratch)
     constexpr int G = 32;
     const unsigned gmask = 0xffffffffu;
     const char* q = ps;
@@ -384,7 +378,6 @@ __device__ RTK_RG_NOINLINE void rg_path_quality(rg_ctx& C, const char* __restric
     }
     nw_dist = __shfl_sync(gmask, nw_dist, (nb - 1) % G);
     __syncwarp();
-    // ---- traceback walk (rtk_traceback_kernel), lane 0; diagonal moves onto identical characters earn best_q
     if (lane == 0) {
         const int last_row = (qlen - 1) & 63;
         int i = qlen - 1, c = tlen - 1, cur_score = nw_dist;
@@ -436,6 +429,148 @@ __device__ RTK_RG_NOINLINE void rg_path_quality(rg_ctx& C, const char* __restric
         }
     }
     __syncwarp();
+}
+
+// rows[r] = D[r + 1][tlen] of the NW matrix of q against t (both read backwards when rev): the last column edlib's
+// divide-and-conquer needs from the forward left half and the reversed right half (src/edlib.cpp:1234-1330).  A distance
+// sweep in which every lane keeps the score of its block's anchor row; the rows follow from the final vertical deltas.
+__device__ RTK_RG_NOINLINE void rg_lastcol_rows(rg_ctx& C, const char* __restrict__ q, const int qlen, const char* __restrict__ t, const int tlen,
+                                                const bool rev, int32_t* __restrict__ rows) {
+    const uint32_t lane = C.lane;
+    if (tlen == 0) { for (int r = (int)lane; r < qlen; r += 32) rows[r] = r + 1; __syncwarp(); return; }
+    ++C.n_aligns;
+    constexpr int G = 32;
+    const unsigned gmask = 0xffffffffu;
+    const int nb = (qlen + 63) >> 6;
+    const int rounds = (nb + G - 1) / G;
+    int8_t* hb = C.hb;
+    bool t_amb = false;
+    for (int i = (int)lane; i < tlen; i += G) { const char ch = t[i]; t_amb |= (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T'); }
+    t_amb = __any_sync(gmask, t_amb);
+    for (int r = 0; r < rounds; ++r) {
+        const int b = r * G + (int)lane;
+        const bool has = b < nb;
+        const int arow = (b == nb - 1) ? ((qlen - 1) & 63) : 63;
+        uint64_t PB0 = 0, PB1 = 0, PB2 = 0, PB3 = 0;
+        if (has) {
+            const int lo = b << 6;
+            const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+            for (int i = 0; i < n; ++i) {
+                const uint64_t m = rtk_iupac_mask(rev ? q[qlen - 1 - (lo + i)] : q[lo + i]);
+                PB0 |= (m & 1) << i; PB1 |= ((m >> 1) & 1) << i; PB2 |= ((m >> 2) & 1) << i; PB3 |= ((m >> 3) & 1) << i;
+            }
+        }
+        uint64_t Pv = ~0ULL, Mv = 0;
+        int hout = 0;
+        int score = (b << 6) + arow + 1;
+        const bool spill = (lane == G - 1) && (r + 1 < rounds);
+        const int steps = tlen + (nb < G ? nb : G) - 1;
+        char tc_next = (lane == 0) ? (rev ? t[tlen - 1] : t[0]) : (char)0;
+        const bool top_spilled = (lane == 0) && (r != 0);
+        for (int s = 0; s < steps; ++s) {
+            const int from_left = __shfl_up_sync(gmask, hout, 1, G);
+            const int col = s - (int)lane;
+            const char tc = tc_next;
+            tc_next = ((unsigned)(col + 1) < (unsigned)tlen) ? (rev ? t[tlen - 2 - col] : t[col + 1]) : (char)0;
+            const bool active = has && ((unsigned)col < (unsigned)tlen);
+            int hin = (lane == 0) ? 1 : from_left;
+            if (top_spilled && active) hin = (int)hb[col];
+            uint64_t Eq = (tc == 'A') ? PB0 : (tc == 'C') ? PB1 : (tc == 'G') ? PB2 : (tc == 'T') ? PB3 : 0ULL;
+            if (t_amb && active && tc != 'A' && tc != 'C' && tc != 'G' && tc != 'T') {
+                const int lo = b << 6;
+                const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+                for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(rev ? q[qlen - 1 - (lo + i)] : q[lo + i], tc) << i;
+            }
+            const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
+            const uint64_t Xv = Eq | Mv;
+            Eq |= neg;
+            const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+            uint64_t Ph = Mv | ~(Xh | Pv);
+            uint64_t Mh = Pv & Xh;
+            hout = active ? ((int)(Ph >> 63) - (int)(Mh >> 63)) : 0;
+            score += active ? ((int)((Ph >> arow) & 1) - (int)((Mh >> arow) & 1)) : 0;
+            Ph = (Ph << 1) | ((hin > 0) ? 1ULL : 0ULL);
+            Mh = (Mh << 1) | neg;
+            const uint64_t nPv = Mh | ~(Xv | Ph), nMv = Ph & Xv;
+            Pv = active ? nPv : Pv;
+            Mv = active ? nMv : Mv;
+            if (spill && active) hb[col] = (int8_t)hout;
+        }
+        if (has) {   // rows of this block from the anchor row upwards: D(r) = D(r + 1) - delta(r + 1)
+            int sc = score;
+            rows[(b << 6) + arow] = sc;
+            for (int rr = arow - 1; rr >= 0; --rr) {
+                sc -= (int)((Pv >> (rr + 1)) & 1) - (int)((Mv >> (rr + 1)) & 1);
+                rows[(b << 6) + rr] = sc;
+            }
+        }
+        __syncwarp(gmask);
+    }
+}
+
+// edlib's obtainAlignment for an NW problem of any size (src/edlib.cpp:1164-1399): below the 1 MiB switch the direct
+// traceback; above it the target is halved, the last columns of the forward left half and of the reversed right half give
+// the first query row at which the two halves add up to the distance (:1330-1356), and both quadrants are solved the same
+// way.  Only the matched positions are wanted here, so the quadrants are simply worked off a stack.
+__device__ RTK_RG_NOINLINE void rg_nw_quality(rg_ctx& C, const char* __restrict__ ps, const int qlen, const char* __restrict__ t, const int tlen,
+                                              const char best_q, char* __restrict__ qual_out) {
+    const uint32_t lane = C.lane;
+    uint4* st = C.hstack;
+    int sp = 0;
+    if (lane == 0) st[0] = make_uint4(0u, (uint32_t)qlen, 0u, (uint32_t)tlen);
+    sp = 1;
+    __syncwarp();
+    while (sp > 0 && !C.bail) {
+        const uint4 nd = st[--sp];
+        __syncwarp();
+        const uint32_t qx = nd.x, qy = nd.y, tu = nd.z, tv = nd.w;
+        const uint32_t ql = qy - qx, tl = tv - tu;
+        if (ql == 0 || tl == 0) continue;
+        if (!rg_needs_hirschberg(C, ql, tl)) { rg_quality_direct(C, ps + qx, (int)ql, t + tu, (int)tl, best_q, qual_out + qx); continue; }
+        if ((uint64_t)ql * 8 > (uint64_t)C.p->mat_cells * 16 || sp + 2 > RTK_RG_HSTACK) { C.bail = RTK_RG_BAIL_HIRSCH; break; }
+        const uint32_t left = tl / 2, right = tl - left;
+        int32_t* L = (int32_t*)C.mat;
+        int32_t* Rr = L + ql;
+        rg_lastcol_rows(C, ps + qx, (int)ql, t + tu, (int)left, false, L);
+        rg_lastcol_rows(C, ps + qx, (int)ql, t + tu + left, (int)right, true, Rr);   // Rr[i] = dist(reversed q prefix i + 1, reversed right half)
+        const int best = rg_myers(C, ps + qx, (int)ql, t + tu, (int)tl, 0).dist;
+        __syncwarp();
+        // first row r in [0, ql - 1) with L[r] + R(r + 1) == best, R(j) = Rr[ql - 1 - j] = dist(q[j:], right half)
+        int split = -2;
+        for (uint32_t base = 0; base + 1 < ql && split == -2; base += 32) {
+            const uint32_t r = base + lane;
+            const bool hit = (r + 1 < ql) && (L[r] + Rr[ql - 2 - r] == best);
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) split = (int)(base + (uint32_t)(__ffs(m) - 1));
+        }
+        if (split == -2 && (int)left + Rr[ql - 1] == best) split = -1;
+        if (split == -2 && L[ql - 1] + (int)right == best) split = (int)ql - 1;
+        if (split == -2) { C.bail = RTK_RG_BAIL_LOGIC; break; }
+        const uint32_t ul_h = (uint32_t)(split + 1);
+        __syncwarp();
+        if (lane == 0) {
+            st[sp] = make_uint4(qx, qx + ul_h, tu, tu + left);
+            st[sp + 1] = make_uint4(qx + ul_h, qy, tu + left, tv);
+        }
+        sp += 2;
+        __syncwarp();
+    }
+}
+
+// getScorePath(opt, path, ref, ref_len, best, second) (src/GraphTraversal.cpp:722-772): per-base quality of a kept path.
+// SHW alignment of the spelled path `ps` against the window `t` (edlib PATH task = distance + first end column from the
+// distance sweep, then the NW path against that target prefix, src/edlib.cpp:262-279); every path base that sits on an exact
+// match of an M run gets `best_q`, the others `base_q`.
+__device__ RTK_RG_NOINLINE void rg_path_quality(rg_ctx& C, const char* __restrict__ ps, const int qlen, const char* __restrict__ t, const int tlen_full,
+                                                const char base_q, const char best_q, char* __restrict__ qual_out) {
+    const uint32_t lane = C.lane;
+    for (int i = (int)lane; i < qlen; i += 32) qual_out[i] = base_q;
+    __syncwarp();
+    if (qlen == 0 || tlen_full == 0) return;
+    const rg_dist d = rg_myers(C, ps, qlen, t, tlen_full, 1);
+    const int tlen = d.first + 1;       // SHW ending "before the target starts" (position -1): every path base unaligned
+    if (tlen <= 0) return;
+    rg_nw_quality(C, ps, qlen, t, tlen, best_q, qual_out);
 }
 
 // ------------------------------------------------------------------------------------------------ burst (K2/K3 + leaf K4)
@@ -1166,7 +1301,7 @@ __global__ void __launch_bounds__(32) rtk_region_kernel(const rtk_rg_params p) {
         C.p = &p; C.lane = lane;
         C.sA = (char*)(S + L.sA); C.sB = (char*)(S + L.sB); C.sC = (char*)(S + L.sC); C.hb = (int8_t*)(S + L.hb);
         C.mat = (ulonglong2*)(S + L.mat); C.anc = (int32_t*)(S + L.anc);
-        C.dfs = (rtk_dfs_frame*)(S + L.dfs); C.dfs_cur = (rtk_dfs_frame*)(S + L.dfs_cur); C.segs = (rtk_region_seg_t*)(S + L.segs);
+        C.dfs = (rtk_dfs_frame*)(S + L.dfs); C.dfs_cur = (rtk_dfs_frame*)(S + L.dfs_cur); C.segs = (rtk_region_seg_t*)(S + L.segs); C.hstack = (uint4*)(S + L.hstack);
         C.tmpT = S + L.tmpT; C.tmpN = S + L.tmpN; C.arena = S + L.arena;
         C.q_items = (uint32_t*)(S + L.q_items); C.v_items = (uint32_t*)(S + L.v_items); C.vt_items = (uint32_t*)(S + L.vt_items);
         C.ch_nodes = (rtk_rg_node*)(S + L.ch_nodes); C.ch_qual = (char*)(S + L.ch_qual);

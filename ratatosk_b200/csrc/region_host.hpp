@@ -12,6 +12,7 @@
 
 #include "../../include/rtk.h"
 #include "region.cuh"
+#include "traceback_host.hpp"
 
 namespace rtk {
 
@@ -42,6 +43,7 @@ inline void region_fill_params(rtk_rg_params& p, const rtk_opt& opt, int pass, c
     p.max_len_subpath = (uint32_t)static_cast<size_t>(opt.k * opt.large_k_factor);   // src/GraphTraversal.cpp:594
     p.out_qual = opt.out_qual; p.max_qual = opt.max_qual;
     p.wrlf = opt.weak_region_len_factor; p.min_score = opt.min_score;
+    p.tb_limit = tb_limit();
 }
 
 inline void region_check_calls(uint32_t n_calls, const rtk_region_call_t* calls, uint64_t win_bytes, uint64_t n_weak, uint64_t n_pids, uint64_t n_unitigs,

@@ -9,6 +9,7 @@
 // problems) and direct tracebacks, this file drives the recursion level by level so that every level is
 // one batch.
 #pragma once
+#include <cstdlib>
 #include <stdint.h>
 
 #include <algorithm>
@@ -17,9 +18,16 @@
 
 namespace rtk {
 
+// edlib's switch between the direct traceback and its divide-and-conquer: 1 MiB of alignment state (src/edlib.cpp:1191-1193).
+// RTK_TB_LIMIT lowers it for tests that compare the two implementations of the divide-and-conquer (device engine vs K5 host
+// driver) on small inputs; never set in production (the reference's switch is part of its output).
+inline uint64_t tb_limit() {
+    static const uint64_t v = [] { const char* e = getenv("RTK_TB_LIMIT"); return e ? (uint64_t)strtoull(e, nullptr, 10) : 1024ull * 1024ull; }();
+    return v;
+}
 inline bool tb_needs_hirschberg(uint64_t qlen, uint64_t tlen) {
     const uint64_t nb = (qlen + 63) / 64;
-    return (2ull * 8 + 4) * nb * tlen + 2ull * 4 * tlen >= 1024ull * 1024ull;
+    return (2ull * 8 + 4) * nb * tlen + 2ull * 4 * tlen >= tb_limit();
 }
 
 struct TbItem {

@@ -21,6 +21,8 @@
 
 struct sim_dim3 { unsigned x = 1, y = 1, z = 1; };
 struct ulonglong2 { unsigned long long x, y; };
+struct uint4 { unsigned x, y, z, w; };
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 
 extern thread_local sim_dim3 threadIdx, blockIdx;
 extern sim_dim3 blockDim, gridDim;

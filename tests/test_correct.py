@@ -221,3 +221,35 @@ def test_correction_cuda_matches_reference_library_on_fresh_reads():
     assert len(unstable) <= 0.03 * len(reads), unstable
     ctx.close()
     g.close()
+
+
+F4 = os.path.join(ROOT, "bench_data", "F4")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(F4, "index.k31.rtsk")), reason="bench_data/F4 not generated (scripts/make_f4.sh)")
+def test_two_pass_cuda_matches_reference_cli_at_chr20_scale():
+    """BASELINE configs[2] scale: the 64 Mbp diploid index built by the unmodified reference (bench_data/F4: k = 31 graph
+    coloured by 30x PE150, k = 63 graph coloured by 3x pass-1-corrected long reads; slabs of 1.3 GB / 0.9 GB, far beyond the
+    L2) and the first 200 long reads of the recipe.  Expected = the reference CLI's own files: `correct -1` and
+    `correct -2 -O` (phasing + second pass)."""
+    raw = read_fastq(os.path.join(F4, "reads200.fastq.gz"))
+    gold1 = read_fastq(os.path.join(F4, "corrected200_pass1.fastq.gz"))
+    gold2 = read_fastq(os.path.join(F4, "corrected200_pass2.fastq.gz"))
+    g = rb.Graph.load(os.path.join(F4, "index.k31.fasta.gz"), os.path.join(F4, "index.k31.rtsk"), 31)
+    ctx = rb.Context(0)
+    ctx.upload(g)
+    p1 = ctx.correct([r[1] for r in raw], [r[2] for r in raw])
+    bad = [i for i in range(len(raw)) if p1[i] != (gold1[i][1], gold1[i][2])]
+    assert len(bad) <= 2, ("pass 1", bad[:10])   # colour-set ties the reference breaks by pointer order (see the fresh-reads test)
+    ctx.close()
+    g.close()
+    g = rb.Graph.load(os.path.join(F4, "index.k63.fasta.gz"), os.path.join(F4, "index.k63.rtsk"), 63)
+    ctx = rb.Context(0)
+    ctx.upload(g)
+    ph = ctx.phasing([r[1].upper() for r in raw], [r[1] for r in gold1], [r[2] for r in gold1])
+    fin = ctx.correct([o[0] for o in ph], [o[1] for o in ph], pass_no=2)
+    bad = [i for i in range(len(raw)) if fin[i] != (gold2[i][1], gold2[i][2])]
+    assert len(bad) <= 2, ("pass 2", bad[:10])
+    ctx.close()
+    g.close()
