@@ -13,6 +13,8 @@
 //   4. exact sweep of the reverted neighbourhoods; bases of the result covered by a graph k-mer get the maximum
 //      quality (:1054-1080; K1 exact kernel, batched)
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -79,6 +81,14 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
     const size_t max_limit_nb_pids = 1000, nb_bits_elem_tbf = 14;
     out_seq.assign(n, std::string());
     out_qual.assign(n, std::string());
+    const bool prof = getenv("RTK_BROKER_PROFILE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!prof) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[phasing] %s: %.1f ms\n", what, std::chrono::duration_cast<std::chrono::microseconds>(now - t_prev).count() / 1e3);
+        t_prev = now;
+    };
 
     // 1. map the corrected reads (one exact sweep for the whole batch)
     std::vector<std::vector<rtk_hit>> hits;
@@ -88,6 +98,7 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
         search_sequence_host(ctx, n, corr_pool + corr_off[0], off.data(), RTK_SEARCH_EXACT, hits, nullptr);
     }
 
+    lap("exact sweep of the corrected reads");
     // 2. positions to revert, per read
     std::vector<std::vector<uint8_t>> pos2rm(n);
     parallel_for(n, [&](size_t rb, size_t re) {
@@ -157,6 +168,7 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
     }
     });
 
+    lap("colour sketches / compatibility");
     // 3. whole-read NW paths raw (query) vs corrected (target).  The walk below only ever departs from the corrected read at
     // positions marked in pos2rm: a read without any marked position comes out as its corrected self whatever the alignment
     // is, so its (10 kb x 10 kb) alignment is not computed.  (The reference aligns every read, :1001; with one side empty it
@@ -187,6 +199,8 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
         run_path_batch(ctx, std::vector<PathReq*>(1, &rq));
         for (size_t i = 0; i < aidx.size(); ++i) ops[aidx[i]] = std::move(aops[i]);
     }
+    if (prof) fprintf(stderr, "[phasing] %zu of %u reads aligned\n", ajobs.size(), n);
+    lap("whole-read alignments");
     for (uint32_t r = 0; r < n; ++r) {
         // not aligned: an all-match walk over the corrected read (no position is marked) / nothing when a side is empty
         if (!need[r] && raw_off[r + 1] != raw_off[r] && corr_off[r + 1] != corr_off[r]) ops[r].assign(jobs[r].t.size(), 2);
@@ -245,6 +259,7 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
     }
     });
 
+    lap("revert walk");
     // 4. reverted bases that sit in a graph k-mer after all get the maximum quality (:1081-1090)
     {
         std::string pool;
@@ -258,6 +273,7 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
                 for (size_t j = h.pos; j < h.pos + k && j < out_qual[r].size(); ++j)
                     if (out_qual[r][j] == q_min) out_qual[r][j] = q_max;
     }
+    lap("second sweep");
 }
 
 }  // namespace rtk

@@ -137,12 +137,15 @@ struct CudaTbBackend : TbBackend {
         float t = 0.f;
         RTK_CUDA(cudaEventElapsedTime(&t, c->ev0, c->ev1));
         ms += t;
-        for (uint32_t a = 0; a < n; ++a) {
-            const uint32_t nb = (items[a].q_len + 63) / 64;
-            std::vector<uint64_t> P(nb), M(nb);
-            for (uint32_t b = 0; b < nb; ++b) { P[b] = cells[2 * (pl.mat_off[a] + b)]; M[b] = cells[2 * (pl.mat_off[a] + b) + 1]; }
-            tb_rows_from_column(items[a].q_len, P.data(), M.data(), anchor.data() + pl.mat_off[a], rows[a]);
-        }
+        parallel_for(n, [&](size_t ab, size_t ae) {
+            std::vector<uint64_t> P, M;
+            for (size_t a = ab; a < ae; ++a) {
+                const uint32_t nb = (items[a].q_len + 63) / 64;
+                P.resize(nb); M.resize(nb);
+                for (uint32_t b = 0; b < nb; ++b) { P[b] = cells[2 * (pl.mat_off[a] + b)]; M[b] = cells[2 * (pl.mat_off[a] + b) + 1]; }
+                tb_rows_from_column(items[a].q_len, P.data(), M.data(), anchor.data() + pl.mat_off[a], rows[a]);
+            }
+        });
     }
 };
 

@@ -10,6 +10,7 @@
 // one batch.
 #pragma once
 #include <cstdlib>
+#include <functional>
 #include <stdint.h>
 
 #include <algorithm>
@@ -17,6 +18,10 @@
 #include <vector>
 
 namespace rtk {
+
+// chunked parallel loop supplied by the including library (rtk_graph_api.cpp: parallel_for)
+void parallel_for(size_t n, const std::function<void(size_t, size_t)>& body);
+inline void tb_parallel_for(size_t n, const std::function<void(size_t, size_t)>& body) { parallel_for(n, body); }
 
 // edlib's switch between the direct traceback and its divide-and-conquer: 1 MiB of alignment state (src/edlib.cpp:1191-1193).
 // RTK_TB_LIMIT lowers it for tests that compare the two implementations of the divide-and-conquer (device engine vs K5 host
@@ -116,26 +121,37 @@ inline void solve_nw_paths(TbBackend& be, uint32_t n, const uint64_t* q_beg, con
             }
             std::vector<std::vector<int32_t>> rows;
             be.last_column(items, rows);
+            // the split row of every big problem (independent of one another): first query row at which the two halves add up
+            std::vector<int> splits(big_ids.size(), -2);
+            std::vector<int32_t> bests(big_ids.size(), -1);
+            tb_parallel_for(big_ids.size(), [&](size_t ib, size_t ie) {
+                for (size_t i = ib; i < ie; ++i) {
+                    const int id = big_ids[i];
+                    const uint32_t ql = nodes[id].qy - nodes[id].qx, tl = nodes[id].tv - nodes[id].tu;
+                    const uint32_t left = tl / 2, right = tl - left;
+                    const std::vector<int32_t>& L = rows[3 * i];
+                    const std::vector<int32_t>& Rr = rows[3 * i + 1];   // Rr[i'] = dist(rev q prefix i'+1, rev right half)
+                    const int32_t best = rows[3 * i + 2][ql - 1];
+                    auto R = [&](uint32_t j) { return Rr[ql - 1 - j]; };  // dist(q[j:], right half)
+                    int split = -2;
+                    for (uint32_t r = 0; r + 1 < ql; ++r)
+                        if (L[r] + R(r + 1) == best) { split = (int)r; break; }
+                    if (split == -2 && (int32_t)left + R(0) == best) split = -1;
+                    if (split == -2 && L[ql - 1] + (int32_t)right == best) split = (int)ql - 1;
+                    splits[i] = split; bests[i] = best;
+                }
+            });
             for (size_t i = 0; i < big_ids.size(); ++i) {
                 const int id = big_ids[i];
-                const uint32_t ql = nodes[id].qy - nodes[id].qx, tl = nodes[id].tv - nodes[id].tu;
-                const uint32_t left = tl / 2, right = tl - left;
-                const std::vector<int32_t>& L = rows[3 * i];
-                const std::vector<int32_t>& Rr = rows[3 * i + 1];   // Rr[i'] = dist(rev q prefix i'+1, rev right half)
-                const int32_t best = rows[3 * i + 2][ql - 1];
-                auto R = [&](uint32_t j) { return Rr[ql - 1 - j]; };  // dist(q[j:], right half)
-                int split = -2, lscore = -1, rscore = -1;
-                for (uint32_t r = 0; r + 1 < ql; ++r)
-                    if (L[r] + R(r + 1) == best) { split = (int)r; lscore = L[r]; rscore = R(r + 1); break; }
-                if (split == -2 && (int32_t)left + R(0) == best) { split = -1; lscore = (int32_t)left; rscore = R(0); }
-                if (split == -2 && L[ql - 1] + (int32_t)right == best) { split = (int)ql - 1; lscore = L[ql - 1]; rscore = (int32_t)right; }
+                const uint32_t tl = nodes[id].tv - nodes[id].tu;
+                const uint32_t left = tl / 2;
+                const int split = splits[i];
                 if (split == -2) throw std::runtime_error("alignment split not found");
-                (void)lscore; (void)rscore;
                 const uint32_t ul_h = (uint32_t)(split + 1);
                 const Node parent = nodes[id];
                 Node ul{parent.a, parent.qx, parent.qx + ul_h, parent.tu, parent.tu + left, {-1, -1}, {}, -1};
                 Node lr{parent.a, parent.qx + ul_h, parent.qy, parent.tu + left, parent.tv, {-1, -1}, {}, -1};
-                nodes[id].dist = best;
+                nodes[id].dist = bests[i];
                 nodes[id].child[0] = (int)nodes.size(); nodes.push_back(ul); next.push_back(nodes[id].child[0]);
                 nodes[id].child[1] = (int)nodes.size(); nodes.push_back(lr); next.push_back(nodes[id].child[1]);
             }
