@@ -1,0 +1,440 @@
+// rtk_cli.cpp — host driver: FASTQ -> librtk_b200.so -> FASTQ.  The ticket loop of the reference's search()
+// (src/Ratatosk.cpp:727-906), its ordered block writer (:869-886, :919-999) and writeCorrectedOutput with -t trimming
+// (:510-616) around the C ABI of include/rtk.h.  Same command line as `Ratatosk correct -1 | -2` from an index
+// (src/Ratatosk.cpp:151-296): the files it writes are byte-identical to the reference's.
+//
+//   rtk_correct correct -1 -g G.k31.fasta.gz -d G.k31.rtsk -l reads.fastq[.gz] -o out            -> out.2.fastq
+//   rtk_correct correct -2 -g G.k63.fasta.gz -d G.k63.rtsk -l out.2.fastq -L reads.fastq -o out  -> out.fastq[.gz with -G]
+//
+// What differs from the reference, by design:
+//   * a ticket is --ticket-bases (default 32 Mi) of reads, not buffer_sz = 1 MiB: one ticket = one rtk_correct_batch call, and
+//     the GPU wants thousands of regions per call.  Ticket size is not observable in the output (blocks are written in ticket
+//     order, which the reference restores with its re-ordering pass for pass 1 and for pass 2 under -O).
+//   * tickets are dealt to --gpus devices (one calling thread + one context per device, graph uploaded once per device);
+//     blocks are formatted (and gzip-compressed, one member per block, when -G) by the device threads in parallel and written by
+//     one ordered writer: no temporary file, no second pass over the output.
+//   * pass 2 always runs phasing() (the reference's multi-thread branch, `-c` >= 2) and always writes in input order (`-O`).
+//   * there is no CPU path: without a CUDA device rtk_ctx_create fails and the driver exits with its message.
+#include <getopt.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/rtk.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- FASTA / FASTQ reader
+// kseq semantics (Bifrost/src/File_Parser.hpp -> kseq.h): name = header up to the first white space, multi-line records,
+// '>' records have no quality string; plain or gzip input.
+class SeqReader {
+  public:
+    explicit SeqReader(const std::vector<std::string>& files) : files_(files) {}
+    ~SeqReader() { if (gz_) gzclose(gz_); }
+    bool next(std::string& name, std::string& seq, std::string& qual, bool& has_qual) {
+        for (;;) {
+            if (!gz_ && !open_next()) return false;
+            if (read_record(name, seq, qual, has_qual)) return true;
+            gzclose(gz_); gz_ = nullptr;
+        }
+    }
+    const std::string& error() const { return err_; }
+
+  private:
+    bool open_next() {
+        if (fi_ >= files_.size()) return false;
+        gz_ = gzopen(files_[fi_].c_str(), "rb");
+        if (!gz_) { err_ = "cannot open " + files_[fi_]; fi_ = files_.size(); return false; }
+        gzbuffer(gz_, 1u << 20);
+        ++fi_; pos_ = len_ = 0; eof_ = false; pending_ = 0;
+        return true;
+    }
+    int getc_() {
+        if (pos_ == len_) {
+            if (eof_) return -1;
+            const int n = gzread(gz_, buf_, sizeof(buf_));
+            if (n <= 0) { eof_ = true; return -1; }
+            len_ = (size_t)n; pos_ = 0;
+        }
+        return (unsigned char)buf_[pos_++];
+    }
+    // appends the rest of the current line to s (without the line end); false at end of file with nothing read
+    bool getline_(std::string& s) {
+        bool any = false;
+        for (;;) {
+            if (pos_ == len_) { if (getc_() < 0) return any; --pos_; }
+            const char* b = buf_ + pos_;
+            const char* e = (const char*)memchr(b, '\n', len_ - pos_);
+            any = true;
+            if (e) { s.append(b, e); pos_ += (size_t)(e - b) + 1; break; }
+            s.append(b, (size_t)(len_ - pos_)); pos_ = len_;
+        }
+        if (!s.empty() && s.back() == '\r') s.pop_back();
+        return true;
+    }
+    bool read_record(std::string& name, std::string& seq, std::string& qual, bool& has_qual) {
+        int c = pending_;
+        pending_ = 0;
+        while (c != '>' && c != '@') { c = getc_(); if (c < 0) return false; }   // skip to the next header
+        line_.clear();
+        if (!getline_(line_)) return false;
+        size_t e = 0;
+        while (e < line_.size() && !isspace((unsigned char)line_[e])) ++e;
+        name.assign(line_, 0, e);
+        seq.clear(); qual.clear(); has_qual = false;
+        for (;;) {   // sequence lines up to '+', the next header or the end of the file
+            c = getc_();
+            if (c < 0) return true;
+            if (c == '+' || c == '>' || c == '@') break;
+            if (c == '\n' || c == '\r') continue;
+            seq.push_back((char)c);
+            getline_(seq);
+        }
+        if (c != '+') { pending_ = c; return true; }
+        line_.clear(); getline_(line_);   // rest of the '+' line
+        has_qual = true;
+        while (qual.size() < seq.size()) { const size_t before = qual.size(); if (!getline_(qual) && qual.size() == before) break; }
+        return true;
+    }
+    std::vector<std::string> files_;
+    size_t fi_ = 0;
+    gzFile gz_ = nullptr;
+    char buf_[1 << 16];
+    size_t pos_ = 0, len_ = 0;
+    bool eof_ = false;
+    int pending_ = 0;
+    std::string line_, err_;
+};
+
+// ---------------------------------------------------------------------------------------------- options
+struct Options {   // the `correct` fields of Correct_Opt the path reads (src/Common.hpp:16-158), reference defaults
+    std::vector<std::string> long_in, long_raw;
+    std::string out, graph, data;
+    bool pass1 = false, pass2 = false, gzip_out = false, verbose = false, force_snp = false, force_order = false;
+    int threads = 1, trim_qual = 0, max_qual = 40, insert_sz = 500, k1 = 31, k2 = 63, rounds = 1, w1 = 1000, w2 = 5000;
+    double min_conf_snp = 0.9;
+    int gpus = 1, first_gpu = 0;
+    uint64_t ticket_bases = 32ull << 20;
+    bool has_phase_files = false;
+};
+
+void usage() {
+    fprintf(stderr,
+            "rtk_correct correct (-1 | -2) -g <graph.fasta[.gz]> -d <graph.rtsk> -l <long reads> [-L <raw long reads>] -o <prefix>\n"
+            "  same options as `Ratatosk correct` from an index: -c -t -m -i -k -K -w -W -r -Q -O -G -v\n"
+            "  --gpus N          devices to deal tickets to (default 1)\n"
+            "  --first-gpu D     first CUDA device ordinal (default 0)\n"
+            "  --ticket-bases B  read bases per library call (default 33554432)\n");
+}
+
+int parse(int argc, char** argv, Options& o) {
+    if (argc < 2 || strcmp(argv[1], "correct") != 0) { usage(); return 1; }
+    static struct option lo[] = {{"in-long", required_argument, 0, 'l'}, {"out-long", required_argument, 0, 'o'}, {"cores", required_argument, 0, 'c'},
+                                 {"trim-split", required_argument, 0, 't'}, {"in-graph", required_argument, 0, 'g'}, {"in-unitig-data", required_argument, 0, 'd'},
+                                 {"min-conf-snp-corr", required_argument, 0, 'm'}, {"insert-sz", required_argument, 0, 'i'}, {"k1", required_argument, 0, 'k'},
+                                 {"k2", required_argument, 0, 'K'}, {"max-len-weak1", required_argument, 0, 'w'}, {"max-len-weak2", required_argument, 0, 'W'},
+                                 {"correction-rounds", required_argument, 0, 'r'}, {"in-long-raw", required_argument, 0, 'L'}, {"in-long-phase", required_argument, 0, 'P'},
+                                 {"in-short-phase", required_argument, 0, 'p'}, {"max-base-qual", required_argument, 0, 'Q'}, {"1st-pass-only", no_argument, 0, '1'},
+                                 {"2nd-pass-only", no_argument, 0, '2'}, {"force-correct-snp", no_argument, 0, 'f'}, {"force-io-order", no_argument, 0, 'O'},
+                                 {"gzip-out", no_argument, 0, 'G'}, {"verbose", no_argument, 0, 'v'}, {"gpus", required_argument, 0, 1000},
+                                 {"first-gpu", required_argument, 0, 1001}, {"ticket-bases", required_argument, 0, 1002}, {0, 0, 0, 0}};
+    int c;
+    while ((c = getopt_long(argc - 1, argv + 1, "l:o:c:t:g:d:m:i:k:K:w:W:r:L:P:p:Q:12fOGv", lo, nullptr)) != -1) {
+        switch (c) {
+            case 'l': o.long_in.push_back(optarg); break;
+            case 'L': o.long_raw.push_back(optarg); break;
+            case 'o': o.out = optarg; break;
+            case 'g': o.graph = optarg; break;
+            case 'd': o.data = optarg; break;
+            case 'c': o.threads = atoi(optarg); break;
+            case 't': o.trim_qual = atoi(optarg); break;
+            case 'm': o.min_conf_snp = atof(optarg); break;
+            case 'i': o.insert_sz = atoi(optarg); break;
+            case 'k': o.k1 = atoi(optarg); break;
+            case 'K': o.k2 = atoi(optarg); break;
+            case 'w': o.w1 = atoi(optarg); break;
+            case 'W': o.w2 = atoi(optarg); break;
+            case 'r': o.rounds = atoi(optarg); break;
+            case 'Q': o.max_qual = atoi(optarg); break;
+            case 'P': case 'p': o.has_phase_files = true; break;
+            case '1': o.pass1 = true; break;
+            case '2': o.pass2 = true; break;
+            case 'f': o.force_snp = true; break;
+            case 'O': o.force_order = true; break;
+            case 'G': o.gzip_out = true; break;
+            case 'v': o.verbose = true; break;
+            case 1000: o.gpus = atoi(optarg); break;
+            case 1001: o.first_gpu = atoi(optarg); break;
+            case 1002: o.ticket_bases = strtoull(optarg, nullptr, 10); break;
+            default: usage(); return 1;
+        }
+    }
+    // check_ProgramOptions (src/Ratatosk.cpp:303-420), the checks that concern this path, same wording
+    bool ok = true;
+    auto bad = [&](const std::string& m) { fprintf(stderr, "Ratatosk::Ratatosk(): %s\n", m.c_str()); ok = false; };
+    if (o.trim_qual < 0 || o.trim_qual > o.max_qual) bad("Quality score trimming threshold cannot be less than 0 or more than " + std::to_string(o.max_qual) + " (" + std::to_string(o.trim_qual) + " given).");
+    if (o.k2 <= o.k1) bad("Length of long k-mers for 2nd correction pass cannot be less than or equal to length of short k-mers for 1st correction pass (" + std::to_string(o.k2) + " and " + std::to_string(o.k1) + " given).");
+    if (o.insert_sz <= 0) bad("Insert size of short reads cannot be less than or equal to 0");
+    if (o.max_qual < 0) bad("Maximum base quality cannot be less than 0");
+    if (o.rounds < 1) bad("At least one short read correction round is required.");
+    if (o.min_conf_snp < 0.0) bad("Minimum confidence threshold to correct a SNP must be greater or equal to 0.0.");
+    if (o.min_conf_snp > 1.0) bad("Minimum confidence threshold to correct a SNP must be lower or equal to 1.0.");
+    if (o.w1 <= 0 || o.w2 <= 0) bad("Maximum length of a weak region to correct cannot be less than or equal to 0");
+    if (o.pass1 && o.pass2) bad("-1 and -2 are mutually exclusive (perform *only* one of the two correction passes). To perform both, remove -1 and -2 from your command line.");
+    if (!o.pass1 && !o.pass2) bad("rtk_correct runs one pass from its index: give -1 or -2 (building / colouring the graphs is the reference's `index` step).");
+    if (o.graph.empty() != o.data.empty()) bad("One of the input index files is missing (either the graph or the data).");
+    if (o.graph.empty()) bad("rtk_correct needs the index of the pass (-g and -d).");
+    if (o.long_in.empty()) bad("Missing input long reads (-l).");
+    if (o.out.empty()) bad("Missing output prefix (-o).");
+    if (o.pass2 && o.long_raw.empty()) bad("Missing input raw long reads (-L) for the 2nd correction pass.");
+    if (o.has_phase_files) bad("phasing files (-p / -P) are not supported by this driver.");
+    if (o.gpus < 1) bad("--gpus must be at least 1.");
+    return ok ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------- tickets
+struct Ticket {
+    uint64_t id = 0;
+    std::vector<std::string> names;
+    std::string seq, qual, raw;
+    std::vector<uint64_t> off{0}, raw_off{0};
+    bool has_qual = true;
+};
+struct Block { std::string bytes; uint64_t reads = 0, bases = 0; };
+
+template <class T>
+class Channel {   // bounded queue between the reader and the device threads
+  public:
+    explicit Channel(size_t cap) : cap_(cap) {}
+    void push(T&& v) {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return q_.size() < cap_ || closed_; });
+        q_.push_back(std::move(v));
+        cv_.notify_all();
+    }
+    bool pop(T& v) {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return !q_.empty() || closed_; });
+        if (q_.empty()) return false;
+        v = std::move(q_.front());
+        q_.pop_front();
+        cv_.notify_all();
+        return true;
+    }
+    void close() { std::lock_guard<std::mutex> l(m_); closed_ = true; cv_.notify_all(); }
+
+  private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<T> q_;
+    size_t cap_;
+    bool closed_ = false;
+};
+
+// writeCorrectedOutput (src/Ratatosk.cpp:510-558): a record, or with trim > 0 its stretches of >= k bases whose quality
+// is at least trim, named name/1, name/2, ...
+void format_record(std::string& out, const std::string& name, const char* seq, const char* qual, const uint64_t len, const int k, const int trim) {
+    if (trim == 0) {
+        out.push_back('@'); out += name; out.push_back('\n'); out.append(seq, len); out += "\n+\n"; out.append(qual, len); out.push_back('\n');
+        return;
+    }
+    const char c_min = (char)(trim + 33);
+    int64_t start = -1, run = -1, id = 1;
+    auto flush = [&] {
+        if (run >= k) {
+            out.push_back('@'); out += name; out.push_back('/'); out += std::to_string(id++); out.push_back('\n');
+            out.append(seq + start, (size_t)run); out += "\n+\n"; out.append(qual + start, (size_t)run); out.push_back('\n');
+        }
+    };
+    for (int64_t p = 0; p < (int64_t)len; ++p) {
+        if (qual[p] >= c_min) { if (start == -1) { start = p; run = 0; } ++run; }
+        else { flush(); start = -1; run = -1; }
+    }
+    flush();
+}
+
+bool gzip_member(const std::string& in, std::string& out) {   // one gzip member per block: members concatenate into a valid .gz
+    z_stream z; memset(&z, 0, sizeof(z));
+    if (deflateInit2(&z, Z_DEFAULT_COMPRESSION, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    out.resize(deflateBound(&z, in.size()) + 64);
+    z.next_in = (Bytef*)in.data(); z.avail_in = (uInt)in.size();
+    z.next_out = (Bytef*)&out[0]; z.avail_out = (uInt)out.size();
+    const int rc = deflate(&z, Z_FINISH);
+    out.resize(z.total_out);
+    deflateEnd(&z);
+    return rc == Z_STREAM_END;
+}
+
+struct Shared {
+    std::mutex m;
+    std::condition_variable cv;
+    std::map<uint64_t, Block> done;   // finished blocks waiting for their turn
+    std::string error;
+    std::atomic<bool> failed{false};
+    void fail(const std::string& e) { std::lock_guard<std::mutex> l(m); if (error.empty()) error = e; failed = true; cv.notify_all(); }
+};
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Options o;
+    if (parse(argc, argv, o)) return 1;
+    const int pass = o.pass2 ? 2 : 1;
+    const int k = pass == 2 ? o.k2 : o.k1;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto secs = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
+
+    // ---- graph: loaded + flattened once, uploaded to every device (src/Ratatosk.cpp:1087-1089)
+    if (o.verbose) printf("Ratatosk::Ratatosk(): Loading graph (%d/2).\n", pass);
+    rtk_host_graph* hg = nullptr;
+    if (rtk_graph_load(o.graph.c_str(), o.data.c_str(), k, &hg) != RTK_OK) { fprintf(stderr, "Ratatosk::Ratatosk(): %s\n", rtk_last_error()); return 1; }
+    std::vector<rtk_ctx*> ctx((size_t)o.gpus, nullptr);
+    for (int d = 0; d < o.gpus; ++d) {
+        if (rtk_ctx_create(o.first_gpu + d, &ctx[d]) != RTK_OK || rtk_graph_upload(ctx[d], hg) != RTK_OK) {
+            fprintf(stderr, "Ratatosk::Ratatosk(): %s\n", rtk_last_error());
+            return 1;
+        }
+    }
+    if (o.verbose) { rtk_graph_info gi; rtk_graph_get_info(hg, &gi); printf("rtk_correct: graph resident on %d GPU(s) after %.1f s (%llu unitigs, %llu k-mers, %.1f MB slab)\n", o.gpus, secs(), (unsigned long long)gi.n_unitigs, (unsigned long long)gi.n_kmers, gi.slab_bytes / 1e6); }
+
+    rtk_opt ropt;
+    rtk_opt_default(&ropt, pass);
+    ropt.k = (uint32_t)k; ropt.insert_sz = (uint32_t)o.insert_sz; ropt.max_len_weak_region1 = (uint32_t)o.w1; ropt.max_len_weak_region2 = (uint32_t)o.w2;
+    ropt.nb_correction_rounds = (uint32_t)o.rounds; ropt.max_qual = o.max_qual; ropt.trim_qual = o.trim_qual;
+    ropt.min_confidence_snp_corr = o.min_conf_snp; ropt.force_unres_snp_corr = o.force_snp ? 1u : 0u;
+    if (pass == 2 && o.verbose && o.force_snp) fprintf(stderr, "Ratatosk::search(): Force unresolved SNP correction is activated.\n");
+
+    // ---- output file: <out>.2.fastq after pass 1 (src/Ratatosk.cpp:1079), <out>.fastq[.gz] after pass 2 (:621, :909-911)
+    const bool gz_out = o.gzip_out && pass == 2;
+    const std::string fn_out = o.out + (pass == 1 ? ".2" : "") + ".fastq" + (gz_out ? ".gz" : "");
+    for (const auto* v : {&o.long_in, &o.long_raw})
+        for (const auto& f : *v)
+            if (f == fn_out) { fprintf(stderr, "Ratatosk::search(): output file %s is also an input file\n", fn_out.c_str()); return 1; }
+    FILE* fout = fopen(fn_out.c_str(), "wb");
+    if (!fout) { fprintf(stderr, "Ratatosk::search(): cannot open %s for writing\n", fn_out.c_str()); return 1; }
+    setvbuf(fout, nullptr, _IOFBF, 8 << 20);
+    if (o.verbose) printf("Ratatosk::Ratatosk(): Correcting long reads (%d/2).\n", pass);
+
+    Shared sh;
+    Channel<Ticket> tickets((size_t)o.gpus * 2);
+    std::atomic<uint64_t> n_tickets{0};
+    std::atomic<bool> reader_done{false};
+
+    // ---- reader: the ticket dispenser (src/Ratatosk.cpp:746-800)
+    std::thread reader([&] {
+        SeqReader in(o.long_in), raw(o.long_raw);
+        Ticket t;
+        std::string name, seq, qual, rname, rseq, rqual;
+        bool hq = false, rhq = false;
+        uint64_t id = 0, n_reads = 0;
+        auto flush = [&] {
+            if (t.names.empty()) return;
+            t.id = id++;
+            n_tickets = id;
+            tickets.push(std::move(t));
+            t = Ticket();
+        };
+        while (!sh.failed && in.next(name, seq, qual, hq)) {
+            if (pass == 2) {   // the raw read of the same rank must carry the same name (:788-799, first character skipped)
+                if (!raw.next(rname, rseq, rqual, rhq) || name.compare(1, std::string::npos, rname, 1, std::string::npos) != 0) {
+                    sh.fail("Ratatosk::correct(): Corrected read file is not in the same order as input long read file. Abort.");
+                    break;
+                }
+                t.raw += rseq;
+                t.raw_off.push_back(t.raw.size());
+            }
+            if (hq && qual.size() != seq.size()) qual.resize(seq.size(), '!');
+            if (!hq) t.has_qual = false;
+            t.names.push_back(name);
+            t.seq += seq;
+            if (hq) t.qual += qual; else t.qual.append(seq.size(), '!');
+            t.off.push_back(t.seq.size());
+            if (o.verbose && (++n_reads % 1000 == 0)) printf("Ratatosk::correct(): Processed %llu reads \n", (unsigned long long)n_reads);
+            if (t.seq.size() >= o.ticket_bases) flush();
+        }
+        if (!in.error().empty()) sh.fail(in.error());
+        flush();
+        reader_done = true;
+        tickets.close();
+        std::lock_guard<std::mutex> l(sh.m);
+        sh.cv.notify_all();
+    });
+
+    // ---- device threads: one per GPU, each owning a context; a ticket = one library call per stage
+    std::vector<std::thread> workers;
+    for (int d = 0; d < o.gpus; ++d) {
+        workers.emplace_back([&, d] {
+            Ticket t;
+            while (!sh.failed && tickets.pop(t)) {
+                const uint32_t n = (uint32_t)t.names.size();
+                char *cs = nullptr, *cq = nullptr;
+                uint64_t* co = nullptr;
+                const char* qual_in = t.has_qual ? t.qual.data() : nullptr;
+                int rc;
+                if (pass == 1) {
+                    rc = rtk_correct_batch(ctx[d], &ropt, 1, n, t.seq.data(), t.off.data(), qual_in, t.off.data(), &cs, &cq, &co, nullptr);
+                } else {
+                    // upper-case the pass-1 reads (:814); phasing (:832) then getSeeds + correctSequence (:838/:840)
+                    for (char& ch : t.seq) ch = (char)toupper((unsigned char)ch);
+                    char *ps = nullptr, *pq = nullptr;
+                    uint64_t* po = nullptr;
+                    rc = rtk_phasing_batch(ctx[d], &ropt, n, t.raw.data(), t.raw_off.data(), t.seq.data(), t.off.data(), t.qual.data(), t.off.data(), &ps, &pq, &po);
+                    if (rc == RTK_OK) rc = rtk_correct_batch(ctx[d], &ropt, 2, n, ps, po, pq, po, &cs, &cq, &co, nullptr);
+                    rtk_free(ps); rtk_free(pq); rtk_free(po);
+                }
+                if (rc != RTK_OK) { sh.fail(std::string("Ratatosk::search(): ") + rtk_last_error()); break; }
+                Block b;
+                b.reads = n; b.bases = t.seq.size();
+                std::string text;
+                text.reserve((size_t)(co[n] * 2 + (uint64_t)n * 64));
+                for (uint32_t i = 0; i < n; ++i) format_record(text, t.names[i], cs + co[i], cq + co[i], co[i + 1] - co[i], k, pass == 2 ? o.trim_qual : 0);
+                rtk_free(cs); rtk_free(cq); rtk_free(co);
+                if (gz_out) { if (!gzip_member(text, b.bytes)) { sh.fail("Ratatosk::search(): gzip compression failed"); break; } }
+                else b.bytes.swap(text);
+                std::lock_guard<std::mutex> l(sh.m);
+                sh.done.emplace(t.id, std::move(b));
+                sh.cv.notify_all();
+            }
+        });
+    }
+
+    // ---- ordered writer (replaces the (ticket_id, size, offset) list + re-ordering pass, :869-886, :919-999)
+    uint64_t next = 0, reads = 0, bases = 0;
+    {
+        std::unique_lock<std::mutex> l(sh.m);
+        for (;;) {
+            sh.cv.wait(l, [&] { return sh.failed || sh.done.count(next) || (reader_done && next >= n_tickets); });
+            if (sh.failed) break;
+            auto it = sh.done.find(next);
+            if (it == sh.done.end()) break;   // every ticket written
+            Block b = std::move(it->second);
+            sh.done.erase(it);
+            l.unlock();
+            if (fwrite(b.bytes.data(), 1, b.bytes.size(), fout) != b.bytes.size()) sh.fail("Ratatosk::search(): write error on " + fn_out);
+            reads += b.reads; bases += b.bases;
+            ++next;
+            l.lock();
+        }
+    }
+    tickets.close();
+    reader.join();
+    for (auto& w : workers) w.join();
+    fclose(fout);
+    for (auto c : ctx) rtk_ctx_destroy(c);
+    rtk_graph_free(hg);
+    if (sh.failed) { fprintf(stderr, "%s\n", sh.error.c_str()); remove(fn_out.c_str()); return 1; }
+    if (o.verbose) printf("rtk_correct: %llu reads, %llu bases, %llu tickets in %.1f s -> %s\n", (unsigned long long)reads, (unsigned long long)bases, (unsigned long long)next, secs(), fn_out.c_str());
+    return 0;
+}

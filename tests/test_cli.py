@@ -1,0 +1,180 @@
+"""The host driver (ratatosk_b200/host/rtk_cli.cpp): FASTQ -> library -> FASTQ, compared as FILES with what the
+unmodified reference CLI writes (`Ratatosk correct -1` -> <out>.2.fastq, `correct -2 -O` -> <out>.fastq; src/Ratatosk.cpp:
+510-616 writeCorrectedOutput incl. -t trimming, :727-906 ticket loop, :919-999 block re-ordering).
+
+CPU: the same driver source linked against the kernel-source simulator library (tests/hostsim), a few reads.
+GPU: the product binary ratatosk_b200/rtk_correct on whole fixtures, against the committed golden files (recorded from the
+reference CLI) and, where the reference binary travelled to the box (oracle/_ref), against a fresh reference run with -t."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+from common import GOLDEN, HERE, ROOT, ensure_built
+
+SIM_CLI = os.path.join(HERE, "hostsim", "_build", "rtk_correct_sim")
+GPU_CLI = os.path.join(ROOT, "ratatosk_b200", "rtk_correct")
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "Ratatosk")
+F3 = os.path.join(ROOT, "bench_data", "F3")
+
+
+def _head_fastq(src_gz, dst, n_reads):
+    with gzip.open(src_gz, "rb") as f, open(dst, "wb") as o:
+        for _ in range(4 * n_reads):
+            line = f.readline()
+            if not line:
+                break
+            o.write(line)
+
+
+def _golden_bytes(path_gz, n_reads=None):
+    with gzip.open(path_gz, "rb") as f:
+        data = f.read()
+    if n_reads is None:
+        return data
+    return b"\n".join(data.split(b"\n")[:4 * n_reads]) + b"\n"
+
+
+def _run(cli, args):
+    r = subprocess.run([cli, "correct"] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode(errors="replace")[-2000:]
+    return r.stdout.decode(errors="replace")
+
+
+def _two_pass(cli, d, tmp, reads, extra1=(), extra2=(), tag="ours"):
+    o = os.path.join(tmp, tag)
+    _run(cli, ["-1", "-g", os.path.join(d, "index.k31.fasta.gz"), "-d", os.path.join(d, "index.k31.rtsk"), "-l", reads, "-o", o] + list(extra1))
+    _run(cli, ["-2", "-O", "-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk"), "-l", o + ".2.fastq", "-L", reads,
+               "-o", o] + list(extra2))
+    return o + ".2.fastq", o + ".fastq"
+
+
+@pytest.fixture(scope="module")
+def sim_cli():
+    ensure_built()
+    if not os.path.exists(SIM_CLI):
+        subprocess.check_call(["make", "-C", os.path.join(HERE, "hostsim")])
+    return SIM_CLI
+
+
+def test_cli_two_pass_files_match_reference_cli_on_simulator(sim_cli, tmp_path):
+    """12 F1 reads, tickets of ~20 kb dealt to two contexts: <out>.2.fastq and <out>.fastq equal the reference CLI's files"""
+    d = os.path.join(GOLDEN, "F1")
+    reads = str(tmp_path / "r.fastq")
+    _head_fastq(os.path.join(d, "reads.fastq.gz"), reads, 12)
+    p1, p2 = _two_pass(sim_cli, d, str(tmp_path), reads, extra1=["--ticket-bases", "20000", "--gpus", "2"], extra2=["--ticket-bases", "20000", "--gpus", "2"])
+    assert open(p1, "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass1.fastq.gz"), 12)
+    assert open(p2, "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass2.fastq.gz"), 12)
+
+
+def test_cli_reads_gzip_and_multiline_input_and_writes_gzip(sim_cli, tmp_path):
+    """gz input, a FASTQ with wrapped sequence / quality lines, header comments dropped (kseq name), -G output"""
+    d = os.path.join(GOLDEN, "F1")
+    plain = str(tmp_path / "r.fastq")
+    _head_fastq(os.path.join(d, "reads.fastq.gz"), plain, 4)
+    recs = open(plain).read().split("\n")
+    wrapped = str(tmp_path / "wrapped_in.fastq.gz")
+    with gzip.open(wrapped, "wt") as f:
+        for i in range(0, len(recs) - 3, 4):
+            s, q = recs[i + 1], recs[i + 3]
+            f.write(recs[i] + " some comment\n")
+            f.write("\n".join(s[j:j + 70] for j in range(0, len(s), 70)) + "\n+" + recs[i][1:] + "\n")
+            f.write("\n".join(q[j:j + 70] for j in range(0, len(q), 70)) + "\n")
+    o = str(tmp_path / "w")
+    _run(sim_cli, ["-1", "-g", os.path.join(d, "index.k31.fasta.gz"), "-d", os.path.join(d, "index.k31.rtsk"), "-l", wrapped, "-o", o])
+    assert open(o + ".2.fastq", "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass1.fastq.gz"), 4)
+    _run(sim_cli, ["-2", "-G", "-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk"), "-l", o + ".2.fastq", "-L", wrapped,
+                   "-o", o, "--ticket-bases", "10000"])
+    assert gzip.open(o + ".fastq.gz", "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass2.fastq.gz"), 4)
+
+
+def _trim_reference(name, seq, qual, k, trim):
+    """writeCorrectedOutput with trim > 0, restated (src/Ratatosk.cpp:518-555)"""
+    out, start, run, sub = [], -1, -1, 1
+    cmin = chr(trim + 33)
+    for p, c in enumerate(qual):
+        if c >= cmin:
+            if start == -1:
+                start, run = p, 0
+            run += 1
+        else:
+            if run >= k:
+                out.append("@%s/%d\n%s\n+\n%s\n" % (name, sub, seq[start:start + run], qual[start:start + run]))
+                sub += 1
+            start, run = -1, -1
+    if run >= k:
+        out.append("@%s/%d\n%s\n+\n%s\n" % (name, sub, seq[start:start + run], qual[start:start + run]))
+    return "".join(out)
+
+
+def test_cli_trim_split_matches_write_corrected_output(sim_cli, tmp_path):
+    """-t 20 on pass 2: sub-reads name/1, name/2 ... of >= k bases at or above Q20, derived from the golden untrimmed output"""
+    d = os.path.join(GOLDEN, "F1")
+    reads = str(tmp_path / "r.fastq")
+    _head_fastq(os.path.join(d, "reads.fastq.gz"), reads, 6)
+    _, p2 = _two_pass(sim_cli, d, str(tmp_path), reads, extra2=["-t", "20"])
+    gold = _golden_bytes(os.path.join(d, "corrected_pass2.fastq.gz"), 6).decode().split("\n")
+    want = "".join(_trim_reference(gold[i][1:], gold[i + 1], gold[i + 3], 63, 20) for i in range(0, len(gold) - 3, 4))
+    got = open(p2).read()
+    assert got == want
+    assert "/2\n" in got   # the case splits at least one read
+
+
+def test_cli_rejects_bad_command_lines(sim_cli, tmp_path):
+    d = os.path.join(GOLDEN, "F1")
+    base = ["-g", os.path.join(d, "index.k31.fasta.gz"), "-d", os.path.join(d, "index.k31.rtsk"), "-l", "x.fastq", "-o", str(tmp_path / "o")]
+    for args in (["-1", "-2"] + base, base, ["-1", "-t", "99"] + base, ["-2"] + base, ["-1", "-g", "a", "-l", "x", "-o", "y"]):
+        r = subprocess.run([sim_cli, "correct"] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        assert r.returncode != 0
+    # pass 2 with raw reads in another order: the reference aborts (src/Ratatosk.cpp:788-799)
+    reads = str(tmp_path / "r.fastq")
+    _head_fastq(os.path.join(d, "reads.fastq.gz"), reads, 2)
+    L = open(reads).read().split("\n")
+    swapped = str(tmp_path / "s.fastq")
+    open(swapped, "w").write("\n".join(L[4:8] + L[0:4]) + "\n")
+    r = subprocess.run([sim_cli, "correct", "-2", "-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk"), "-l", reads, "-L", swapped,
+                        "-o", str(tmp_path / "o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode != 0 and b"not in the same order" in r.stdout
+
+
+# ----------------------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("recipe", ["F1", "F2"])
+def test_cli_cuda_files_identical_to_reference_cli(recipe, tmp_path):
+    """whole fixture through ratatosk_b200/rtk_correct: both output FILES equal the reference CLI's (golden, recorded from
+    `Ratatosk correct -1 -c 8` and `correct -2 -O -c 8`)"""
+    d = os.path.join(GOLDEN, recipe)
+    reads = str(tmp_path / "reads.fastq")
+    with gzip.open(os.path.join(d, "reads.fastq.gz"), "rb") as f:
+        open(reads, "wb").write(f.read())
+    p1, p2 = _two_pass(GPU_CLI, d, str(tmp_path), reads, extra1=["--ticket-bases", "200000"], extra2=["--ticket-bases", "200000"])
+    assert open(p1, "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass1.fastq.gz"))
+    assert open(p2, "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass2.fastq.gz"))
+
+
+@pytest.mark.gpu
+def test_cli_cuda_ecoli_scale_files_identical_to_reference_cli(tmp_path):
+    """E. coli-scale indexes (bench_data/F3), 200 reads: cmp against the reference CLI's files"""
+    reads = str(tmp_path / "reads.fastq")
+    with gzip.open(os.path.join(F3, "reads200.fastq.gz"), "rb") as f:
+        open(reads, "wb").write(f.read())
+    p1, p2 = _two_pass(GPU_CLI, F3, str(tmp_path), reads)
+    assert open(p1, "rb").read() == _golden_bytes(os.path.join(F3, "corrected200_pass1.fastq.gz"))
+    assert open(p2, "rb").read() == _golden_bytes(os.path.join(F3, "corrected200_pass2.fastq.gz"))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/Ratatosk did not travel to this box")
+def test_cli_cuda_trim_and_gzip_against_fresh_reference_run(tmp_path):
+    """-t 15 and -G on F2 against the reference binary run here with the same flags"""
+    d = os.path.join(GOLDEN, "F2")
+    reads = str(tmp_path / "reads.fastq")
+    with gzip.open(os.path.join(d, "reads.fastq.gz"), "rb") as f:
+        open(reads, "wb").write(f.read())
+    p1, p2 = _two_pass(GPU_CLI, d, str(tmp_path), reads, extra2=["-t", "15", "-G"])
+    ref = str(tmp_path / "ref")
+    cores = str(max(2, min(8, os.cpu_count() or 2)))
+    subprocess.check_call([REF_CLI, "correct", "-2", "-O", "-G", "-t", "15", "-c", cores, "-g", os.path.join(d, "index.k63.fasta.gz"), "-d",
+                           os.path.join(d, "index.k63.rtsk"), "-l", p1, "-L", reads, "-o", ref], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert gzip.open(p2 + ".gz", "rb").read() == gzip.open(ref + ".fastq.gz", "rb").read()
