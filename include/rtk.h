@@ -286,6 +286,15 @@ int rtk_phasing_batch(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const 
                       const char* corr_pool, const uint64_t* corr_off, const char* qual_pool, const uint64_t* qual_off,
                       char** out_seq_pool, char** out_qual_pool, uint64_t** out_off);
 
+/* ---- fixSNPs (src/Alignment.cpp:846-964; `-f` / Correct_Opt::force_unres_snp_corr, called on the pass-1 read before phasing and
+ * getSeeds of the second pass, src/Ratatosk.cpp:672 / :828): an IUPAC code left by pass 1 is replaced by a base when exactly one
+ * of its bases puts a k-mer of the graph over it.  One warp per read (the scan is order-dependent within a read), K1 lookups.
+ * Reads upper-case.  Output: the reads at the same offsets (rebased to seq_off[0]), library-allocated (rtk_free); *n_fixed
+ * (optional) = codes replaced.  rtk_phasing_batch runs this step itself when opt->force_unres_snp_corr is set; callers that
+ * skip phasing (the reference's single-thread branch) call it before rtk_correct_batch(pass 2). */
+int rtk_fix_snps_batch(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
+                       char** out_seq_pool, uint64_t* n_fixed);
+
 #ifdef __cplusplus
 }
 #endif

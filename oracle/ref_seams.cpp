@@ -12,6 +12,7 @@
 //   ref_get_seeds                     getSeeds (src/Graph.cpp:3)
 //   ref_correct_read                  the per-read body of search() (src/Ratatosk.cpp:808-867)
 //   ref_phasing                       phasing (src/Graph.cpp:869), second pass, multi-thread branch
+//   ref_fix_snps                      fixSNPs (src/Alignment.cpp:846), second pass with -f
 //   ref_edlib                         edlibAlign (src/edlib.cpp:141)
 //
 // Nothing in the product library links, includes or dlopens this file.
@@ -256,6 +257,16 @@ int ref_phasing(void* h, const char* s_raw, const char* s_corr, const char* q_co
     pair<string, string> r = phasing(*g->dbg, g->opt, raw, corr, qual);
     *s_out = strdup(r.first.c_str());
     *q_out = strdup(r.second.c_str());
+    return 0;
+}
+
+// fixSNPs() (src/Alignment.cpp:846): `-f`, applied to the pass-1 read before phasing / getSeeds of the second pass
+int ref_fix_snps(void* h, const char* s_corr, char** s_out) {
+    RefGraph* g = (RefGraph*)h;
+    string corr(s_corr);
+    std::transform(corr.begin(), corr.end(), corr.begin(), ::toupper);
+    const string r = fixSNPs(g->opt, *g->dbg, corr);
+    *s_out = strdup(r.c_str());
     return 0;
 }
 

@@ -148,6 +148,8 @@ def load_library(path=None):
                                                  C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_char_p,
                                                  C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                  C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
+    L.rtk_fix_snps_batch.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.rtk_phasing_batch.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.c_char_p,
                                     C.POINTER(C.c_uint64), C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64))]
@@ -375,6 +377,17 @@ class Context:
         if stats is not None:
             stats.extend(list(st))
         return out
+
+    def fix_snps(self, reads, opt=None):
+        """fixSNPs (src/Alignment.cpp:846) for a batch of pass-1 reads on the k = 63 graph -> (list of reads, codes replaced)"""
+        opt = opt or default_opt(2)
+        pool, off = pack_reads(reads)
+        out, nf = C.c_void_p(), C.c_uint64()
+        _check(self.L, self.L.rtk_fix_snps_batch(self.h, C.byref(opt), len(reads), pool, off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                 C.byref(out), C.byref(nf)))
+        buf = C.string_at(out, int(off[-1]))
+        self.L.rtk_free(out)
+        return [buf[int(off[i]):int(off[i + 1])].decode("latin1") for i in range(len(reads))], nf.value
 
     def phasing(self, raw_reads, corr_reads, corr_quals, opt=None):
         """phasing() of the second pass (src/Graph.cpp:869) for a batch -> list of (sequence, quality string)"""

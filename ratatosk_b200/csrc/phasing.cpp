@@ -69,6 +69,31 @@ inline bool is_branching(const rtk_graph_view& g, uint32_t u) { return (g.kmcov[
 
 }  // namespace
 
+// fixSNPs (src/Alignment.cpp:846-964) for a batch: the positions that are not A/C/G/T (Bifrost isDNA: either case) are listed
+// here, the order-dependent resolution runs one warp per read on the device (fixsnps.cuh)
+uint64_t fix_snps_batch_host(rtk_ctx* ctx, uint32_t n, char* seq_pool, const uint64_t* seq_off) {
+    if (!ctx->has_graph || !ctx->host_graph) throw std::invalid_argument("no graph uploaded to this context");
+    std::vector<std::vector<uint32_t>> per(n);
+    parallel_for(n, [&](size_t rb, size_t re) {
+        for (size_t r = rb; r < re; ++r) {
+            const char* s = seq_pool + seq_off[r];
+            const uint64_t L = seq_off[r + 1] - seq_off[r];
+            if (L >= 0xFFFFFFFFull) throw std::invalid_argument("fixSNPs: read longer than 4 Gbases");
+            for (uint64_t i = 0; i < L; ++i) {
+                const char c = (char)(s[i] & 0xDF);
+                if (c != 'A' && c != 'C' && c != 'G' && c != 'T') per[r].push_back((uint32_t)i);
+            }
+        }
+    });
+    std::vector<uint64_t> amb_off(n + 1, 0);
+    for (uint32_t r = 0; r < n; ++r) amb_off[r + 1] = amb_off[r] + per[r].size();
+    std::vector<uint32_t> amb_pos(amb_off[n]);
+    for (uint32_t r = 0; r < n; ++r) if (!per[r].empty()) memcpy(amb_pos.data() + amb_off[r], per[r].data(), per[r].size() * 4);
+    uint64_t fixed = 0;
+    fix_snps_host(ctx, n, seq_pool, seq_off, amb_pos, amb_off, &fixed);
+    return fixed;
+}
+
 void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char* raw_pool, const uint64_t* raw_off, const char* corr_pool,
                         const uint64_t* corr_off, const char* qual_pool, const uint64_t* qual_off, std::vector<std::string>& out_seq,
                         std::vector<std::string>& out_qual) {
@@ -90,6 +115,18 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
         t_prev = now;
     };
 
+    // 0. `-f` (Correct_Opt::force_unres_snp_corr): fixSNPs on the pass-1 read before anything else (src/Ratatosk.cpp:828)
+    std::string fixed_pool;
+    std::vector<uint64_t> fixed_off;
+    if (opt.force_unres_snp_corr) {
+        fixed_pool.assign(corr_pool + corr_off[0], (size_t)(corr_off[n] - corr_off[0]));
+        fixed_off.resize(n + 1);
+        for (uint32_t i = 0; i <= n; ++i) fixed_off[i] = corr_off[i] - corr_off[0];
+        fix_snps_batch_host(ctx, n, &fixed_pool[0], fixed_off.data());
+        corr_pool = fixed_pool.data();
+        corr_off = fixed_off.data();
+        lap("fixSNPs");
+    }
     // 1. map the corrected reads (one exact sweep for the whole batch)
     std::vector<std::vector<rtk_hit>> hits;
     {
@@ -279,6 +316,27 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
 }  // namespace rtk
 
 using namespace rtk;
+
+extern "C" int rtk_fix_snps_batch(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
+                                  char** out_seq_pool, uint64_t* n_fixed) {
+    return guarded([&] {
+        if (!ctx || !opt || !seq_pool || !seq_off || !out_seq_pool) throw std::invalid_argument("null argument");
+        if (!ctx->has_graph) throw std::invalid_argument("no graph uploaded to this context");
+        if (opt->k != ctx->hdr.k) throw std::invalid_argument("rtk_opt.k does not match the graph's k");
+        DeviceBind bind(ctx);
+        const uint64_t total = seq_off[n_reads] - seq_off[0];
+        char* out = (char*)malloc(total + 1);
+        if (!out) throw std::bad_alloc();
+        memcpy(out, seq_pool + seq_off[0], total);
+        out[total] = 0;
+        std::vector<uint64_t> off(n_reads + 1);
+        for (uint32_t i = 0; i <= n_reads; ++i) off[i] = seq_off[i] - seq_off[0];
+        uint64_t fixed = 0;
+        try { fixed = fix_snps_batch_host(ctx, n_reads, out, off.data()); } catch (...) { free(out); throw; }
+        *out_seq_pool = out;
+        if (n_fixed) *n_fixed = fixed;
+    });
+}
 
 extern "C" int rtk_phasing_batch(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const char* raw_pool, const uint64_t* raw_off,
                                  const char* corr_pool, const uint64_t* corr_off, const char* qual_pool, const uint64_t* qual_off,

@@ -226,6 +226,7 @@ void rtk_ctx_destroy(rtk_ctx* c) {
     for (auto& b : c->h_pin) b.release();
     for (auto& b : c->d_rg) b.release();
     for (auto& b : c->h_rg) b.release();
+    c->d_fs.release(); c->h_fs.release();
     if (c->host_copy.data) free(c->host_copy.data);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

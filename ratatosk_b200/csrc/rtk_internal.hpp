@@ -117,6 +117,8 @@ struct rtk_ctx {
     rtk::PinBuf h_pin[16];   // pinned landing zones of the D2H copies (one slot per copy site, see PinnedD2H)
     rtk::DevBuf d_rg[7];     // region engine: [0] packed inputs, [1] results, [2] out vertices, [3] out chars, [4] counters, [5] per-warp scratch, [6] out segments
     rtk::PinBuf h_rg[3];     // region engine: [0] packed upload, [1] results + counters, [2] output pools
+    rtk::DevBuf d_fs;        // fixSNPs: packed reads + ambiguity lists
+    rtk::PinBuf h_fs;
     int sm_count = 148;
     // forked contexts kept for re-use (fork_acquire / fork_release): the broker's service contexts and the correction gangs are
     // needed again by every batch; re-creating them per call means re-growing their device / pinned buffers every time, and a
@@ -250,6 +252,13 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
 // full searchSequence for a host batch -> per read ordered hits
 void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                           std::vector<std::vector<rtk_hit>>& per_read, uint64_t* stats);
+
+// fixSNPs (src/Alignment.cpp:846) on the device (fixsnps.cu / tests/hostsim/sim_fixsnps.cpp): reads rewritten in place;
+// amb_pos / amb_off = positions of the non-ACGT characters of each read (ascending, CSR over the reads)
+void fix_snps_host(rtk_ctx* c, uint32_t n_reads, char* seq_pool, const uint64_t* seq_off, const std::vector<uint32_t>& amb_pos,
+                   const std::vector<uint64_t>& amb_off, uint64_t* n_fixed);
+// lists the non-ACGT positions and runs fix_snps_host (phasing.cpp); returns the number of codes replaced
+uint64_t fix_snps_batch_host(rtk_ctx* ctx, uint32_t n_reads, char* seq_pool, const uint64_t* seq_off);
 
 // per-read correction of a batch (correct.cpp)
 void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,

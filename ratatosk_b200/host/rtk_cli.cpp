@@ -168,7 +168,7 @@ int parse(int argc, char** argv, Options& o) {
             case 'W': o.w2 = atoi(optarg); break;
             case 'r': o.rounds = atoi(optarg); break;
             case 'Q': o.max_qual = atoi(optarg); break;
-            case 'P': case 'p': o.has_phase_files = true; break;
+            case 'P': case 'p': o.has_phase_files = true; break;   // accepted and unused, like the reference when it corrects from an index
             case '1': o.pass1 = true; break;
             case '2': o.pass2 = true; break;
             case 'f': o.force_snp = true; break;
@@ -199,7 +199,9 @@ int parse(int argc, char** argv, Options& o) {
     if (o.long_in.empty()) bad("Missing input long reads (-l).");
     if (o.out.empty()) bad("Missing output prefix (-o).");
     if (o.pass2 && o.long_raw.empty()) bad("Missing input raw long reads (-L) for the 2nd correction pass.");
-    if (o.has_phase_files) bad("phasing files (-p / -P) are not supported by this driver.");
+    // -p / -P: with an index (-g -d) the reference never fills its HapReads (hapPass1 / hapPass2 stay empty on the hasIndex
+    // branches, src/Ratatosk.cpp:1062-1090, :1213-1217), so hap_id is ~0 for every read: the files are ignored here as well
+    if (o.has_phase_files && o.verbose) fprintf(stderr, "rtk_correct: phasing files are not used when correcting from an index (as in the reference)\n");
     if (o.gpus < 1) bad("--gpus must be at least 1.");
     return ok ? 0 : 1;
 }

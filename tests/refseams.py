@@ -45,6 +45,7 @@ def lib():
         L.ref_correct_read.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.ref_phasing.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        L.ref_fix_snps.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
         L.ref_edlib.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_int)),
                                 C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.c_int)]
@@ -181,6 +182,17 @@ def _phasing(self, raw, corr, qual):
 
 
 RefGraph.phasing = _phasing
+
+
+def _fix_snps(self, corr):
+    so = C.c_void_p()
+    lib().ref_fix_snps(self.h, corr.encode(), C.byref(so))
+    rs = C.string_at(so).decode()
+    lib().ref_free(so)
+    return rs
+
+
+RefGraph.fix_snps = _fix_snps
 
 
 def edlib(q, t, mode, task=0, k=-1, iupac=True):

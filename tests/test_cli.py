@@ -178,3 +178,15 @@ def test_cli_cuda_trim_and_gzip_against_fresh_reference_run(tmp_path):
     subprocess.check_call([REF_CLI, "correct", "-2", "-O", "-G", "-t", "15", "-c", cores, "-g", os.path.join(d, "index.k63.fasta.gz"), "-d",
                            os.path.join(d, "index.k63.rtsk"), "-l", p1, "-L", reads, "-o", ref], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     assert gzip.open(p2 + ".gz", "rb").read() == gzip.open(ref + ".fastq.gz", "rb").read()
+
+
+@pytest.mark.gpu
+def test_cli_cuda_force_snp_correction_matches_reference_cli(tmp_path):
+    """--force-correct-snp (fixSNPs before phasing, src/Ratatosk.cpp:828) on F2 == the reference CLI with the same flag"""
+    d = os.path.join(GOLDEN, "F2")
+    reads, p1 = str(tmp_path / "reads.fastq"), str(tmp_path / "p1.fastq")
+    open(reads, "wb").write(gzip.open(os.path.join(d, "reads.fastq.gz"), "rb").read())
+    open(p1, "wb").write(gzip.open(os.path.join(d, "corrected_pass1.fastq.gz"), "rb").read())
+    o = str(tmp_path / "o")
+    _run(GPU_CLI, ["-2", "--force-correct-snp", "-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk"), "-l", p1, "-L", reads, "-o", o])
+    assert open(o + ".fastq", "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass2_forcesnp.fastq.gz"))
