@@ -76,8 +76,16 @@ int rtk_graph_from_unitigs(int k, uint64_t n, const char* const* seqs, rtk_host_
 void rtk_graph_free(rtk_host_graph* g);
 int rtk_graph_get_info(const rtk_host_graph* g, rtk_graph_info* info);
 const void* rtk_graph_slab(const rtk_host_graph* g, uint64_t* bytes);
-int rtk_graph_save(const rtk_host_graph* g, const char* path);   /* flat cache file */
+/* Flat cache file = the slab itself (versioned header + 256-byte aligned sections, offsets relative to the file start):
+ * rtk_graph_open maps it read-only and uses it in place (no parse, no flatten; the page cache is shared by the processes
+ * of a node).  Replaces readGraphData's per-unitig find + Roaring deserialisation (src/Graph.cpp:722-801) on every run.
+ * rtk_graph_save writes atomically (temporary file + rename).  rtk_graph_load_cached = rtk_graph_load through the cache
+ * file cache_path (NULL: "<rtsk_path>.k<k>.rtkflat"): opened when it is at least as recent as the index files, else the
+ * index is parsed and the cache (re)written; *from_cache (optional) tells which happened. */
+int rtk_graph_save(const rtk_host_graph* g, const char* path);
 int rtk_graph_open(const char* path, rtk_host_graph** out);
+int rtk_graph_load_cached(const char* fasta_path, const char* rtsk_path, int k, const char* cache_path, rtk_host_graph** out,
+                          int* from_cache);
 /* per-unitig accessors over the host slab (tests / host-side callers) */
 int rtk_graph_unitig_seq(const rtk_host_graph* g, uint32_t unitig, char* buf, uint64_t cap, uint64_t* len);
 int rtk_graph_unitig_words(const rtk_host_graph* g, uint32_t unitig, uint64_t* kmcov, uint64_t* shared, uint32_t adj[8]);

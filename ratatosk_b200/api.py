@@ -120,6 +120,7 @@ def load_library(path=None):
     L.rtk_graph_slab.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.rtk_graph_save.argtypes = [C.c_void_p, C.c_char_p]
     L.rtk_graph_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.rtk_graph_load_cached.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
     L.rtk_graph_unitig_seq.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.rtk_graph_unitig_words.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                          C.POINTER(C.c_uint32 * 8)]
@@ -227,6 +228,15 @@ class Graph:
         h = C.c_void_p()
         _check(L, L.rtk_graph_open(path.encode(), C.byref(h)))
         return cls(h, lib)
+
+    @classmethod
+    def load_cached(cls, fasta, rtsk, k, cache=None, lib=None):
+        """rtk_graph_load through the flat cache file (mmap-ed in place when valid) -> (Graph, came_from_cache)"""
+        L = load_library(lib)
+        h, fc = C.c_void_p(), C.c_int()
+        _check(L, L.rtk_graph_load_cached(fasta.encode(), (rtsk or "").encode() if rtsk else None, k, cache.encode() if cache else None,
+                                          C.byref(h), C.byref(fc)))
+        return cls(h, lib), bool(fc.value)
 
     def save(self, path):
         _check(self.L, self.L.rtk_graph_save(self.h, path.encode()))

@@ -27,6 +27,7 @@ struct HostGraph {
 struct rtk_slab {
     unsigned char* data = nullptr;  // 256-byte aligned, starts with rtk_slab_header
     uint64_t bytes = 0;
+    bool mapped = false;            // data is a read-only file mapping (rtk_graph_open): released with munmap
 };
 
 HostGraph load_index(const std::string& fasta, const std::string& rtsk, int k);

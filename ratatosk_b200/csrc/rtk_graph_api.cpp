@@ -8,6 +8,11 @@
 #include <thread>
 
 #include "kmer.cuh"
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "rtk_host_common.hpp"
 
 namespace rtk {
@@ -123,7 +128,8 @@ int rtk_graph_from_unitigs(int k, uint64_t n, const char* const* seqs, rtk_host_
 
 void rtk_graph_free(rtk_host_graph* g) {
     if (!g) return;
-    free(g->slab.data);
+    if (g->slab.mapped) munmap(g->slab.data, (size_t)g->slab.bytes);
+    else free(g->slab.data);
     delete g;
 }
 
@@ -141,32 +147,64 @@ const void* rtk_graph_slab(const rtk_host_graph* g, uint64_t* bytes) {
     return g->slab.data;
 }
 
+// The flat cache file IS the slab (flat_graph.h): a versioned header followed by 256-byte aligned SoA / CSR sections whose
+// offsets are relative to the file start, so it can be used in place from a read-only mapping - by the host-side logic, by
+// the one H2D copy of rtk_graph_upload, and by several processes of one node sharing the page cache.  Replaces re-running
+// CompactedDBG::read + readGraphData + the flattening on every `correct` (src/Graph.cpp:722-801, Bifrost/src/IO.tcc:936-1165).
 int rtk_graph_save(const rtk_host_graph* g, const char* path) {
     return guarded([&] {
-        FILE* f = fopen(path, "wb");
-        if (!f) throw std::runtime_error(std::string("cannot write ") + path);
+        if (!g || !path) throw std::invalid_argument("null argument");
+        const std::string tmp = std::string(path) + ".tmp." + std::to_string((long)getpid());
+        FILE* f = fopen(tmp.c_str(), "wb");
+        if (!f) throw std::runtime_error(std::string("cannot write ") + tmp);
         const size_t w = fwrite(g->slab.data, 1, g->slab.bytes, f);
-        fclose(f);
-        if (w != g->slab.bytes) throw std::runtime_error("short write");
+        const bool ok = (fclose(f) == 0) && w == g->slab.bytes;
+        if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); throw std::runtime_error(std::string("cannot write ") + path); }
     });
 }
 
 int rtk_graph_open(const char* path, rtk_host_graph** out) {
     return guarded([&] {
-        FILE* f = fopen(path, "rb");
-        if (!f) throw std::runtime_error(std::string("cannot open ") + path);
-        fseek(f, 0, SEEK_END);
-        const long sz = ftell(f);
-        fseek(f, 0, SEEK_SET);
+        if (!path || !out) throw std::invalid_argument("null argument");
+        const int fd = open(path, O_RDONLY);
+        if (fd < 0) throw std::runtime_error(std::string("cannot open ") + path);
+        struct stat st;
+        if (fstat(fd, &st) != 0 || st.st_size < (off_t)sizeof(rtk_slab_header)) { close(fd); throw std::runtime_error(std::string("not a flat graph file: ") + path); }
+        void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        close(fd);
+        if (m == MAP_FAILED) throw std::runtime_error(std::string("cannot map ") + path);
+        madvise(m, (size_t)st.st_size, MADV_WILLNEED);
         rtk_host_graph* g = new rtk_host_graph();
-        g->slab.bytes = (uint64_t)sz;
-        g->slab.data = (unsigned char*)aligned_alloc(256, ((size_t)sz + 255) & ~(size_t)255);
-        const size_t r = fread(g->slab.data, 1, (size_t)sz, f);
-        fclose(f);
-        if (r != (size_t)sz) { free(g->slab.data); delete g; throw std::runtime_error("short read"); }
-        try { finish_host_graph(g); } catch (...) { free(g->slab.data); delete g; throw; }
+        g->slab.data = (unsigned char*)m;
+        g->slab.bytes = (uint64_t)st.st_size;
+        g->slab.mapped = true;
+        try { finish_host_graph(g); } catch (...) { munmap(m, (size_t)st.st_size); delete g; throw; }
         *out = g;
     });
+}
+
+// rtk_graph_load through the cache: `cache_path` (NULL: <rtsk_path>.k<k>.rtkflat, or <fasta_path>.k<k>.rtkflat without colours) is
+// opened in place when it exists, is at least as recent as both index files and holds a slab of this k; otherwise the index
+// is parsed and flattened and the cache is (re)written - a failed write is not an error, the in-memory graph is returned.
+int rtk_graph_load_cached(const char* fasta_path, const char* rtsk_path, int k, const char* cache_path, rtk_host_graph** out, int* from_cache) {
+    if (from_cache) *from_cache = 0;
+    if (!fasta_path || !out) { set_error("null argument"); return RTK_EINVAL; }
+    const bool has_rtsk = rtsk_path && *rtsk_path;
+    const std::string cache = (cache_path && *cache_path) ? std::string(cache_path)
+                                                          : std::string(has_rtsk ? rtsk_path : fasta_path) + ".k" + std::to_string(k) + ".rtkflat";
+    struct stat sc, sf, sr;
+    if (stat(cache.c_str(), &sc) == 0 && stat(fasta_path, &sf) == 0 && sc.st_mtime >= sf.st_mtime &&
+        (!has_rtsk || (stat(rtsk_path, &sr) == 0 && sc.st_mtime >= sr.st_mtime))) {
+        rtk_host_graph* g = nullptr;
+        if (rtk_graph_open(cache.c_str(), &g) == RTK_OK) {
+            if ((int)g->hdr.k == k) { *out = g; if (from_cache) *from_cache = 1; return RTK_OK; }
+            rtk_graph_free(g);
+        }
+    }
+    const int rc = rtk_graph_load(fasta_path, rtsk_path, k, out);
+    if (rc != RTK_OK) return rc;
+    rtk_graph_save(*out, cache.c_str());   // best effort
+    return RTK_OK;
 }
 
 int rtk_graph_unitig_seq(const rtk_host_graph* g, uint32_t u, char* buf, uint64_t cap, uint64_t* len) {

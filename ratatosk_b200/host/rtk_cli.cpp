@@ -128,6 +128,8 @@ struct Options {   // the `correct` fields of Correct_Opt the path reads (src/Co
     int gpus = 1, first_gpu = 0;
     uint64_t ticket_bases = 32ull << 20;
     bool has_phase_files = false;
+    bool no_cache = false;       // parse the index files even when a flat cache exists, and write none
+    std::string cache;           // flat cache file (default: <rtsk>.k<k>.rtkflat next to the index)
 };
 
 void usage() {
@@ -136,7 +138,9 @@ void usage() {
             "  same options as `Ratatosk correct` from an index: -c -t -m -i -k -K -w -W -r -Q -O -G -v\n"
             "  --gpus N          devices to deal tickets to (default 1)\n"
             "  --first-gpu D     first CUDA device ordinal (default 0)\n"
-            "  --ticket-bases B  read bases per library call (default 33554432)\n");
+            "  --ticket-bases B  read bases per library call (default 33554432)\n"
+            "  --cache FILE      flat graph cache (default <rtsk>.k<k>.rtkflat; written on first use, mapped in place afterwards)\n"
+            "  --no-cache        always parse the index files, write no cache\n");
 }
 
 int parse(int argc, char** argv, Options& o) {
@@ -149,7 +153,8 @@ int parse(int argc, char** argv, Options& o) {
                                  {"in-short-phase", required_argument, 0, 'p'}, {"max-base-qual", required_argument, 0, 'Q'}, {"1st-pass-only", no_argument, 0, '1'},
                                  {"2nd-pass-only", no_argument, 0, '2'}, {"force-correct-snp", no_argument, 0, 'f'}, {"force-io-order", no_argument, 0, 'O'},
                                  {"gzip-out", no_argument, 0, 'G'}, {"verbose", no_argument, 0, 'v'}, {"gpus", required_argument, 0, 1000},
-                                 {"first-gpu", required_argument, 0, 1001}, {"ticket-bases", required_argument, 0, 1002}, {0, 0, 0, 0}};
+                                 {"first-gpu", required_argument, 0, 1001}, {"ticket-bases", required_argument, 0, 1002}, {"no-cache", no_argument, 0, 1003},
+                                 {"cache", required_argument, 0, 1004}, {0, 0, 0, 0}};
     int c;
     while ((c = getopt_long(argc - 1, argv + 1, "l:o:c:t:g:d:m:i:k:K:w:W:r:L:P:p:Q:12fOGv", lo, nullptr)) != -1) {
         switch (c) {
@@ -178,6 +183,8 @@ int parse(int argc, char** argv, Options& o) {
             case 1000: o.gpus = atoi(optarg); break;
             case 1001: o.first_gpu = atoi(optarg); break;
             case 1002: o.ticket_bases = strtoull(optarg, nullptr, 10); break;
+            case 1003: o.no_cache = true; break;
+            case 1004: o.cache = optarg; break;
             default: usage(); return 1;
         }
     }
@@ -301,7 +308,10 @@ int main(int argc, char** argv) {
     // ---- graph: loaded + flattened once, uploaded to every device (src/Ratatosk.cpp:1087-1089)
     if (o.verbose) printf("Ratatosk::Ratatosk(): Loading graph (%d/2).\n", pass);
     rtk_host_graph* hg = nullptr;
-    if (rtk_graph_load(o.graph.c_str(), o.data.c_str(), k, &hg) != RTK_OK) { fprintf(stderr, "Ratatosk::Ratatosk(): %s\n", rtk_last_error()); return 1; }
+    int from_cache = 0;
+    const int grc = o.no_cache ? rtk_graph_load(o.graph.c_str(), o.data.c_str(), k, &hg)
+                               : rtk_graph_load_cached(o.graph.c_str(), o.data.c_str(), k, o.cache.empty() ? nullptr : o.cache.c_str(), &hg, &from_cache);
+    if (grc != RTK_OK) { fprintf(stderr, "Ratatosk::Ratatosk(): %s\n", rtk_last_error()); return 1; }
     std::vector<rtk_ctx*> ctx((size_t)o.gpus, nullptr);
     for (int d = 0; d < o.gpus; ++d) {
         if (rtk_ctx_create(o.first_gpu + d, &ctx[d]) != RTK_OK || rtk_graph_upload(ctx[d], hg) != RTK_OK) {
@@ -309,7 +319,7 @@ int main(int argc, char** argv) {
             return 1;
         }
     }
-    if (o.verbose) { rtk_graph_info gi; rtk_graph_get_info(hg, &gi); printf("rtk_correct: graph resident on %d GPU(s) after %.1f s (%llu unitigs, %llu k-mers, %.1f MB slab)\n", o.gpus, secs(), (unsigned long long)gi.n_unitigs, (unsigned long long)gi.n_kmers, gi.slab_bytes / 1e6); }
+    if (o.verbose) { rtk_graph_info gi; rtk_graph_get_info(hg, &gi); printf("rtk_correct: graph%s resident on %d GPU(s) after %.1f s (%llu unitigs, %llu k-mers, %.1f MB slab)\n", from_cache ? " (flat cache, mapped in place)" : "", o.gpus, secs(), (unsigned long long)gi.n_unitigs, (unsigned long long)gi.n_kmers, gi.slab_bytes / 1e6); }
 
     rtk_opt ropt;
     rtk_opt_default(&ropt, pass);

@@ -100,6 +100,45 @@ def test_slab_roundtrip(loaded, tmp_path, sim_lib):
     g2.close()
 
 
+def test_flat_cache_is_written_once_then_mapped_in_place(tmp_path, sim_lib):
+    """rtk_graph_load_cached: first call parses the index and writes the cache, the second maps the file (same slab bytes, same
+    anchors); a stale cache (older than the index) and a cache of another k are rebuilt, a corrupt one is rejected by open"""
+    import shutil
+    import time
+    d = tmp_path / "idx"
+    d.mkdir()
+    fa, rt = golden_paths("F1")
+    fa2, rt2 = str(d / "g.fasta.gz"), str(d / "g.rtsk")
+    shutil.copy(fa, fa2); shutil.copy(rt, rt2)
+    g1, c1 = rb.Graph.load_cached(fa2, rt2, 31, lib=sim_lib)
+    cache = rt2 + ".k31.rtkflat"
+    assert not c1 and os.path.exists(cache)
+    g2, c2 = rb.Graph.load_cached(fa2, rt2, 31, lib=sim_lib)
+    assert c2 and np.array_equal(g1.slab(), g2.slab())
+    ctx = rb.Context(0, lib=sim_lib)
+    ctx.upload(g2)
+    gold = np.load(os.path.join(GOLDEN, "F1", "golden_hits.npz"))
+    reads = [s for _, s, _ in load_golden_reads("F1")][:3]
+    solid, weak = ctx.get_seeds(reads)
+    for i in range(len(reads)):
+        assert np.array_equal(solid[i], gold["solid_%d" % i]) and np.array_equal(weak[i], gold["weak_%d" % i])
+    ctx.close()
+    g1.close(); g2.close()
+    # stale: index newer than the cache
+    os.utime(cache, (time.time() - 1000, time.time() - 1000))
+    g3, c3 = rb.Graph.load_cached(fa2, rt2, 31, lib=sim_lib)
+    assert not c3
+    g3.close()
+    # explicit cache path; a truncated file is not a slab
+    other = str(tmp_path / "other.rtkflat")
+    g4, c4 = rb.Graph.load_cached(fa2, rt2, 31, cache=other, lib=sim_lib)
+    assert not c4 and os.path.exists(other)
+    g4.close()
+    open(other, "r+b").truncate(1000)
+    with pytest.raises(rb.RtkError):
+        rb.Graph.open(other, lib=sim_lib)
+
+
 def test_masked_reads_with_isolated_n_keep_their_deletion_hits(loaded):
     """The K1 driver skips tiles that cannot hold a valid window (the masked copies of getSeeds are mostly 'N').  A deletion
     window may drop an 'N' that sits between two short valid stretches: such tiles must stay.  Checked against the CPU oracle."""
