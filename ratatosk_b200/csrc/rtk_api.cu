@@ -22,7 +22,7 @@ static inline double now_ns() {
 
 // ---------------------------------------------------------------- K1 driver
 uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint64_t* d_seq_off,
-                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms, const char* h_seq) {
+                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms, const char* h_seq, bool dense) {
     if (!ctx->has_graph) throw std::invalid_argument("no graph uploaded to this context");
     if (n_reads >= (1u << RTK_HIT_READ_BITS)) throw std::invalid_argument("more than 2^24 reads in one batch");
     const uint32_t k = ctx->hdr.k;
@@ -38,6 +38,10 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
     ctx->d_counters.reserve(64);
     RTK_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
     if (n_tiles == 0) {
+        if (dense) {   // nothing to probe: every position answers "not in the graph"
+            ctx->d_hits.reserve(total * 8 + 64);
+            RTK_CUDA(cudaMemsetAsync(ctx->d_hits.p, 0xFF, total * 8, ctx->stream));
+        }
         if (n_probes) *n_probes = 0;
         if (kernel_ms) *kernel_ms = 0.f;
         return 0;
@@ -45,10 +49,12 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
     ctx->d_tiles.reserve(tiles.size() * 4);
     RTK_CUDA(counted_memcpy_async(ctx->d_tiles.p, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 
+    if (dense && !exact) throw std::invalid_argument("dense output is an exact-sweep mode");
     uint64_t cap = std::max<uint64_t>(1u << 20, exact ? total + 1024 : 2 * total + 1024);
     for (int attempt = 0; attempt < 3; ++attempt) {
-        ctx->d_hits.reserve(cap * sizeof(rtk_raw_hit));
-        cap = ctx->d_hits.cap / sizeof(rtk_raw_hit);
+        ctx->d_hits.reserve(dense ? total * 8 + 64 : cap * sizeof(rtk_raw_hit));
+        cap = dense ? ~0ull : ctx->d_hits.cap / sizeof(rtk_raw_hit);
+        if (dense) RTK_CUDA(cudaMemsetAsync(ctx->d_hits.p, 0xFF, total * 8, ctx->stream));
         rtk_k1_params p;
         p.table = ctx->dview.table; p.n_buckets = ctx->dview.n_buckets; p.pool = ctx->dview.pool; p.k = (int)k;
         p.seq = d_seq; p.seq_off = d_seq_off; p.tiles = ctx->d_tiles.as<uint32_t>(); p.n_tiles = n_tiles; p.tile = tile;
@@ -59,6 +65,7 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
         p.n_hits = ctx->d_counters.as<unsigned long long>();
         p.hit_cap = cap;
         p.n_probes = n_probes ? ctx->d_counters.as<unsigned long long>() + 1 : nullptr;
+        p.dense = dense ? ctx->d_hits.as<uint64_t>() : nullptr;
         RTK_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
         // grid: whole waves of resident CTAs (148 SMs x 8 CTAs of 256 threads), grid-stride over tiles
         const uint32_t grid = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * 8u);
@@ -106,13 +113,25 @@ void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, 
     }
     uint64_t probes = 0;
     float kms = 0.f;
-    const uint64_t n_raw = k1_launch(ctx, n_reads, d_seq, d_off, rel.data(), flags, &probes, &kms, seq_pool + seq_off[0]);
-    RawHitVec raw(n_raw);
-    if (n_raw) {
-        RTK_CUDA(counted_memcpy_async(raw.data(), ctx->d_hits.p, n_raw * sizeof(RawHit), cudaMemcpyDeviceToHost, ctx->stream));
-        RTK_CUDA(cudaStreamSynchronize(ctx->stream));
+    // exact sweeps come back DENSE (8 bytes per read position, read order) through pinned memory: no labels, no sort, no
+    // bucketing; the list form (16 bytes per hit, any order) is kept for the sparse one-edit sweeps.  RTK_K1_LIST=1: list form.
+    static const bool list_only = getenv("RTK_K1_LIST") != nullptr;
+    const bool dense = (flags == RTK_SEARCH_EXACT) && !list_only && total != 0;
+    const uint64_t n_raw = k1_launch(ctx, n_reads, d_seq, d_off, rel.data(), flags, &probes, &kms, seq_pool + seq_off[0], dense);
+    if (dense) {
+        ctx->h_dense.reserve(total * 8 + 64);
+        // chunked so that decoding could overlap; one stream, pinned landing zone
+        RTK_CUDA(counted_memcpy_async(ctx->h_dense.p, ctx->d_hits.p, total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        stream_wait(ctx->stream);
+        resolve_exact_dense(ctx->host_graph->view, n_reads, rel.data(), ctx->h_dense.as<uint64_t>(), per_read);
+    } else {
+        RawHitVec raw(n_raw);
+        if (n_raw) {
+            RTK_CUDA(counted_memcpy_async(raw.data(), ctx->d_hits.p, n_raw * sizeof(RawHit), cudaMemcpyDeviceToHost, ctx->stream));
+            RTK_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        resolve_batch(ctx->host_graph->view, n_reads, seq_pool, seq_off, flags, raw, per_read);
     }
-    resolve_batch(ctx->host_graph->view, n_reads, seq_pool, seq_off, flags, raw, per_read);
     if (stats) {
         stats[0] += probes;
         stats[1] += n_raw;
@@ -226,7 +245,7 @@ void rtk_ctx_destroy(rtk_ctx* c) {
     for (auto& b : c->h_pin) b.release();
     for (auto& b : c->d_rg) b.release();
     for (auto& b : c->h_rg) b.release();
-    c->d_fs.release(); c->h_fs.release();
+    c->d_fs.release(); c->h_fs.release(); c->h_dense.release();
     if (c->host_copy.data) free(c->host_copy.data);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

@@ -119,6 +119,7 @@ struct rtk_ctx {
     rtk::PinBuf h_rg[3];     // region engine: [0] packed upload, [1] results + counters, [2] output pools
     rtk::DevBuf d_fs;        // fixSNPs: packed reads + ambiguity lists
     rtk::PinBuf h_fs;
+    rtk::PinBuf h_dense;     // exact sweeps: dense per-position answers (8 B per read base)
     int sm_count = 148;
     // forked contexts kept for re-use (fork_acquire / fork_release): the broker's service contexts and the correction gangs are
     // needed again by every batch; re-creating them per call means re-growing their device / pinned buffers every time, and a
@@ -160,7 +161,7 @@ void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_p
 // K1 driver: runs the exact and/or inexact kernels over reads resident on the device and leaves the
 // raw labelled hits in ctx->d_hits.  Returns raw hit count; *n_probes / *kernel_ms optional.
 uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint64_t* d_seq_off,
-                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms, const char* h_seq = nullptr);
+                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms, const char* h_seq = nullptr, bool dense = false);
 
 #ifndef RTK_HOSTSIM
 // Wait for a stream without monopolising a core: the service threads of the correction broker outnumber the spare cores, and

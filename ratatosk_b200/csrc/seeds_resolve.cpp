@@ -133,6 +133,43 @@ void resolve_inexact(const rtk_graph_view& g, const char* s, uint32_t slen, bool
     }
 }
 
+void resolve_exact_dense(const rtk_graph_view& g, uint32_t n_reads, const uint64_t* seq_off, const uint64_t* dense,
+                         std::vector<std::vector<rtk_hit>>& per_read) {
+    per_read.assign(n_reads, {});
+    const uint32_t k = g.k;
+    parallel_for(n_reads, [&](size_t rb, size_t re) {
+        for (size_t r = rb; r < re; ++r) {
+            const uint64_t len = seq_off[r + 1] - seq_off[r];
+            if (len < k) continue;
+            const uint64_t* d = dense + (seq_off[r] - seq_off[0]);
+            const uint32_t npos = (uint32_t)(len - k + 1);
+            size_t n_hits = 0;
+            for (uint32_t l = 0; l < npos; ++l) n_hits += (d[l] != ~0ULL);
+            std::vector<rtk_hit>& out = per_read[r];
+            out.reserve(n_hits);
+            uint32_t l = 0;
+            while (l < npos) {
+                if (d[l] == ~0ULL) { ++l; continue; }
+                // a findUnitig run (CompactedDBG.tcc:4479-4548): consecutive read positions on consecutive k-mers of one unitig, same
+                // strand; a k-mer one pool position further is always in the same unitig (a k-mer never straddles two unitigs)
+                const uint64_t P0 = d[l] & RTK_POS_MASK;
+                const uint32_t strand = (uint32_t)((d[l] >> 40) & 1);
+                const uint32_t u = rtk_unitig_of(g.blk2unitig, g.unitig_off, P0);
+                const uint64_t ub = g.unitig_off[u], usize = g.unitig_off[u + 1] - ub;
+                const uint32_t off0 = (uint32_t)(P0 - ub);
+                uint32_t run = 1;
+                if (usize != k) {   // short / abundant unitigs are never extended (CompactedDBG.tcc:4489)
+                    if (strand) while (l + run < npos && d[l + run] == ((P0 + run) | (1ULL << 40))) ++run;
+                    else while (l + run < npos && run <= off0 && d[l + run] == (P0 - run)) ++run;
+                }
+                if (strand) for (uint32_t j = 0; j < run; ++j) out.push_back({l + j, u, off0 + j, 1u});
+                else for (uint32_t j = run; j-- > 0;) out.push_back({l + j, u, off0 - j, 0u});   // Search.tcc:700: read position descends
+                l += run;
+            }
+        }
+    });
+}
+
 void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                    RawHitVec& raw, std::vector<std::vector<rtk_hit>>& per_read) {
     per_read.assign(n_reads, {});

@@ -42,4 +42,9 @@ void resolve_exact(const rtk_graph_view& g, const RawHit* raw, size_t n, std::ve
 void resolve_inexact(const rtk_graph_view& g, const char* s, uint32_t slen, bool or_exclusive, const RawHit* raw,
                      size_t n, std::vector<rtk_hit>& out);
 
+// dense exact sweep (rtk_k1_params::dense): dense[seq_off[r] - seq_off[0] + l] = P | strand << 40 or ~0.  Same output as
+// resolve_exact on the sorted hit list of every read; reads in parallel.
+void resolve_exact_dense(const rtk_graph_view& g, uint32_t n_reads, const uint64_t* seq_off, const uint64_t* dense,
+                         std::vector<std::vector<rtk_hit>>& per_read);
+
 }  // namespace rtk

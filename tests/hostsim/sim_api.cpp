@@ -13,7 +13,7 @@
 namespace rtk {
 
 static uint64_t sim_k1(rtk_ctx* ctx, uint32_t n_reads, const char* seq, const uint64_t* seq_off, uint32_t flags,
-                       RawHitVec& raw, uint64_t* n_probes) {
+                       RawHitVec& raw, uint64_t* n_probes, std::vector<uint64_t>* dense = nullptr) {
     const rtk_graph_view& g = ctx->host_graph->view;
     const uint32_t k = g.k;
     const bool exact = flags & RTK_SEARCH_EXACT;
@@ -23,8 +23,9 @@ static uint64_t sim_k1(rtk_ctx* ctx, uint32_t n_reads, const char* seq, const ui
     std::vector<uint32_t> tiles;
     build_tiles(n_reads, seq_off, k, tile, tiles, seq, exact ? k : k - 1, exact ? k : k + 1);
     const uint32_t n_tiles = (uint32_t)(tiles.size() / 2);
-    if (!n_tiles) return 0;
     const uint64_t total = seq_off[n_reads] - seq_off[0];
+    if (dense) dense->assign(total + 1, ~0ULL);
+    if (!n_tiles) return 0;
     uint64_t cap = 4 * total + 1024;
     std::vector<rtk_raw_hit> hits(cap);
     unsigned long long counters[2] = {0, 0};
@@ -35,6 +36,8 @@ static uint64_t sim_k1(rtk_ctx* ctx, uint32_t n_reads, const char* seq, const ui
     p.do_ins = (flags & RTK_SEARCH_INS) ? 1 : 0;
     p.do_del = (flags & RTK_SEARCH_DEL) ? 1 : 0;
     p.hits = hits.data(); p.n_hits = &counters[0]; p.hit_cap = cap; p.n_probes = &counters[1];
+    p.dense = nullptr;
+    if (dense) p.dense = dense->data();
     const unsigned grid = std::min<uint32_t>(n_tiles, 7);  // fewer blocks than tiles: exercises the grid-stride loop
     if (exact) {
         if (k <= 32) sim_launch(grid, RTK_K1_THREADS, [&] { rtk_k1_exact_kernel<uint64_t>(p); });
@@ -43,6 +46,8 @@ static uint64_t sim_k1(rtk_ctx* ctx, uint32_t n_reads, const char* seq, const ui
         if (k <= 32) sim_launch(grid, RTK_K1_THREADS, [&] { rtk_k1_inexact_kernel<uint64_t>(p); });
         else sim_launch(grid, RTK_K1_THREADS, [&] { rtk_k1_inexact_kernel<rtk_u128>(p); });
     }
+    if (n_probes) *n_probes = counters[1];
+    if (dense) return counters[0];
     if (counters[0] > cap) throw std::runtime_error("hostsim: hit buffer overflow");
     raw.resize(counters[0]);
     for (size_t i = 0; i < raw.size(); ++i) { raw[i].a = hits[i].a; raw[i].b = hits[i].b; }
@@ -54,9 +59,18 @@ void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, 
                           std::vector<std::vector<rtk_hit>>& per_read, uint64_t* stats) {
     if (!ctx->has_graph || !ctx->host_graph) throw std::invalid_argument("no graph uploaded to this context");
     RawHitVec raw;
-    uint64_t probes = 0;
-    const uint64_t n_raw = sim_k1(ctx, n_reads, seq_pool, seq_off, flags, raw, &probes);
-    resolve_batch(ctx->host_graph->view, n_reads, seq_pool, seq_off, flags, raw, per_read);
+    uint64_t probes = 0, n_raw;
+    static const bool list_only = getenv("RTK_K1_LIST") != nullptr;
+    if (flags == RTK_SEARCH_EXACT && !list_only && seq_off[n_reads] != seq_off[0]) {   // dense exact sweep, like the product
+        std::vector<uint64_t> dense;
+        std::vector<uint64_t> rel(n_reads + 1);
+        for (uint32_t i = 0; i <= n_reads; ++i) rel[i] = seq_off[i] - seq_off[0];
+        n_raw = sim_k1(ctx, n_reads, seq_pool + seq_off[0], rel.data(), flags, raw, &probes, &dense);
+        resolve_exact_dense(ctx->host_graph->view, n_reads, rel.data(), dense.data(), per_read);
+    } else {
+        n_raw = sim_k1(ctx, n_reads, seq_pool, seq_off, flags, raw, &probes);
+        resolve_batch(ctx->host_graph->view, n_reads, seq_pool, seq_off, flags, raw, per_read);
+    }
     if (stats) { stats[0] += probes; stats[1] += n_raw; }
 }
 
