@@ -24,6 +24,7 @@
 
 #include "broker.hpp"
 #include "rtk_host_common.hpp"
+#include "traceback_host.hpp"
 #include "traverse.hpp"
 
 namespace rtk {
@@ -210,45 +211,41 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
     // positions marked in pos2rm: a read without any marked position comes out as its corrected self whatever the alignment
     // is, so its (10 kb x 10 kb) alignment is not computed.  (The reference aligns every read, :1001; with one side empty it
     // gets no alignment and emits nothing, which the unaligned walk below reproduces.)
-    std::vector<uint8_t> need(n, 0);
+    // The alignment is only READ at marked positions, so sub-problems of edlib's divide-and-conquer whose target columns hold no
+    // mark are not solved (traceback_host.hpp: TbNeed); what is solved follows edlib's splits exactly, so the path through the
+    // marked stretches is the reference's.
+    std::vector<uint64_t> need_off(n + 1, 0);
+    for (uint32_t r = 0; r < n; ++r) need_off[r + 1] = need_off[r] + (corr_off[r + 1] - corr_off[r]) + 2;
+    std::vector<uint32_t> need_prefix(need_off[n] + 1, 0);
+    std::vector<uint8_t> aligned(n, 0);
     parallel_for(n, [&](size_t rb, size_t re) {
         for (size_t r = rb; r < re; ++r) {
-            const bool empty_side = (raw_off[r + 1] == raw_off[r]) || (corr_off[r + 1] == corr_off[r]);
-            bool any = false;
-            for (const uint8_t x : pos2rm[r]) if (x) { any = true; break; }
-            need[r] = (any && !empty_side) ? 1 : 0;
+            const size_t tl = (size_t)(corr_off[r + 1] - corr_off[r]);
+            const bool empty_side = (raw_off[r + 1] == raw_off[r]) || tl == 0;
+            uint32_t* pf = need_prefix.data() + need_off[r];
+            uint32_t c = 0;
+            pf[0] = 0;
+            for (size_t p = 0; p <= tl; ++p) { c += (!empty_side && p < pos2rm[r].size() && pos2rm[r][p]) ? 1u : 0u; pf[p + 1] = c; }
+            aligned[r] = c != 0;
         }
     });
-    std::vector<AlignJob> jobs(n);
-    std::vector<AlignJob> ajobs;
-    std::vector<uint32_t> aidx;
-    for (uint32_t r = 0; r < n; ++r) {
-        jobs[r].q.assign(raw_pool + raw_off[r], (size_t)(raw_off[r + 1] - raw_off[r]));
-        jobs[r].t.assign(corr_pool + corr_off[r], (size_t)(corr_off[r + 1] - corr_off[r]));
-        jobs[r].mode = 0;
-        if (need[r]) { ajobs.push_back(jobs[r]); aidx.push_back(r); }
+    std::vector<std::vector<TbRun>> runs;
+    {
+        const TbNeed tn{need_prefix.data(), need_off.data()};
+        float kms = 0.f;
+        nw_path_runs_masked(ctx, n, raw_pool, raw_off, corr_pool, corr_off, tn, runs, &kms);
     }
-    std::vector<std::vector<uint8_t>> ops(n);
-    if (!ajobs.empty()) {
-        std::vector<int32_t> dist;
-        std::vector<std::vector<uint8_t>> aops;
-        PathReq rq{&ajobs, &dist, &aops};
-        run_path_batch(ctx, std::vector<PathReq*>(1, &rq));
-        for (size_t i = 0; i < aidx.size(); ++i) ops[aidx[i]] = std::move(aops[i]);
-    }
-    if (prof) fprintf(stderr, "[phasing] %zu of %u reads aligned\n", ajobs.size(), n);
+    if (prof) { size_t na = 0; for (uint32_t r = 0; r < n; ++r) na += aligned[r]; fprintf(stderr, "[phasing] %zu of %u reads aligned\n", na, n); }
     lap("whole-read alignments");
-    for (uint32_t r = 0; r < n; ++r) {
-        // not aligned: an all-match walk over the corrected read (no position is marked) / nothing when a side is empty
-        if (!need[r] && raw_off[r + 1] != raw_off[r] && corr_off[r + 1] != corr_off[r]) ops[r].assign(jobs[r].t.size(), 2);
-    }
+    // edlibAlign returns no alignment when one side is empty (:160-176): nothing is emitted for such a read
+    for (uint32_t r = 0; r < n; ++r) if (raw_off[r + 1] == raw_off[r] || corr_off[r + 1] == corr_off[r]) runs[r].clear();
 
     // walk the alignment (:1001-1052) and collect the reverted neighbourhoods
     std::vector<std::string> s_new(n);
     parallel_for(n, [&](size_t rb, size_t re) {
     for (size_t r = rb; r < re; ++r) {
-        const std::string& s_raw = jobs[r].q;
-        const std::string& s_corr = jobs[r].t;
+        const char* s_raw = raw_pool + raw_off[r];
+        const char* s_corr = corr_pool + corr_off[r];
         const char* q_corr = qual_pool + qual_off[r];
         const std::vector<uint8_t>& rm = pos2rm[r];
         auto to_rm = [&](size_t p) { return p < rm.size() && rm[p]; };
@@ -256,13 +253,11 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
         std::string& q_out = out_qual[r];
         std::vector<size_t> new_base_pos;
         size_t target_pos = 0, query_pos = 0;
-        const std::vector<uint8_t>& o = ops[r];
-        // edlibAlign returns no alignment when one side is empty (:160-176): nothing is emitted
-        for (size_t a = 0; a < o.size();) {
-            const uint8_t kind = (o[a] == 1) ? 1 : (o[a] == 2) ? 2 : 0;   // CIGAR standard: M (match or mismatch), I, D
-            size_t b = a;
-            while (b < o.size() && (((o[b] == 1) ? 1 : (o[b] == 2) ? 2 : 0) == kind)) ++b;
-            const size_t l = b - a;
+        s_out.reserve((size_t)(corr_off[r + 1] - corr_off[r]) + 64);
+        q_out.reserve((size_t)(corr_off[r + 1] - corr_off[r]) + 64);
+        for (const TbRun& run : runs[r]) {   // CIGAR standard: M (match or mismatch), I, D
+            const uint8_t kind = run.kind;
+            const size_t l = run.len;
             if (kind == 0) {
                 for (size_t i = target_pos; i < target_pos + l; ++i) {
                     if (to_rm(i)) {
@@ -275,7 +270,7 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
             } else if (kind == 1) {
                 if (to_rm(target_pos)) {
                     for (size_t i = 0, sl = s_out.length(); i < l; ++i) new_base_pos.push_back(sl + i);
-                    s_out += s_raw.substr(query_pos, l);
+                    s_out.append(s_raw + query_pos, l);
                     q_out += std::string(l, q_min);
                 }
                 query_pos += l;
@@ -284,7 +279,6 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
                     if (!to_rm(i)) { s_out += s_corr[i]; q_out += q_corr[i]; }
                 target_pos += l;
             }
-            a = b;
         }
         std::string& sn = s_new[r];
         sn.assign(s_out.length(), 'N');

@@ -250,6 +250,12 @@ struct RegionBatchOut {
 void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls, const rtk_region_call_t* calls, const char* win_pool,
                       uint64_t win_bytes, const rtk_hit* weak_pool, uint64_t n_weak, const uint32_t* pid_pool, uint64_t n_pids, RegionBatchOut& out);
 
+// phasing()'s whole-read NW paths as runs, only where the caller reads them (traceback.cu / tests/hostsim/sim_traceback.cpp)
+struct TbNeed;
+struct TbRun;
+void nw_path_runs_masked(rtk_ctx* c, uint32_t n, const char* q_pool, const uint64_t* q_off, const char* t_pool, const uint64_t* t_off,
+                         const TbNeed& need, std::vector<std::vector<TbRun>>& runs, float* kernel_ms);
+
 // full searchSequence for a host batch -> per read ordered hits
 void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                           std::vector<std::vector<rtk_hit>>& per_read, uint64_t* stats);

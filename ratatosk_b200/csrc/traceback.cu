@@ -149,6 +149,56 @@ struct CudaTbBackend : TbBackend {
     }
 };
 
+// NW paths of n problems as runs, restricted to the target columns the caller reads (TbNeed): phasing()'s whole-read alignments.
+// Pools are used in place (problem a = q_pool[q_off[a], q_off[a+1]) vs t_pool[t_off[a], t_off[a+1])); forward and reversed copies
+// go up once, every level of the divide-and-conquer is one fused launch.
+void nw_path_runs_masked(rtk_ctx* c, uint32_t n, const char* q_pool, const uint64_t* q_off, const char* t_pool, const uint64_t* t_off,
+                         const TbNeed& need, std::vector<std::vector<TbRun>>& runs, float* kernel_ms) {
+    runs.assign(n, {});
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (!n) return;
+    cudaStream_t st = c->stream;
+    const uint64_t qb = q_off[n] - q_off[0], tb = t_off[n] - t_off[0];
+    std::vector<uint64_t> qrel(n + 1), trel(n + 1);
+    std::vector<uint32_t> qlen(n + 1, 0), tlen(n + 1, 0);
+    for (uint32_t i = 0; i <= n; ++i) { qrel[i] = q_off[i] - q_off[0]; trel[i] = t_off[i] - t_off[0]; }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (q_off[i + 1] - q_off[i] >= 0xFFFFFFFFull || t_off[i + 1] - t_off[i] >= 0xFFFFFFFFull) throw std::invalid_argument("alignment side longer than 4 Gbases");
+        qlen[i] = (uint32_t)(q_off[i + 1] - q_off[i]); tlen[i] = (uint32_t)(t_off[i + 1] - t_off[i]);
+    }
+    c->d_aux[0].reserve(qb + 16);
+    c->d_aux[1].reserve(tb + 16);
+    c->d_sub[7].reserve(qb + tb + 32);
+    PinBuf& H = c->h_pin[12];
+    PinBuf& HR = c->h_pin[13];
+    H.reserve(qb + tb + 64);
+    HR.reserve(qb + tb + 64);
+    char* hq = H.as<char>(); char* ht = hq + qb;
+    char* rq = HR.as<char>(); char* rt = rq + qb;
+    parallel_for(n, [&](size_t ab, size_t ae) {
+        for (size_t a = ab; a < ae; ++a) {
+            const char* qs = q_pool + q_off[a];
+            const char* ts = t_pool + t_off[a];
+            memcpy(hq + qrel[a], qs, qlen[a]);
+            memcpy(ht + trel[a], ts, tlen[a]);
+            if (need.any((uint32_t)a, 0, tlen[a])) {   // reversed copies feed the divide-and-conquer of solved problems only
+                char* dq = rq + qrel[a]; char* dt = rt + trel[a];
+                for (uint32_t i = 0; i < qlen[a]; ++i) dq[i] = qs[qlen[a] - 1 - i];
+                for (uint32_t i = 0; i < tlen[a]; ++i) dt[i] = ts[tlen[a] - 1 - i];
+            }
+        }
+    });
+    if (qb) RTK_CUDA(counted_memcpy_async(c->d_aux[0].p, hq, qb, cudaMemcpyHostToDevice, st));
+    if (tb) RTK_CUDA(counted_memcpy_async(c->d_aux[1].p, ht, tb, cudaMemcpyHostToDevice, st));
+    if (qb) RTK_CUDA(counted_memcpy_async(c->d_sub[7].p, rq, qb, cudaMemcpyHostToDevice, st));
+    if (tb) RTK_CUDA(counted_memcpy_async(c->d_sub[7].as<char>() + qb + 8, rt, tb, cudaMemcpyHostToDevice, st));
+    CudaTbBackend be;
+    be.c = c; be.d_q = c->d_aux[0].as<char>(); be.d_t = c->d_aux[1].as<char>();
+    be.d_rq = c->d_sub[7].as<char>(); be.d_rt = c->d_sub[7].as<char>() + qb + 8;
+    solve_nw_runs(be, n, qrel.data(), qlen.data(), trel.data(), tlen.data(), &need, runs);
+    if (kernel_ms) *kernel_ms = be.ms;
+}
+
 }  // namespace rtk
 
 using namespace rtk;

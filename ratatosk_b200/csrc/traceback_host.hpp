@@ -72,20 +72,34 @@ inline void tb_rows_from_column(uint32_t qlen, const uint64_t* P, const uint64_t
     }
 }
 
-// NW alignment paths of n problems: problem a = q_pool[q_beg[a], +q_len[a]) vs t_pool[t_beg[a], +t_len[a]); the reversed
-// pools hold each string reversed at the same offsets.  ops[a] / dist[a] out.  Problems with an empty side must not be passed.
-inline void solve_nw_paths(TbBackend& be, uint32_t n, const uint64_t* q_beg, const uint32_t* q_len, const uint64_t* t_beg,
-                           const uint32_t* t_len, std::vector<std::vector<uint8_t>>& ops, std::vector<int32_t>& dist) {
-    struct Node {
-        uint32_t a;                 // problem
-        uint32_t qx, qy, tu, tv;    // sub-ranges [qx,qy) x [tu,tv) of the problem's strings
-        int child[2];
-        std::vector<uint8_t> ops;
-        int32_t dist;
-    };
-    std::vector<Node> nodes;
+// Which target columns of a problem matter to the caller (phasing() only reads the path where the corrected read is marked
+// for reversal, src/Graph.cpp:1001-1052): prefix[off[a] + p] = number of marked target positions < p, p in [0, t_len + 1].
+// A sub-problem of the divide-and-conquer whose closed column range [tu, tv] holds no marked position is not solved: its
+// path is replaced by "all its query bases unaligned, then all its target bases unaligned", which consumes the same bases.
+struct TbNeed {
+    const uint32_t* prefix;
+    const uint64_t* off;
+    bool any(uint32_t a, uint32_t tu, uint32_t tv) const { return prefix[off[a] + tv + 1] != prefix[off[a] + tu]; }
+};
+struct TbRun { uint8_t kind; uint32_t len; };   // kind 0: aligned pair (match or mismatch), 1: query base unaligned, 2: target base unaligned
+
+struct TbNode {
+    uint32_t a;                 // problem
+    uint32_t qx, qy, tu, tv;    // sub-ranges [qx,qy) x [tu,tv) of the problem's strings
+    int child[2];
+    std::vector<uint8_t> ops;
+    int32_t dist;
+    uint8_t pruned;
+};
+
+// The recursion tree of n NW problems: problem a = q_pool[q_beg[a], +q_len[a]) vs t_pool[t_beg[a], +t_len[a]); the reversed
+// pools hold each string reversed at the same offsets.  nodes[a] is the root of problem a; leaves carry ops.
+inline void solve_nw_tree(TbBackend& be, uint32_t n, const uint64_t* q_beg, const uint32_t* q_len, const uint64_t* t_beg,
+                          const uint32_t* t_len, const TbNeed* need, std::vector<TbNode>& nodes) {
+    typedef TbNode Node;
+    nodes.clear();
     std::vector<int> work;
-    for (uint32_t a = 0; a < n; ++a) { nodes.push_back({a, 0, q_len[a], 0, t_len[a], {-1, -1}, {}, -1}); work.push_back((int)a); }
+    for (uint32_t a = 0; a < n; ++a) { nodes.push_back({a, 0, q_len[a], 0, t_len[a], {-1, -1}, {}, -1, 0}); work.push_back((int)a); }
     auto fw_item = [&](const Node& nd, uint32_t tu, uint32_t tv) {
         return TbItem{q_beg[nd.a] + nd.qx, t_beg[nd.a] + tu, nd.qy - nd.qx, tv - tu, 0};
     };
@@ -97,7 +111,8 @@ inline void solve_nw_paths(TbBackend& be, uint32_t n, const uint64_t* q_beg, con
         for (int id : work) {
             Node& nd = nodes[id];
             const uint32_t ql = nd.qy - nd.qx, tl = nd.tv - nd.tu;
-            if (ql == 0 || tl == 0) { nd.ops.assign((size_t)ql + tl, ql == 0 ? 2 : 1); nd.dist = (int32_t)(ql + tl); }  // :1171-1178
+            if (need && !need->any(nd.a, nd.tu, nd.tv)) { nd.pruned = 1; nd.dist = -1; }
+            else if (ql == 0 || tl == 0) { nd.ops.assign((size_t)ql + tl, ql == 0 ? 2 : 1); nd.dist = (int32_t)(ql + tl); }  // :1171-1178
             else if (!tb_needs_hirschberg(ql, tl)) direct_ids.push_back(id);
             else big_ids.push_back(id);
         }
@@ -117,11 +132,12 @@ inline void solve_nw_paths(TbBackend& be, uint32_t n, const uint64_t* q_beg, con
                 const uint32_t left = (nd.tv - nd.tu) / 2;
                 items.push_back(fw_item(nd, nd.tu, nd.tu + left));            // left half, forward
                 items.push_back(rev_item(nd, nd.tu + left, nd.tv));           // right half, reversed
-                items.push_back(fw_item(nd, nd.tu, nd.tv));                   // whole problem: its distance = bestScore
             }
             std::vector<std::vector<int32_t>> rows;
             be.last_column(items, rows);
-            // the split row of every big problem (independent of one another): first query row at which the two halves add up
+            // The split row of every big problem (independent of one another): the first query row at which the two halves add
+            // up to the problem's distance (src/edlib.cpp:1330-1337).  The distance is the minimum of those sums over all the
+            // ways to cut, so it needs no sweep of its own.
             std::vector<int> splits(big_ids.size(), -2);
             std::vector<int32_t> bests(big_ids.size(), -1);
             tb_parallel_for(big_ids.size(), [&](size_t ib, size_t ie) {
@@ -129,13 +145,14 @@ inline void solve_nw_paths(TbBackend& be, uint32_t n, const uint64_t* q_beg, con
                     const int id = big_ids[i];
                     const uint32_t ql = nodes[id].qy - nodes[id].qx, tl = nodes[id].tv - nodes[id].tu;
                     const uint32_t left = tl / 2, right = tl - left;
-                    const std::vector<int32_t>& L = rows[3 * i];
-                    const std::vector<int32_t>& Rr = rows[3 * i + 1];   // Rr[i'] = dist(rev q prefix i'+1, rev right half)
-                    const int32_t best = rows[3 * i + 2][ql - 1];
+                    const int32_t* L = rows[2 * i].data();
+                    const int32_t* Rr = rows[2 * i + 1].data();   // Rr[i'] = dist(rev q prefix i'+1, rev right half)
                     auto R = [&](uint32_t j) { return Rr[ql - 1 - j]; };  // dist(q[j:], right half)
+                    int32_t best = std::min((int32_t)left + R(0), L[ql - 1] + (int32_t)right);
+                    for (uint32_t r = 0; r + 1 < ql; ++r) best = std::min(best, L[r] + Rr[ql - 2 - r]);
                     int split = -2;
                     for (uint32_t r = 0; r + 1 < ql; ++r)
-                        if (L[r] + R(r + 1) == best) { split = (int)r; break; }
+                        if (L[r] + Rr[ql - 2 - r] == best) { split = (int)r; break; }
                     if (split == -2 && (int32_t)left + R(0) == best) split = -1;
                     if (split == -2 && L[ql - 1] + (int32_t)right == best) split = (int)ql - 1;
                     splits[i] = split; bests[i] = best;
@@ -148,29 +165,73 @@ inline void solve_nw_paths(TbBackend& be, uint32_t n, const uint64_t* q_beg, con
                 const int split = splits[i];
                 if (split == -2) throw std::runtime_error("alignment split not found");
                 const uint32_t ul_h = (uint32_t)(split + 1);
-                const Node parent = nodes[id];
-                Node ul{parent.a, parent.qx, parent.qx + ul_h, parent.tu, parent.tu + left, {-1, -1}, {}, -1};
-                Node lr{parent.a, parent.qx + ul_h, parent.qy, parent.tu + left, parent.tv, {-1, -1}, {}, -1};
+                const uint32_t pa = nodes[id].a, pqx = nodes[id].qx, pqy = nodes[id].qy, ptu = nodes[id].tu, ptv = nodes[id].tv;
                 nodes[id].dist = bests[i];
-                nodes[id].child[0] = (int)nodes.size(); nodes.push_back(ul); next.push_back(nodes[id].child[0]);
-                nodes[id].child[1] = (int)nodes.size(); nodes.push_back(lr); next.push_back(nodes[id].child[1]);
+                const int c0 = (int)nodes.size();
+                nodes.push_back({pa, pqx, pqx + ul_h, ptu, ptu + left, {-1, -1}, {}, -1, 0});
+                nodes.push_back({pa, pqx + ul_h, pqy, ptu + left, ptv, {-1, -1}, {}, -1, 0});
+                nodes[id].child[0] = c0; nodes[id].child[1] = c0 + 1;
+                next.push_back(c0); next.push_back(c0 + 1);
             }
         }
         work.swap(next);
     }
+}
+
+// in-order concatenation of the leaves: ops[a] / dist[a]
+inline void solve_nw_paths(TbBackend& be, uint32_t n, const uint64_t* q_beg, const uint32_t* q_len, const uint64_t* t_beg,
+                           const uint32_t* t_len, std::vector<std::vector<uint8_t>>& ops, std::vector<int32_t>& dist) {
+    std::vector<TbNode> nodes;
+    solve_nw_tree(be, n, q_beg, q_len, t_beg, t_len, nullptr, nodes);
     ops.assign(n, {});
     dist.assign(n, -1);
-    // in-order concatenation of the leaves
-    for (uint32_t a = 0; a < n; ++a) {
-        std::vector<int> st(1, (int)a);
-        while (!st.empty()) {
-            const int id = st.back();
-            st.pop_back();
-            if (nodes[id].child[0] < 0) ops[a].insert(ops[a].end(), nodes[id].ops.begin(), nodes[id].ops.end());
-            else { st.push_back(nodes[id].child[1]); st.push_back(nodes[id].child[0]); }
+    tb_parallel_for(n, [&](size_t ab, size_t ae) {
+        for (size_t a = ab; a < ae; ++a) {
+            std::vector<int> st(1, (int)a);
+            size_t tot = 0;
+            while (!st.empty()) {
+                const int id = st.back();
+                st.pop_back();
+                if (nodes[id].child[0] < 0) tot += nodes[id].ops.size();
+                else { st.push_back(nodes[id].child[1]); st.push_back(nodes[id].child[0]); }
+            }
+            ops[a].reserve(tot);
+            st.assign(1, (int)a);
+            while (!st.empty()) {
+                const int id = st.back();
+                st.pop_back();
+                if (nodes[id].child[0] < 0) ops[a].insert(ops[a].end(), nodes[id].ops.begin(), nodes[id].ops.end());
+                else { st.push_back(nodes[id].child[1]); st.push_back(nodes[id].child[0]); }
+            }
+            dist[a] = nodes[a].dist;
         }
-        dist[a] = nodes[a].dist;
-    }
+    });
+}
+
+// the same paths as runs of equal kind (match and mismatch are one kind), sub-problems outside `need` replaced as described there
+inline void solve_nw_runs(TbBackend& be, uint32_t n, const uint64_t* q_beg, const uint32_t* q_len, const uint64_t* t_beg,
+                          const uint32_t* t_len, const TbNeed* need, std::vector<std::vector<TbRun>>& runs) {
+    std::vector<TbNode> nodes;
+    solve_nw_tree(be, n, q_beg, q_len, t_beg, t_len, need, nodes);
+    runs.assign(n, {});
+    tb_parallel_for(n, [&](size_t ab, size_t ae) {
+        for (size_t a = ab; a < ae; ++a) {
+            std::vector<TbRun>& out = runs[a];
+            auto push = [&](uint8_t kind, uint32_t len) {
+                if (!len) return;
+                if (!out.empty() && out.back().kind == kind) out.back().len += len; else out.push_back({kind, len});
+            };
+            std::vector<int> st(1, (int)a);
+            while (!st.empty()) {
+                const int id = st.back();
+                st.pop_back();
+                const TbNode& nd = nodes[id];
+                if (nd.child[0] >= 0) { st.push_back(nd.child[1]); st.push_back(nd.child[0]); continue; }
+                if (nd.pruned) { push(1, nd.qy - nd.qx); push(2, nd.tv - nd.tu); continue; }
+                for (const uint8_t o : nd.ops) push((o == 1) ? 1 : (o == 2) ? 2 : 0, 1);
+            }
+        }
+    });
 }
 
 // placement of a set of items in the matrix / ops scratch, per lane-group class

@@ -88,6 +88,30 @@ struct SimTbBackend : TbBackend {
     }
 };
 
+namespace rtk {
+void nw_path_runs_masked(rtk_ctx*, uint32_t n, const char* q_pool, const uint64_t* q_off, const char* t_pool, const uint64_t* t_off,
+                         const TbNeed& need, std::vector<std::vector<TbRun>>& runs, float* kernel_ms) {
+    runs.assign(n, {});
+    if (kernel_ms) *kernel_ms = 0.f;
+    if (!n) return;
+    const uint64_t qb = q_off[n] - q_off[0], tb = t_off[n] - t_off[0];
+    std::vector<uint64_t> qrel(n + 1), trel(n + 1);
+    std::vector<uint32_t> qlen(n + 1, 0), tlen(n + 1, 0);
+    for (uint32_t i = 0; i <= n; ++i) { qrel[i] = q_off[i] - q_off[0]; trel[i] = t_off[i] - t_off[0]; }
+    for (uint32_t i = 0; i < n; ++i) { qlen[i] = (uint32_t)(q_off[i + 1] - q_off[i]); tlen[i] = (uint32_t)(t_off[i + 1] - t_off[i]); }
+    std::string rq(qb + 1, 'N'), rt(tb + 1, 'N');
+    for (uint32_t a = 0; a < n; ++a) {
+        const char* qs = q_pool + q_off[a];
+        for (uint32_t i = 0; i < qlen[a]; ++i) rq[qrel[a] + i] = qs[qlen[a] - 1 - i];
+        const char* ts = t_pool + t_off[a];
+        for (uint32_t i = 0; i < tlen[a]; ++i) rt[trel[a] + i] = ts[tlen[a] - 1 - i];
+    }
+    SimTbBackend be;
+    be.q = q_pool + q_off[0]; be.t = t_pool + t_off[0]; be.rq = rq.data(); be.rt = rt.data();
+    solve_nw_runs(be, n, qrel.data(), qlen.data(), trel.data(), tlen.data(), &need, runs);
+}
+}  // namespace rtk
+
 extern "C" int rtk_edlib_path_batch(rtk_ctx* c, uint32_t n, const char* q_pool, const uint64_t* q_off, const char* t_pool,
                                     const uint64_t* t_off, const uint8_t* mode, int32_t* dist, int32_t* end_loc,
                                     uint8_t** ops, uint64_t** ops_off, uint8_t* flags, uint64_t*) {
