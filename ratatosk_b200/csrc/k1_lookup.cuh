@@ -53,7 +53,7 @@ struct rtk_k1_params {
     unsigned long long* n_hits;
     uint64_t hit_cap;
     unsigned long long* n_probes;  // optional probe counter (may be null)
-    uint64_t* dense;               // exact sweep only, optional: dense[seq_off[read] + l] = P | strand << 40 of position l's k-mer,
+    uint64_t* dense;               // exact sweep only, optional: dense[seq_off[read] - seq_off[0] + l] = P | strand << 40 of position l's k-mer,
                                    // ~0 when it is not in the graph (pre-set by the caller); `hits` is then unused.  On corrected
                                    // reads (second pass, phasing) nearly every position hits: a dense array in read order needs
                                    // neither labels nor a sort, and the runs of findUnitig fall out of consecutive entries
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(RTK_K1_THREADS) rtk_k1_exact_kernel(const rtk_
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (p.dense) {
-            if (hit) p.dense[base + l] = h.P | ((uint64_t)h.strand << 40);
+            if (hit) p.dense[base - p.seq_off[0] + l] = h.P | ((uint64_t)h.strand << 40);   // relative to the first read of this launch
             if ((threadIdx.x & 31) == 0 && m) atomicAdd(p.n_hits, (unsigned long long)__popc(m));
         } else if (m) {
             const int lane = threadIdx.x & 31;
