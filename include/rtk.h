@@ -285,6 +285,10 @@ int rtk_correct_batch_resident(rtk_ctx* ctx, const rtk_opt* opt, int pass, uint3
                                const char* qual_pool, const uint64_t* qual_off, char** out_seq_pool, char** out_qual_pool,
                                uint64_t** out_off, uint64_t* stats);
 
+/* Measurement aid like rtk_correct_batch_resident: tells ctx that the reads of its NEXT rtk_correct_batch / rtk_correct_two_pass_batch
+ * call (same n_reads, same bytes, upper-case) are already in HBM at dev_seq_pool with offsets dev_seq_off (rebased to 0). */
+int rtk_ctx_resident_reads(rtk_ctx* ctx, const char* dev_seq_pool, const uint64_t* dev_seq_off, uint32_t n_reads, uint64_t total_bases);
+
 /* ---- phasing (src/Graph.hpp:53, src/Graph.cpp:869-1097): the step the multi-thread branch of search() runs on every read
  * of the SECOND pass before getSeeds (src/Ratatosk.cpp:832).  raw = the uncorrected read, corr / qual = its pass-1 correction.
  * Stretches of corr whose long-read colours are compatible with no other stretch of the read are reverted to raw; output
@@ -293,6 +297,18 @@ int rtk_correct_batch_resident(rtk_ctx* ctx, const rtk_opt* opt, int pass, uint3
 int rtk_phasing_batch(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const char* raw_pool, const uint64_t* raw_off,
                       const char* corr_pool, const uint64_t* corr_off, const char* qual_pool, const uint64_t* qual_off,
                       char** out_seq_pool, char** out_qual_pool, uint64_t** out_off);
+
+/* ---- both passes of a ticket as one pipeline: pass 1 on ctx1 (k1 graph), then phasing and pass 2 on ctx2 (k2 graph; same device),
+ * i.e. what `Ratatosk correct -1` followed by `correct -2 -O` from the two indexes compute for these reads (src/Ratatosk.cpp:808-867
+ * run twice).  Every stage of a read depends only on that read and on the read-only graphs, so the library cuts the ticket into
+ * gangs of reads that flow through the three stages independently: the stages of different gangs overlap on the device and on the
+ * host instead of each waiting for the slowest read of the previous stage.  Same bytes out as the three separate calls.
+ * p1_* (all three or none): the pass-1 output (what <out>.2.fastq holds).  stats1 / stats2: as rtk_correct_batch, per pass;
+ * stage_ns (optional, 3 x u64, accumulated): mean over the gangs of the time spent in pass 1, phasing, pass 2. */
+int rtk_correct_two_pass_batch(rtk_ctx* ctx1, rtk_ctx* ctx2, const rtk_opt* opt1, const rtk_opt* opt2, uint32_t n_reads,
+                               const char* seq_pool, const uint64_t* seq_off, const char* qual_pool, const uint64_t* qual_off,
+                               char** out_seq_pool, char** out_qual_pool, uint64_t** out_off, char** p1_seq_pool, char** p1_qual_pool,
+                               uint64_t** p1_off, uint64_t* stats1, uint64_t* stats2, uint64_t* stage_ns);
 
 /* ---- fixSNPs (src/Alignment.cpp:846-964; `-f` / Correct_Opt::force_unres_snp_corr, called on the pass-1 read before phasing and
  * getSeeds of the second pass, src/Ratatosk.cpp:672 / :828): an IUPAC code left by pass 1 is replaced by a base when exactly one

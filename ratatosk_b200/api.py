@@ -151,6 +151,11 @@ def load_library(path=None):
                                                  C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
     L.rtk_fix_snps_batch.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    u64p_ = C.POINTER(C.c_uint64)
+    L.rtk_correct_two_pass_batch.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RtkOpt), C.POINTER(RtkOpt), C.c_uint32, C.c_char_p, u64p_, C.c_char_p, u64p_,
+                                             C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(u64p_), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                             C.POINTER(u64p_), u64p_, u64p_, u64p_]
+    L.rtk_ctx_resident_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64]
     L.rtk_phasing_batch.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.c_char_p,
                                     C.POINTER(C.c_uint64), C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64))]
@@ -387,6 +392,30 @@ class Context:
         if stats is not None:
             stats.extend(list(st))
         return out
+
+    def correct_two_pass(self, ctx2, reads, quals, opt1=None, opt2=None, want_pass1=False):
+        """pass 1 on this context (k1 graph) + phasing + pass 2 on ctx2 (k2 graph) as one pipeline (rtk_correct_two_pass_batch)
+        -> list of (sequence, quality) [, the same for the pass-1 output]"""
+        opt1, opt2 = opt1 or default_opt(1), opt2 or default_opt(2)
+        pool, off = pack_reads(reads)
+        qpool, qoff = pack_reads(quals)
+        u64p = C.POINTER(C.c_uint64)
+        os_, oq_, oo = C.c_void_p(), C.c_void_p(), u64p()
+        ps_, pq_, po = C.c_void_p(), C.c_void_p(), u64p()
+        _check(self.L, self.L.rtk_correct_two_pass_batch(self.h, ctx2.h, C.byref(opt1), C.byref(opt2), len(reads), pool, off.ctypes.data_as(u64p), qpool,
+                                                         qoff.ctypes.data_as(u64p), C.byref(os_), C.byref(oq_), C.byref(oo),
+                                                         C.byref(ps_) if want_pass1 else None, C.byref(pq_) if want_pass1 else None,
+                                                         C.byref(po) if want_pass1 else None, None, None, None))
+
+        def take(sp, qp, op):
+            n = len(reads)
+            offs = [op[i] for i in range(n + 1)]
+            sbuf, qbuf = C.string_at(sp, offs[-1]), C.string_at(qp, offs[-1])
+            out = [(sbuf[offs[i]:offs[i + 1]].decode("latin1"), qbuf[offs[i]:offs[i + 1]].decode("latin1")) for i in range(n)]
+            self.L.rtk_free(sp); self.L.rtk_free(qp); self.L.rtk_free(C.cast(op, C.c_void_p))
+            return out
+        fin = take(os_, oq_, oo)
+        return (fin, take(ps_, pq_, po)) if want_pass1 else fin
 
     def fix_snps(self, reads, opt=None):
         """fixSNPs (src/Alignment.cpp:846) for a batch of pass-1 reads on the k = 63 graph -> (list of reads, codes replaced)"""

@@ -1304,6 +1304,118 @@ void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_r
 #endif
 }
 
+// Both passes of a batch as ONE pipeline (rtk_correct_two_pass_batch).  The stages of a read depend only on that read and on
+// the two read-only graphs, so the batch is cut into gangs (contiguous read ranges) and every gang runs pass 1 -> phasing ->
+// pass 2 on its own reads with its own forked contexts of both graphs.  The gangs drift apart (they take turns at the
+// host-heavy anchor stage), so while one gang's longest second-pass regions occupy a few SMs, another gang's k-mer sweeps,
+// first-pass regions or whole-read alignments fill the rest of the device and the host threads: no stage waits for the
+// slowest read of the previous stage of the WHOLE batch, as three separate calls would.
+void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char* raw_pool, const uint64_t* raw_off, const char* corr_pool,
+                        const uint64_t* corr_off, const char* qual_pool, const uint64_t* qual_off, std::vector<std::string>& out_seq,
+                        std::vector<std::string>& out_qual);
+
+static void pack_strings(const std::string* v, uint32_t n, std::string& pool, std::vector<uint64_t>& off) {
+    off.assign(n + 1, 0);
+    for (uint32_t r = 0; r < n; ++r) off[r + 1] = off[r] + v[r].size();
+    pool.assign(off[n] + 1, '\0');
+    char* dst = &pool[0];
+    parallel_for(n, [&](size_t rb, size_t re) { for (size_t r = rb; r < re; ++r) memcpy(dst + off[r], v[r].data(), v[r].size()); });
+}
+
+void correct_two_pass_host(rtk_ctx* ctx1, rtk_ctx* ctx2, const rtk_opt& opt1, const rtk_opt& opt2, uint32_t n_reads, const char* seq_pool,
+                           const uint64_t* seq_off, const char* qual_pool, const uint64_t* qual_off, std::vector<std::string>& p1_seq,
+                           std::vector<std::string>& p1_qual, std::vector<std::string>& out_seq, std::vector<std::string>& out_qual,
+                           uint64_t* stats1, uint64_t* stats2, uint64_t* stage_ns) {
+    if (!ctx1->has_graph || !ctx1->host_graph || !ctx2->has_graph || !ctx2->host_graph) throw std::invalid_argument("no graph uploaded to a context");
+    if (opt1.k != ctx1->host_graph->view.k || opt2.k != ctx2->host_graph->view.k) throw std::invalid_argument("rtk_opt.k does not match the graph's k");
+#ifndef RTK_HOSTSIM
+    if (ctx1->device != ctx2->device) throw std::invalid_argument("the two contexts must live on the same device");
+    const uint64_t launches0 = g_launches, h2d0 = g_h2d_bytes, d2h0 = g_d2h_bytes;
+#endif
+    p1_seq.assign(n_reads, std::string()); p1_qual.assign(n_reads, std::string());
+    out_seq.assign(n_reads, std::string()); out_qual.assign(n_reads, std::string());
+    if (!n_reads) return;
+    const char* e = getenv("RTK_GANGS2");
+    unsigned n_gangs = e ? (unsigned)std::max(1, atoi(e)) : 4u;
+    const uint64_t total_bases = seq_off[n_reads] - seq_off[0];
+    const char* e_min = getenv("RTK_GANGS_MIN_BASES");   // tests force several gangs on small fixtures
+    const uint64_t min_bases = e_min ? (uint64_t)std::max(1ll, atoll(e_min)) : (2ull << 20);
+    n_gangs = (unsigned)std::min<uint64_t>(n_gangs, std::max<uint64_t>(1, total_bases / min_bases));   // at least ~2 Mbases per gang
+    n_gangs = std::min(n_gangs, std::min(std::max(1u, host_threads()), n_reads));
+    std::vector<uint32_t> cut(n_gangs + 1, n_reads);
+    cut[0] = 0;
+    for (unsigned gi = 1; gi < n_gangs; ++gi) {
+        const uint64_t want = seq_off[0] + total_bases * gi / n_gangs;
+        cut[gi] = (uint32_t)(std::lower_bound(seq_off, seq_off + n_reads + 1, want) - seq_off);
+        cut[gi] = std::max(cut[gi], cut[gi - 1]);
+    }
+    std::vector<std::vector<uint64_t>> gs1(n_gangs, std::vector<uint64_t>(24, 0)), gs2(n_gangs, std::vector<uint64_t>(24, 0));
+    std::vector<std::vector<uint64_t>> gns(n_gangs, std::vector<uint64_t>(3, 0));
+    std::vector<std::string> errors(n_gangs);
+    std::vector<rtk_ctx*> g1(n_gangs, nullptr), g2(n_gangs, nullptr);
+    auto release_all = [&] { for (rtk_ctx* c : g1) fork_release(ctx1, c, false); for (rtk_ctx* c : g2) fork_release(ctx2, c, false); };
+    try { for (unsigned gi = 0; gi < n_gangs; ++gi) { g1[gi] = fork_acquire(ctx1, false); g2[gi] = fork_acquire(ctx2, false); } }
+    catch (...) { release_all(); throw; }
+#ifndef RTK_HOSTSIM
+    if (ctx1->resident_seq && ctx1->resident_n == n_reads) {   // the caller's resident copy of the reads (rtk_ctx_resident_reads): each gang its slice
+        for (unsigned gi = 0; gi < n_gangs; ++gi) {
+            g1[gi]->resident_seq = ctx1->resident_seq; g1[gi]->resident_off = ctx1->resident_off + cut[gi];
+            g1[gi]->resident_n = cut[gi + 1] - cut[gi]; g1[gi]->resident_total = seq_off[cut[gi + 1]] - seq_off[cut[gi]];
+        }
+    }
+    ctx1->resident_seq = nullptr;
+#endif
+    const unsigned budget = std::max(1u, host_threads() / n_gangs);
+    std::mutex seeds_turn;
+    std::vector<std::thread> th;
+    for (unsigned gi = 0; gi < n_gangs; ++gi) {
+        th.emplace_back([&, gi] {
+            set_thread_budget(n_gangs == 1 ? host_threads() : budget);
+            try {
+#ifndef RTK_HOSTSIM
+                DeviceBind bind(g1[gi]);
+#endif
+                const uint32_t r0 = cut[gi], n = cut[gi + 1] - cut[gi];
+                if (!n) return;
+                auto t0 = std::chrono::steady_clock::now();
+                auto lap = [&](int k) { const auto t = std::chrono::steady_clock::now(); gns[gi][k] = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t - t0).count(); t0 = t; };
+                std::mutex* turn = n_gangs > 1 ? &seeds_turn : nullptr;
+                correct_range(g1[gi], opt1, 1, n, seq_pool, seq_off + r0, qual_pool, qual_off ? qual_off + r0 : nullptr, p1_seq.data() + r0, p1_qual.data() + r0,
+                              gs1[gi].data(), turn);
+                lap(0);
+                std::string cp, cq;
+                std::vector<uint64_t> co, qo;
+                pack_strings(p1_seq.data() + r0, n, cp, co);
+                pack_strings(p1_qual.data() + r0, n, cq, qo);
+                std::vector<std::string> ps, pq;
+                phasing_batch_host(g2[gi], opt2, n, seq_pool, seq_off + r0, cp.data(), co.data(), cq.data(), qo.data(), ps, pq);
+                lap(1);
+                pack_strings(ps.data(), n, cp, co);
+                pack_strings(pq.data(), n, cq, qo);
+                correct_range(g2[gi], opt2, 2, n, cp.data(), co.data(), cq.data(), qo.data(), out_seq.data() + r0, out_qual.data() + r0, gs2[gi].data(), turn);
+                lap(2);
+            } catch (const std::exception& ex) { errors[gi] = ex.what(); if (errors[gi].empty()) errors[gi] = "correction gang failed"; }
+            catch (...) { errors[gi] = "correction gang failed (unknown exception)"; }
+        });
+    }
+    for (auto& t : th) t.join();
+    release_all();
+    for (const std::string& er : errors) if (!er.empty()) throw std::runtime_error(er);
+    for (int pass = 0; pass < 2; ++pass) {
+        uint64_t* st = pass ? stats2 : stats1;
+        if (!st) continue;
+        for (int i = 0; i < 24; ++i) {
+            uint64_t sum = 0, mx = 0;
+            for (unsigned gi = 0; gi < n_gangs; ++gi) { const uint64_t v = (pass ? gs2 : gs1)[gi][i]; sum += v; mx = std::max(mx, v); }
+            st[i] += (i == 3 || i == 10 || i == 11) ? mx : sum;
+        }
+    }
+    if (stage_ns) for (int k = 0; k < 3; ++k) { uint64_t sum = 0; for (unsigned gi = 0; gi < n_gangs; ++gi) sum += gns[gi][k]; stage_ns[k] += sum / n_gangs; }
+#ifndef RTK_HOSTSIM
+    if (stats1) { stats1[12] += g_h2d_bytes - h2d0; stats1[13] += g_d2h_bytes - d2h0; stats1[14] += g_launches - launches0; }
+#endif
+}
+
 }  // namespace rtk
 
 using namespace rtk;
@@ -1334,5 +1446,41 @@ extern "C" int rtk_correct_batch(rtk_ctx* ctx, const rtk_opt* opt, int pass, uin
         parallel_for(n_reads, [&](size_t rb, size_t re) {
             for (size_t r = rb; r < re; ++r) { memcpy(sp + oo[r], os[r].data(), os[r].size()); memcpy(qp + oo[r], oq[r].data(), oq[r].size()); }
         });
+    });
+}
+
+static void strings_to_pools(const std::vector<std::string>& os, const std::vector<std::string>& oq, uint32_t n_reads, char** sp_out, char** qp_out, uint64_t** off_out) {
+    uint64_t total = 0;
+    for (const auto& x : os) total += x.size();
+    *off_out = (uint64_t*)malloc((size_t)(n_reads + 1) * 8);
+    *sp_out = (char*)malloc(total + 1);
+    *qp_out = (char*)malloc(total + 1);
+    if (!*off_out || !*sp_out || !*qp_out) { free(*off_out); free(*sp_out); free(*qp_out); *off_out = nullptr; *sp_out = *qp_out = nullptr; throw std::bad_alloc(); }
+    uint64_t t = 0;
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        (*off_out)[r] = t;
+        if (os[r].size() != oq[r].size()) throw std::runtime_error("corrected sequence and quality lengths differ");
+        t += os[r].size();
+    }
+    (*off_out)[n_reads] = t;
+    char* sp = *sp_out; char* qp = *qp_out; const uint64_t* oo = *off_out;
+    parallel_for(n_reads, [&](size_t rb, size_t re) {
+        for (size_t r = rb; r < re; ++r) { memcpy(sp + oo[r], os[r].data(), os[r].size()); memcpy(qp + oo[r], oq[r].data(), oq[r].size()); }
+    });
+}
+
+extern "C" int rtk_correct_two_pass_batch(rtk_ctx* ctx1, rtk_ctx* ctx2, const rtk_opt* opt1, const rtk_opt* opt2, uint32_t n_reads, const char* seq_pool,
+                                          const uint64_t* seq_off, const char* qual_pool, const uint64_t* qual_off, char** out_seq_pool,
+                                          char** out_qual_pool, uint64_t** out_off, char** p1_seq_pool, char** p1_qual_pool, uint64_t** p1_off,
+                                          uint64_t* stats1, uint64_t* stats2, uint64_t* stage_ns) {
+    return guarded([&] {
+        if (!ctx1 || !ctx2 || !opt1 || !opt2 || !seq_pool || !seq_off || !qual_pool || !qual_off || !out_seq_pool || !out_qual_pool || !out_off)
+            throw std::invalid_argument("null argument");
+        if ((p1_seq_pool || p1_qual_pool || p1_off) && !(p1_seq_pool && p1_qual_pool && p1_off)) throw std::invalid_argument("give all three pass-1 outputs or none");
+        DeviceBind bind(ctx1);
+        std::vector<std::string> s1, q1, s2, q2;
+        correct_two_pass_host(ctx1, ctx2, *opt1, *opt2, n_reads, seq_pool, seq_off, qual_pool, qual_off, s1, q1, s2, q2, stats1, stats2, stage_ns);
+        strings_to_pools(s2, q2, n_reads, out_seq_pool, out_qual_pool, out_off);
+        if (p1_off) strings_to_pools(s1, q1, n_reads, p1_seq_pool, p1_qual_pool, p1_off);
     });
 }

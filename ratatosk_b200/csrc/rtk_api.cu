@@ -341,6 +341,12 @@ int rtk_get_seeds(rtk_ctx* c, const rtk_opt* opt, int pass, uint32_t n_reads, co
     });
 }
 
+int rtk_ctx_resident_reads(rtk_ctx* c, const char* dev_seq_pool, const uint64_t* dev_seq_off, uint32_t n_reads, uint64_t total_bases) {
+    if (!c) { set_error("null argument"); return RTK_EINVAL; }
+    c->resident_seq = dev_seq_pool; c->resident_off = dev_seq_off; c->resident_n = n_reads; c->resident_total = total_bases;
+    return RTK_OK;
+}
+
 int rtk_correct_batch_resident(rtk_ctx* c, const rtk_opt* opt, int pass, uint32_t n_reads, const char* seq_pool,
                                const uint64_t* seq_off, const char* dev_seq_pool, const uint64_t* dev_seq_off,
                                const char* qual_pool, const uint64_t* qual_off, char** out_seq_pool, char** out_qual_pool,

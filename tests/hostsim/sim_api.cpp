@@ -93,6 +93,7 @@ int rtk_graph_upload(rtk_ctx* c, const rtk_host_graph* g) {
     return RTK_OK;
 }
 int rtk_ctx_sync(rtk_ctx*) { return RTK_OK; }
+int rtk_ctx_resident_reads(rtk_ctx*, const char*, const uint64_t*, uint32_t, uint64_t) { return RTK_OK; }
 int rtk_is_hostsim(void) { return 1; }
 
 int rtk_search_sequence(rtk_ctx* c, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,

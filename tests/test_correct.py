@@ -253,3 +253,43 @@ def test_two_pass_cuda_matches_reference_cli_at_chr20_scale():
     assert len(bad) <= 2, ("pass 2", bad[:10])
     ctx.close()
     g.close()
+
+
+# ---- both passes as one pipeline (rtk_correct_two_pass_batch): same bytes as pass 1, phasing, pass 2 called one after the other
+def _two_pass_fused(recipe, lib, idx=None, gangs=None):
+    d = os.path.join(GOLDEN, recipe)
+    g1 = rb.Graph.load(os.path.join(d, "index.k31.fasta.gz"), os.path.join(d, "index.k31.rtsk"), 31, lib=lib)
+    g2 = rb.Graph.load(os.path.join(d, "index.k63.fasta.gz"), os.path.join(d, "index.k63.rtsk"), 63, lib=lib)
+    c1, c2 = rb.Context(0, lib=lib), rb.Context(0, lib=lib)
+    c1.upload(g1); c2.upload(g2)
+    raw = read_fastq(os.path.join(d, "reads.fastq.gz"))
+    gp1 = read_fastq(os.path.join(d, "corrected_pass1.fastq.gz"))
+    gp2 = read_fastq(os.path.join(d, "corrected_pass2.fastq.gz"))
+    idx = list(range(len(raw))) if idx is None else idx
+    if gangs:
+        os.environ["RTK_GANGS2"] = str(gangs)
+    try:
+        fin, p1 = c1.correct_two_pass(c2, [raw[i][1] for i in idx], [raw[i][2] for i in idx], want_pass1=True)
+    finally:
+        os.environ.pop("RTK_GANGS2", None)
+    bad1 = [i for j, i in enumerate(idx) if p1[j] != (gp1[i][1], gp1[i][2])]
+    bad2 = [i for j, i in enumerate(idx) if fin[j] != (gp2[i][1], gp2[i][2])]
+    c1.close(); c2.close(); g1.close(); g2.close()
+    return bad1, bad2
+
+
+def test_two_pass_pipeline_kernel_sources_match_reference_cli(sim_lib):
+    """reads 7 (changed by phasing) and 0-2 of F1 through the fused pipeline on the simulator == the reference CLI's two files"""
+    assert _two_pass_fused("F1", sim_lib, idx=[7, 0, 1, 2]) == ([], [])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("recipe,gangs", [("F1", None), ("F2", None), ("F2", 3)])
+def test_two_pass_pipeline_cuda_matches_reference_cli(recipe, gangs):
+    """whole fixture through rtk_correct_two_pass_batch (several gangs forced on the small fixture): <out>.2.fastq and <out>.fastq
+    of `Ratatosk correct -1` + `correct -2 -O`"""
+    os.environ["RTK_GANGS_MIN_BASES"] = "1"
+    try:
+        assert _two_pass_fused(recipe, None, gangs=gangs) == ([], [])
+    finally:
+        os.environ.pop("RTK_GANGS_MIN_BASES", None)
