@@ -1336,7 +1336,7 @@ void correct_two_pass_host(rtk_ctx* ctx1, rtk_ctx* ctx2, const rtk_opt& opt1, co
     out_seq.assign(n_reads, std::string()); out_qual.assign(n_reads, std::string());
     if (!n_reads) return;
     const char* e = getenv("RTK_GANGS2");
-    unsigned n_gangs = e ? (unsigned)std::max(1, atoi(e)) : 4u;
+    unsigned n_gangs = e ? (unsigned)std::max(1, atoi(e)) : 3u;
     const uint64_t total_bases = seq_off[n_reads] - seq_off[0];
     const char* e_min = getenv("RTK_GANGS_MIN_BASES");   // tests force several gangs on small fixtures
     const uint64_t min_bases = e_min ? (uint64_t)std::max(1ll, atoll(e_min)) : (2ull << 20);
@@ -1379,7 +1379,8 @@ void correct_two_pass_host(rtk_ctx* ctx1, rtk_ctx* ctx2, const rtk_opt& opt1, co
                 if (!n) return;
                 auto t0 = std::chrono::steady_clock::now();
                 auto lap = [&](int k) { const auto t = std::chrono::steady_clock::now(); gns[gi][k] = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t - t0).count(); t0 = t; };
-                std::mutex* turn = n_gangs > 1 ? &seeds_turn : nullptr;
+                static const bool no_turn = getenv("RTK_NO_SEEDS_TURN") != nullptr;
+                std::mutex* turn = (n_gangs > 1 && !no_turn) ? &seeds_turn : nullptr;
                 correct_range(g1[gi], opt1, 1, n, seq_pool, seq_off + r0, qual_pool, qual_off ? qual_off + r0 : nullptr, p1_seq.data() + r0, p1_qual.data() + r0,
                               gs1[gi].data(), turn);
                 lap(0);

@@ -7,6 +7,7 @@
 // pruning, colour-consistency of adjacent solid runs.  All graph state is read from the host
 // mirror of the slab.
 #include <algorithm>
+#include <cstdio>
 #include <chrono>
 #include <cstring>
 #include <map>
@@ -29,6 +30,8 @@ struct Anchor {
     rtk_hit h;
     KW km;       // mapped k-mer in read orientation (mappedSequenceToString as a number)
     bool empty;  // const_UnitigMap::isEmpty
+    bool exact;  // found by the exact sweep: the read's own k-mer, solid by construction (km is only fetched when an inexact hit may
+                 // share its position, i.e. in pass 1, where it breaks the sort tie of Graph.cpp:9-14)
 };
 
 inline KW mapped_kmer(const rtk_graph_view& g, const rtk_hit& h) {
@@ -175,11 +178,16 @@ void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads
     const bool pass2 = (pass == 2);
     solid_out.assign(n_reads, {});
     weak_out.assign(n_reads, {});
+    const bool prof = getenv("RTK_BROKER_PROFILE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    double laps[5] = {0, 0, 0, 0, 0};
+    auto lap = [&](int i) { const auto n = std::chrono::steady_clock::now(); laps[i] = std::chrono::duration_cast<std::chrono::microseconds>(n - t_prev).count() / 1e3; t_prev = n; };
 
     // 1. exact hits of every read (Graph.cpp:97)
     std::vector<std::vector<rtk_hit>> exact;
     search_sequence_host(ctx, n_reads, seq_pool, seq_off, RTK_SEARCH_EXACT, exact, stats);
 
+    lap(0);
     std::vector<std::vector<Anchor>> v_um(n_reads);
     std::vector<std::string> l_s_of(n_reads);  // pass 1: masked copy of each read that needs the inexact sweep
     parallel_for(n_reads, [&](size_t rb, size_t re) {
@@ -189,8 +197,8 @@ void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads
         if (slen <= k) continue;  // Graph.cpp:49
         std::vector<Anchor>& v = v_um[r];
         v.reserve(exact[r].size());
-        for (const rtk_hit& h : exact[r]) v.push_back({h, mapped_kmer(g, h), false});
-        if (pass2) continue;
+        if (pass2) { for (const rtk_hit& h : exact[r]) v.push_back({h, (KW)0, false, true}); continue; }   // positions are unique: no tie to break
+        for (const rtk_hit& h : exact[r]) v.push_back({h, mapped_kmer(g, h), false, true});
         // 2. pass 1: mask the well-anchored stretches, search the rest inexactly (Graph.cpp:100-196)
         std::string& l_s = l_s_of[r];
         l_s.assign(slen, 'N');
@@ -252,17 +260,22 @@ void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads
         }
     }
 
+    lap(1);
     // 3. inexact sweep over the masked strings (Graph.cpp:193)
     if (!mread.empty()) {
         std::vector<std::vector<rtk_hit>> inexact;
         search_sequence_host(ctx, (uint32_t)mread.size(), masked.data(), moff.data(),
                              RTK_SEARCH_INS | RTK_SEARCH_DEL | RTK_SEARCH_SUBST | RTK_SEARCH_OR_EXCL, inexact, stats);
-        for (size_t m = 0; m < mread.size(); ++m) {
-            std::vector<Anchor>& v = v_um[mread[m]];
-            for (const rtk_hit& h : inexact[m]) v.push_back({h, mapped_kmer(g, h), false});
-        }
+        parallel_for(mread.size(), [&](size_t mb, size_t me) {
+            for (size_t m = mb; m < me; ++m) {
+                std::vector<Anchor>& v = v_um[mread[m]];
+                v.reserve(v.size() + inexact[m].size());
+                for (const rtk_hit& h : inexact[m]) v.push_back({h, mapped_kmer(g, h), false, false});
+            }
+        });
     }
 
+    lap(2);
     const double t0 = (double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
     // 4. per read: sort, split, prune (Graph.cpp:201-372)
     parallel_for(n_reads, [&](size_t rb, size_t re) {
@@ -276,7 +289,7 @@ void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads
         for (size_t i = 0; i < v.size(); ++i) {
             if (i != 0 && same_hit(v[i].h, v[i - 1].h)) continue;
             bool eq = true;
-            for (size_t t = 0; t < k && eq; ++t) eq = (s[v[i].h.pos + t] == "ACGT"[(int)((v[i].km >> (2 * (k - 1 - t))) & 3)]);
+            if (!v[i].exact) for (size_t t = 0; t < k && eq; ++t) eq = (s[v[i].h.pos + t] == "ACGT"[(int)((v[i].km >> (2 * (k - 1 - t))) & 3)]);
             (eq ? solid : weak).push_back(v[i]);
         }
         v.clear();
@@ -327,6 +340,8 @@ void get_seeds_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads
     }
     });
     if (stats) stats[4] += (uint64_t)((double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0);
+    lap(3);
+    if (prof) fprintf(stderr, "[getSeeds] pass %d, %u reads: exact sweep %.1f ms, masks %.1f ms, one-edit sweep %.1f ms, anchors %.1f ms\n", pass, n_reads, laps[0], laps[1], laps[2], laps[3]);
 }
 
 }  // namespace rtk
