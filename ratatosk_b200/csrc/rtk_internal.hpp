@@ -8,6 +8,8 @@
 #include <sched.h>
 
 #include <atomic>
+#include <chrono>
+#include <time.h>
 #include <mutex>
 #include <cstdlib>
 #include <cstring>
@@ -170,11 +172,24 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
 inline void stream_wait(cudaStream_t st) {
     static const bool spin = getenv("RTK_SPIN_SYNC") != nullptr;
     if (spin) { RTK_CUDA(cudaStreamSynchronize(st)); return; }
+    // Every cudaStreamQuery takes the context lock that the other service threads need for their launches and copies: a
+    // thread waiting on a long kernel (a bulk region launch runs for hundreds of ms) must not hammer it.  Yield-poll for the
+    // first ~30 us (short alignment batches finish within that), then sleep with a doubling period capped at 200 us.
+    static const bool no_backoff = getenv("RTK_NO_WAIT_BACKOFF") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    long sleep_ns = 0;
     for (;;) {
         const cudaError_t e = cudaStreamQuery(st);
         if (e == cudaSuccess) return;
         if (e != cudaErrorNotReady) RTK_CUDA(e);
-        sched_yield();
+        if (sleep_ns == 0) {
+            sched_yield();
+            if (!no_backoff && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(30)) sleep_ns = 10000;
+        } else {
+            struct timespec ts = {0, sleep_ns};
+            nanosleep(&ts, nullptr);
+            if (sleep_ns < 200000) sleep_ns *= 2;
+        }
     }
 }
 

@@ -79,8 +79,27 @@ void resolve_inexact(const rtk_graph_view& g, const char* s, uint32_t slen, bool
     const uint32_t k = g.k;
     std::vector<Decoded> d(n);
     for (size_t i = 0; i < n; ++i) d[i] = decode(g, raw[i]);
-    std::unordered_set<PosKm, PosKmHash> us_pos_km;
-    us_pos_km.reserve(n * 2 + 16);
+    // us_pos_km (Search.tcc:566): insert-if-absent and membership only, at most one key per raw hit -> a flat open-addressing
+    // table reused by the thread (std::unordered_set's node allocations were the bulk of this stage)
+    static thread_local std::vector<PosKm> tl_tab;
+    size_t cap = 64;
+    while (cap < 2 * n + 16) cap <<= 1;
+    if (tl_tab.size() < cap) tl_tab.resize(cap);
+    PosKm* tab = tl_tab.data();
+    for (size_t i = 0; i < cap; ++i) tab[i].pos = ~0ULL;
+    const size_t tmask = cap - 1;
+    auto tab_contains = [&](const PosKm& key) {
+        for (size_t h = PosKmHash()(key) & tmask;; h = (h + 1) & tmask) {
+            if (tab[h].pos == ~0ULL) return false;
+            if (tab[h] == key) return true;
+        }
+    };
+    auto tab_insert = [&](const PosKm& key) {   // true when the key was not there
+        for (size_t h = PosKmHash()(key) & tmask;; h = (h + 1) & tmask) {
+            if (tab[h].pos == ~0ULL) { tab[h] = key; return true; }
+            if (tab[h] == key) return false;
+        }
+    };
     size_t gi = 0;
     while (gi < n) {
         size_t ge = gi;
@@ -106,7 +125,7 @@ void resolve_inexact(const rtk_graph_view& g, const char* s, uint32_t slen, bool
             bool cond = (l_pos_s + k - 1 < slen) && is_dna(s[l_pos_s]) && is_dna(s[l_pos_s + k - 1]);
             if (cond && or_exclusive) {
                 // rpos is empty (no exact pass in the same call); key = the variant k-mer itself
-                cond = (us_pos_km.find(PosKm{l_pos_s, (h.P << 1) | h.strand}) == us_pos_km.end());
+                cond = !tab_contains(PosKm{l_pos_s, (h.P << 1) | h.strand});
             }
             if (!cond) { ++i; continue; }
             const size_t len = run_length(d, i, ge, k, g);
@@ -125,7 +144,7 @@ void resolve_inexact(const rtk_graph_view& g, const char* s, uint32_t slen, bool
                     if (usz == k) { if (j == 0) key = ((g.unitig_off[h.unitig]) << 1) | h.strand; }  // isShort: pos+dist==0
                     else if (j < usz - k + 1) key = ((g.unitig_off[h.unitig] + j) << 1) | h.strand;
                 }
-                if (us_pos_km.insert(PosKm{l_pos_seq, key}).second) out.push_back({(uint32_t)l_pos_seq, h.unitig, j, h.strand});
+                if (tab_insert(PosKm{l_pos_seq, key})) out.push_back({(uint32_t)l_pos_seq, h.unitig, j, h.strand});
             }
             i += len;
         }
