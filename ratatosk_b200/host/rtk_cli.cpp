@@ -121,7 +121,7 @@ class SeqReader {
 // ---------------------------------------------------------------------------------------------- options
 struct Options {   // the `correct` fields of Correct_Opt the path reads (src/Common.hpp:16-158), reference defaults
     std::vector<std::string> long_in, long_raw;
-    std::string out, graph, data;
+    std::string out, graph, data, graph2, data2;   // graph2 / data2: the k2 index of the two-pass mode
     bool pass1 = false, pass2 = false, gzip_out = false, verbose = false, force_snp = false, force_order = false;
     int threads = 1, trim_qual = 0, max_qual = 40, insert_sz = 500, k1 = 31, k2 = 63, rounds = 1, w1 = 1000, w2 = 5000;
     double min_conf_snp = 0.9;
@@ -139,6 +139,8 @@ void usage() {
             "  --gpus N          devices to deal tickets to (default 1)\n"
             "  --first-gpu D     first CUDA device ordinal (default 0)\n"
             "  --ticket-bases B  read bases per library call (default 33554432)\n"
+            "  --in-graph2 G2 --in-unitig-data2 D2   (without -1 / -2) both passes as one pipeline: -g -d = k1 index, G2 D2 = k2 index;\n"
+            "                    writes <prefix>.fastq[.gz] like `correct -1` followed by `correct -2 -O`\n"
             "  --cache FILE      flat graph cache (default <rtsk>.k<k>.rtkflat; written on first use, mapped in place afterwards)\n"
             "  --no-cache        always parse the index files, write no cache\n");
 }
@@ -153,7 +155,7 @@ int parse(int argc, char** argv, Options& o) {
                                  {"in-short-phase", required_argument, 0, 'p'}, {"max-base-qual", required_argument, 0, 'Q'}, {"1st-pass-only", no_argument, 0, '1'},
                                  {"2nd-pass-only", no_argument, 0, '2'}, {"force-correct-snp", no_argument, 0, 'f'}, {"force-io-order", no_argument, 0, 'O'},
                                  {"gzip-out", no_argument, 0, 'G'}, {"verbose", no_argument, 0, 'v'}, {"gpus", required_argument, 0, 1000},
-                                 {"first-gpu", required_argument, 0, 1001}, {"ticket-bases", required_argument, 0, 1002}, {"no-cache", no_argument, 0, 1003},
+                                 {"first-gpu", required_argument, 0, 1001}, {"ticket-bases", required_argument, 0, 1002}, {"no-cache", no_argument, 0, 1003}, {"in-graph2", required_argument, 0, 1005}, {"in-unitig-data2", required_argument, 0, 1006},
                                  {"cache", required_argument, 0, 1004}, {0, 0, 0, 0}};
     int c;
     while ((c = getopt_long(argc - 1, argv + 1, "l:o:c:t:g:d:m:i:k:K:w:W:r:L:P:p:Q:12fOGv", lo, nullptr)) != -1) {
@@ -185,6 +187,8 @@ int parse(int argc, char** argv, Options& o) {
             case 1002: o.ticket_bases = strtoull(optarg, nullptr, 10); break;
             case 1003: o.no_cache = true; break;
             case 1004: o.cache = optarg; break;
+            case 1005: o.graph2 = optarg; break;
+            case 1006: o.data2 = optarg; break;
             default: usage(); return 1;
         }
     }
@@ -200,7 +204,11 @@ int parse(int argc, char** argv, Options& o) {
     if (o.min_conf_snp > 1.0) bad("Minimum confidence threshold to correct a SNP must be lower or equal to 1.0.");
     if (o.w1 <= 0 || o.w2 <= 0) bad("Maximum length of a weak region to correct cannot be less than or equal to 0");
     if (o.pass1 && o.pass2) bad("-1 and -2 are mutually exclusive (perform *only* one of the two correction passes). To perform both, remove -1 and -2 from your command line.");
-    if (!o.pass1 && !o.pass2) bad("rtk_correct runs one pass from its index: give -1 or -2 (building / colouring the graphs is the reference's `index` step).");
+    const bool two_pass = !o.pass1 && !o.pass2;
+    if (two_pass && (o.graph2.empty() || o.data2.empty()))
+        bad("rtk_correct corrects from indexes: give -1 or -2 with the index of that pass (-g -d), or both indexes (-g -d for k1, --in-graph2 --in-unitig-data2 for k2) to run the two passes as one pipeline (building / colouring the graphs is the reference's `index` step).");
+    if (!two_pass && (!o.graph2.empty() || !o.data2.empty())) bad("--in-graph2 / --in-unitig-data2 belong to the two-pass mode (no -1 / -2).");
+    if (two_pass && !o.cache.empty()) bad("--cache names one file: not usable with two indexes.");
     if (o.graph.empty() != o.data.empty()) bad("One of the input index files is missing (either the graph or the data).");
     if (o.graph.empty()) bad("rtk_correct needs the index of the pass (-g and -d).");
     if (o.long_in.empty()) bad("Missing input long reads (-l).");
@@ -300,13 +308,14 @@ struct Shared {
 int main(int argc, char** argv) {
     Options o;
     if (parse(argc, argv, o)) return 1;
-    const int pass = o.pass2 ? 2 : 1;
-    const int k = pass == 2 ? o.k2 : o.k1;
+    const int pass = o.pass2 ? 2 : o.pass1 ? 1 : 0;   // 0: both passes as one pipeline (rtk_correct_two_pass_batch)
+    const int k = pass == 1 ? o.k1 : (pass == 2 ? o.k2 : o.k1);   // k of the graph given with -g / -d
+    const int k_out = pass == 1 ? o.k1 : o.k2;   // k of the pass that writes the file (minimum length of a trimmed sub-read)
     const auto t_start = std::chrono::steady_clock::now();
     auto secs = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
 
     // ---- graph: loaded + flattened once, uploaded to every device (src/Ratatosk.cpp:1087-1089)
-    if (o.verbose) printf("Ratatosk::Ratatosk(): Loading graph (%d/2).\n", pass);
+    if (o.verbose) printf("Ratatosk::Ratatosk(): Loading graph (%d/2).\n", pass ? pass : 1);
     rtk_host_graph* hg = nullptr;
     int from_cache = 0;
     const int grc = o.no_cache ? rtk_graph_load(o.graph.c_str(), o.data.c_str(), k, &hg)
@@ -321,15 +330,32 @@ int main(int argc, char** argv) {
     }
     if (o.verbose) { rtk_graph_info gi; rtk_graph_get_info(hg, &gi); printf("rtk_correct: graph%s resident on %d GPU(s) after %.1f s (%llu unitigs, %llu k-mers, %.1f MB slab)\n", from_cache ? " (flat cache, mapped in place)" : "", o.gpus, secs(), (unsigned long long)gi.n_unitigs, (unsigned long long)gi.n_kmers, gi.slab_bytes / 1e6); }
 
+    // two-pass mode: the k2 graph next to the k1 graph on every device
+    rtk_host_graph* hg2 = nullptr;
+    std::vector<rtk_ctx*> ctx2((size_t)o.gpus, nullptr);
+    if (pass == 0) {
+        if (o.verbose) printf("Ratatosk::Ratatosk(): Loading graph (2/2).\n");
+        const int rc2 = o.no_cache ? rtk_graph_load(o.graph2.c_str(), o.data2.c_str(), o.k2, &hg2)
+                                   : rtk_graph_load_cached(o.graph2.c_str(), o.data2.c_str(), o.k2, nullptr, &hg2, nullptr);
+        if (rc2 != RTK_OK) { fprintf(stderr, "Ratatosk::Ratatosk(): %s\n", rtk_last_error()); return 1; }
+        for (int d = 0; d < o.gpus; ++d)
+            if (rtk_ctx_create(o.first_gpu + d, &ctx2[d]) != RTK_OK || rtk_graph_upload(ctx2[d], hg2) != RTK_OK) { fprintf(stderr, "Ratatosk::Ratatosk(): %s\n", rtk_last_error()); return 1; }
+    }
+    rtk_opt ropt2;   // second pass of the two-pass mode
+    rtk_opt_default(&ropt2, 2);
+    ropt2.k = (uint32_t)o.k2; ropt2.insert_sz = (uint32_t)o.insert_sz; ropt2.max_len_weak_region1 = (uint32_t)o.w1; ropt2.max_len_weak_region2 = (uint32_t)o.w2;
+    ropt2.nb_correction_rounds = (uint32_t)o.rounds; ropt2.max_qual = o.max_qual; ropt2.trim_qual = o.trim_qual;
+    ropt2.min_confidence_snp_corr = o.min_conf_snp; ropt2.force_unres_snp_corr = o.force_snp ? 1u : 0u;
+
     rtk_opt ropt;
-    rtk_opt_default(&ropt, pass);
+    rtk_opt_default(&ropt, pass == 2 ? 2 : 1);
     ropt.k = (uint32_t)k; ropt.insert_sz = (uint32_t)o.insert_sz; ropt.max_len_weak_region1 = (uint32_t)o.w1; ropt.max_len_weak_region2 = (uint32_t)o.w2;
     ropt.nb_correction_rounds = (uint32_t)o.rounds; ropt.max_qual = o.max_qual; ropt.trim_qual = o.trim_qual;
     ropt.min_confidence_snp_corr = o.min_conf_snp; ropt.force_unres_snp_corr = o.force_snp ? 1u : 0u;
-    if (pass == 2 && o.verbose && o.force_snp) fprintf(stderr, "Ratatosk::search(): Force unresolved SNP correction is activated.\n");
+    if (pass != 1 && o.verbose && o.force_snp) fprintf(stderr, "Ratatosk::search(): Force unresolved SNP correction is activated.\n");
 
     // ---- output file: <out>.2.fastq after pass 1 (src/Ratatosk.cpp:1079), <out>.fastq[.gz] after pass 2 (:621, :909-911)
-    const bool gz_out = o.gzip_out && pass == 2;
+    const bool gz_out = o.gzip_out && pass != 1;
     const std::string fn_out = o.out + (pass == 1 ? ".2" : "") + ".fastq" + (gz_out ? ".gz" : "");
     for (const auto* v : {&o.long_in, &o.long_raw})
         for (const auto& f : *v)
@@ -337,7 +363,7 @@ int main(int argc, char** argv) {
     FILE* fout = fopen(fn_out.c_str(), "wb");
     if (!fout) { fprintf(stderr, "Ratatosk::search(): cannot open %s for writing\n", fn_out.c_str()); return 1; }
     setvbuf(fout, nullptr, _IOFBF, 8 << 20);
-    if (o.verbose) printf("Ratatosk::Ratatosk(): Correcting long reads (%d/2).\n", pass);
+    if (o.verbose) printf(pass ? "Ratatosk::Ratatosk(): Correcting long reads (%d/2).\n" : "Ratatosk::Ratatosk(): Correcting long reads (both passes).\n", pass);
 
     Shared sh;
     Channel<Ticket> tickets((size_t)o.gpus * 2);
@@ -395,7 +421,11 @@ int main(int argc, char** argv) {
                 uint64_t* co = nullptr;
                 const char* qual_in = t.has_qual ? t.qual.data() : nullptr;
                 int rc;
-                if (pass == 1) {
+                if (pass == 0) {
+                    if (!t.has_qual) { sh.fail("Ratatosk::search(): the two-pass mode needs FASTQ input (quality strings)"); break; }
+                    rc = rtk_correct_two_pass_batch(ctx[d], ctx2[d], &ropt, &ropt2, n, t.seq.data(), t.off.data(), t.qual.data(), t.off.data(), &cs, &cq, &co,
+                                                    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+                } else if (pass == 1) {
                     rc = rtk_correct_batch(ctx[d], &ropt, 1, n, t.seq.data(), t.off.data(), qual_in, t.off.data(), &cs, &cq, &co, nullptr);
                 } else {
                     // upper-case the pass-1 reads (:814); phasing (:832) then getSeeds + correctSequence (:838/:840)
@@ -411,7 +441,7 @@ int main(int argc, char** argv) {
                 b.reads = n; b.bases = t.seq.size();
                 std::string text;
                 text.reserve((size_t)(co[n] * 2 + (uint64_t)n * 64));
-                for (uint32_t i = 0; i < n; ++i) format_record(text, t.names[i], cs + co[i], cq + co[i], co[i + 1] - co[i], k, pass == 2 ? o.trim_qual : 0);
+                for (uint32_t i = 0; i < n; ++i) format_record(text, t.names[i], cs + co[i], cq + co[i], co[i + 1] - co[i], k_out, pass != 1 ? o.trim_qual : 0);
                 rtk_free(cs); rtk_free(cq); rtk_free(co);
                 if (gz_out) { if (!gzip_member(text, b.bytes)) { sh.fail("Ratatosk::search(): gzip compression failed"); break; } }
                 else b.bytes.swap(text);
@@ -445,7 +475,9 @@ int main(int argc, char** argv) {
     for (auto& w : workers) w.join();
     fclose(fout);
     for (auto c : ctx) rtk_ctx_destroy(c);
+    for (auto c : ctx2) rtk_ctx_destroy(c);
     rtk_graph_free(hg);
+    rtk_graph_free(hg2);
     if (sh.failed) { fprintf(stderr, "%s\n", sh.error.c_str()); remove(fn_out.c_str()); return 1; }
     if (o.verbose) printf("rtk_correct: %llu reads, %llu bases, %llu tickets in %.1f s -> %s\n", (unsigned long long)reads, (unsigned long long)bases, (unsigned long long)next, secs(), fn_out.c_str());
     return 0;

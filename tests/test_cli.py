@@ -190,3 +190,30 @@ def test_cli_cuda_force_snp_correction_matches_reference_cli(tmp_path):
     o = str(tmp_path / "o")
     _run(GPU_CLI, ["-2", "--force-correct-snp", "-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk"), "-l", p1, "-L", reads, "-o", o])
     assert open(o + ".fastq", "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass2_forcesnp.fastq.gz"))
+
+
+def _two_pass_mode(cli, d, tmp, reads, extra=()):
+    o = os.path.join(tmp, "tp")
+    _run(cli, ["-g", os.path.join(d, "index.k31.fasta.gz"), "-d", os.path.join(d, "index.k31.rtsk"), "--in-graph2", os.path.join(d, "index.k63.fasta.gz"),
+               "--in-unitig-data2", os.path.join(d, "index.k63.rtsk"), "-l", reads, "-o", o] + list(extra))
+    return o + ".fastq"
+
+
+def test_cli_two_pass_mode_equals_the_two_reference_commands_on_simulator(sim_cli, tmp_path):
+    """both indexes given, neither -1 nor -2: one pipelined library call per ticket (rtk_correct_two_pass_batch); the file equals
+    what `Ratatosk correct -1` followed by `correct -2 -O` writes"""
+    d = os.path.join(GOLDEN, "F1")
+    reads = str(tmp_path / "r.fastq")
+    _head_fastq(os.path.join(d, "reads.fastq.gz"), reads, 9)
+    out = _two_pass_mode(sim_cli, d, str(tmp_path), reads, extra=["--ticket-bases", "25000"])
+    assert open(out, "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass2.fastq.gz"), 9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("recipe", ["F1", "F2"])
+def test_cli_cuda_two_pass_mode_identical_to_reference_cli(recipe, tmp_path):
+    d = os.path.join(GOLDEN, recipe)
+    reads = str(tmp_path / "reads.fastq")
+    open(reads, "wb").write(gzip.open(os.path.join(d, "reads.fastq.gz"), "rb").read())
+    out = _two_pass_mode(GPU_CLI, d, str(tmp_path), reads)
+    assert open(out, "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass2.fastq.gz"))
