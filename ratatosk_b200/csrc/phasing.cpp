@@ -298,7 +298,7 @@ void phasing_batch_host(rtk_ctx* ctx, const rtk_opt& opt, uint32_t n, const char
         for (uint32_t r = 0; r < n; ++r) { pool += s_new[r]; off.push_back(pool.size()); }
         pool.push_back('\0');
         std::vector<std::vector<rtk_hit>> h2;
-        search_sequence_host(ctx, n, pool.data(), off.data(), RTK_SEARCH_EXACT, h2, nullptr);
+        search_sequence_host(ctx, n, pool.data(), off.data(), RTK_SEARCH_EXACT | RTK_SEARCH_SPARSE_HINT, h2, nullptr);   // s_new is 'N' but for the reverted neighbourhoods
         for (uint32_t r = 0; r < n; ++r)
             for (const rtk_hit& h : h2[r])
                 for (size_t j = h.pos; j < h.pos + k && j < out_qual[r].size(); ++j)

@@ -22,7 +22,7 @@ static inline double now_ns() {
 
 // ---------------------------------------------------------------- K1 driver
 uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint64_t* d_seq_off,
-                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms, const char* h_seq, bool dense) {
+                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms, const char* h_seq, bool dense, bool sparse_tiles) {
     if (!ctx->has_graph) throw std::invalid_argument("no graph uploaded to this context");
     if (n_reads >= (1u << RTK_HIT_READ_BITS)) throw std::invalid_argument("more than 2^24 reads in one batch");
     const uint32_t k = ctx->hdr.k;
@@ -33,7 +33,9 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
 
     const uint32_t tile = k1_tile_size(k, exact);
     std::vector<uint32_t> tiles;
-    build_tiles(n_reads, h_seq_off, k, tile, tiles, exact ? nullptr : h_seq, k - 1, k + 1);   // the exact sweep runs on whole reads: nothing to skip
+    // the exact sweep normally runs on whole reads (nothing to skip) unless the caller says they are mostly masked (list form + h_seq)
+    if (exact && !dense && h_seq && sparse_tiles) build_tiles(n_reads, h_seq_off, k, tile, tiles, h_seq, k, k);
+    else build_tiles(n_reads, h_seq_off, k, tile, tiles, exact ? nullptr : h_seq, k - 1, k + 1);
     const uint32_t n_tiles = (uint32_t)(tiles.size() / 2);
     ctx->d_counters.reserve(64);
     RTK_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
@@ -94,6 +96,8 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
 void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                           std::vector<std::vector<rtk_hit>>& per_read, uint64_t* stats) {
     const double t_start = now_ns();
+    const bool sparse_hint = (flags & RTK_SEARCH_SPARSE_HINT) != 0;
+    flags &= ~RTK_SEARCH_SPARSE_HINT;
     if (!ctx->has_graph || !ctx->host_graph) throw std::invalid_argument("no graph uploaded to this context");
     const uint64_t total = seq_off[n_reads] - seq_off[0];
     // offsets relative to the start of this batch's pool
@@ -116,8 +120,8 @@ void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, 
     // exact sweeps come back DENSE (8 bytes per read position, read order) through pinned memory: no labels, no sort, no
     // bucketing; the list form (16 bytes per hit, any order) is kept for the sparse one-edit sweeps.  RTK_K1_LIST=1: list form.
     static const bool list_only = getenv("RTK_K1_LIST") != nullptr;
-    const bool dense = (flags == RTK_SEARCH_EXACT) && !list_only && total != 0;
-    const uint64_t n_raw = k1_launch(ctx, n_reads, d_seq, d_off, rel.data(), flags, &probes, &kms, seq_pool + seq_off[0], dense);
+    const bool dense = (flags == RTK_SEARCH_EXACT) && !list_only && !sparse_hint && total != 0;
+    const uint64_t n_raw = k1_launch(ctx, n_reads, d_seq, d_off, rel.data(), flags, &probes, &kms, seq_pool + seq_off[0], dense, sparse_hint);
     if (dense) {
         ctx->h_dense.reserve(total * 8 + 64);
         // chunked so that decoding could overlap; one stream, pinned landing zone

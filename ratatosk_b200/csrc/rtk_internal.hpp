@@ -163,7 +163,7 @@ void resolve_batch(const rtk_graph_view& hv, uint32_t n_reads, const char* seq_p
 // K1 driver: runs the exact and/or inexact kernels over reads resident on the device and leaves the
 // raw labelled hits in ctx->d_hits.  Returns raw hit count; *n_probes / *kernel_ms optional.
 uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint64_t* d_seq_off,
-                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms, const char* h_seq = nullptr, bool dense = false);
+                   const uint64_t* h_seq_off, uint32_t flags, uint64_t* n_probes, float* kernel_ms, const char* h_seq = nullptr, bool dense = false, bool sparse_tiles = false);
 
 #ifndef RTK_HOSTSIM
 // Wait for a stream without monopolising a core: the service threads of the correction broker outnumber the spare cores, and
@@ -271,6 +271,9 @@ struct TbRun;
 void nw_path_runs_masked(rtk_ctx* c, uint32_t n, const char* q_pool, const uint64_t* q_off, const char* t_pool, const uint64_t* t_off,
                          const TbNeed& need, std::vector<std::vector<TbRun>>& runs, float* kernel_ms);
 
+// internal flag for search_sequence_host: the reads are mostly masked ('N'), hits will be rare -> labelled hit list instead of the
+// dense per-position answer, tiles without a valid window skipped
+#define RTK_SEARCH_SPARSE_HINT (1u << 16)
 // full searchSequence for a host batch -> per read ordered hits
 void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                           std::vector<std::vector<rtk_hit>>& per_read, uint64_t* stats);

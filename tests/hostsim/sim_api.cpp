@@ -58,10 +58,12 @@ static uint64_t sim_k1(rtk_ctx* ctx, uint32_t n_reads, const char* seq, const ui
 void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                           std::vector<std::vector<rtk_hit>>& per_read, uint64_t* stats) {
     if (!ctx->has_graph || !ctx->host_graph) throw std::invalid_argument("no graph uploaded to this context");
+    const bool sparse_hint = (flags & RTK_SEARCH_SPARSE_HINT) != 0;
+    flags &= ~RTK_SEARCH_SPARSE_HINT;
     RawHitVec raw;
     uint64_t probes = 0, n_raw;
     static const bool list_only = getenv("RTK_K1_LIST") != nullptr;
-    if (flags == RTK_SEARCH_EXACT && !list_only && seq_off[n_reads] != seq_off[0]) {   // dense exact sweep, like the product
+    if (flags == RTK_SEARCH_EXACT && !list_only && !sparse_hint && seq_off[n_reads] != seq_off[0]) {   // dense exact sweep, like the product
         std::vector<uint64_t> dense;
         std::vector<uint64_t> rel(n_reads + 1);
         for (uint32_t i = 0; i <= n_reads; ++i) rel[i] = seq_off[i] - seq_off[0];
