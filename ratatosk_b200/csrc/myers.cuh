@@ -50,14 +50,15 @@ struct rtk_myers_params {
 
 // IUPAC membership mask of a character: A1 C2 G4 T8, ambiguity codes = union (the index of the letter
 // in ambiguity_c[], src/Common.hpp:260); 0 for anything else.
+// Branch-free: the 25 letters 'A'..'Y' index two packed nibble tables.  (A switch here compiled to a branch tree executed once per
+// query character of every alignment: 15 % of the region engine's instructions and 44 % of its stall samples, profiles/r2_region_lines.md.)
 RTK_HD uint32_t rtk_iupac_mask(const char c) {
-    switch (c) {
-        case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': return 8;
-        case 'M': return 3; case 'R': return 5; case 'S': return 6; case 'V': return 7;
-        case 'W': return 9; case 'Y': return 10; case 'H': return 11; case 'K': return 12;
-        case 'D': return 13; case 'B': return 14; case 'N': return 15;
-        default: return 0;
-    }
+    const uint32_t i = (uint32_t)(unsigned char)c - 65u;                 // 'A' -> 0
+    const uint64_t lo = 0x00F30C00B400D2E1ULL;                            // P O N M L K J I H G F E D C B A
+    const uint64_t hi = 0x0000000A09708650ULL;                            //               Y X W V U T S R Q
+    const uint64_t w = (i < 16u) ? lo : hi;
+    const uint32_t m = (uint32_t)(w >> ((i & 15u) << 2)) & 15u;
+    return (i < 25u) ? m : 0u;
 }
 
 // edlib equality: identical characters, or {ambiguity code, one of its bases} in either order
@@ -67,6 +68,16 @@ RTK_HD bool rtk_iupac_eq(const char a, const char b) {
     const uint32_t ma = rtk_iupac_mask(a), mb = rtk_iupac_mask(b);
     const bool base_a = ma && !(ma & (ma - 1)), base_b = mb && !(mb & (mb - 1));
     return (base_a != base_b) && (ma & mb);  // exactly one side is a plain base and the code contains it
+}
+
+// Eq word of a block against an AMBIGUITY CODE in the target (mask mt with several bits): the code equals the plain query bases it
+// contains and itself (rtk_iupac_eq), both read off the block's four profile words - plain = exactly one plane set, itself = exactly
+// the code's planes.  Bits past the query's end are clear in every plane, so they stay clear.
+RTK_HD uint64_t rtk_iupac_eq_word(const uint32_t mt, const uint64_t PB0, const uint64_t PB1, const uint64_t PB2, const uint64_t PB3) {
+    const uint64_t multi = (PB0 & PB1) | (PB0 & PB2) | (PB0 & PB3) | (PB1 & PB2) | (PB1 & PB3) | (PB2 & PB3);
+    const uint64_t cover = ((mt & 1u) ? PB0 : 0ULL) | ((mt & 2u) ? PB1 : 0ULL) | ((mt & 4u) ? PB2 : 0ULL) | ((mt & 8u) ? PB3 : 0ULL);
+    const uint64_t same = ((mt & 1u) ? PB0 : ~PB0) & ((mt & 2u) ? PB1 : ~PB1) & ((mt & 4u) ? PB2 : ~PB2) & ((mt & 8u) ? PB3 : ~PB3);
+    return (cover & ~multi) | same;
 }
 
 // One wavefront sweep of a round (see rtk_myers_body): RARE = false drops the loop-invariant rare branches at compile time.
@@ -81,9 +92,14 @@ RTK_HD bool rtk_iupac_eq(const char a, const char b) {
             if (RARE && top_spilled && active) hin = (int)hb[col]; \
             uint64_t Eq = (tc == 'A') ? PB0 : (tc == 'C') ? PB1 : (tc == 'G') ? PB2 : (tc == 'T') ? PB3 : 0ULL; \
             if (RARE && t_amb && active && tc != 'A' && tc != 'C' && tc != 'G' && tc != 'T') { \
-                const int lo = b << 6; \
-                const int n = (qlen - lo < 64) ? (qlen - lo) : 64; \
-                for (int i = 0; i < n; ++i) Eq |= (uint64_t)(plain ? (q[lo + i] == tc) : rtk_iupac_eq(q[lo + i], tc)) << i; \
+                const uint32_t mt = rtk_iupac_mask(tc); \
+                if (mt != 0u && !plain) { \
+                    Eq = rtk_iupac_eq_word(mt, PB0, PB1, PB2, PB3); \
+                } else { \
+                    const int lo = b << 6; \
+                    const int n = (qlen - lo < 64) ? (qlen - lo) : 64; \
+                    for (int i = 0; i < n; ++i) Eq |= (uint64_t)(plain ? (q[lo + i] == tc) : rtk_iupac_eq(q[lo + i], tc)) << i; \
+                } \
             } \
             const uint64_t neg = (hin < 0) ? 1ULL : 0ULL; \
             const uint64_t Xv = Eq | Mv; \

@@ -349,9 +349,13 @@ __device__ RTK_RG_NOINLINE void rg_quality_direct(rg_ctx& C, const char* __restr
             if (top_spilled && active) hin = (int)hb[col];
             uint64_t Eq = (tc == 'A') ? PB0 : (tc == 'C') ? PB1 : (tc == 'G') ? PB2 : (tc == 'T') ? PB3 : 0ULL;
             if (t_amb && active && tc != 'A' && tc != 'C' && tc != 'G' && tc != 'T') {
-                const int lo = b << 6;
-                const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
-                for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(q[lo + i], tc) << i;
+                const uint32_t mt = rtk_iupac_mask(tc);
+                if (mt != 0u) Eq = rtk_iupac_eq_word(mt, PB0, PB1, PB2, PB3);   // ambiguity code: bit-parallel, see myers.cuh
+                else {
+                    const int lo = b << 6;
+                    const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+                    for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(q[lo + i], tc) << i;
+                }
             }
             const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
             const uint64_t Xv = Eq | Mv;
@@ -477,9 +481,13 @@ __device__ RTK_RG_NOINLINE void rg_lastcol_rows(rg_ctx& C, const char* __restric
             if (top_spilled && active) hin = (int)hb[col];
             uint64_t Eq = (tc == 'A') ? PB0 : (tc == 'C') ? PB1 : (tc == 'G') ? PB2 : (tc == 'T') ? PB3 : 0ULL;
             if (t_amb && active && tc != 'A' && tc != 'C' && tc != 'G' && tc != 'T') {
-                const int lo = b << 6;
-                const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
-                for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(rev ? q[qlen - 1 - (lo + i)] : q[lo + i], tc) << i;
+                const uint32_t mt = rtk_iupac_mask(tc);
+                if (mt != 0u) Eq = rtk_iupac_eq_word(mt, PB0, PB1, PB2, PB3);   // ambiguity code: bit-parallel, see myers.cuh
+                else {
+                    const int lo = b << 6;
+                    const int n = (qlen - lo < 64) ? (qlen - lo) : 64;
+                    for (int i = 0; i < n; ++i) Eq |= (uint64_t)rtk_iupac_eq(rev ? q[qlen - 1 - (lo + i)] : q[lo + i], tc) << i;
+                }
             }
             const uint64_t neg = (hin < 0) ? 1ULL : 0ULL;
             const uint64_t Xv = Eq | Mv;

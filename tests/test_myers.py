@@ -68,3 +68,42 @@ def test_myers_cuda_matches_oracle_on_seeded_pairs():
     d0, _ = ctx.edlib_batch(qs, qs, [0] * len(qs))
     assert (d0 == 0).all()
     ctx.close()
+
+
+def _iupac_pairs(n, seed):
+    """pairs dense in ambiguity codes on BOTH sides (the second pass aligns pass-1 reads that carry unresolved SNP codes)"""
+    import random
+    rng = random.Random(seed)
+    codes = "MRSVWYHKDBN"
+    qs, ts, ms = [], [], []
+    for i in range(n):
+        tl = rng.choice([rng.randint(1, 70), rng.randint(60, 200), rng.randint(200, 400)])
+        t = "".join(rng.choice(codes) if rng.random() < 0.12 else rng.choice("ACGT") for _ in range(tl))
+        q = "".join(c for c in t if rng.random() > 0.06)
+        q = "".join(rng.choice(codes + "ACGT") if rng.random() < 0.10 else c for c in q) or "R"
+        if i % 17 == 0:
+            t = t[:len(t) // 2] + "." + t[len(t) // 2:]   # a character outside the alphabet: equal to itself only
+        qs.append(q); ts.append(t); ms.append(i % 3)
+    return qs, ts, ms
+
+
+def test_myers_kernel_source_iupac_codes_on_both_sides(sim_lib):
+    """the bit-parallel treatment of ambiguity codes in the TARGET (rtk_iupac_eq_word) against the oracle's per-pair equality"""
+    qs, ts, ms = _iupac_pairs(60, 4242)
+    ctx = rb.Context(0, lib=sim_lib)
+    dist, ends = ctx.edlib_batch(qs, ts, ms)
+    for i in range(len(qs)):
+        d, e = oracle_edit_distance(qs[i], ts[i], ms[i])
+        assert int(dist[i]) == d and ends[i].tolist() == e, (i, ms[i], qs[i], ts[i])
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_myers_cuda_iupac_codes_on_both_sides():
+    qs, ts, ms = _iupac_pairs(600, 777)
+    ctx = rb.Context(0)
+    dist, ends = ctx.edlib_batch(qs, ts, ms)
+    for i in range(len(qs)):
+        d, e = oracle_edit_distance(qs[i], ts[i], ms[i])
+        assert int(dist[i]) == d and ends[i].tolist() == e, (i, ms[i], len(qs[i]), len(ts[i]))
+    ctx.close()
