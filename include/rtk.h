@@ -248,7 +248,7 @@ typedef struct rtk_region_result_t {
     uint32_t n_hops, n_pops, n_cands, n_aligns;   /* work done: BFS calls, queue pops, candidates scored, alignments */
     uint64_t seg_off;        /* segs[seg_off, +n_segs): every extractSemiWeakPaths call of the region, in order; the fields above */
     uint32_t n_segs;         /* describe the last one */
-    uint32_t reserved;
+    uint32_t reserved;       /* work done, continued: DP cells swept by the call's alignments / 1024 (saturating) */
 } rtk_region_result_t;
 
 typedef struct rtk_region_out {
@@ -272,7 +272,7 @@ void rtk_region_out_free(rtk_region_out* out);
  * host replay), [5] batched GPU service calls, [6] GPU requests served, [7] K4 / [8] K5 / [9] K2+K3+K4 kernel ns (CUDA
  * events on the launching streams; the services overlap), [10] getSeeds stage ns, [11] region stage ns, [12] bytes copied host->device, [13] device->host, [14] kernels launched
  * (process-wide tallies: exact when one batch runs at a time), [16] region-engine kernel ns, [17] region-engine calls, [18] calls
- * the engine declined (served by the request-at-a-time path instead). */
+ * the engine declined (served by the request-at-a-time path instead), [19] DP cells swept inside the engine / 1024. */
 int rtk_correct_batch(rtk_ctx* ctx, const rtk_opt* opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
                       const char* qual_pool, const uint64_t* qual_off, char** out_seq_pool, char** out_qual_pool,
                       uint64_t** out_off, uint64_t* stats);

@@ -26,6 +26,7 @@ GpuBroker* current_broker() { return tl_broker; }
 // ------------------------------------------------------------------ batched execution
 // RTK_BROKER_PROFILE: host time spent assembling a batch, inside the C-ABI call, scattering the answers; GPU kernel time
 static std::atomic<uint64_t> g_prof[4][4];
+static std::atomic<uint64_t> g_region_kcells{0};
 static std::atomic<uint64_t> g_region_stats[18];   // [0] calls, [1] bails, [2 + reason] bails by reason
 static std::atomic<uint64_t> g_mix[2][3][2];   // [dist|path][mode NW/SHW/HW][requests with one job | with several]: requests, jobs
 struct ProfTimer {
@@ -294,6 +295,7 @@ void run_region_batch(rtk_ctx* ctx, const std::vector<RegionReq*>& reqs, uint64_
                 }
             }
         });
+        { uint64_t kc = 0; for (size_t i = 0; i < out.results.size(); ++i) kc += out.results[i].reserved; g_region_kcells += kc; }
         g_region_stats[0] += n;
         g_region_stats[1] += n_bail.load();
         for (int j = 0; j < 16; ++j) g_region_stats[2 + j] += by_reason[j].load();
@@ -723,6 +725,7 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
     uint64_t prof0[4][4], rs0[18];
     for (int k = 0; k < 4; ++k) for (int j = 0; j < 4; ++j) prof0[k][j] = g_prof[k][j];
     for (int j = 0; j < 18; ++j) rs0[j] = g_region_stats[j];
+    const uint64_t kcells0 = g_region_kcells;
     for (unsigned t = 0; t < n_workers; ++t) {
         Worker* w = new Worker();
         w->slab_bytes = cap_per_worker * (stack_bytes + kGuardBytes);
@@ -765,6 +768,7 @@ void GpuBroker::run(size_t n, unsigned inflight, const std::function<void(size_t
     for (int k = 0; k < 4; ++k) for (int j = 0; j < 4; ++j) prof[k][j] = g_prof[k][j] - prof0[k][j];
     for (int k = 0; k < 4; ++k) kernel_ns[k] += prof[k][3];
     region_calls += g_region_stats[0] - rs0[0]; region_bails += g_region_stats[1] - rs0[1];
+    region_kcells += g_region_kcells - kcells0;
     for (int j = 0; j < 16; ++j) region_bail_reason[j] += g_region_stats[2 + j] - rs0[2 + j];
     if (getenv("RTK_BROKER_PROFILE")) {
         const double total_ms = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_begin).count() / 1e6;

@@ -106,6 +106,7 @@ public:
     uint64_t waves = 0, jobs = 0;   // batched service calls issued / requests served
     uint64_t kernel_ns[4] = {0, 0, 0, 0};   // GPU kernel time (CUDA events) of the dist / path / subgraph / region services
     uint64_t region_calls = 0, region_bails = 0, region_bail_reason[16] = {0};
+    uint64_t region_kcells = 0;   // DP cells swept inside the engine / 1024
 
     struct Worker;    // one host thread: scheduler context, live fibers, ready list
     struct Fiber;

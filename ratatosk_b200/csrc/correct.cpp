@@ -1216,7 +1216,7 @@ static void correct_range(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n
         if (stats) {
             stats[5] += broker.waves; stats[6] += broker.jobs;
             for (int s3 = 0; s3 < 3; ++s3) stats[7 + s3] += broker.kernel_ns[s3];
-            stats[16] += broker.kernel_ns[3]; stats[17] += broker.region_calls; stats[18] += broker.region_bails;
+            stats[16] += broker.kernel_ns[3]; stats[17] += broker.region_calls; stats[18] += broker.region_bails; stats[19] += broker.region_kcells;
             stats[10] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t_broker - t_seeds).count();
             stats[11] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_broker).count();
         }

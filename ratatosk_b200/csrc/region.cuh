@@ -166,6 +166,7 @@ struct rg_ctx {
     uint32_t arena_top;
     uint32_t bail;
     uint32_t n_hops, n_pops, n_cands, n_aligns;
+    uint64_t n_cells;            // DP cells swept (|query| x |target| of every alignment), the engine's unit of work
 };
 
 __device__ __forceinline__ uint32_t rg_usize(const rg_ctx& C, const uint32_t u) { return (uint32_t)(C.p->unitig_off[u + 1] - C.p->unitig_off[u]); }
@@ -218,6 +219,7 @@ struct rg_dist { int dist, first, last; };
 __device__ RTK_RG_NOINLINE rg_dist rg_myers(rg_ctx& C, const char* __restrict__ q, const int qlen, const char* __restrict__ t, const int tlen, const int mode) {
     rg_dist R;
     ++C.n_aligns;
+    C.n_cells += (uint64_t)qlen * (uint64_t)tlen;
     if (qlen == 0 || tlen == 0) {   // edlibAlign's special case (src/edlib.cpp:160-176)
         if (mode == 0) { R.dist = qlen > tlen ? qlen : tlen; R.first = R.last = tlen - 1; }
         else { R.dist = qlen; R.first = R.last = -1; }
@@ -308,6 +310,7 @@ __device__ RTK_RG_NOINLINE void rg_quality_direct(rg_ctx& C, const char* __restr
     const int nb = (qlen + 63) >> 6;
     if ((uint64_t)nb * (uint64_t)tlen > (uint64_t)C.p->mat_cells) { C.bail = RTK_RG_BAIL_HIRSCH; return; }
     ++C.n_aligns;
+    C.n_cells += (uint64_t)qlen * (uint64_t)tlen;
     constexpr int G = 32;
     const unsigned gmask = 0xffffffffu;
     const char* q = ps;
@@ -443,6 +446,7 @@ __device__ RTK_RG_NOINLINE void rg_lastcol_rows(rg_ctx& C, const char* __restric
     const uint32_t lane = C.lane;
     if (tlen == 0) { for (int r = (int)lane; r < qlen; r += 32) rows[r] = r + 1; __syncwarp(); return; }
     ++C.n_aligns;
+    C.n_cells += (uint64_t)qlen * (uint64_t)tlen;
     constexpr int G = 32;
     const unsigned gmask = 0xffffffffu;
     const int nb = (qlen + 63) >> 6;
@@ -1269,7 +1273,8 @@ __device__ __forceinline__ void rg_region(rg_ctx& C, const rtk_rg_task& T, rtk_r
         s_pos = vw[i_w_s].pos; s_unitig = vw[i_w_s].unitig; s_dist = vw[i_w_s].dist; s_strand = vw[i_w_s].strand;
     }
     R.n_hops = C.n_hops; R.n_pops = C.n_pops; R.n_cands = C.n_cands; R.n_aligns = C.n_aligns;
-    R.seg_off = 0; R.n_segs = 0; R.reserved = 0;
+    R.seg_off = 0; R.n_segs = 0;
+    { const uint64_t kc = C.n_cells >> 10; R.reserved = kc > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)kc; }   // kilo-cells
     if (!C.bail) {   // the segment descriptors, contiguous
         unsigned long long seg_base = 0;
         if (lane == 0) seg_base = atomicAdd(&p.out_top[2], (unsigned long long)n_segs);
@@ -1314,7 +1319,7 @@ __global__ void __launch_bounds__(32) rtk_region_kernel(const rtk_rg_params p) {
         C.q_items = (uint32_t*)(S + L.q_items); C.v_items = (uint32_t*)(S + L.v_items); C.vt_items = (uint32_t*)(S + L.vt_items);
         C.ch_nodes = (rtk_rg_node*)(S + L.ch_nodes); C.ch_qual = (char*)(S + L.ch_qual);
         const uint32_t id = p.order ? p.order[ti] : ti;
-        C.arena_top = 0; C.bail = 0; C.n_hops = C.n_pops = C.n_cands = C.n_aligns = 0;
+        C.arena_top = 0; C.bail = 0; C.n_hops = C.n_pops = C.n_cands = C.n_aligns = 0; C.n_cells = 0;
         rtk_rg_result R;
         rg_region(C, p.tasks[id], R);
         __syncwarp();
