@@ -24,6 +24,7 @@
 #include <chrono>
 
 #include "broker.hpp"
+#include "subgraph_host.hpp"   // RTK_DFS_MAX_NODES
 
 namespace rtk {
 
@@ -1131,6 +1132,10 @@ static void correct_range(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n
                           std::mutex* seeds_turn = nullptr) {
     const rtk_graph_view& g = ctx->host_graph->view;
     const bool pass2 = (pass == 2);
+    // exploreSubGraphLong expands a partial path while it spells fewer than k * large_k_factor bases: every unitig adds at least one
+    // base, so a burst holds at most k * large_k_factor - k + 2 unitigs; the kernels' per-burst capacity is fixed (subgraph.cuh)
+    if (pass2 && (double)opt.k * opt.large_k_factor - (double)opt.k + 2.0 > (double)RTK_DFS_MAX_NODES)
+        throw std::invalid_argument("large_k_factor too large for this build: k * large_k_factor - k + 2 must not exceed " + std::to_string(RTK_DFS_MAX_NODES) + " unitigs per burst");
     const size_t max_km_cov = std::max<size_t>(ctx->host_graph->hdr.max_km_cov_graph, opt.max_km_cov);  // src/Ratatosk.cpp:625
     parallel_for(n_reads, [&](size_t rb, size_t re) {
         for (size_t r = rb; r < re; ++r) {

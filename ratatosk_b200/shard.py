@@ -27,8 +27,9 @@ def deal(tickets, world_size):
     return [[t for t in range(len(tickets)) if t % world_size == r] for r in range(world_size)]
 
 
-def merge_ordered(per_rank_blocks):
-    """per_rank_blocks: iterable of dict {ticket id: list of output records}; -> records in input order"""
+def merge_ordered(per_rank_blocks, n_tickets=None):
+    """per_rank_blocks: iterable of dict {ticket id: list of output records}; -> records in input order.
+    n_tickets (the dealer's count): a missing TRAILING ticket is detected as well"""
     merged = {}
     for blocks in per_rank_blocks:
         for t, recs in blocks.items():
@@ -36,7 +37,7 @@ def merge_ordered(per_rank_blocks):
                 raise ValueError("ticket %d produced twice" % t)
             merged[t] = recs
     out = []
-    for t in range(len(merged)):
+    for t in range(len(merged) if n_tickets is None else n_tickets):
         if t not in merged:
             raise ValueError("ticket %d missing" % t)
         out.extend(merged[t])
