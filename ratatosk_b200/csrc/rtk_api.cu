@@ -197,15 +197,6 @@ int rtk_ctx_create(int device, rtk_ctx** out) {
         // cores, blocking in the driver (RTK_BLOCKING_SYNC=1) frees cores for the workers but adds wake-up latency to
         // every batch and lowers throughput by ~30 % (the region chains are latency-bound).
         if (getenv("RTK_BLOCKING_SYNC")) { if (cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync) != cudaSuccess) cudaGetLastError(); }
-        // The k-mer index is probed at random, one 32-byte sector per probe, in a table far larger than L2: fetching 64 / 128 bytes
-        // per miss wastes most of the DRAM traffic (ncu on the 1.34 GB chr20-scale table: 105 B of DRAM reads per probe for 16
-        // algorithmic bytes, 62 % of the DRAM throughput, profiles/r2_k1_inexact_ncu_full.md).  Ask for sector-sized fetches; the
-        // streaming kernels of the path work out of L2 / registers.  RTK_L2_FETCH=<bytes> overrides (0: leave the default).
-        {
-            const char* e = getenv("RTK_L2_FETCH");
-            const size_t want = e ? (size_t)atoi(e) : 32;
-            if (want && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, want) != cudaSuccess) cudaGetLastError();   // a hint: not fatal
-        }
         rtk_ctx* c = new rtk_ctx();
         c->device = device;
         RTK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
