@@ -1341,7 +1341,9 @@ void correct_two_pass_host(rtk_ctx* ctx1, rtk_ctx* ctx2, const rtk_opt& opt1, co
     out_seq.assign(n_reads, std::string()); out_qual.assign(n_reads, std::string());
     if (!n_reads) return;
     const char* e = getenv("RTK_GANGS2");
-    unsigned n_gangs = e ? (unsigned)std::max(1, atoi(e)) : 3u;
+    // default 3; a rank with few host threads (several ranks sharing a node's cores) runs fewer, larger gangs: measured with 4
+    // threads, 2 gangs 7.6 Mbases/s, 3 gangs 6.9, 1 gang 6.5 (scripts/r2_sweep_lowthreads.sh)
+    unsigned n_gangs = e ? (unsigned)std::max(1, atoi(e)) : std::min(3u, std::max(1u, host_threads() / 2));
     const uint64_t total_bases = seq_off[n_reads] - seq_off[0];
     const char* e_min = getenv("RTK_GANGS_MIN_BASES");   // tests force several gangs on small fixtures
     const uint64_t min_bases = e_min ? (uint64_t)std::max(1ll, atoll(e_min)) : (2ull << 20);
