@@ -489,6 +489,7 @@ static std::mutex g_sim_launch_mu;   // the CPU simulator runs one launch at a t
 #endif
 
 void GpuBroker::service_main(Service* s) {
+    DeviceBind bind(s->ctx);   // a new thread starts on device 0: every CUDA call of this service belongs to its context's device
     set_thread_budget(run_budget);   // parallel_for inside a service (bulk pack / unpack) stays within the gang's share of the cores
     std::vector<std::pair<void*, Fiber*>> batch;
     const char* e_mb = getenv("RTK_SERVICE_MIN_BATCH");
@@ -629,6 +630,7 @@ void GpuBroker::fiber_body(Fiber* f) {
 // scheduler loop of a worker thread: resume served fibers, start new tasks while there is room, sleep when every
 // live fiber is waiting for the GPU; exits when it has no live fiber and no task is left
 void GpuBroker::worker_main(Worker* w) {
+    DeviceBind bind(ctx);   // fibers may call into the device directly (declined regions): same device as the broker's context
     tl_broker = this;
     tl_worker = w;
     const size_t stack_bytes = fiber_stack_bytes();

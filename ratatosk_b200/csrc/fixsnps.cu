@@ -14,6 +14,7 @@ void fix_snps_host(rtk_ctx* c, uint32_t n_reads, char* seq_pool, const uint64_t*
     if (n_fixed) *n_fixed = 0;
     if (!n_reads || amb_pos.empty()) return;
     if (c->hdr.k > RTK_FS_MAXK) throw std::invalid_argument("fixSNPs: k > 64");
+    DeviceBind bind(c);
     cudaStream_t st = c->stream;
     const uint64_t total = seq_off[n_reads] - seq_off[0];
     std::vector<uint64_t> off0(n_reads + 1);

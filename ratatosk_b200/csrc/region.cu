@@ -31,6 +31,7 @@ void region_batch_run(rtk_ctx* c, const rtk_opt& opt, int pass, uint32_t n_calls
     if (!n_calls) return;
     if (!c->has_graph) throw std::invalid_argument("no graph uploaded to this context");
     if (opt.k != c->hdr.k) throw std::invalid_argument("rtk_opt.k does not match the graph's k");
+    DeviceBind bind(c);   // called from the broker's service threads as well as from the C entry
     region_check_calls(n_calls, calls, win_bytes, n_weak, n_pids, c->hdr.n_unitigs, c->hdr.k);
     cudaStream_t st = c->stream;
     const RegionCaps caps = region_caps();

@@ -96,6 +96,7 @@ uint64_t k1_launch(rtk_ctx* ctx, uint32_t n_reads, const char* d_seq, const uint
 void search_sequence_host(rtk_ctx* ctx, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off, uint32_t flags,
                           std::vector<std::vector<rtk_hit>>& per_read, uint64_t* stats) {
     const double t_start = now_ns();
+    DeviceBind bind(ctx);
     const bool sparse_hint = (flags & RTK_SEARCH_SPARSE_HINT) != 0;
     flags &= ~RTK_SEARCH_SPARSE_HINT;
     if (!ctx->has_graph || !ctx->host_graph) throw std::invalid_argument("no graph uploaded to this context");

@@ -157,6 +157,7 @@ void nw_path_runs_masked(rtk_ctx* c, uint32_t n, const char* q_pool, const uint6
     runs.assign(n, {});
     if (kernel_ms) *kernel_ms = 0.f;
     if (!n) return;
+    DeviceBind bind(c);
     cudaStream_t st = c->stream;
     const uint64_t qb = q_off[n] - q_off[0], tb = t_off[n] - t_off[0];
     std::vector<uint64_t> qrel(n + 1), trel(n + 1);
