@@ -319,6 +319,24 @@ int rtk_correct_two_pass_batch(rtk_ctx* ctx1, rtk_ctx* ctx2, const rtk_opt* opt1
 int rtk_fix_snps_batch(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
                        char** out_seq_pool, uint64_t* n_fixed);
 
+/* ---- graph annotation: detectSNPs (src/Graph.hpp:24, body src/Graph.cpp:484-720 with isValidSNPcandidate,
+ * src/GraphTraversal.cpp:1057-1147) and detectShortCycles (src/Graph.hpp:25, body src/Graph.cpp:4660-4854), the two steps the
+ * reference runs on the coloured graph after addCoverage when it builds an index (src/Ratatosk.cpp:1124-1134, :1230-1240).  Both
+ * read only the colours, edge flags and sequences of the graph resident on ctx and return what the reference stores per unitig:
+ *   rtk_detect_snps: UnitigData::ambiguity_ids - amb_ids[amb_off[u], amb_off[u+1]) = (position << 4 | IUPAC base set A1 C2 G4 T8),
+ *     ascending; K1 substitution sweep of every coloured unitig against the graph + one warp per unitig replaying its ordered
+ *     candidates with the two local traversals of isValidSNPcandidate.
+ *   rtk_detect_short_cycles: UnitigData::isShortCycle() as is_cycle[u] and the compactedCycles blob
+ *     cyc_pool[cyc_off[u], cyc_off[u+1]) (NUL-terminated strings, discovery order); one warp per unitig.
+ * Only opt->min_cov_vertices is read (opt may be NULL: 2).  Buffers are library-allocated (rtk_free).
+ * stats (optional, 10 x u64, accumulated): [0] K1 probes, [1] K1 raw hits, [2] K1 kernel ns, [3] K1 stage ns, [4] candidates,
+ * [5] unitigs with candidates, [6] local traversals started, [7] annotation kernel ns, [8] unitigs re-run with the large arena. */
+int rtk_detect_snps(rtk_ctx* ctx, const rtk_opt* opt, uint64_t** amb_off, uint32_t** amb_ids, uint64_t* stats);
+int rtk_detect_short_cycles(rtk_ctx* ctx, const rtk_opt* opt, uint8_t** is_cycle, uint64_t** cyc_off, char** cyc_pool, uint64_t* stats);
+/* what the loaded index stores for a unitig (host slab): its ambiguity ids and its compacted-cycles blob */
+int rtk_graph_unitig_annotations(const rtk_host_graph* g, uint32_t unitig, const uint32_t** amb_ids, uint64_t* n_amb,
+                                 const char** cyc, uint64_t* cyc_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,12 @@ def load_library(path=None):
     L.rtk_graph_unitig_colors.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(C.c_uint32)),
                                           C.POINTER(C.c_uint64), C.POINTER(C.POINTER(C.c_uint32)),
                                           C.POINTER(C.c_uint64)]
+    L.rtk_graph_unitig_annotations.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64),
+                                               C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.rtk_detect_snps.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.POINTER(C.c_uint32)),
+                                  C.POINTER(C.c_uint64)]
+    L.rtk_detect_short_cycles.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.POINTER(C.POINTER(C.c_uint8)),
+                                          C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.rtk_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.rtk_ctx_destroy.argtypes = [C.c_void_p]
     L.rtk_graph_upload.argtypes = [C.c_void_p, C.c_void_p]
@@ -275,6 +281,12 @@ class Graph:
         ng, nl = C.c_uint64(), C.c_uint64()
         _check(self.L, self.L.rtk_graph_unitig_colors(self.h, u, C.byref(pg), C.byref(ng), C.byref(pl), C.byref(nl)))
         return [pg[i] for i in range(ng.value)], [pl[i] for i in range(nl.value)]
+
+    def unitig_annotations(self, u):
+        """what the index stores for unitig u: (ambiguity ids [(pos << 4) | base set], compacted-cycles blob bytes)"""
+        pa, na, pc, nc = C.POINTER(C.c_uint32)(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+        _check(self.L, self.L.rtk_graph_unitig_annotations(self.h, u, C.byref(pa), C.byref(na), C.byref(pc), C.byref(nc)))
+        return [pa[i] for i in range(na.value)], (C.string_at(pc, nc.value) if nc.value else b"")
 
     def close(self):
         if self.h:
@@ -427,6 +439,33 @@ class Context:
         buf = C.string_at(out, int(off[-1]))
         self.L.rtk_free(out)
         return [buf[int(off[i]):int(off[i + 1])].decode("latin1") for i in range(len(reads))], nf.value
+
+    def detect_snps(self, opt=None, stats=None):
+        """detectSNPs (src/Graph.cpp:484) on the resident graph -> per unitig the sorted ambiguity ids (pos << 4 | base set)"""
+        po, pi = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)()
+        st = (C.c_uint64 * 10)()
+        _check(self.L, self.L.rtk_detect_snps(self.h, C.byref(opt) if opt else None, C.byref(po), C.byref(pi), st))
+        n = self.graph.info()["n_unitigs"]
+        off = np.ctypeslib.as_array(po, shape=(n + 1,)).copy()
+        ids = np.ctypeslib.as_array(pi, shape=(int(off[-1]) + 1,))[:int(off[-1])].copy()
+        self.L.rtk_free(C.cast(po, C.c_void_p)); self.L.rtk_free(C.cast(pi, C.c_void_p))
+        if stats is not None:
+            stats[:] = list(st)
+        return off, ids
+
+    def detect_short_cycles(self, opt=None, stats=None):
+        """detectShortCycles (src/Graph.cpp:4660) on the resident graph -> (is_cycle u8[n], blob offsets u64[n+1], blob bytes)"""
+        pf, po, pp = C.POINTER(C.c_uint8)(), C.POINTER(C.c_uint64)(), C.c_void_p()
+        st = (C.c_uint64 * 10)()
+        _check(self.L, self.L.rtk_detect_short_cycles(self.h, C.byref(opt) if opt else None, C.byref(pf), C.byref(po), C.byref(pp), st))
+        n = self.graph.info()["n_unitigs"]
+        flags = np.ctypeslib.as_array(pf, shape=(n + 1,))[:n].copy()
+        off = np.ctypeslib.as_array(po, shape=(n + 1,)).copy()
+        pool = C.string_at(pp, int(off[-1]))
+        self.L.rtk_free(C.cast(pf, C.c_void_p)); self.L.rtk_free(C.cast(po, C.c_void_p)); self.L.rtk_free(pp)
+        if stats is not None:
+            stats[:] = list(st)
+        return flags, off, pool
 
     def phasing(self, raw_reads, corr_reads, corr_quals, opt=None):
         """phasing() of the second pass (src/Graph.cpp:869) for a batch -> list of (sequence, quality string)"""

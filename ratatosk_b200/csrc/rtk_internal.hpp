@@ -22,6 +22,9 @@
 #include "graph_build.hpp"
 #include "seeds_resolve.hpp"
 
+struct rtk_snp_job;    // annotate.cuh
+struct rtk_snp_cand;
+
 struct rtk_host_graph {
     rtk::rtk_slab slab;
     rtk_slab_header hdr;
@@ -284,6 +287,16 @@ void fix_snps_host(rtk_ctx* c, uint32_t n_reads, char* seq_pool, const uint64_t*
                    const std::vector<uint64_t>& amb_off, uint64_t* n_fixed);
 // lists the non-ACGT positions and runs fix_snps_host (phasing.cpp); returns the number of codes replaced
 uint64_t fix_snps_batch_host(rtk_ctx* ctx, uint32_t n_reads, char* seq_pool, const uint64_t* seq_off);
+
+// graph annotation (annotate.cu / tests/hostsim/sim_annotate.cpp launch the kernels of annotate.cuh; annotate_host.cpp drives them)
+// detectShortCycles over unitigs list[0..n) (list == nullptr: first .. first + n): status per job (0 none, 1 cycles, 2 arena
+// overflow) and the cycle records {job, length, chars padded to 4} in discovery order per job
+void cycles_run(rtk_ctx* c, uint32_t min_cov, const uint32_t* list, uint32_t first, uint32_t n, uint32_t arena_cap,
+                std::vector<uint8_t>& status, std::vector<uint32_t>& records, float* kernel_ms);
+// detectSNPs candidate replay: fin (in: the unitigs' own bases as sets, out: seq_final) per slot
+void snp_run(rtk_ctx* c, uint32_t min_cov, const std::vector<rtk_snp_job>& jobs, const std::vector<rtk_snp_cand>& cands,
+             std::vector<uint8_t>& fin, uint32_t n_bslots, uint32_t arena_cap, std::vector<uint8_t>& status, uint64_t* n_walks,
+             float* kernel_ms);
 
 // per-read correction of a batch (correct.cpp)
 void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
