@@ -270,6 +270,40 @@ int ref_fix_snps(void* h, const char* s_corr, char** s_out) {
     return 0;
 }
 
+// detectSNPs (src/Graph.cpp:484) + detectShortCycles (src/Graph.cpp:4660) re-run on the loaded graph with the given
+// min_cov_vertices: the stored annotations are cleared first, then one text line per unitig with a non-empty result goes to
+// `path`:  sequence \t ambiguity ids (decimal, comma separated) \t isShortCycle \t compacted cycles (';' after each string)
+int ref_annotate(void* h, int min_cov, int threads, const char* path) {
+    RefGraph* g = (RefGraph*)h;
+    Correct_Opt opt = g->opt;
+    opt.min_cov_vertices = (size_t)min_cov;
+    opt.nb_threads = (size_t)threads;
+    opt.verbose = false;
+    for (auto& um : *g->dbg) {
+        UnitigData* ud = um.getData();
+        ud->ambiguity_ids = PairID();
+        if (ud->compactedCycles.second != nullptr) delete[] ud->compactedCycles.second;
+        ud->compactedCycles = pair<size_t, char*>(0, nullptr);
+        ud->setIsCycle(false);
+    }
+    detectSNPs(*g->dbg, opt);
+    detectShortCycles(*g->dbg, opt);
+    FILE* f = fopen(path, "w");
+    if (!f) return -1;
+    for (const auto& um : *g->dbg) {
+        const UnitigData* ud = um.getData();
+        const vector<const char*> cyc = ud->getCompactCycles();
+        if (ud->ambiguity_ids.isEmpty() && cyc.empty() && !ud->isShortCycle()) continue;
+        fprintf(f, "%s\t", um.referenceUnitigToString().c_str());
+        for (const uint32_t id : ud->ambiguity_ids) fprintf(f, "%u,", id);
+        fprintf(f, "\t%d\t", (int)ud->isShortCycle());
+        for (const char* c : cyc) fprintf(f, "%s;", c);
+        fputc('\n', f);
+    }
+    fclose(f);
+    return 0;
+}
+
 // edlibAlign with the reference's IUPAC equality table (src/Common.hpp:262-276) when iupac != 0.
 // mode: 0 NW, 1 SHW, 2 HW (EdlibAlignMode); task: 0 DISTANCE, 1 LOC, 2 PATH.
 int ref_edlib(const char* q, int ql, const char* t, int tl, int mode, int task, int k, int iupac,

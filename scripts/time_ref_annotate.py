@@ -22,7 +22,7 @@ for line in p.stdout:
     t = time.time() - t0
     for key, tag in (("Adding colors and coverage", "addCoverage"), ("Adding SNPs candidates", "detectSNPs"),
                      ("Adding micro/mini-satellites", "detectShortCycles"), ("Writing index", "write")):
-        if key in line and tag not in marks:
+        if key in line and (tag not in marks or tag == "write"):   # "Writing index" is printed for the graph too: keep the last
             marks[tag] = t
 p.wait()
 out = {"genome_len": glen, "threads": threads, "total_s": time.time() - t0, "marks_s": marks}

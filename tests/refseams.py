@@ -50,6 +50,7 @@ def lib():
                                 C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_int)),
                                 C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.c_int)]
         L.ref_free.argtypes = [C.c_void_p]
+        L.ref_annotate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
         L.ref_explore_subgraph.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_int, C.c_uint32, C.c_char_p,
                                            C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32,
                                            C.POINTER(C.c_double), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
@@ -90,6 +91,18 @@ class RefGraph:
     def dump(self, path):
         if lib().ref_graph_dump(self.h, path.encode()) != 0:
             raise RuntimeError("dump failed")
+
+    def annotate(self, min_cov, threads=1):
+        """re-run detectSNPs + detectShortCycles with min_cov_vertices = min_cov -> {unitig sequence: (ambiguity ids, flag, blob)}"""
+        import tempfile
+        with tempfile.NamedTemporaryFile(suffix=".tsv") as t:
+            if lib().ref_annotate(self.h, int(min_cov), int(threads), t.name.encode()) != 0:
+                raise RuntimeError("annotate failed")
+            out = {}
+            for line in open(t.name):
+                seq, amb, flag, cyc = line.rstrip("\n").split("\t")
+                out[seq] = ([int(x) for x in amb.split(",") if x], int(flag), cyc.replace(";", "\0").encode())
+            return out
 
     def search_sequence(self, s, exact, ins, dele, subst, or_excl):
         p = C.POINTER(RefHit)()

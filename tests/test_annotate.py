@@ -83,6 +83,43 @@ def test_detect_snps_kernel_source_matches_reference_index(recipe, k, sim_lib):
     _check_snps(recipe, k, sim_lib, 90 if recipe == "F2" else 0)
 
 
+def _check_min_cov_vectors(lib):
+    """min_cov_vertices 1, 2, 3, 5 against the reference re-run through the seam probe (tests/golden/make_golden_annotate.py)"""
+    import gzip
+    import json
+    vec = json.load(gzip.open(os.path.join(GOLDEN, "annotate_vectors.json.gz"), "rt"))
+    n_marks = 0
+    for fx in ("F1", "F2"):
+        for k in (31, 63):
+            g, ctx = _load(fx, k, lib)
+            n = g.info()["n_unitigs"]
+            for mc, want in sorted(vec[fx][str(k)].items()):
+                opt = rb.default_opt(1 if k == 31 else 2, lib=lib)
+                opt.min_cov_vertices = int(mc)
+                off, ids = ctx.detect_snps(opt=opt)
+                flags, coff, pool = ctx.detect_short_cycles(opt=opt)
+                got = {}
+                for u in range(n):
+                    a = list(map(int, ids[int(off[u]):int(off[u + 1])]))
+                    b = pool[int(coff[u]):int(coff[u + 1])]
+                    if a or b or flags[u]:
+                        got[str(u)] = [a, int(flags[u]), b.decode("latin1")]
+                assert got == want, (fx, k, mc, [u for u in set(got) | set(want) if got.get(u) != want.get(u)][:10])
+                n_marks += sum(len(v[0]) for v in want.values())
+            ctx.close()
+            g.close()
+    assert n_marks > 10000
+
+
+def test_annotation_min_cov_variants_match_reference(sim_lib):
+    _check_min_cov_vectors(sim_lib)
+
+
+@pytest.mark.gpu
+def test_annotation_min_cov_variants_match_reference_cuda():
+    _check_min_cov_vectors(None)
+
+
 def _check_small_arena(lib, monkeypatch):
     """first-attempt arenas of 3 entries: most unitigs overflow and are re-run with the large arena; same bytes out"""
     monkeypatch.setenv("RTK_AN_ARENA", "3")
