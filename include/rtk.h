@@ -333,6 +333,12 @@ int rtk_fix_snps_batch(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const
  * [5] unitigs with candidates, [6] local traversals started, [7] annotation kernel ns, [8] unitigs re-run with the large arena. */
 int rtk_detect_snps(rtk_ctx* ctx, const rtk_opt* opt, uint64_t** amb_off, uint32_t** amb_ids, uint64_t* stats);
 int rtk_detect_short_cycles(rtk_ctx* ctx, const rtk_opt* opt, uint8_t** is_cycle, uint64_t** cyc_off, char** cyc_pool, uint64_t* stats);
+/* Index file with these annotations: a copy of rtsk_in (the .rtsk g was loaded from) in which, per unitig, the short-cycle flag, the
+ * ambiguity ids and the compacted-cycles blob are replaced by the given ones and everything else is kept byte for byte - the part of
+ * writeGraphData (src/Graph.cpp:786-801, UnitigData::write src/UnitigData.hpp:493-517) that detectSNPs / detectShortCycles own.  The
+ * reference reads the result (readGraphData).  Written atomically (temporary file + rename); rtsk_out may equal rtsk_in. */
+int rtk_rtsk_write_annotations(const rtk_host_graph* g, const char* rtsk_in, const char* rtsk_out, const uint64_t* amb_off,
+                               const uint32_t* amb_ids, const uint8_t* is_cycle, const uint64_t* cyc_off, const char* cyc_pool);
 /* what the loaded index stores for a unitig (host slab): its ambiguity ids and its compacted-cycles blob */
 int rtk_graph_unitig_annotations(const rtk_host_graph* g, uint32_t unitig, const uint32_t** amb_ids, uint64_t* n_amb,
                                  const char** cyc, uint64_t* cyc_bytes);

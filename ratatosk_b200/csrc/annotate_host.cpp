@@ -297,6 +297,14 @@ int rtk_detect_short_cycles(rtk_ctx* c, const rtk_opt* opt, uint8_t** is_cycle, 
     });
 }
 
+int rtk_rtsk_write_annotations(const rtk_host_graph* g, const char* rtsk_in, const char* rtsk_out, const uint64_t* amb_off,
+                               const uint32_t* amb_ids, const uint8_t* is_cycle, const uint64_t* cyc_off, const char* cyc_pool) {
+    return guarded([&] {
+        if (!g || !rtsk_in || !rtsk_out || !amb_off || !amb_ids || !is_cycle || !cyc_off || !cyc_pool) throw std::invalid_argument("null argument");
+        patch_rtsk_annotations(g->view, rtsk_in, rtsk_out, amb_off, amb_ids, is_cycle, cyc_off, cyc_pool);
+    });
+}
+
 int rtk_graph_unitig_annotations(const rtk_host_graph* g, uint32_t u, const uint32_t** amb_ids, uint64_t* n_amb, const char** cyc,
                                  uint64_t* cyc_bytes) {
     if (!g || u >= g->hdr.n_unitigs || !amb_ids || !n_amb || !cyc || !cyc_bytes) { set_error("bad unitig id"); return RTK_EINVAL; }

@@ -437,4 +437,106 @@ HostGraph load_index(const std::string& fasta, const std::string& rtsk, int k) {
     return hg;
 }
 
+
+// ------------------------------------------------------------------ .rtsk writer for the annotation fields
+// PairID::write (src/PairID.cpp:1135-1172) of a sorted id list, in container kinds PairID::read accepts: the 61-bit vector
+// (empty set included), the single id, or a CRoaring portable blob of array / bitset containers without runs
+// (Bifrost/src/roaring.c:10554-10700).  The reference's behaviour depends on the set only, not on the container kind.
+static void write_pairid(std::string& out, const uint32_t* ids, uint64_t n) {
+    auto put = [&](const void* p, size_t b) { out.append((const char*)p, b); };
+    if (n == 0 || ids[n - 1] < 61) {
+        uint64_t w = 1;
+        for (uint64_t i = 0; i < n; ++i) w |= 1ULL << (ids[i] + 3);
+        put(&w, 8);
+        return;
+    }
+    if (n == 1) { const uint64_t w = ((uint64_t)ids[0] << 3) | 2ULL; put(&w, 8); return; }
+    std::vector<std::pair<uint16_t, std::pair<uint64_t, uint64_t>>> cont;   // key, [begin, end)
+    for (uint64_t i = 0; i < n;) {
+        uint64_t j = i;
+        while (j < n && (ids[j] >> 16) == (ids[i] >> 16)) ++j;
+        cont.push_back({(uint16_t)(ids[i] >> 16), {i, j}});
+        i = j;
+    }
+    std::string blob;
+    auto bput = [&](const void* p, size_t b) { blob.append((const char*)p, b); };
+    const uint32_t cookie = 12346, nc = (uint32_t)cont.size();
+    bput(&cookie, 4); bput(&nc, 4);
+    for (const auto& c : cont) { const uint16_t card1 = (uint16_t)(c.second.second - c.second.first - 1); bput(&c.first, 2); bput(&card1, 2); }
+    uint32_t off = 8 + 8 * nc;
+    for (const auto& c : cont) { bput(&off, 4); const uint64_t card = c.second.second - c.second.first; off += (card > 4096) ? 8192u : (uint32_t)(2 * card); }
+    for (const auto& c : cont) {
+        const uint64_t card = c.second.second - c.second.first;
+        if (card > 4096) {
+            std::vector<uint64_t> bits(1024, 0);
+            for (uint64_t i = c.second.first; i < c.second.second; ++i) bits[(ids[i] & 0xffff) >> 6] |= 1ULL << (ids[i] & 63);
+            bput(bits.data(), 8192);
+        } else {
+            for (uint64_t i = c.second.first; i < c.second.second; ++i) { const uint16_t v = (uint16_t)(ids[i] & 0xffff); bput(&v, 2); }
+        }
+    }
+    const uint64_t w = ((uint64_t)blob.size() << 3) | 3ULL;
+    put(&w, 8);
+    out += blob;
+}
+
+template <typename KT>
+static uint32_t unitig_of_head(const rtk_graph_view& g, const uint64_t l0, const uint64_t l1) {
+    const int k = (int)g.k;
+    KT fw;
+    if (sizeof(KT) == 8) fw = (KT)(l0 >> (64 - 2 * k));
+    else fw = (KT)(((((rtk_u128)l0) << 64) | (rtk_u128)l1) >> (128 - 2 * k));
+    rtk_kmer_hit h;
+    if (!rtk_lookup<KT>(g.table, g.n_buckets, g.pool, k, fw, KmerOps<KT>::rc(fw, k), h)) throw std::runtime_error("rtsk: head k-mer not found in graph");
+    const uint32_t u = rtk_unitig_of(g.blk2unitig, g.unitig_off, h.P);
+    if (!h.strand || h.P != g.unitig_off[u]) throw std::runtime_error("rtsk: record does not start a unitig of this graph (index files of another graph?)");
+    return u;
+}
+
+// Copy of rtsk_in with, per unitig, the fields detectSNPs / detectShortCycles own replaced: bit 8 of shared_pids (isShortCycle),
+// the ambiguity PairID and the compactedCycles blob (UnitigData::write, src/UnitigData.hpp:493-517).  Everything else is copied
+// byte for byte.  g must be the graph loaded from rtsk_in (unitig ids and orientation).
+void patch_rtsk_annotations(const rtk_graph_view& g, const std::string& rtsk_in, const std::string& rtsk_out, const uint64_t* amb_off,
+                            const uint32_t* amb_ids, const uint8_t* is_cycle, const uint64_t* cyc_off, const char* cyc_pool) {
+    const std::vector<unsigned char> buf = slurp(rtsk_in);
+    ByteReader r{buf.data(), buf.data() + buf.size()};
+    std::string out;
+    out.reserve(buf.size());
+    std::vector<uint32_t> tmp;
+    std::vector<bool> seen(g.n_unitigs, false);
+    while (!r.eof()) {
+        const unsigned char* rec = r.p;
+        const uint64_t l0 = r.u64(), l1 = r.u64();
+        const uint32_t u = (g.k <= 32) ? unitig_of_head<uint64_t>(g, l0, l1) : unitig_of_head<rtk_u128>(g, l0, l1);
+        if (seen[u]) throw std::runtime_error("rtsk: unitig listed twice");
+        seen[u] = true;
+        const uint64_t kmcov = r.u64();
+        uint64_t shared = r.u64();
+        shared = (shared & ~0x100ULL) | (is_cycle[u] ? 0x100ULL : 0ULL);
+        out.append((const char*)rec, 16);
+        out.append((const char*)&kmcov, 8);
+        out.append((const char*)&shared, 8);
+        const unsigned char* c0 = r.p;
+        parse_pairid(r, tmp);   // global set
+        parse_pairid(r, tmp);   // local set
+        out.append((const char*)c0, (size_t)(r.p - c0));
+        parse_pairid(r, tmp);   // stored ambiguity ids: dropped
+        write_pairid(out, amb_ids + amb_off[u], amb_off[u + 1] - amb_off[u]);
+        const unsigned char* h0 = r.p;
+        parse_pairid(r, tmp);   // hap ids
+        out.append((const char*)h0, (size_t)(r.p - h0));
+        const uint64_t old_cl = r.u64();
+        if (old_cl) r.bytes(old_cl);
+        const uint64_t cl = cyc_off[u + 1] - cyc_off[u];
+        out.append((const char*)&cl, 8);
+        if (cl) out.append(cyc_pool + cyc_off[u], cl);
+    }
+    const std::string tmp_path = rtsk_out + ".tmp";
+    FILE* f = fopen(tmp_path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot write " + tmp_path);
+    const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    if (fclose(f) != 0 || !ok) { remove(tmp_path.c_str()); throw std::runtime_error("short write to " + tmp_path); }
+    if (rename(tmp_path.c_str(), rtsk_out.c_str()) != 0) { remove(tmp_path.c_str()); throw std::runtime_error("cannot rename to " + rtsk_out); }
+}
+
 }  // namespace rtk

@@ -32,5 +32,7 @@ struct rtk_slab {
 
 HostGraph load_index(const std::string& fasta, const std::string& rtsk, int k);
 rtk_slab build_slab(const HostGraph& hg);
+void patch_rtsk_annotations(const rtk_graph_view& g, const std::string& rtsk_in, const std::string& rtsk_out, const uint64_t* amb_off,
+                            const uint32_t* amb_ids, const uint8_t* is_cycle, const uint64_t* cyc_off, const char* cyc_pool);
 
 }  // namespace rtk

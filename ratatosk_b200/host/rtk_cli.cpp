@@ -142,7 +142,9 @@ void usage() {
             "  --in-graph2 G2 --in-unitig-data2 D2   (without -1 / -2) both passes as one pipeline: -g -d = k1 index, G2 D2 = k2 index;\n"
             "                    writes <prefix>.fastq[.gz] like `correct -1` followed by `correct -2 -O`\n"
             "  --cache FILE      flat graph cache (default <rtsk>.k<k>.rtkflat; written on first use, mapped in place afterwards)\n"
-            "  --no-cache        always parse the index files, write no cache\n");
+            "  --no-cache        always parse the index files, write no cache\n"
+            "rtk_correct annotate -g <graph.fasta[.gz]> -d <graph.rtsk> -o <out.rtsk> [-k K] [--min-cov N] [--no-snp] [--first-gpu D] [-v]\n"
+            "  detectSNPs + detectShortCycles of the reference's index build, recomputed on the GPU from the colours of the index\n");
 }
 
 int parse(int argc, char** argv, Options& o) {
@@ -303,9 +305,76 @@ struct Shared {
     void fail(const std::string& e) { std::lock_guard<std::mutex> l(m); if (error.empty()) error = e; failed = true; cv.notify_all(); }
 };
 
+
+
+// `rtk_correct annotate`: the last two steps of the reference's index build (src/Ratatosk.cpp:1124-1134) on an existing index -
+// detectSNPs + detectShortCycles recomputed on the GPU from the colours and edge flags the index holds, written as a new .rtsk
+int run_annotate(int argc, char** argv) {
+    std::string graph, data, out;
+    int k = 31, device = 0, min_cov = 2;
+    bool verbose = false, no_snp = false;
+    static struct option lo[] = {{"in-graph", required_argument, 0, 'g'}, {"in-unitig-data", required_argument, 0, 'd'}, {"out-unitig-data", required_argument, 0, 'o'},
+                                 {"k", required_argument, 0, 'k'}, {"min-cov", required_argument, 0, 1000}, {"no-snp", no_argument, 0, 1001},
+                                 {"first-gpu", required_argument, 0, 1002}, {"verbose", no_argument, 0, 'v'}, {0, 0, 0, 0}};
+    int c;
+    while ((c = getopt_long(argc - 1, argv + 1, "g:d:o:k:v", lo, nullptr)) != -1) {
+        switch (c) {
+            case 'g': graph = optarg; break;
+            case 'd': data = optarg; break;
+            case 'o': out = optarg; break;
+            case 'k': k = atoi(optarg); break;
+            case 'v': verbose = true; break;
+            case 1000: min_cov = atoi(optarg); break;
+            case 1001: no_snp = true; break;
+            case 1002: device = atoi(optarg); break;
+            default: usage(); return 1;
+        }
+    }
+    if (graph.empty() || data.empty() || out.empty() || min_cov < 1) { usage(); return 1; }
+    const auto t0 = std::chrono::steady_clock::now();
+    auto secs = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    auto die = [&]() { fprintf(stderr, "Ratatosk::Ratatosk(): %s\n", rtk_last_error()); return 1; };
+    rtk_host_graph* hg = nullptr;
+    rtk_ctx* ctx = nullptr;
+    if (rtk_graph_load(graph.c_str(), data.c_str(), k, &hg) != RTK_OK) return die();
+    if (rtk_ctx_create(device, &ctx) != RTK_OK || rtk_graph_upload(ctx, hg) != RTK_OK) return die();
+    rtk_graph_info gi;
+    rtk_graph_get_info(hg, &gi);
+    rtk_opt ropt;
+    rtk_opt_default(&ropt, 1);
+    ropt.k = (uint32_t)k; ropt.min_cov_vertices = (uint32_t)min_cov;
+    uint64_t *amb_off = nullptr, *cyc_off = nullptr, st[10] = {0};
+    uint32_t* amb_ids = nullptr;
+    uint8_t* is_cycle = nullptr;
+    char* cyc_pool = nullptr;
+    if (no_snp) {   // force_no_snp_corr: no candidates are added (src/Ratatosk.cpp:1124)
+        amb_off = (uint64_t*)calloc(gi.n_unitigs + 1, 8);
+        amb_ids = (uint32_t*)calloc(1, 4);
+        if (verbose) printf("Ratatosk::Ratatosk(): SNPs candidate detection is disabled.\n");
+    } else {
+        if (verbose) printf("Ratatosk::Ratatosk(): Adding SNPs candidates to graph.\n");
+        if (rtk_detect_snps(ctx, &ropt, &amb_off, &amb_ids, st) != RTK_OK) return die();
+    }
+    if (verbose) printf("Ratatosk::Ratatosk(): Adding micro/mini-satellites motif candidates to graph.\n");
+    if (rtk_detect_short_cycles(ctx, &ropt, &is_cycle, &cyc_off, &cyc_pool, st) != RTK_OK) return die();
+    if (verbose) printf("Ratatosk::Ratatosk(): Writing index to disk.\n");
+    if (rtk_rtsk_write_annotations(hg, data.c_str(), out.c_str(), amb_off, amb_ids, is_cycle, cyc_off, cyc_pool) != RTK_OK) return die();
+    if (verbose) {
+        uint64_t n_cyc = 0;
+        for (uint64_t u = 0; u < gi.n_unitigs; ++u) n_cyc += is_cycle[u];
+        printf("rtk_correct: %llu unitigs, %llu SNP marks (%llu candidates, %llu traversals), %llu unitigs in short cycles, %.2f s\n", (unsigned long long)gi.n_unitigs,
+               (unsigned long long)amb_off[gi.n_unitigs], (unsigned long long)st[4], (unsigned long long)st[6], (unsigned long long)n_cyc, secs());
+    }
+    rtk_free(amb_off); rtk_free(amb_ids); rtk_free(is_cycle); rtk_free(cyc_off); rtk_free(cyc_pool);
+    rtk_ctx_destroy(ctx);
+    rtk_graph_free(hg);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
+    if (argc >= 2 && strcmp(argv[1], "annotate") == 0) return run_annotate(argc, argv);
     Options o;
     if (parse(argc, argv, o)) return 1;
     const int pass = o.pass2 ? 2 : o.pass1 ? 1 : 0;   // 0: both passes as one pipeline (rtk_correct_two_pass_batch)

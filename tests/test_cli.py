@@ -217,3 +217,55 @@ def test_cli_cuda_two_pass_mode_identical_to_reference_cli(recipe, tmp_path):
     open(reads, "wb").write(gzip.open(os.path.join(d, "reads.fastq.gz"), "rb").read())
     out = _two_pass_mode(GPU_CLI, d, str(tmp_path), reads)
     assert open(out, "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass2.fastq.gz"))
+
+
+# ---------------------------------------------------------------------------------------------- rtk_correct annotate
+def _dump_lines(fasta, rtsk, k, tmp, tag):
+    from refseams import RefGraph
+    g = RefGraph(fasta, rtsk, k)
+    p = os.path.join(tmp, tag + ".dump")
+    g.dump(p)
+    g.close()
+    return sorted(open(p).read().split("\n"))
+
+
+def _check_annotate_cli(cli, tmp, lib):
+    """`rtk_correct annotate` (detectSNPs + detectShortCycles + the .rtsk fields they own) on the F2 k = 31 index: an index stripped
+    of its annotations gets them back; the REFERENCE reads the rewritten file as the same graph (per-unitig dump through the seam
+    library: flags, colours, ambiguity characters, cycles) and corrects reads with it to the same bytes."""
+    import ratatosk_b200 as rb
+    import refseams
+    d = os.path.join(GOLDEN, "F2")
+    fa, rt = os.path.join(d, "index.k31.fasta.gz"), os.path.join(d, "index.k31.rtsk")
+    stripped, redone = os.path.join(tmp, "stripped.rtsk"), os.path.join(tmp, "redone.rtsk")
+    r = subprocess.run([cli, "annotate", "-g", fa, "-d", rt, "-o", stripped, "-k", "31", "--no-snp", "--min-cov", "1000000000"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode(errors="replace")[-2000:]
+    r = subprocess.run([cli, "annotate", "-g", fa, "-d", stripped, "-o", redone, "-k", "31", "-v"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode(errors="replace")[-2000:]
+    assert b"2997 SNP marks" in r.stdout and b"250 unitigs in short cycles" in r.stdout, r.stdout
+    g0, g1, g2 = (rb.Graph.load(fa, x, 31, lib=lib) for x in (rt, stripped, redone))
+    n = g0.info()["n_unitigs"]
+    assert all(g1.unitig_annotations(u) == ([], b"") and not (g1.unitig_words(u)[1] >> 8) & 1 for u in range(n))
+    assert all(g2.unitig_annotations(u) == g0.unitig_annotations(u) and g2.unitig_words(u) == g0.unitig_words(u)
+               and g2.unitig_colors(u) == g0.unitig_colors(u) for u in range(n))
+    for g in (g0, g1, g2):
+        g.close()
+    if refseams.available():
+        want = _dump_lines(fa, rt, 31, tmp, "orig")
+        assert _dump_lines(fa, redone, 31, tmp, "redone") == want
+        assert _dump_lines(fa, stripped, 31, tmp, "stripped") != want
+    if os.path.exists(REF_CLI):
+        reads = os.path.join(tmp, "r.fastq")
+        _head_fastq(os.path.join(d, "reads.fastq.gz"), reads, 1000)   # all 26 reads
+        o = os.path.join(tmp, "ref_on_redone")
+        subprocess.check_call([REF_CLI, "correct", "-1", "-c", "4", "-g", fa, "-d", redone, "-l", reads, "-o", o], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert open(o + ".2.fastq", "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass1.fastq.gz"))
+
+
+def test_cli_annotate_rewrites_index_the_reference_accepts(sim_cli, sim_lib, tmp_path):
+    _check_annotate_cli(sim_cli, str(tmp_path), sim_lib)
+
+
+@pytest.mark.gpu
+def test_cli_annotate_cuda_rewrites_index_the_reference_accepts(tmp_path):
+    _check_annotate_cli(GPU_CLI, str(tmp_path), None)
