@@ -333,6 +333,23 @@ int rtk_fix_snps_batch(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const
  * [5] unitigs with candidates, [6] local traversals started, [7] annotation kernel ns, [8] unitigs re-run with the large arena. */
 int rtk_detect_snps(rtk_ctx* ctx, const rtk_opt* opt, uint64_t** amb_off, uint32_t** amb_ids, uint64_t* stats);
 int rtk_detect_short_cycles(rtk_ctx* ctx, const rtk_opt* opt, uint8_t** is_cycle, uint64_t** cyc_off, char** cyc_pool, uint64_t* stats);
+/* ---- colouring a graph with long reads: the long_read_correct branch of addCoverage (src/Graph.hpp, body src/Graph.cpp:1561-3366) as
+ * run by `Ratatosk index -2` on the k2 graph with the pass-1 corrected reads (src/Ratatosk.cpp:1213-1221).  ctx holds the graph (no
+ * colours needed: rtk_graph_load with rtsk_path NULL).  Reads shorter than min_len (Correct_Opt::min_len_2nd_pass, 3000) or k are
+ * skipped, bases whose quality is below getQual(min_conf) (Correct_Opt::min_confidence_2nd_pass, 0.0 -> every base pass 1 left at
+ * '!') are masked, reads of the same name (name_pool / name_off, optional) share an id.  K1 exact sweep of all reads + per-unitig
+ * aggregation + one warp per unitig for the edge flags.  Out, per unitig u (library-allocated, rtk_free): kmcov[u] =
+ * UnitigData::kmCov_cardBranches (unphased coverage in bits 31..61, isBranching in bit 63), shared[u] bits 0..7 = the edge flags
+ * (UnitigData::shared_pids), colours col_ids[col_off[u], col_off[u+1]) ascending; read_id (optional) = the id each input read
+ * received (0xFFFFFFFF: none).  The reference deals the ids in an order that depends on thread timing (src/Graph.cpp:1655-1663), so
+ * its colouring is reproduced up to a relabelling of the ids.  Fails when the estimated haplotype coverage reaches 10 (the
+ * reference then subsamples at random, :2312).  stats (optional, 10 x u64): [0..3] K1 as above, [4] (unitig, read) pairs,
+ * [5] ids dealt, [7] flag kernel ns, [8] estimated haplotype coverage. */
+int rtk_color_long_reads(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
+                         const char* qual_pool, const uint64_t* qual_off, const char* name_pool, const uint64_t* name_off,
+                         uint32_t min_len, double min_conf, uint64_t** kmcov, uint64_t** shared, uint64_t** col_off, uint32_t** col_ids,
+                         uint32_t** read_id, uint64_t* stats);
+
 /* Index file with these annotations: a copy of rtsk_in (the .rtsk g was loaded from) in which, per unitig, the short-cycle flag, the
  * ambiguity ids and the compacted-cycles blob are replaced by the given ones and everything else is kept byte for byte - the part of
  * writeGraphData (src/Graph.cpp:786-801, UnitigData::write src/UnitigData.hpp:493-517) that detectSNPs / detectShortCycles own.  The

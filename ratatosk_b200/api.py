@@ -133,6 +133,10 @@ def load_library(path=None):
                                   C.POINTER(C.c_uint64)]
     L.rtk_detect_short_cycles.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.POINTER(C.POINTER(C.c_uint8)),
                                           C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    u64pp, u32pp = C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.POINTER(C.c_uint32))
+    L.rtk_color_long_reads.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.c_char_p,
+                                       C.POINTER(C.c_uint64), C.c_char_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_double,
+                                       u64pp, u64pp, u64pp, u32pp, u32pp, C.POINTER(C.c_uint64)]
     L.rtk_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.rtk_ctx_destroy.argtypes = [C.c_void_p]
     L.rtk_graph_upload.argtypes = [C.c_void_p, C.c_void_p]
@@ -439,6 +443,31 @@ class Context:
         buf = C.string_at(out, int(off[-1]))
         self.L.rtk_free(out)
         return [buf[int(off[i]):int(off[i + 1])].decode("latin1") for i in range(len(reads))], nf.value
+
+    def color_long_reads(self, reads, quals=None, names=None, opt=None, min_len=3000, min_conf=0.0, stats=None):
+        """addCoverage for long reads (`Ratatosk index -2`) -> (kmcov u64[n], shared u64[n], col_off u64[n+1], col_ids u32[], read ids)"""
+        u64p = C.POINTER(C.c_uint64)
+        sp, so = pack_reads(reads)
+        qp, qo = pack_reads(quals) if quals is not None else (None, None)
+        np_, no = pack_reads(names) if names is not None else (None, None)
+        pk, ps, po, pi, pr = u64p(), u64p(), u64p(), C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)()
+        st = (C.c_uint64 * 10)()
+        rc = self.L.rtk_color_long_reads(self.h, C.byref(opt) if opt else None, len(reads), sp, so.ctypes.data_as(u64p),
+                                         qp, qo.ctypes.data_as(u64p) if qo is not None else None,
+                                         np_, no.ctypes.data_as(u64p) if no is not None else None, min_len, min_conf,
+                                         C.byref(pk), C.byref(ps), C.byref(po), C.byref(pi), C.byref(pr), st)
+        if stats is not None:
+            stats[:] = list(st)
+        _check(self.L, rc)
+        n = self.graph.info()["n_unitigs"]
+        kmcov = np.ctypeslib.as_array(pk, shape=(n + 1,))[:n].copy()
+        shared = np.ctypeslib.as_array(ps, shape=(n + 1,))[:n].copy()
+        off = np.ctypeslib.as_array(po, shape=(n + 1,)).copy()
+        ids = np.ctypeslib.as_array(pi, shape=(int(off[-1]) + 1,))[:int(off[-1])].copy()
+        rid = np.ctypeslib.as_array(pr, shape=(len(reads) + 1,))[:len(reads)].copy()
+        for p in (pk, ps, po, pi, pr):
+            self.L.rtk_free(C.cast(p, C.c_void_p))
+        return kmcov, shared, off, ids, rid
 
     def detect_snps(self, opt=None, stats=None):
         """detectSNPs (src/Graph.cpp:484) on the resident graph -> per unitig the sorted ambiguity ids (pos << 4 | base set)"""

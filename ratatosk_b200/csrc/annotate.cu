@@ -129,4 +129,42 @@ void snp_run(rtk_ctx* c, uint32_t min_cov, const std::vector<rtk_snp_job>& jobs,
     if (n_walks) *n_walks += walks;
 }
 
+void edge_flags_run(rtk_ctx* c, uint32_t min_cov, const uint64_t* col_off, const uint32_t* col_ids, uint64_t* kmcov, uint64_t* shared,
+                    float* kernel_ms) {
+    if (kernel_ms) *kernel_ms = 0.f;
+    const uint32_t n = (uint32_t)c->hdr.n_unitigs;
+    if (!n) return;
+    DeviceBind bind(c);
+    cudaStream_t st = c->stream;
+    const uint64_t n_ids = col_off[n];
+    // packed: [col_off][kmcov][shared][col_ids]
+    const uint64_t b_off = (uint64_t)(n + 1) * 8, b_w = (uint64_t)n * 8, b_ids = (n_ids * 4 + 15) & ~15ull;
+    const uint64_t o_km = b_off, o_sh = o_km + b_w, o_ids = o_sh + b_w, bytes = o_ids + b_ids + 16;
+    PinBuf& H = c->h_fs;
+    H.reserve(bytes);
+    char* h = H.as<char>();
+    memcpy(h, col_off, b_off);
+    memcpy(h + o_km, kmcov, b_w);
+    memcpy(h + o_sh, shared, b_w);
+    if (n_ids) memcpy(h + o_ids, col_ids, n_ids * 4);
+    DevBuf& D = c->d_aux[0];
+    D.reserve(bytes);
+    char* d = D.as<char>();
+    RTK_CUDA(counted_memcpy_async(d, h, bytes - 16, cudaMemcpyHostToDevice, st));
+    rtk_edge_params p;
+    p.adj = c->dview.adj; p.col_off = (const uint64_t*)d; p.col_ids = (const uint32_t*)(d + o_ids); p.kmcov = (uint64_t*)(d + o_km);
+    p.shared = (uint64_t*)(d + o_sh); p.n = n; p.min_cov = min_cov;
+    const uint32_t grid = an_grid(c, n, 0);
+    RTK_CUDA(cudaEventRecord(c->ev0, st));
+    ++g_launches;
+    rtk_edge_flags_kernel<<<grid, RTK_AN_WARPS * 32, 0, st>>>(p);
+    RTK_CUDA(cudaGetLastError());
+    RTK_CUDA(cudaEventRecord(c->ev1, st));
+    PinnedD2H back(c, st);
+    back.copy(0, kmcov, d + o_km, b_w);
+    back.copy(1, shared, d + o_sh, b_w);
+    back.sync();
+    if (kernel_ms) RTK_CUDA(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
+}
+
 }  // namespace rtk

@@ -86,6 +86,15 @@ struct rtk_snp_params {
     unsigned long long* n_walks;    // isValidSNPcandidate calls (statistics)
 };
 
+struct rtk_edge_params {
+    const uint32_t* adj;
+    const uint64_t* col_off;    // n + 1
+    const uint32_t* col_ids;    // sorted per unitig
+    uint64_t* kmcov;            // in / out: bit 63 = isBranching
+    uint64_t* shared;           // in / out: bits 0..7 = edge flags
+    uint32_t n, min_cov;
+};
+
 #if defined(__CUDACC__) || defined(__CUDACC_SIM__)
 
 struct rtk_colset {
@@ -355,6 +364,40 @@ __global__ void __launch_bounds__(RTK_AN_WARPS * 32) rtk_snp_kernel(const rtk_sn
         if (lane == 0) p.status[job] = overflow ? 2 : 0;
     }
     if (lane == 0 && walks && p.n_walks) atomicAdd(p.n_walks, walks);
+}
+
+// ------------------------------------------------------------------------------------------------ edge flags (addCoverage)
+// postProcessUnitigs of addCoverage (src/Graph.cpp:1986-2023): a unitig is branching when it has more than one predecessor or
+// successor; the 1-bit flag of an edge (forward successors in bits 4..7, successors of the reversed unitig in bits 0..3, base
+// index A1 C2 G4 T8 = last base of the neighbour's mapped head) is set when the two unitigs share >= min_cov read ids.
+// One warp per unitig, the colours given as one sorted list per unitig (CSR).
+__global__ void __launch_bounds__(RTK_AN_WARPS * 32) rtk_edge_flags_kernel(const rtk_edge_params p) {
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * RTK_AN_WARPS + w, nw = gridDim.x * RTK_AN_WARPS;
+    for (uint32_t u = gw; u < p.n; u += nw) {
+        const uint32_t* X = p.col_ids + p.col_off[u];
+        const uint32_t nx = (uint32_t)(p.col_off[u + 1] - p.col_off[u]);
+        uint32_t flags = 0, n_fw = 0, n_bw = 0;
+        for (uint32_t b = 0; b < 4; ++b) {
+            for (uint32_t dir = 0; dir < 2; ++dir) {
+                // dir 0: successor of the forward unitig through base b; dir 1: successor of the reversed unitig through base b
+                const uint32_t slot = dir ? p.adj[8 * (uint64_t)u + 4 + (3 - b)] : p.adj[8 * (uint64_t)u + b];
+                if (slot == RTK_NONE32) continue;
+                if (dir) ++n_bw; else ++n_fw;
+                const uint32_t v = slot & 0x7fffffffu;
+                const uint32_t* Y = p.col_ids + p.col_off[v];
+                const uint32_t ny = (uint32_t)(p.col_off[v + 1] - p.col_off[v]);
+                uint32_t cnt;
+                if (v == u) cnt = nx;
+                else cnt = rtk_warp_intersect(X, nx, Y, ny, p.min_cov, lane);
+                if (cnt >= p.min_cov) flags |= dir ? (1u << b) : ((1u << b) << 4);
+            }
+        }
+        if (lane == 0) {
+            p.shared[u] = (p.shared[u] & ~0xffULL) | flags;
+            p.kmcov[u] = (p.kmcov[u] & 0x7fffffffffffffffULL) | ((uint64_t)((n_fw > 1) || (n_bw > 1)) << 63);
+        }
+    }
 }
 
 #endif  // __CUDACC__ || __CUDACC_SIM__

@@ -298,6 +298,10 @@ void snp_run(rtk_ctx* c, uint32_t min_cov, const std::vector<rtk_snp_job>& jobs,
              std::vector<uint8_t>& fin, uint32_t n_bslots, uint32_t arena_cap, std::vector<uint8_t>& status, uint64_t* n_walks,
              float* kernel_ms);
 
+// addCoverage's postProcessUnitigs: branching bit (kmcov bit 63) and edge flags (shared bits 0..7) from per-unitig colour lists
+void edge_flags_run(rtk_ctx* c, uint32_t min_cov, const uint64_t* col_off, const uint32_t* col_ids, uint64_t* kmcov, uint64_t* shared,
+                    float* kernel_ms);
+
 // per-read correction of a batch (correct.cpp)
 void correct_batch_host(rtk_ctx* ctx, const rtk_opt& opt, int pass, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
                         const char* qual_pool, const uint64_t* qual_off, std::vector<std::string>& out_seq, std::vector<std::string>& out_qual,

@@ -57,4 +57,16 @@ void snp_run(rtk_ctx* c, uint32_t min_cov, const std::vector<rtk_snp_job>& jobs,
     if (n_walks) *n_walks += walks;
 }
 
+void edge_flags_run(rtk_ctx* c, uint32_t min_cov, const uint64_t* col_off, const uint32_t* col_ids, uint64_t* kmcov, uint64_t* shared,
+                    float* kernel_ms) {
+    if (kernel_ms) *kernel_ms = 0.f;
+    const rtk_graph_view& g = c->host_graph->view;
+    const uint32_t n = (uint32_t)g.n_unitigs;
+    if (!n) return;
+    rtk_edge_params p;
+    p.adj = g.adj; p.col_off = col_off; p.col_ids = col_ids; p.kmcov = kmcov; p.shared = shared; p.n = n; p.min_cov = min_cov;
+    const unsigned grid = std::min<uint32_t>((n + RTK_AN_WARPS - 1) / RTK_AN_WARPS, 5);
+    sim_launch(grid, RTK_AN_WARPS * 32, [&] { rtk_edge_flags_kernel(p); });
+}
+
 }  // namespace rtk
