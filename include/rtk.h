@@ -350,6 +350,15 @@ int rtk_color_long_reads(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, con
                          uint32_t min_len, double min_conf, uint64_t** kmcov, uint64_t** shared, uint64_t** col_off, uint32_t** col_ids,
                          uint32_t** read_id, uint64_t* stats);
 
+/* The graph of g with the words and colours rtk_color_long_reads returned (a new host graph; no annotations yet): upload it and run
+ * rtk_detect_snps / rtk_detect_short_cycles on it, like the reference runs them on the graph addCoverage has just coloured. */
+int rtk_graph_recolor(const rtk_host_graph* g, const uint64_t* kmcov, const uint64_t* shared, const uint64_t* col_off,
+                      const uint32_t* col_ids, rtk_host_graph** out);
+/* writeGraphData (src/Graph.cpp:786-801) for a whole graph: head k-mer + UnitigData::write (src/UnitigData.hpp:493-517) per unitig, from
+ * the words and colours of g and the given annotations; the file `Ratatosk correct -d` reads.  Written atomically. */
+int rtk_rtsk_write(const rtk_host_graph* g, const char* path, const uint64_t* amb_off, const uint32_t* amb_ids, const uint8_t* is_cycle,
+                   const uint64_t* cyc_off, const char* cyc_pool);
+
 /* Index file with these annotations: a copy of rtsk_in (the .rtsk g was loaded from) in which, per unitig, the short-cycle flag, the
  * ambiguity ids and the compacted-cycles blob are replaced by the given ones and everything else is kept byte for byte - the part of
  * writeGraphData (src/Graph.cpp:786-801, UnitigData::write src/UnitigData.hpp:493-517) that detectSNPs / detectShortCycles own.  The

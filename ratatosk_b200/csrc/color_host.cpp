@@ -258,4 +258,24 @@ int rtk_color_long_reads(rtk_ctx* c, const rtk_opt* opt, uint32_t n_reads, const
     });
 }
 
+int rtk_graph_recolor(const rtk_host_graph* g, const uint64_t* kmcov, const uint64_t* shared, const uint64_t* col_off, const uint32_t* col_ids,
+                      rtk_host_graph** out) {
+    return guarded([&] {
+        if (!g || !kmcov || !shared || !col_off || !col_ids || !out) throw std::invalid_argument("null argument");
+        const HostGraph hg = recolored_graph(g->view, kmcov, shared, col_off, col_ids);
+        rtk_host_graph* r = new rtk_host_graph();
+        r->slab = build_slab(hg);
+        finish_host_graph(r);
+        *out = r;
+    });
+}
+
+int rtk_rtsk_write(const rtk_host_graph* g, const char* path, const uint64_t* amb_off, const uint32_t* amb_ids, const uint8_t* is_cycle,
+                   const uint64_t* cyc_off, const char* cyc_pool) {
+    return guarded([&] {
+        if (!g || !path || !amb_off || !amb_ids || !is_cycle || !cyc_off || !cyc_pool) throw std::invalid_argument("null argument");
+        write_rtsk(g->view, path, amb_off, amb_ids, is_cycle, cyc_off, cyc_pool);
+    });
+}
+
 }  // extern "C"

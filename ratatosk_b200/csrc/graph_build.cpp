@@ -539,4 +539,60 @@ void patch_rtsk_annotations(const rtk_graph_view& g, const std::string& rtsk_in,
     if (rename(tmp_path.c_str(), rtsk_out.c_str()) != 0) { remove(tmp_path.c_str()); throw std::runtime_error("cannot rename to " + rtsk_out); }
 }
 
+
+// The graph of a slab with other per-unitig words and colours (one local set per unitig, no annotations): what addCoverage
+// leaves before detectSNPs / detectShortCycles run.
+HostGraph recolored_graph(const rtk_graph_view& g, const uint64_t* kmcov, const uint64_t* shared, const uint64_t* col_off, const uint32_t* col_ids) {
+    HostGraph hg;
+    hg.k = (int)g.k;
+    const uint64_t n = g.n_unitigs;
+    hg.unitigs.resize(n);
+    hg.kmcov.assign(kmcov, kmcov + n);
+    hg.shared.assign(shared, shared + n);
+    hg.global_ids.assign(n, {}); hg.local_ids.assign(n, {}); hg.amb_ids.assign(n, {}); hg.hap_ids.assign(n, {});
+    hg.cycles.assign(n, {});
+    for (uint64_t u = 0; u < n; ++u) {
+        const uint64_t ub = g.unitig_off[u], len = g.unitig_off[u + 1] - ub;
+        std::string& s = hg.unitigs[u];
+        s.resize(len);
+        for (uint64_t i = 0; i < len; ++i) s[i] = "ACGT"[rtk_pool_base(g.pool, ub + i)];
+        hg.local_ids[u].assign(col_ids + col_off[u], col_ids + col_off[u + 1]);
+    }
+    return hg;
+}
+
+// writeGraphData (src/Graph.cpp:786-801) for a whole graph: per unitig its head k-mer (Kmer::write: MAX_KMER_SIZE = 64 -> two
+// words, first base in the top bits of word 0) and UnitigData::write (src/UnitigData.hpp:493-517) - the words and colours of the
+// slab, the given annotations, no haplotype ids.
+void write_rtsk(const rtk_graph_view& g, const std::string& path, const uint64_t* amb_off, const uint32_t* amb_ids, const uint8_t* is_cycle,
+                const uint64_t* cyc_off, const char* cyc_pool) {
+    std::string out;
+    const uint32_t k = g.k;
+    for (uint64_t u = 0; u < g.n_unitigs; ++u) {
+        uint64_t l[2] = {0, 0};
+        const uint64_t ub = g.unitig_off[u];
+        for (uint32_t i = 0; i < k; ++i) l[i >> 5] |= (uint64_t)rtk_pool_base(g.pool, ub + i) << (62 - 2 * (i & 31));
+        out.append((const char*)l, 16);
+        const uint64_t kmcov = g.kmcov[u] & ~(1ULL << 62);   // the visit mark is scratch
+        const uint64_t shared = (g.shared[u] & 0xffULL) | (is_cycle[u] ? 0x100ULL : 0ULL);
+        out.append((const char*)&kmcov, 8);
+        out.append((const char*)&shared, 8);
+        const uint32_t gs = g.gset_of[u];
+        if (gs == RTK_NONE32) write_pairid(out, nullptr, 0);
+        else write_pairid(out, g.gset_ids + g.gset_off[gs], g.gset_off[gs + 1] - g.gset_off[gs]);
+        write_pairid(out, g.loc_ids + g.loc_off[u], g.loc_off[u + 1] - g.loc_off[u]);
+        write_pairid(out, amb_ids + amb_off[u], amb_off[u + 1] - amb_off[u]);
+        write_pairid(out, nullptr, 0);
+        const uint64_t cl = cyc_off[u + 1] - cyc_off[u];
+        out.append((const char*)&cl, 8);
+        if (cl) out.append(cyc_pool + cyc_off[u], cl);
+    }
+    const std::string tmp_path = path + ".tmp";
+    FILE* f = fopen(tmp_path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot write " + tmp_path);
+    const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    if (fclose(f) != 0 || !ok) { remove(tmp_path.c_str()); throw std::runtime_error("short write to " + tmp_path); }
+    if (rename(tmp_path.c_str(), path.c_str()) != 0) { remove(tmp_path.c_str()); throw std::runtime_error("cannot rename to " + path); }
+}
+
 }  // namespace rtk

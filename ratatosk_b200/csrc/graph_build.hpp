@@ -32,6 +32,9 @@ struct rtk_slab {
 
 HostGraph load_index(const std::string& fasta, const std::string& rtsk, int k);
 rtk_slab build_slab(const HostGraph& hg);
+HostGraph recolored_graph(const rtk_graph_view& g, const uint64_t* kmcov, const uint64_t* shared, const uint64_t* col_off, const uint32_t* col_ids);
+void write_rtsk(const rtk_graph_view& g, const std::string& path, const uint64_t* amb_off, const uint32_t* amb_ids, const uint8_t* is_cycle,
+                const uint64_t* cyc_off, const char* cyc_pool);
 void patch_rtsk_annotations(const rtk_graph_view& g, const std::string& rtsk_in, const std::string& rtsk_out, const uint64_t* amb_off,
                             const uint32_t* amb_ids, const uint8_t* is_cycle, const uint64_t* cyc_off, const char* cyc_pool);
 

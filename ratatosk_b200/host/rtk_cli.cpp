@@ -144,7 +144,9 @@ void usage() {
             "  --cache FILE      flat graph cache (default <rtsk>.k<k>.rtkflat; written on first use, mapped in place afterwards)\n"
             "  --no-cache        always parse the index files, write no cache\n"
             "rtk_correct annotate -g <graph.fasta[.gz]> -d <graph.rtsk> -o <out.rtsk> [-k K] [--min-cov N] [--no-snp] [--first-gpu D] [-v]\n"
-            "  detectSNPs + detectShortCycles of the reference's index build, recomputed on the GPU from the colours of the index\n");
+            "  detectSNPs + detectShortCycles of the reference's index build, recomputed on the GPU from the colours of the index\n"
+            "rtk_correct index2 -g <graph.k2.fasta[.gz]> -l <pass-1 corrected long reads> -o <prefix> [-K k2] [-M f] [-C n] [-Q n] [--min-cov N] [--no-snp] [-v]\n"
+            "  `Ratatosk index -2`: colours the k2 graph with the long reads, adds SNP and short-cycle annotations, writes <prefix>.index.k<k2>.rtsk\n");
 }
 
 int parse(int argc, char** argv, Options& o) {
@@ -371,10 +373,109 @@ int run_annotate(int argc, char** argv) {
     return 0;
 }
 
+// `rtk_correct index2`: `Ratatosk index -2` (src/Ratatosk.cpp:1205-1260) - the k2 graph coloured with the pass-1 corrected long reads
+// (addCoverage, long-read branch), then detectSNPs and detectShortCycles, then <prefix>.index.k<K>.rtsk
+int run_index2(int argc, char** argv) {
+    std::string graph, out;
+    std::vector<std::string> reads;
+    int k = 63, device = 0, min_cov = 2, min_len = 3000, max_qual = 40;
+    double min_conf = 0.0;
+    bool verbose = false, no_snp = false;
+    static struct option lo[] = {{"in-graph", required_argument, 0, 'g'}, {"in-long", required_argument, 0, 'l'}, {"out-long", required_argument, 0, 'o'},
+                                 {"k2", required_argument, 0, 'K'}, {"min-conf-color2", required_argument, 0, 'M'}, {"min-len-color2", required_argument, 0, 'C'},
+                                 {"max-base-qual", required_argument, 0, 'Q'}, {"min-cov", required_argument, 0, 1000}, {"no-snp", no_argument, 0, 1001},
+                                 {"first-gpu", required_argument, 0, 1002}, {"verbose", no_argument, 0, 'v'}, {0, 0, 0, 0}};
+    int c;
+    while ((c = getopt_long(argc - 1, argv + 1, "g:l:o:K:M:C:Q:v", lo, nullptr)) != -1) {
+        switch (c) {
+            case 'g': graph = optarg; break;
+            case 'l': reads.push_back(optarg); break;
+            case 'o': out = optarg; break;
+            case 'K': k = atoi(optarg); break;
+            case 'M': min_conf = atof(optarg); break;
+            case 'C': min_len = atoi(optarg); break;
+            case 'Q': max_qual = atoi(optarg); break;
+            case 'v': verbose = true; break;
+            case 1000: min_cov = atoi(optarg); break;
+            case 1001: no_snp = true; break;
+            case 1002: device = atoi(optarg); break;
+            default: usage(); return 1;
+        }
+    }
+    if (graph.empty() || reads.empty() || out.empty() || min_cov < 1 || min_len < 0 || min_conf < 0.0 || min_conf > 1.0) { usage(); return 1; }
+    const auto t0 = std::chrono::steady_clock::now();
+    auto secs = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    auto die = [&]() { fprintf(stderr, "Ratatosk::Ratatosk(): %s\n", rtk_last_error()); return 1; };
+    if (verbose) printf("Ratatosk::Ratatosk(): Loading graph (2/2).\n");
+    rtk_host_graph *hg = nullptr, *hg2 = nullptr;
+    rtk_ctx *ctx = nullptr, *ctx2 = nullptr;
+    if (rtk_graph_load(graph.c_str(), nullptr, k, &hg) != RTK_OK) return die();
+    if (rtk_ctx_create(device, &ctx) != RTK_OK || rtk_graph_upload(ctx, hg) != RTK_OK) return die();
+    rtk_graph_info gi;
+    rtk_graph_get_info(hg, &gi);
+    // the reads: sequences, qualities and names as three pools
+    std::string seq_pool, qual_pool, name_pool, name, seq, qual;
+    std::vector<uint64_t> seq_off(1, 0), name_off(1, 0);
+    {
+        SeqReader rd(reads);
+        bool has_qual = false, all_qual = true;
+        while (rd.next(name, seq, qual, has_qual)) {
+            if (!has_qual || qual.size() != seq.size()) { all_qual = false; qual.assign(seq.size(), 'I'); }
+            seq_pool += seq; qual_pool += qual; name_pool += name;
+            seq_off.push_back(seq_pool.size()); name_off.push_back(name_pool.size());
+        }
+        if (!rd.error().empty()) { fprintf(stderr, "Ratatosk::Ratatosk(): %s\n", rd.error().c_str()); return 1; }
+        if (!all_qual && verbose) printf("rtk_correct: records without quality string are not masked\n");
+    }
+    const uint32_t n_reads = (uint32_t)(seq_off.size() - 1);
+    rtk_opt ropt;
+    rtk_opt_default(&ropt, 2);
+    ropt.k = (uint32_t)k; ropt.min_cov_vertices = (uint32_t)min_cov; ropt.max_qual = max_qual;
+    if (verbose) printf("Ratatosk::Ratatosk(): Adding colors and coverage to graph (2/2).\n");
+    uint64_t *kmcov = nullptr, *shared = nullptr, *col_off = nullptr, st[10] = {0};
+    uint32_t* col_ids = nullptr;
+    if (rtk_color_long_reads(ctx, &ropt, n_reads, seq_pool.data(), seq_off.data(), qual_pool.data(), seq_off.data(), name_pool.data(), name_off.data(),
+                             (uint32_t)min_len, min_conf, &kmcov, &shared, &col_off, &col_ids, nullptr, st) != RTK_OK) return die();
+    if (rtk_graph_recolor(hg, kmcov, shared, col_off, col_ids, &hg2) != RTK_OK) return die();
+    rtk_ctx_destroy(ctx);
+    rtk_graph_free(hg);
+    if (rtk_ctx_create(device, &ctx2) != RTK_OK || rtk_graph_upload(ctx2, hg2) != RTK_OK) return die();
+    uint64_t *amb_off = nullptr, *cyc_off = nullptr, st2[10] = {0};
+    uint32_t* amb_ids = nullptr;
+    uint8_t* is_cycle = nullptr;
+    char* cyc_pool = nullptr;
+    if (no_snp) {
+        amb_off = (uint64_t*)calloc(gi.n_unitigs + 1, 8);
+        amb_ids = (uint32_t*)calloc(1, 4);
+        if (verbose) printf("Ratatosk::Ratatosk(): SNPs candidate detection is disabled (2/2).\n");
+    } else {
+        if (verbose) printf("Ratatosk::Ratatosk(): Adding SNPs candidates to graph (2/2).\n");
+        if (rtk_detect_snps(ctx2, &ropt, &amb_off, &amb_ids, st2) != RTK_OK) return die();
+    }
+    if (verbose) printf("Ratatosk::Ratatosk(): Adding micro/mini-satellites motif candidates to graph (2/2).\n");
+    if (rtk_detect_short_cycles(ctx2, &ropt, &is_cycle, &cyc_off, &cyc_pool, st2) != RTK_OK) return die();
+    const std::string path = out + ".index.k" + std::to_string(k) + ".rtsk";
+    if (verbose) printf("Ratatosk::Ratatosk(): Writing index to disk (2/2).\n");
+    if (rtk_rtsk_write(hg2, path.c_str(), amb_off, amb_ids, is_cycle, cyc_off, cyc_pool) != RTK_OK) return die();
+    if (verbose) {
+        uint64_t n_cyc = 0;
+        for (uint64_t u = 0; u < gi.n_unitigs; ++u) n_cyc += is_cycle[u];
+        printf("rtk_correct: %llu unitigs coloured by %llu of %u reads (%llu unitig-read pairs), %llu SNP marks, %llu unitigs in short cycles, %.2f s\n",
+               (unsigned long long)gi.n_unitigs, (unsigned long long)st[5], n_reads, (unsigned long long)st[4], (unsigned long long)amb_off[gi.n_unitigs],
+               (unsigned long long)n_cyc, secs());
+    }
+    rtk_free(kmcov); rtk_free(shared); rtk_free(col_off); rtk_free(col_ids);
+    rtk_free(amb_off); rtk_free(amb_ids); rtk_free(is_cycle); rtk_free(cyc_off); rtk_free(cyc_pool);
+    rtk_ctx_destroy(ctx2);
+    rtk_graph_free(hg2);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
     if (argc >= 2 && strcmp(argv[1], "annotate") == 0) return run_annotate(argc, argv);
+    if (argc >= 2 && strcmp(argv[1], "index2") == 0) return run_index2(argc, argv);
     Options o;
     if (parse(argc, argv, o)) return 1;
     const int pass = o.pass2 ? 2 : o.pass1 ? 1 : 0;   // 0: both passes as one pipeline (rtk_correct_two_pass_batch)

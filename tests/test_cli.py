@@ -269,3 +269,62 @@ def test_cli_annotate_rewrites_index_the_reference_accepts(sim_cli, sim_lib, tmp
 @pytest.mark.gpu
 def test_cli_annotate_cuda_rewrites_index_the_reference_accepts(tmp_path):
     _check_annotate_cli(GPU_CLI, str(tmp_path), None)
+
+
+# ---------------------------------------------------------------------------------------------- rtk_correct index2
+def _dump_records(fasta, rtsk, k, tmp, tag):
+    """per unitig sequence -> (kmcov, shared, colour set, ambiguity chars, cycles, branching, short-cycle) as the REFERENCE reads the index"""
+    from refseams import RefGraph
+    g = RefGraph(fasta, rtsk, k)
+    p = os.path.join(tmp, tag + ".dump")
+    g.dump(p)
+    g.close()
+    out = {}
+    for line in open(p):
+        f = line.rstrip("\n").split("\t")
+        ids = set(int(x) for x in (f[4] + f[5]).split(",") if x)
+        out[f[1]] = (int(f[2]), int(f[3]), ids, f[6], f[7], f[8], f[9], f[10])
+    return out
+
+
+def _check_index2_cli(cli, tmp):
+    """`rtk_correct index2` = `Ratatosk index -2` (colour the k2 graph with the pass-1 reads, detectSNPs, detectShortCycles, write the
+    .rtsk).  The REFERENCE reads both files (readGraphData); per unitig everything must agree with the index the reference built from
+    the same inputs - coverage word, flags word (edge flags + short-cycle bit), ambiguity characters, cycles - and the colour sets under
+    one relabelling of the read ids (the reference's own ids depend on thread timing)."""
+    import refseams
+    if not refseams.available():
+        pytest.skip("reference seam library not built")
+    d = os.path.join(GOLDEN, "F2")
+    fa = os.path.join(d, "index.k63.fasta.gz")
+    reads = os.path.join(tmp, "p1.fastq")
+    _head_fastq(os.path.join(d, "corrected_pass1.fastq.gz"), reads, 1000)
+    r = subprocess.run([cli, "index2", "-g", fa, "-l", reads, "-o", os.path.join(tmp, "ours"), "-v"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode(errors="replace")[-2000:]
+    ours = _dump_records(fa, os.path.join(tmp, "ours.index.k63.rtsk"), 63, tmp, "ours")
+    want = _dump_records(fa, os.path.join(d, "index.k63.rtsk"), 63, tmp, "want")
+    assert set(ours) == set(want) and len(want) == 1926
+    assert all(ours[s][:2] == want[s][:2] and ours[s][3:] == want[s][3:] for s in want), [s[:20] for s in want if ours[s][:2] != want[s][:2] or ours[s][3:] != want[s][3:]][:5]
+    assert sum(1 for s in want if want[s][3]) > 50 and sum(1 for s in want if want[s][5]) > 50      # SNP marks and cycles are there
+    m, changed = {}, True
+    while changed:
+        changed = False
+        for s in want:
+            a, b = ours[s][2], want[s][2]
+            assert len(a) == len(b)
+            un = [x for x in a if x not in m]
+            rem = b - set(m[x] for x in a if x in m)
+            if len(un) == 1 and len(rem) == 1:
+                m[un[0]] = next(iter(rem))
+                changed = True
+    assert len(m) == 23 and len(set(m.values())) == 23
+    assert all(set(m[x] for x in ours[s][2]) == want[s][2] for s in want)
+
+
+def test_cli_index2_writes_the_index_the_reference_builds(sim_cli, tmp_path):
+    _check_index2_cli(sim_cli, str(tmp_path))
+
+
+@pytest.mark.gpu
+def test_cli_index2_cuda_writes_the_index_the_reference_builds(tmp_path):
+    _check_index2_cli(GPU_CLI, str(tmp_path))
