@@ -137,6 +137,10 @@ def load_library(path=None):
     L.rtk_color_long_reads.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64), C.c_char_p,
                                        C.POINTER(C.c_uint64), C.c_char_p, C.POINTER(C.c_uint64), C.c_uint32, C.c_double,
                                        u64pp, u64pp, u64pp, u32pp, u32pp, C.POINTER(C.c_uint64)]
+    u64p__, u32p__ = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    L.rtk_graph_recolor.argtypes = [C.c_void_p, u64p__, u64p__, u64p__, u32p__, C.POINTER(C.c_void_p)]
+    L.rtk_rtsk_write.argtypes = [C.c_void_p, C.c_char_p, u64p__, u32p__, C.POINTER(C.c_uint8), u64p__, C.c_char_p]
+    L.rtk_rtsk_write_annotations.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, u64p__, u32p__, C.POINTER(C.c_uint8), u64p__, C.c_char_p]
     L.rtk_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.rtk_ctx_destroy.argtypes = [C.c_void_p]
     L.rtk_graph_upload.argtypes = [C.c_void_p, C.c_void_p]
@@ -220,6 +224,7 @@ class Graph:
 
     def __init__(self, handle, lib=None):
         self.L = load_library(lib)
+        self.lib = lib
         self.h = handle
 
     @classmethod
@@ -285,6 +290,24 @@ class Graph:
         ng, nl = C.c_uint64(), C.c_uint64()
         _check(self.L, self.L.rtk_graph_unitig_colors(self.h, u, C.byref(pg), C.byref(ng), C.byref(pl), C.byref(nl)))
         return [pg[i] for i in range(ng.value)], [pl[i] for i in range(nl.value)]
+
+    def recolor(self, kmcov, shared, col_off, col_ids):
+        """new Graph: same unitigs, the given words and colours (rtk_color_long_reads output), no annotations"""
+        u64p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+        a = [np.ascontiguousarray(kmcov, dtype=np.uint64), np.ascontiguousarray(shared, dtype=np.uint64),
+             np.ascontiguousarray(col_off, dtype=np.uint64), np.ascontiguousarray(np.append(np.asarray(col_ids, dtype=np.uint32), np.uint32(0)))]
+        h = C.c_void_p()
+        _check(self.L, self.L.rtk_graph_recolor(self.h, a[0].ctypes.data_as(u64p), a[1].ctypes.data_as(u64p), a[2].ctypes.data_as(u64p),
+                                                a[3].ctypes.data_as(u32p), C.byref(h)))
+        return Graph(h, self.lib)
+
+    def write_rtsk(self, path, amb_off, amb_ids, is_cycle, cyc_off, cyc_pool):
+        """writeGraphData: the words and colours of this graph + the given annotations -> .rtsk"""
+        u64p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+        a = [np.ascontiguousarray(amb_off, dtype=np.uint64), np.ascontiguousarray(np.append(np.asarray(amb_ids, dtype=np.uint32), np.uint32(0))),
+             np.ascontiguousarray(np.append(np.asarray(is_cycle, dtype=np.uint8), np.uint8(0))), np.ascontiguousarray(cyc_off, dtype=np.uint64)]
+        _check(self.L, self.L.rtk_rtsk_write(self.h, path.encode(), a[0].ctypes.data_as(u64p), a[1].ctypes.data_as(u32p),
+                                             a[2].ctypes.data_as(C.POINTER(C.c_uint8)), a[3].ctypes.data_as(u64p), bytes(cyc_pool) + b"\0"))
 
     def unitig_annotations(self, u):
         """what the index stores for unitig u: (ambiguity ids [(pos << 4) | base set], compacted-cycles blob bytes)"""
