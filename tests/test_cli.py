@@ -328,3 +328,64 @@ def test_cli_index2_writes_the_index_the_reference_builds(sim_cli, tmp_path):
 @pytest.mark.gpu
 def test_cli_index2_cuda_writes_the_index_the_reference_builds(tmp_path):
     _check_index2_cli(GPU_CLI, str(tmp_path))
+
+
+def _mutated_reads(path, seed):
+    """pass-1 reads of F2 made awkward: random '!' qualities (masked bases), lower case, IUPAC codes, lengths around min_len_2nd_pass,
+    a duplicated name, a read without any graph k-mer"""
+    import numpy as np
+    from common import read_fastq
+    rng = np.random.RandomState(seed)
+    recs = read_fastq(os.path.join(GOLDEN, "F2", "corrected_pass1.fastq.gz"))
+    out = []
+    for i, (name, s, q) in enumerate(recs):
+        s, q = list(s), list(q)
+        for j in rng.randint(0, len(s), len(s) // 50):
+            q[j] = "!"
+        for j in rng.randint(0, len(s), 3):
+            s[j] = "RYKMSWN"[int(rng.randint(7))]
+        if i % 3 == 0:
+            s = [c.lower() for c in s]
+        if i % 5 == 1:
+            cut = (2999, 3000, 3001, 200)[(i // 5) % 4]
+            s, q = s[:cut], q[:cut]
+        out.append((name, "".join(s), "".join(q)))
+    out.append((out[2][0], out[7][1], out[7][2]))                       # the name of read 2 again, with other bases
+    out.append(("junk", "ACGT" * 1000, "I" * 4000))
+    with open(path, "w") as f:
+        for name, s, q in out:
+            f.write("@%s\n%s\n+\n%s\n" % (name, s, q))
+
+
+@pytest.mark.parametrize("seed,extra", [(1, []), (2, ["-M", "0.5", "-C", "1000"])])
+def test_cli_index2_matches_reference_cli_on_awkward_reads(seed, extra, sim_cli, tmp_path):
+    """`rtk_correct index2` against a fresh `Ratatosk index -2` run on the same awkward reads (and with -M / -C): per unitig the
+    reference reads the same words, marks and cycles from both files, and the colour sets agree under one relabelling"""
+    import refseams
+    if not (refseams.available() and os.path.exists(REF_CLI)):
+        pytest.skip("reference not built")
+    tmp = str(tmp_path)
+    fa = os.path.join(GOLDEN, "F2", "index.k63.fasta.gz")
+    reads = os.path.join(tmp, "reads.fastq")
+    _mutated_reads(reads, seed)
+    subprocess.check_call([REF_CLI, "index", "-2", "-c", "4", "-g", fa, "-l", reads, "-o", os.path.join(tmp, "ref")] + extra,
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    r = subprocess.run([sim_cli, "index2", "-g", fa, "-l", reads, "-o", os.path.join(tmp, "ours")] + extra, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode(errors="replace")[-2000:]
+    ours = _dump_records(fa, os.path.join(tmp, "ours.index.k63.rtsk"), 63, tmp, "ours")
+    want = _dump_records(fa, os.path.join(tmp, "ref.index.k63.rtsk"), 63, tmp, "want")
+    bad = [s[:24] for s in want if ours[s][:2] != want[s][:2] or ours[s][3:] != want[s][3:] or len(ours[s][2]) != len(want[s][2])]
+    assert not bad, (len(bad), bad[:5])
+    m, changed = {}, True
+    while changed:
+        changed = False
+        for s in want:
+            a, b = ours[s][2], want[s][2]
+            un = [x for x in a if x not in m]
+            rem = b - set(m[x] for x in a if x in m)
+            if len(un) == 1 and len(rem) == 1:
+                m[un[0]] = next(iter(rem))
+                changed = True
+    n_ids = len(set().union(*[want[s][2] for s in want]))
+    assert len(m) == n_ids and len(set(m.values())) == n_ids and n_ids >= 15
+    assert all(set(m[x] for x in ours[s][2]) == want[s][2] for s in want)
