@@ -136,6 +136,7 @@ void usage() {
     fprintf(stderr,
             "rtk_correct correct (-1 | -2) -g <graph.fasta[.gz]> -d <graph.rtsk> -l <long reads> [-L <raw long reads>] -o <prefix>\n"
             "  same options as `Ratatosk correct` from an index: -c -t -m -i -k -K -w -W -r -Q -O -G -v\n"
+            "  -c 1 (default) = the reference's single-thread branch: the 2nd pass runs without phasing; -c N > 1 = with phasing\n"
             "  --gpus N          devices to deal tickets to (default 1)\n"
             "  --first-gpu D     first CUDA device ordinal (default 0)\n"
             "  --ticket-bases B  read bases per library call (default 33554432)\n"
@@ -602,9 +603,18 @@ int main(int argc, char** argv) {
                     for (char& ch : t.seq) ch = (char)toupper((unsigned char)ch);
                     char *ps = nullptr, *pq = nullptr;
                     uint64_t* po = nullptr;
+                    if (o.threads == 1) {
+                        // -c 1 (the reference's default): the single-thread branch of search() has no phasing step - fixSNPs when
+                        // forced (:672), then getSeeds + correctSequence (:674/:676)
+                        rc = RTK_OK;
+                        if (o.force_snp) rc = rtk_fix_snps_batch(ctx[d], &ropt, n, t.seq.data(), t.off.data(), &ps, nullptr);
+                        if (rc == RTK_OK) rc = rtk_correct_batch(ctx[d], &ropt, 2, n, ps ? ps : t.seq.data(), t.off.data(), t.qual.data(), t.off.data(), &cs, &cq, &co, nullptr);
+                        rtk_free(ps);
+                    } else {
                     rc = rtk_phasing_batch(ctx[d], &ropt, n, t.raw.data(), t.raw_off.data(), t.seq.data(), t.off.data(), t.qual.data(), t.off.data(), &ps, &pq, &po);
                     if (rc == RTK_OK) rc = rtk_correct_batch(ctx[d], &ropt, 2, n, ps, po, pq, po, &cs, &cq, &co, nullptr);
                     rtk_free(ps); rtk_free(pq); rtk_free(po);
+                    }
                 }
                 if (rc != RTK_OK) { sh.fail(std::string("Ratatosk::search(): ") + rtk_last_error()); break; }
                 Block b;

@@ -45,7 +45,7 @@ def _run(cli, args):
 def _two_pass(cli, d, tmp, reads, extra1=(), extra2=(), tag="ours"):
     o = os.path.join(tmp, tag)
     _run(cli, ["-1", "-g", os.path.join(d, "index.k31.fasta.gz"), "-d", os.path.join(d, "index.k31.rtsk"), "-l", reads, "-o", o] + list(extra1))
-    _run(cli, ["-2", "-O", "-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk"), "-l", o + ".2.fastq", "-L", reads,
+    _run(cli, ["-2", "-O", "-c", "8", "-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk"), "-l", o + ".2.fastq", "-L", reads,
                "-o", o] + list(extra2))
     return o + ".2.fastq", o + ".fastq"
 
@@ -84,7 +84,7 @@ def test_cli_reads_gzip_and_multiline_input_and_writes_gzip(sim_cli, tmp_path):
     o = str(tmp_path / "w")
     _run(sim_cli, ["-1", "-g", os.path.join(d, "index.k31.fasta.gz"), "-d", os.path.join(d, "index.k31.rtsk"), "-l", wrapped, "-o", o])
     assert open(o + ".2.fastq", "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass1.fastq.gz"), 4)
-    _run(sim_cli, ["-2", "-G", "-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk"), "-l", o + ".2.fastq", "-L", wrapped,
+    _run(sim_cli, ["-2", "-G", "-c", "8", "-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk"), "-l", o + ".2.fastq", "-L", wrapped,
                    "-o", o, "--ticket-bases", "10000"])
     assert gzip.open(o + ".fastq.gz", "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass2.fastq.gz"), 4)
 
@@ -188,7 +188,7 @@ def test_cli_cuda_force_snp_correction_matches_reference_cli(tmp_path):
     open(reads, "wb").write(gzip.open(os.path.join(d, "reads.fastq.gz"), "rb").read())
     open(p1, "wb").write(gzip.open(os.path.join(d, "corrected_pass1.fastq.gz"), "rb").read())
     o = str(tmp_path / "o")
-    _run(GPU_CLI, ["-2", "--force-correct-snp", "-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk"), "-l", p1, "-L", reads, "-o", o])
+    _run(GPU_CLI, ["-2", "--force-correct-snp", "-c", "8", "-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk"), "-l", p1, "-L", reads, "-o", o])
     assert open(o + ".fastq", "rb").read() == _golden_bytes(os.path.join(d, "corrected_pass2_forcesnp.fastq.gz"))
 
 
@@ -389,3 +389,27 @@ def test_cli_index2_matches_reference_cli_on_awkward_reads(seed, extra, sim_cli,
     n_ids = len(set().union(*[want[s][2] for s in want]))
     assert len(m) == n_ids and len(set(m.values())) == n_ids and n_ids >= 15
     assert all(set(m[x] for x in ours[s][2]) == want[s][2] for s in want)
+
+
+def test_cli_single_thread_branch_has_no_phasing(sim_cli, tmp_path):
+    """`-c 1` (the reference's default): the single-thread branch of search() (src/Ratatosk.cpp:660-703) corrects pass-2 reads
+    without phasing(); files equal the reference CLI's `correct -2 -c 1` golden, and with --force-correct-snp a fresh reference run"""
+    d = os.path.join(GOLDEN, "F1")
+    tmp = str(tmp_path)
+    p1, raw = os.path.join(tmp, "p1.fastq"), os.path.join(tmp, "raw.fastq")
+    _head_fastq(os.path.join(d, "corrected_pass1.fastq.gz"), p1, 12)
+    _head_fastq(os.path.join(d, "reads.fastq.gz"), raw, 12)
+    idx = ["-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk")]
+    _run(sim_cli, ["-2", "-c", "1"] + idx + ["-l", p1, "-L", raw, "-o", os.path.join(tmp, "st")])
+    got = open(os.path.join(tmp, "st.fastq"), "rb").read()
+    assert got == _golden_bytes(os.path.join(d, "corrected_pass2_nophasing.fastq.gz"), 12)
+    assert got != _golden_bytes(os.path.join(d, "corrected_pass2.fastq.gz"), 12)          # phasing changes these reads
+    if os.path.exists(REF_CLI):
+        d2 = os.path.join(GOLDEN, "F2")
+        _head_fastq(os.path.join(d2, "corrected_pass1.fastq.gz"), p1, 8)
+        _head_fastq(os.path.join(d2, "reads.fastq.gz"), raw, 8)
+        idx2 = ["-g", os.path.join(d2, "index.k63.fasta.gz"), "-d", os.path.join(d2, "index.k63.rtsk")]
+        args = ["-2", "-c", "1", "--force-correct-snp"] + idx2 + ["-l", p1, "-L", raw]
+        _run(sim_cli, args + ["-o", os.path.join(tmp, "fs")])
+        subprocess.check_call([REF_CLI, "correct"] + args + ["-o", os.path.join(tmp, "ref_fs")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert open(os.path.join(tmp, "fs.fastq"), "rb").read() == open(os.path.join(tmp, "ref_fs.fastq"), "rb").read()
