@@ -164,33 +164,54 @@ void detect_snps_host(rtk_ctx* ctx, const rtk_opt* opt, std::vector<std::vector<
             }
         });
 
-        // jobs: slots = distinct positions, verdict slots = distinct candidate unitigs
+        // jobs: slots = distinct positions, verdict slots = distinct candidate unitigs (both numbered in order of first appearance);
+        // built per unitig in parallel, laid out by a prefix sum
+        struct JobTmp { std::vector<uint32_t> xs, bs; std::vector<rtk_snp_cand> cs; };
+        std::vector<JobTmp> tmp(nr);
+        parallel_for(nr, [&](size_t rb, size_t re) {
+            std::unordered_map<uint32_t, uint32_t> slot_of, bslot_of;
+            for (size_t r = rb; r < re; ++r) {
+                if (cand[r].empty()) continue;
+                JobTmp& T = tmp[r];
+                slot_of.clear(); bslot_of.clear();
+                T.cs.reserve(cand[r].size());
+                for (const Cand& c : cand[r]) {
+                    const auto it = slot_of.emplace(c.x, (uint32_t)T.xs.size());
+                    if (it.second) T.xs.push_back(c.x);
+                    const auto ib = bslot_of.emplace(c.b & 0x7fffffffu, (uint32_t)T.bs.size());
+                    if (ib.second) T.bs.push_back(c.b & 0x7fffffffu);
+                    T.cs.push_back(rtk_snp_cand{it.first->second, c.b, ib.first->second, c.alt});
+                }
+            }
+        });
         std::vector<rtk_snp_job> jobs;
-        std::vector<rtk_snp_cand> cands;
-        std::vector<uint8_t> fin;
-        std::vector<uint32_t> job_read, slot_pos, job_slot0;
+        std::vector<uint32_t> job_read, job_slot0;
         uint32_t n_bslots = 0;
+        uint64_t n_cands = 0, n_slots = 0;
         for (uint32_t r = 0; r < nr; ++r) {
             if (cand[r].empty()) continue;
             rtk_snp_job J;
-            J.unitig = ids[r]; J.cand_off = (uint32_t)cands.size(); J.n_cand = (uint32_t)cand[r].size(); J.bslot_off = n_bslots;
-            std::unordered_map<uint32_t, uint32_t> slot_of, bslot_of;
-            job_slot0.push_back((uint32_t)fin.size());
-            const char* s = pool.data() + off[r];
-            for (const Cand& c : cand[r]) {
-                auto it = slot_of.find(c.x);
-                if (it == slot_of.end()) {
-                    it = slot_of.emplace(c.x, (uint32_t)fin.size()).first;
-                    fin.push_back((uint8_t)(1u << rtk_base_code(s[c.x])));
-                    slot_pos.push_back(c.x);
-                }
-                auto ib = bslot_of.emplace(c.b & 0x7fffffffu, (uint32_t)bslot_of.size()).first;
-                cands.push_back(rtk_snp_cand{it->second, c.b, ib->second, c.alt});
-            }
-            n_bslots += (uint32_t)bslot_of.size();
+            J.unitig = ids[r]; J.cand_off = (uint32_t)n_cands; J.n_cand = (uint32_t)tmp[r].cs.size(); J.bslot_off = n_bslots;
+            job_slot0.push_back((uint32_t)n_slots);
+            n_cands += tmp[r].cs.size(); n_slots += tmp[r].xs.size(); n_bslots += (uint32_t)tmp[r].bs.size();
             jobs.push_back(J);
             job_read.push_back(r);
         }
+        if (n_cands >= 0xFFFFFFFFull || n_slots >= 0xFFFFFFFFull) throw std::runtime_error("detectSNPs: batch too large");
+        std::vector<rtk_snp_cand> cands(n_cands);
+        std::vector<uint8_t> fin(n_slots);
+        std::vector<uint32_t> slot_pos(n_slots);
+        parallel_for(jobs.size(), [&](size_t jb, size_t je) {
+            for (size_t j = jb; j < je; ++j) {
+                const uint32_t r = job_read[j], s0 = job_slot0[j];
+                const JobTmp& T = tmp[r];
+                const char* s = pool.data() + off[r];
+                for (size_t i = 0; i < T.xs.size(); ++i) { fin[s0 + i] = (uint8_t)(1u << rtk_base_code(s[T.xs[i]])); slot_pos[s0 + i] = T.xs[i]; }
+                rtk_snp_cand* dst = cands.data() + jobs[j].cand_off;
+                for (size_t i = 0; i < T.cs.size(); ++i) { dst[i] = T.cs[i]; dst[i].slot += s0; }
+            }
+        });
+        tmp.clear(); tmp.shrink_to_fit();
         job_slot0.push_back((uint32_t)fin.size());
         if (stats) { stats[4] += cands.size(); stats[5] += jobs.size(); }
         if (jobs.empty()) continue;
@@ -237,12 +258,14 @@ void detect_snps_host(rtk_ctx* ctx, const rtk_opt* opt, std::vector<std::vector<
             }
         }
         if (stats) { stats[6] += walks; stats[7] += (uint64_t)(ms * 1e6); stats[8] += redo.size(); }
-        for (uint32_t j = 0; j < jobs.size(); ++j) {
-            std::vector<uint32_t>& a = amb[jobs[j].unitig];
-            for (uint32_t sl = job_slot0[j]; sl < job_slot0[j + 1]; ++sl)
-                if (fin[sl] & (fin[sl] - 1)) a.push_back((slot_pos[sl] << 4) | fin[sl]);
-            std::sort(a.begin(), a.end());
-        }
+        parallel_for(jobs.size(), [&](size_t jb, size_t je) {
+            for (size_t j = jb; j < je; ++j) {
+                std::vector<uint32_t>& a = amb[jobs[j].unitig];
+                for (uint32_t sl = job_slot0[j]; sl < job_slot0[j + 1]; ++sl)
+                    if (fin[sl] & (fin[sl] - 1)) a.push_back((slot_pos[sl] << 4) | fin[sl]);
+                std::sort(a.begin(), a.end());
+            }
+        });
     }
 }
 
