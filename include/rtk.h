@@ -365,6 +365,13 @@ int rtk_rtsk_write(const rtk_host_graph* g, const char* path, const uint64_t* am
  * reference reads the result (readGraphData).  Written atomically (temporary file + rename); rtsk_out may equal rtsk_in. */
 int rtk_rtsk_write_annotations(const rtk_host_graph* g, const char* rtsk_in, const char* rtsk_out, const uint64_t* amb_off,
                                const uint32_t* amb_ids, const uint8_t* is_cycle, const uint64_t* cyc_off, const char* cyc_pool);
+/* The same for the unitigs [first_unitig, first_unitig + n_unitigs) only (clamped to the graph): unitigs are independent, so the
+ * ranks of a multi-GPU job, each holding a replica of the graph, take one range each and no collective is needed; the outputs
+ * still span the whole graph (empty outside the range), so partial results merge by concatenating each unitig's list. */
+int rtk_detect_snps_range(rtk_ctx* ctx, const rtk_opt* opt, uint64_t first_unitig, uint64_t n_unitigs, uint64_t** amb_off,
+                          uint32_t** amb_ids, uint64_t* stats);
+int rtk_detect_short_cycles_range(rtk_ctx* ctx, const rtk_opt* opt, uint64_t first_unitig, uint64_t n_unitigs, uint8_t** is_cycle,
+                                  uint64_t** cyc_off, char** cyc_pool, uint64_t* stats);
 /* what the loaded index stores for a unitig (host slab): its ambiguity ids and its compacted-cycles blob */
 int rtk_graph_unitig_annotations(const rtk_host_graph* g, uint32_t unitig, const uint32_t** amb_ids, uint64_t* n_amb,
                                  const char** cyc, uint64_t* cyc_bytes);

@@ -141,6 +141,10 @@ def load_library(path=None):
     L.rtk_graph_recolor.argtypes = [C.c_void_p, u64p__, u64p__, u64p__, u32p__, C.POINTER(C.c_void_p)]
     L.rtk_rtsk_write.argtypes = [C.c_void_p, C.c_char_p, u64p__, u32p__, C.POINTER(C.c_uint8), u64p__, C.c_char_p]
     L.rtk_rtsk_write_annotations.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, u64p__, u32p__, C.POINTER(C.c_uint8), u64p__, C.c_char_p]
+    L.rtk_detect_snps_range.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_uint64, C.c_uint64, C.POINTER(C.POINTER(C.c_uint64)),
+                                        C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]
+    L.rtk_detect_short_cycles_range.argtypes = [C.c_void_p, C.POINTER(RtkOpt), C.c_uint64, C.c_uint64, C.POINTER(C.POINTER(C.c_uint8)),
+                                                C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.rtk_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     L.rtk_ctx_destroy.argtypes = [C.c_void_p]
     L.rtk_graph_upload.argtypes = [C.c_void_p, C.c_void_p]
@@ -492,11 +496,13 @@ class Context:
             self.L.rtk_free(C.cast(p, C.c_void_p))
         return kmcov, shared, off, ids, rid
 
-    def detect_snps(self, opt=None, stats=None):
-        """detectSNPs (src/Graph.cpp:484) on the resident graph -> per unitig the sorted ambiguity ids (pos << 4 | base set)"""
+    def detect_snps(self, opt=None, stats=None, first=0, count=None):
+        """detectSNPs (src/Graph.cpp:484) on the resident graph -> per unitig the sorted ambiguity ids (pos << 4 | base set);
+        first / count: only that range of unitigs (the share of one rank)"""
         po, pi = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint32)()
         st = (C.c_uint64 * 10)()
-        _check(self.L, self.L.rtk_detect_snps(self.h, C.byref(opt) if opt else None, C.byref(po), C.byref(pi), st))
+        _check(self.L, self.L.rtk_detect_snps_range(self.h, C.byref(opt) if opt else None, first, (1 << 64) - 1 if count is None else count,
+                                                    C.byref(po), C.byref(pi), st))
         n = self.graph.info()["n_unitigs"]
         off = np.ctypeslib.as_array(po, shape=(n + 1,)).copy()
         ids = np.ctypeslib.as_array(pi, shape=(int(off[-1]) + 1,))[:int(off[-1])].copy()
@@ -505,11 +511,12 @@ class Context:
             stats[:] = list(st)
         return off, ids
 
-    def detect_short_cycles(self, opt=None, stats=None):
+    def detect_short_cycles(self, opt=None, stats=None, first=0, count=None):
         """detectShortCycles (src/Graph.cpp:4660) on the resident graph -> (is_cycle u8[n], blob offsets u64[n+1], blob bytes)"""
         pf, po, pp = C.POINTER(C.c_uint8)(), C.POINTER(C.c_uint64)(), C.c_void_p()
         st = (C.c_uint64 * 10)()
-        _check(self.L, self.L.rtk_detect_short_cycles(self.h, C.byref(opt) if opt else None, C.byref(pf), C.byref(po), C.byref(pp), st))
+        _check(self.L, self.L.rtk_detect_short_cycles_range(self.h, C.byref(opt) if opt else None, first, (1 << 64) - 1 if count is None else count,
+                                                            C.byref(pf), C.byref(po), C.byref(pp), st))
         n = self.graph.info()["n_unitigs"]
         flags = np.ctypeslib.as_array(pf, shape=(n + 1,))[:n].copy()
         off = np.ctypeslib.as_array(po, shape=(n + 1,)).copy()

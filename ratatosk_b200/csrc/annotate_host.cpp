@@ -64,7 +64,7 @@ void gather_cycles(const std::vector<uint32_t>& rec, const std::vector<uint8_t>&
 
 }  // namespace
 
-void detect_short_cycles_host(rtk_ctx* ctx, const rtk_opt* opt, CycleOut& out, uint64_t* stats) {
+void detect_short_cycles_host(rtk_ctx* ctx, const rtk_opt* opt, CycleOut& out, uint64_t* stats, uint64_t range_first = 0, uint64_t range_n = ~0ULL) {
     if (!ctx->has_graph) throw std::invalid_argument("no graph uploaded to this context");
     const uint64_t n = ctx->hdr.n_unitigs;
     if (ctx->hdr.k > 64) throw std::invalid_argument("detectShortCycles: k > 64");
@@ -74,8 +74,9 @@ void detect_short_cycles_host(rtk_ctx* ctx, const rtk_opt* opt, CycleOut& out, u
     std::vector<uint32_t> redo;
     const uint64_t chunk = 1u << 22;
     float ms_total = 0.f;
-    for (uint64_t first = 0; first < n; first += chunk) {
-        const uint32_t m = (uint32_t)std::min<uint64_t>(chunk, n - first);
+    const uint64_t range_end = (range_first >= n) ? range_first : ((range_n > n - range_first) ? n : range_first + range_n);   // [range_first, range_end) of the unitigs
+    for (uint64_t first = range_first; first < range_end; first += chunk) {
+        const uint32_t m = (uint32_t)std::min<uint64_t>(chunk, range_end - first);
         std::vector<uint8_t> status;
         std::vector<uint32_t> rec;
         float ms = 0.f;
@@ -102,7 +103,7 @@ void detect_short_cycles_host(rtk_ctx* ctx, const rtk_opt* opt, CycleOut& out, u
     if (stats) { stats[7] += (uint64_t)(ms_total * 1e6); stats[8] += redo.size(); }
 }
 
-void detect_snps_host(rtk_ctx* ctx, const rtk_opt* opt, std::vector<std::vector<uint32_t>>& amb, uint64_t* stats) {
+void detect_snps_host(rtk_ctx* ctx, const rtk_opt* opt, std::vector<std::vector<uint32_t>>& amb, uint64_t* stats, uint64_t range_first = 0, uint64_t range_n = ~0ULL) {
     if (!ctx->has_graph || !ctx->host_graph) throw std::invalid_argument("no graph uploaded to this context");
     const rtk_graph_view& g = ctx->host_graph->view;
     const uint64_t n = g.n_unitigs;
@@ -112,14 +113,15 @@ void detect_snps_host(rtk_ctx* ctx, const rtk_opt* opt, std::vector<std::vector<
     amb.assign(n, {});
     // batches of coloured unitigs: bounded pool size, read id within the raw-hit label
     const uint64_t max_bases = 256ull << 20, max_reads = (1u << RTK_HIT_READ_BITS) - 1;
-    uint64_t u0 = 0;
+    const uint64_t range_end = (range_first >= n) ? range_first : ((range_n > n - range_first) ? n : range_first + range_n);   // unitigs [range_first, range_end)
+    uint64_t u0 = range_first;
     std::vector<char> pool;
     std::vector<uint64_t> off;
     std::vector<uint32_t> ids;
-    while (u0 < n) {
+    while (u0 < range_end) {
         ids.clear(); off.assign(1, 0);
         uint64_t bases = 0, u = u0;
-        for (; u < n && ids.size() < max_reads; ++u) {
+        for (; u < range_end && ids.size() < max_reads; ++u) {
             if (!(g.shared[u] & 0xffULL)) continue;                      // hasSharedPids (:503 / :590)
             const uint64_t len = g.unitig_off[u + 1] - g.unitig_off[u];
             if (!ids.empty() && bases + len > max_bases) break;
@@ -276,11 +278,16 @@ using namespace rtk;
 extern "C" {
 
 int rtk_detect_snps(rtk_ctx* c, const rtk_opt* opt, uint64_t** amb_off, uint32_t** amb_ids, uint64_t* stats) {
+    return rtk_detect_snps_range(c, opt, 0, ~0ULL, amb_off, amb_ids, stats);
+}
+
+int rtk_detect_snps_range(rtk_ctx* c, const rtk_opt* opt, uint64_t first_unitig, uint64_t n_unitigs, uint64_t** amb_off, uint32_t** amb_ids,
+                          uint64_t* stats) {
     return guarded([&] {
         if (!c || !amb_off || !amb_ids) throw std::invalid_argument("null argument");
         DeviceBind bind(c);
         std::vector<std::vector<uint32_t>> amb;
-        detect_snps_host(c, opt, amb, stats);
+        detect_snps_host(c, opt, amb, stats, first_unitig, n_unitigs);
         uint64_t total = 0;
         for (const auto& v : amb) total += v.size();
         *amb_off = (uint64_t*)malloc((amb.size() + 1) * sizeof(uint64_t));
@@ -297,11 +304,16 @@ int rtk_detect_snps(rtk_ctx* c, const rtk_opt* opt, uint64_t** amb_off, uint32_t
 }
 
 int rtk_detect_short_cycles(rtk_ctx* c, const rtk_opt* opt, uint8_t** is_cycle, uint64_t** cyc_off, char** cyc_pool, uint64_t* stats) {
+    return rtk_detect_short_cycles_range(c, opt, 0, ~0ULL, is_cycle, cyc_off, cyc_pool, stats);
+}
+
+int rtk_detect_short_cycles_range(rtk_ctx* c, const rtk_opt* opt, uint64_t first_unitig, uint64_t n_unitigs, uint8_t** is_cycle, uint64_t** cyc_off,
+                                  char** cyc_pool, uint64_t* stats) {
     return guarded([&] {
         if (!c || !is_cycle || !cyc_off || !cyc_pool) throw std::invalid_argument("null argument");
         DeviceBind bind(c);
         CycleOut out;
-        detect_short_cycles_host(c, opt, out, stats);
+        detect_short_cycles_host(c, opt, out, stats, first_unitig, n_unitigs);
         const size_t n = out.blob.size();
         uint64_t total = 0;
         for (const auto& b : out.blob) total += b.size();
