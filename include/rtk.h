@@ -47,7 +47,7 @@ typedef struct rtk_opt {
     double min_score;              /* 0.0 */
     double min_confidence_snp_corr;/* 0.9 */
     uint32_t force_unres_snp_corr; /* 0 */
-    uint32_t reserved;
+    uint32_t reserved;             /* bit 0: rtk_color_long_reads keeps all reads where the reference would subsample */
 } rtk_opt;
 
 void rtk_opt_default(rtk_opt* opt, int pass); /* pass 1: k=31, pass 2: k=63 */
@@ -343,7 +343,8 @@ int rtk_detect_short_cycles(rtk_ctx* ctx, const rtk_opt* opt, uint8_t** is_cycle
  * (UnitigData::shared_pids), colours col_ids[col_off[u], col_off[u+1]) ascending; read_id (optional) = the id each input read
  * received (0xFFFFFFFF: none).  The reference deals the ids in an order that depends on thread timing (src/Graph.cpp:1655-1663), so
  * its colouring is reproduced up to a relabelling of the ids.  Fails when the estimated haplotype coverage reaches 10 (the
- * reference then subsamples at random, :2312).  stats (optional, 10 x u64): [0..3] K1 as above, [4] (unitig, read) pairs,
+ * reference then subsamples reads at random, :2312) unless opt->reserved bit 0 is set: then every read is kept (the colouring is a
+ * superset of any subsample the reference could draw; larger index, same meaning of every word).  stats (optional, 10 x u64): [0..3] K1 as above, [4] (unitig, read) pairs,
  * [5] ids dealt, [7] flag kernel ns, [8] estimated haplotype coverage. */
 int rtk_color_long_reads(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, const char* seq_pool, const uint64_t* seq_off,
                          const char* qual_pool, const uint64_t* qual_off, const char* name_pool, const uint64_t* name_off,

@@ -221,7 +221,8 @@ void color_long_reads_host(rtk_ctx* ctx, const rtk_opt* opt, uint32_t n_reads, c
     for (uint64_t u = 0; u < n; ++u) cov[u] = std::min<uint64_t>(cov[u], 0x7fffffffULL);
     const uint64_t hap_cov = estimate_hap_cov(g, cov);
     if (stats) stats[8] = hap_cov;
-    if (hap_cov >= 10) throw std::invalid_argument("colouring: estimated haplotype coverage " + std::to_string(hap_cov) + " >= 10: the reference subsamples the reads here (src/Graph.cpp:2312-3083, random), which this library does not do");
+    const bool keep_all = opt && (opt->reserved & 1u);   // caller accepts the un-subsampled colouring (a superset of any subsample)
+    if (hap_cov >= 10 && !keep_all) throw std::invalid_argument("colouring: estimated haplotype coverage " + std::to_string(hap_cov) + " >= 10: the reference subsamples the reads here (src/Graph.cpp:2312-3083, random), which this library does not do (rtk_opt::reserved bit 0 keeps all reads instead)");
 
     // ---- flags on the device
     float ms = 0.f;

@@ -146,7 +146,7 @@ void usage() {
             "  --no-cache        always parse the index files, write no cache\n"
             "rtk_correct annotate -g <graph.fasta[.gz]> -d <graph.rtsk> -o <out.rtsk> [-k K] [--min-cov N] [--no-snp] [--first-gpu D] [-v]\n"
             "  detectSNPs + detectShortCycles of the reference's index build, recomputed on the GPU from the colours of the index\n"
-            "rtk_correct index2 -g <graph.k2.fasta[.gz]> -l <pass-1 corrected long reads> -o <prefix> [-K k2] [-M f] [-C n] [-Q n] [--min-cov N] [--no-snp] [-v]\n"
+            "rtk_correct index2 -g <graph.k2.fasta[.gz]> -l <pass-1 corrected long reads> -o <prefix> [-K k2] [-M f] [-C n] [-Q n] [--min-cov N] [--no-snp] [--keep-all-reads] [-v]\n"
             "  `Ratatosk index -2`: colours the k2 graph with the long reads, adds SNP and short-cycle annotations, writes <prefix>.index.k<k2>.rtsk\n");
 }
 
@@ -385,7 +385,8 @@ int run_index2(int argc, char** argv) {
     static struct option lo[] = {{"in-graph", required_argument, 0, 'g'}, {"in-long", required_argument, 0, 'l'}, {"out-long", required_argument, 0, 'o'},
                                  {"k2", required_argument, 0, 'K'}, {"min-conf-color2", required_argument, 0, 'M'}, {"min-len-color2", required_argument, 0, 'C'},
                                  {"max-base-qual", required_argument, 0, 'Q'}, {"min-cov", required_argument, 0, 1000}, {"no-snp", no_argument, 0, 1001},
-                                 {"first-gpu", required_argument, 0, 1002}, {"verbose", no_argument, 0, 'v'}, {0, 0, 0, 0}};
+                                 {"first-gpu", required_argument, 0, 1002}, {"keep-all-reads", no_argument, 0, 1003}, {"verbose", no_argument, 0, 'v'}, {0, 0, 0, 0}};
+    bool keep_all = false;
     int c;
     while ((c = getopt_long(argc - 1, argv + 1, "g:l:o:K:M:C:Q:v", lo, nullptr)) != -1) {
         switch (c) {
@@ -400,6 +401,7 @@ int run_index2(int argc, char** argv) {
             case 1000: min_cov = atoi(optarg); break;
             case 1001: no_snp = true; break;
             case 1002: device = atoi(optarg); break;
+            case 1003: keep_all = true; break;
             default: usage(); return 1;
         }
     }
@@ -431,7 +433,7 @@ int run_index2(int argc, char** argv) {
     const uint32_t n_reads = (uint32_t)(seq_off.size() - 1);
     rtk_opt ropt;
     rtk_opt_default(&ropt, 2);
-    ropt.k = (uint32_t)k; ropt.min_cov_vertices = (uint32_t)min_cov; ropt.max_qual = max_qual;
+    ropt.k = (uint32_t)k; ropt.min_cov_vertices = (uint32_t)min_cov; ropt.max_qual = max_qual; ropt.reserved = keep_all ? 1u : 0u;
     if (verbose) printf("Ratatosk::Ratatosk(): Adding colors and coverage to graph (2/2).\n");
     uint64_t *kmcov = nullptr, *shared = nullptr, *col_off = nullptr, st[10] = {0};
     uint32_t* col_ids = nullptr;

@@ -106,3 +106,50 @@ def test_color_long_reads_options(sim_lib):
 @pytest.mark.parametrize("fx", ["F1", "F2", "F3"])
 def test_color_long_reads_cuda_matches_reference_index(fx):
     _check_color(fx, None)
+
+
+def test_color_long_reads_refuses_where_the_reference_subsamples(sim_lib):
+    """the pass-1 reads of F2 given 30 times under different names: the estimated haplotype coverage passes 10, where the reference
+    starts drawing reads at random (src/Graph.cpp:2312) - the call refuses, unless the caller opts into keeping every read"""
+    g, ctx, recs, (km0, sh0, off0, ids0, _), st0 = _color("F2", sim_lib)
+    seqs = [r[1] for r in recs] * 30
+    quals = [r[2] for r in recs] * 30
+    names = ["%s_%d" % (r[0], c) for c in range(30) for r in recs]
+    with pytest.raises(rb.RtkError, match="haplotype coverage"):
+        ctx.color_long_reads(seqs, quals, names)
+    opt = rb.default_opt(2, lib=sim_lib)
+    opt.reserved = 1
+    st = [0] * 10
+    km, sh, off, ids, rid = ctx.color_long_reads(seqs, quals, names, opt=opt, stats=st)
+    assert st[8] >= 10 and st[5] == 30 * st0[5]
+    cov = lambda w: (w >> 31) & 0x7fffffff
+    assert all(cov(int(a)) == 30 * cov(int(b)) for a, b in zip(km, km0))
+    assert all(int(off[u + 1] - off[u]) == 30 * int(off0[u + 1] - off0[u]) for u in range(len(km0)))
+    ctx.close(); g.close()
+
+
+def test_haplotype_coverage_estimate_switches_where_the_reference_does(sim_lib, tmp_path):
+    """estimateHaplotypeCoverage (src/Graph.cpp:4185-4233) restated on the adjacency table: with 23 copies of the F2 reads the
+    reference's `index -2 -v` does not subsample, with 24 it does - the estimate must cross 10 between the two"""
+    import subprocess
+    ref_cli = os.path.join(ROOT, "oracle", "_ref", "Ratatosk")
+    if not os.path.exists(ref_cli):
+        pytest.skip("reference CLI not built")
+    g, ctx, recs, _, _ = _color("F2", sim_lib)
+    fa = os.path.join(GOLDEN, "F2", "index.k63.fasta.gz")
+    opt = rb.default_opt(2, lib=sim_lib)
+    opt.reserved = 1
+    for copies, want in ((23, False), (24, True)):
+        st = [0] * 10
+        ctx.color_long_reads([r[1] for r in recs] * copies, [r[2] for r in recs] * copies,
+                             ["%s_%d" % (r[0], c) for c in range(copies) for r in recs], opt=opt, stats=st)
+        assert (st[8] >= 10) == want, (copies, st[8])
+        reads = str(tmp_path / ("rep%d.fastq" % copies))
+        with open(reads, "w") as f:
+            for c in range(copies):
+                for n, s, q in recs:
+                    f.write("@%s_%d\n%s\n+\n%s\n" % (n, c, s, q))
+        out = subprocess.run([ref_cli, "index", "-2", "-v", "-c", "4", "-g", fa, "-l", reads, "-o", str(tmp_path / "rep")],
+                             capture_output=True, text=True).stdout
+        assert ("Subsampling reads" in out) == want, copies
+    ctx.close(); g.close()
