@@ -413,3 +413,70 @@ def test_cli_single_thread_branch_has_no_phasing(sim_cli, tmp_path):
         _run(sim_cli, args + ["-o", os.path.join(tmp, "fs")])
         subprocess.check_call([REF_CLI, "correct"] + args + ["-o", os.path.join(tmp, "ref_fs")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         assert open(os.path.join(tmp, "fs.fastq"), "rb").read() == open(os.path.join(tmp, "ref_fs.fastq"), "rb").read()
+
+
+def _walk_reads(path, fa, seed, n_reads=60):
+    """long reads spelled along random walks of the k = 63 graph (both orientations, through short unitigs and cycles), with a
+    sprinkle of substitutions and '!' qualities"""
+    import numpy as np
+    import ratatosk_b200 as rb
+    from common import revcomp
+    sim = os.path.join(HERE, "hostsim", "_build", "librtk_hostsim.so")
+    g = rb.Graph.load(fa, "", 63, lib=sim)
+    n = g.info()["n_unitigs"]
+    rng = np.random.RandomState(seed)
+    with open(path, "w") as f:
+        for r in range(n_reads):
+            u, s = int(rng.randint(n)), int(rng.randint(2))
+            seq = g.unitig_seq(u) if s else revcomp(g.unitig_seq(u))
+            target = int(rng.randint(2500, 20000))
+            while len(seq) < target:
+                adj = g.unitig_words(u)[2]
+                nxt = [adj[b] if s else adj[4 + (3 - b)] for b in range(4)]
+                nxt = [x for x in nxt if x != 0xFFFFFFFF]
+                if not nxt:
+                    break
+                x = nxt[int(rng.randint(len(nxt)))]
+                u, s = x & 0x7fffffff, (x >> 31) if s else 1 - (x >> 31)
+                t = g.unitig_seq(u) if s else revcomp(g.unitig_seq(u))
+                assert seq[-62:] == t[:62]
+                seq += t[62:]
+            seq, q = list(seq), ["I"] * len(seq)
+            for j in rng.randint(0, len(seq), max(1, len(seq) // 1500)):
+                seq[j] = "ACGT"[("ACGT".index(seq[j]) + 1 + int(rng.randint(3))) % 4]
+            for j in rng.randint(0, len(seq), max(1, len(seq) // 300)):
+                q[j] = "!"
+            f.write("@w%d\n%s\n+\n%s\n" % (r, "".join(seq), "".join(q)))
+    g.close()
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_cli_index2_matches_reference_cli_on_graph_walk_reads(seed, sim_cli, tmp_path):
+    """`rtk_correct index2` against a fresh `Ratatosk index -2` on reads spelled along random walks of the graph"""
+    import refseams
+    if not (refseams.available() and os.path.exists(REF_CLI)):
+        pytest.skip("reference not built")
+    tmp = str(tmp_path)
+    fa = os.path.join(GOLDEN, "F2", "index.k63.fasta.gz")
+    reads = os.path.join(tmp, "reads.fastq")
+    _walk_reads(reads, fa, seed)
+    subprocess.check_call([REF_CLI, "index", "-2", "-c", "4", "-g", fa, "-l", reads, "-o", os.path.join(tmp, "ref")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    r = subprocess.run([sim_cli, "index2", "-g", fa, "-l", reads, "-o", os.path.join(tmp, "ours")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode(errors="replace")[-2000:]
+    ours = _dump_records(fa, os.path.join(tmp, "ours.index.k63.rtsk"), 63, tmp, "ours")
+    want = _dump_records(fa, os.path.join(tmp, "ref.index.k63.rtsk"), 63, tmp, "want")
+    bad = [s[:24] for s in want if ours[s][:2] != want[s][:2] or ours[s][3:] != want[s][3:] or len(ours[s][2]) != len(want[s][2])]
+    assert not bad, (len(bad), bad[:5], [(ours[s][:2], want[s][:2], ours[s][3:], want[s][3:]) for s in want if s[:24] in bad[:2]])
+    m, changed = {}, True
+    while changed:
+        changed = False
+        for s in want:
+            a, b = ours[s][2], want[s][2]
+            un = [x for x in a if x not in m]
+            rem = b - set(m[x] for x in a if x in m)
+            if len(un) == 1 and len(rem) == 1:
+                m[un[0]] = next(iter(rem))
+                changed = True
+    n_ids = len(set().union(*[want[s][2] for s in want]))
+    assert len(m) == n_ids and n_ids >= 30
+    assert all(set(m[x] for x in ours[s][2]) == want[s][2] for s in want)
