@@ -19,6 +19,9 @@
 // the candidates of the unitig, as the reference's local_graph_traversal objects do.
 //
 // Arena overflow (a unitig in a tangle) is reported per unitig; the host re-runs those unitigs with a larger arena.
+//
+// rtk_edge_flags_kernel (end of file) is the per-unitig step of addCoverage that produces the edge flags both walks read:
+// postProcessUnitigs (src/Graph.cpp:1986-2023), used by the long-read colouring (color_host.cpp).
 #pragma once
 #ifndef RTK_HOSTSIM
 #include <cuda_runtime.h>

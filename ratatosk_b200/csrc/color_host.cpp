@@ -18,8 +18,9 @@
 //   flags       isBranching and the per-edge "shared by >= min_cov_vertices reads" bits (postProcessUnitigs, :1986-2023): one warp
 //               per unitig on the device (rtk_edge_flags_kernel)
 // Not restated: the subsampling branch taken when estimateHaplotypeCoverage() >= 10 (:2312-3083; it draws from
-// std::random_device) - the call fails with RTK_EUNSUPPORTED-style error text when the estimate reaches 10; reads longer than the
-// reference's 1 MB reading buffer are mapped whole (the reference would cut them).
+// std::random_device) - the call fails with RTK_EINVAL and says so when the estimate reaches 10, unless the caller asks to keep
+// every read (rtk_opt::reserved bit 0); reads longer than the reference's 1 MB reading buffer are mapped whole (the reference
+// would cut them).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
