@@ -545,3 +545,41 @@ def test_cli_fresh_graph_walk_reads_match_fresh_reference_runs(seed, sim_cli, tm
     assert same_as_some_reference_run(open(o + ".2.fastq", "rb").read(), ["-1", "-c", "4"] + i1 + ["-l", reads, "-o", r], r + ".2.fastq")
     _run(sim_cli, ["-2", "-O", "-c", "8", "--no-cache"] + i2 + ["-l", o + ".2.fastq", "-L", reads, "-o", o])
     assert same_as_some_reference_run(open(o + ".fastq", "rb").read(), ["-2", "-O", "-c", "4"] + i2 + ["-l", o + ".2.fastq", "-L", reads, "-o", r], r + ".fastq")
+
+
+def test_cli_odd_records_match_fresh_reference_runs(sim_cli, tmp_path):
+    """records the fixtures do not hold - shorter than k, exactly k - 1 / k / 2k, all N, a homopolymer, header comments, FASTA input
+    - next to ordinary noisy reads: pass 1 (FASTQ and FASTA), pass 2 and the two-pass mode against the reference CLI run here"""
+    if not os.path.exists(REF_CLI):
+        pytest.skip("reference CLI not built")
+    d, tmp = os.path.join(GOLDEN, "F2"), str(tmp_path)
+    walk = os.path.join(tmp, "walk.fastq")
+    _ont_walk_reads(walk, os.path.join(d, "index.k31.fasta.gz"), 31, 31, 8)
+    w = open(walk).read().split("\n")
+    recs = [("short", "ACGTACGTAC", "I" * 10), ("k30", "A" * 30, "I" * 30), ("k31", "ACGT" * 7 + "ACG", "I" * 31), ("allN", "N" * 500, "#" * 500)]
+    recs += [(w[i][1:], w[i + 1], w[i + 3]) for i in range(0, len(w) - 3, 4)]
+    recs += [("k62", "ACGT" * 15 + "AC", "I" * 62), ("poly", "A" * 3000, "5" * 3000)]
+    fq, fa = os.path.join(tmp, "odd.fastq"), os.path.join(tmp, "odd.fasta")
+    with open(fq, "w") as f:
+        for n, s, q in recs:
+            f.write("@%s extra comment\n%s\n+\n%s\n" % (n, s, q))
+    with open(fa, "w") as f:
+        for n, s, q in recs:
+            f.write(">%s\n%s\n" % (n, s))
+    i1 = ["-g", os.path.join(d, "index.k31.fasta.gz"), "-d", os.path.join(d, "index.k31.rtsk")]
+    i2 = ["-g", os.path.join(d, "index.k63.fasta.gz"), "-d", os.path.join(d, "index.k63.rtsk")]
+    o, r = os.path.join(tmp, "ours"), os.path.join(tmp, "ref")
+
+    def ref(args):
+        subprocess.check_call([REF_CLI, "correct"] + args, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+    for inp in (fa, fq):
+        _run(sim_cli, ["-1", "--no-cache"] + i1 + ["-l", inp, "-o", o])
+        ref(["-1", "-c", "4"] + i1 + ["-l", inp, "-o", r])
+        assert open(o + ".2.fastq", "rb").read() == open(r + ".2.fastq", "rb").read(), inp
+    _run(sim_cli, ["-2", "-O", "-c", "8", "--no-cache"] + i2 + ["-l", r + ".2.fastq", "-L", fq, "-o", o])
+    ref(["-2", "-O", "-c", "4"] + i2 + ["-l", r + ".2.fastq", "-L", fq, "-o", r])
+    want = open(r + ".fastq", "rb").read()
+    assert open(o + ".fastq", "rb").read() == want
+    _run(sim_cli, ["--no-cache"] + i1 + ["--in-graph2", i2[1], "--in-unitig-data2", i2[3], "-l", fq, "-o", os.path.join(tmp, "tp")])
+    assert open(os.path.join(tmp, "tp.fastq"), "rb").read() == want
